@@ -1,0 +1,851 @@
+// C ABI of the B200-native EFTS-CNN forward path (include/efts_b200.h): context, weight prepack,
+// TMA tensor maps, kernel launches and the forward()/inference() schedules.
+// Reference citations are relative to /root/reference/nntts.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/efts_b200.h"
+#include "gemm_sm100.cuh"
+#include "path_kernels.cuh"
+
+namespace {
+
+using namespace efts;
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                         \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess)                                                                     \
+      return fail(EFTS_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                  __LINE__);                                                                   \
+  } while (0)
+
+#define TRY(expr)              \
+  do {                         \
+    int _r = (expr);           \
+    if (_r != EFTS_OK) return _r; \
+  } while (0)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+// fp16 hi/lo operand planes of one weight tensor, tap-major [Z][N][K].
+struct PackedW {
+  __half* hi = nullptr;
+  __half* lo = nullptr;
+  float* bias = nullptr;
+  int Z = 0, N = 0, K = 0;
+};
+
+struct OpA { const __half* hi; const __half* lo; int B, T, K, ld; };   // [B, T, ld], K valid columns
+struct OpB { const __half* hi; const __half* lo; int Z, N, K, ld; };   // [Z, N, ld], K valid columns
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+inline int round8(int x) { return (x + 7) / 8 * 8; }
+
+// Bump allocator over the caller's workspace.
+struct Arena {
+  char* base;
+  size_t cap, off = 0;
+  bool ok = true;
+  Arena(void* p, size_t n) : base(static_cast<char*>(p)), cap(n) {}
+  template <typename T>
+  T* get(size_t count) {
+    off = align_up(off, 256);
+    T* r = reinterpret_cast<T*>(base + off);
+    off += count * sizeof(T);
+    if (off > cap) ok = false;
+    return r;
+  }
+};
+
+}  // namespace
+
+struct efts_ctx {
+  efts_config cfg;
+  int sm_count = 0;
+  int amode = 0;
+  int skip_pad_tiles = 1;
+  int64_t launches = 0;
+  bool finalized = false;
+  EncodeTiledFn encode = nullptr;
+  std::map<std::string, std::vector<float>> raw;          // host staging until finalize
+  std::map<std::string, std::vector<int64_t>> raw_shape;
+  std::vector<void*> device_allocs;
+  PackedW text[16], mel[16], dec[16], dp[4];
+  PackedW key, value, prenet, melout;
+  float* emb = nullptr;
+  float* ln_g[4] = {nullptr, nullptr, nullptr, nullptr};
+  float* ln_b[4] = {nullptr, nullptr, nullptr, nullptr};
+  float* head_w = nullptr;
+  float* head_b = nullptr;
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// tensor maps
+int make_map(efts_ctx* c, CUtensorMap* m, const __half* ptr, int inner, int rows, int z, int ld,
+             int box_rows) {
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(rows),
+                        static_cast<cuuint64_t>(z)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(rows) * ld * 2};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(GEMM_BK), static_cast<cuuint32_t>(box_rows), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (strides[0] & 15) != 0)
+    return fail(EFTS_ERR_ARG, "TMA operand not 16-byte aligned (ptr %p, ld %d)", (const void*)ptr, ld);
+  CUresult r = c->encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(ptr), dims, strides, box,
+                         estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(EFTS_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) inner=%d rows=%d z=%d ld=%d box=%d",
+                (int)r, inner, rows, z, ld, box_rows);
+  return EFTS_OK;
+}
+
+template <int BN, int AMODE>
+int launch_gemm_t(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, const GemmParams& p) {
+  using Cfg = GemmCfg<BN, AMODE>;
+  static bool attr_set = false;
+  auto kern = gemm_split_kernel<BN, AMODE>;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  alignas(64) CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  TRY(make_map(c, &ma_hi, a.hi, a.K, a.T, a.B, a.ld, Cfg::A_ROWS));
+  TRY(make_map(c, &ma_lo, a.lo, a.K, a.T, a.B, a.ld, Cfg::A_ROWS));
+  TRY(make_map(c, &mb_hi, b.hi, b.K, b.N, b.Z, b.ld, BN));
+  TRY(make_map(c, &mb_lo, b.lo, b.K, b.N, b.Z, b.ld, BN));
+  dim3 grid((p.N + BN - 1) / BN, (p.T + GEMM_BM - 1) / GEMM_BM, p.B);
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+  CUDA_TRY(cudaGetLastError());
+  c->launches++;
+  return EFTS_OK;
+}
+
+int launch_gemm(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, GemmParams p) {
+  p.B = a.B; p.T = a.T; p.K = a.K;
+  if (a.K != b.K) return fail(EFTS_ERR_ARG, "gemm K mismatch %d vs %d", a.K, b.K);
+  if (p.N % 8 != 0) return fail(EFTS_ERR_ARG, "gemm N=%d must be a multiple of 8", p.N);
+  if (p.B > 65535 || (p.T + GEMM_BM - 1) / GEMM_BM > 65535) return fail(EFTS_ERR_ARG, "grid too large");
+  const long row_tiles = static_cast<long>(p.B) * ((p.T + GEMM_BM - 1) / GEMM_BM);
+  int bn = p.N <= 64 ? 64 : (p.N <= 128 ? 128 : 256);
+  // small problems (B = 1 synthesis): narrower column tiles spread the layer over more SMs
+  while (bn > 64 && row_tiles * ((p.N + bn - 1) / bn) < c->sm_count / 2) bn >>= 1;
+  const int am = p.ntaps > 1 ? c->amode : 0;
+#define EFTS_DISPATCH(BN_)                                                       \
+  switch (am) {                                                                  \
+    case 0: return launch_gemm_t<BN_, 0>(c, st, a, b, p);                        \
+    case 1: return launch_gemm_t<BN_, 1>(c, st, a, b, p);                        \
+    default: return launch_gemm_t<BN_, 2>(c, st, a, b, p);                       \
+  }
+  if (bn == 256) { EFTS_DISPATCH(256) }
+  if (bn == 128) { EFTS_DISPATCH(128) }
+  EFTS_DISPATCH(64)
+#undef EFTS_DISPATCH
+}
+
+GemmParams gemm_defaults() {
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.ntaps = 1;
+  p.divisor = 1.0f;
+  return p;
+}
+
+OpB weight_op(const PackedW& w) { return OpB{w.hi, w.lo, w.Z, w.N, w.K, w.K}; }
+
+// ------------------------------------------------------------------------------------------------
+// weights
+int upload(efts_ctx* c, const void* host, size_t bytes, void** dev) {
+  CUDA_TRY(cudaMalloc(dev, bytes));
+  c->device_allocs.push_back(*dev);
+  CUDA_TRY(cudaMemcpy(*dev, host, bytes, cudaMemcpyHostToDevice));
+  return EFTS_OK;
+}
+
+int need(efts_ctx* c, const std::string& name, std::initializer_list<int64_t> shape,
+         const std::vector<float>** out) {
+  auto it = c->raw.find(name);
+  if (it == c->raw.end()) return fail(EFTS_ERR_STATE, "weight '%s' was never set", name.c_str());
+  const std::vector<int64_t>& got = c->raw_shape[name];
+  std::vector<int64_t> want(shape);
+  if (got != want) {
+    std::string g, w;
+    for (auto v : got) g += std::to_string(v) + ",";
+    for (auto v : want) w += std::to_string(v) + ",";
+    return fail(EFTS_ERR_ARG, "weight '%s' has shape [%s], expected [%s]", name.c_str(), g.c_str(), w.c_str());
+  }
+  *out = &it->second;
+  return EFTS_OK;
+}
+
+// [N, K, taps] (torch Conv1d / Linear layout, taps == 1 for Linear) -> planes [taps][N][K]
+int pack_weight(efts_ctx* c, const std::string& wname, const std::string& bname, int N, int K, int taps,
+                PackedW* out) {
+  const std::vector<float>* w;
+  const std::vector<float>* b;
+  if (taps == 1 && c->raw_shape.count(wname) && c->raw_shape[wname].size() == 2) {
+    TRY(need(c, wname, {N, K}, &w));
+  } else {
+    TRY(need(c, wname, {N, K, taps}, &w));
+  }
+  TRY(need(c, bname, {N}, &b));
+  const size_t n = static_cast<size_t>(taps) * N * K;
+  std::vector<__half> hi(n), lo(n);
+  for (int z = 0; z < taps; ++z)
+    for (int o = 0; o < N; ++o)
+      for (int k = 0; k < K; ++k) {
+        const float x = (*w)[(static_cast<size_t>(o) * K + k) * taps + z];
+        if (!(fabsf(x) <= 65504.0f))
+          return fail(EFTS_ERR_UNSUPPORTED, "weight '%s' has a value outside the fp16 operand range", wname.c_str());
+        const __half h = __float2half_rn(x);
+        const size_t d = (static_cast<size_t>(z) * N + o) * K + k;
+        hi[d] = h;
+        lo[d] = __float2half_rn((x - __half2float(h)) * SPLIT_SCALE);
+      }
+  out->Z = taps; out->N = N; out->K = K;
+  TRY(upload(c, hi.data(), n * sizeof(__half), reinterpret_cast<void**>(&out->hi)));
+  TRY(upload(c, lo.data(), n * sizeof(__half), reinterpret_cast<void**>(&out->lo)));
+  TRY(upload(c, b->data(), N * sizeof(float), reinterpret_cast<void**>(&out->bias)));
+  return EFTS_OK;
+}
+
+int upload_vec(efts_ctx* c, const std::string& name, std::initializer_list<int64_t> shape, float** dev) {
+  const std::vector<float>* v;
+  TRY(need(c, name, shape, &v));
+  return upload(c, v->data(), v->size() * sizeof(float), reinterpret_cast<void**>(dev));
+}
+
+// ------------------------------------------------------------------------------------------------
+// workspace layouts
+struct FwdWs {
+  int *tl32, *sl32, *flags;
+  double* acc;
+  float* xt_f[2]; __half *xt_hi[2], *xt_lo[2];
+  __half *key_hi, *key_lo, *val_hi, *val_lo, *valT_hi, *valT_lo;
+  float* dp_f; __half *dp_hi, *dp_lo;
+  float *dur, *e;
+  __half *sp_hi, *sp_lo;
+  float* xm_f[2]; __half *xm_hi[2], *xm_lo[2];
+  float *S, *imv_raw;
+  __half *R_hi, *R_lo;
+  int T1p;
+};
+
+void carve_text(Arena& a, FwdWs& w, int B, int T1, int C) {
+  const size_t m1 = static_cast<size_t>(B) * T1;
+  w.T1p = round8(T1);
+  w.tl32 = a.get<int>(B);
+  w.sl32 = a.get<int>(B);
+  w.flags = a.get<int>(4);
+  w.acc = a.get<double>(2);
+  for (int i = 0; i < 2; ++i) {
+    w.xt_f[i] = a.get<float>(m1 * C);
+    w.xt_hi[i] = a.get<__half>(m1 * C);
+    w.xt_lo[i] = a.get<__half>(m1 * C);
+  }
+  w.key_hi = a.get<__half>(m1 * C); w.key_lo = a.get<__half>(m1 * C);
+  w.val_hi = a.get<__half>(m1 * C); w.val_lo = a.get<__half>(m1 * C);
+  w.valT_hi = a.get<__half>(static_cast<size_t>(B) * C * w.T1p);
+  w.valT_lo = a.get<__half>(static_cast<size_t>(B) * C * w.T1p);
+  w.dp_f = a.get<float>(m1 * C);
+  w.dp_hi = a.get<__half>(m1 * C); w.dp_lo = a.get<__half>(m1 * C);
+  w.dur = a.get<float>(m1);
+  w.e = a.get<float>(m1);
+}
+
+void carve_mel(Arena& a, FwdWs& w, int B, int T2, int C, int odim, bool teacher_forced) {
+  const size_t m2 = static_cast<size_t>(B) * T2;
+  for (int i = 0; i < 2; ++i) {
+    w.xm_f[i] = a.get<float>(m2 * C);
+    w.xm_hi[i] = a.get<__half>(m2 * C);
+    w.xm_lo[i] = a.get<__half>(m2 * C);
+  }
+  w.R_hi = a.get<__half>(m2 * w.T1p);
+  w.R_lo = a.get<__half>(m2 * w.T1p);
+  if (teacher_forced) {
+    w.sp_hi = a.get<__half>(m2 * odim);
+    w.sp_lo = a.get<__half>(m2 * odim);
+    w.S = a.get<float>(m2 * w.T1p);
+    w.imv_raw = a.get<float>(m2);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// schedules shared by the entry points
+
+// x <- x + lrelu(conv_k(x) + b), n layers, ping-ponging between two (fp32, hi, lo) buffer sets.
+// The input lives in set `cur`; returns the index of the set holding the output.  If `final_f`
+// is non-null the last layer writes its fp32 result there instead (planes still go to the set).
+int run_conv_stack(efts_ctx* c, cudaStream_t st, const PackedW* layers, int n, int B, int T, float* f[2],
+                   __half* hi[2], __half* lo[2], const float* first_resid, float* final_f,
+                   const int* skip_lens, int* cur_io) {
+  const int C = c->cfg.n_channels;
+  int cur = *cur_io;
+  for (int l = 0; l < n; ++l) {
+    const int nxt = cur ^ 1;
+    GemmParams p = gemm_defaults();
+    p.N = C;
+    p.ntaps = layers[l].Z;
+    p.pad = (layers[l].Z - 1) / 2;
+    p.act = ACT_LRELU;
+    p.bias = layers[l].bias;
+    p.resid = (l == 0 && first_resid != nullptr) ? first_resid : f[cur];
+    p.out = (l == n - 1 && final_f != nullptr) ? final_f : f[nxt];
+    p.ld_out = C;
+    p.out_hi = hi[nxt]; p.out_lo = lo[nxt]; p.ld_pl = C;
+    if (skip_lens != nullptr && c->skip_pad_tiles) {
+      p.skip_lens = skip_lens;
+      p.skip_halo = p.pad * (n - 1 - l);
+    }
+    TRY(launch_gemm(c, st, OpA{hi[cur], lo[cur], B, T, C, C}, weight_op(layers[l]), p));
+    cur = nxt;
+  }
+  *cur_io = cur;
+  return EFTS_OK;
+}
+
+// Duration predictor body: two (conv k3 -> ReLU -> LayerNorm) layers and the linear head.
+// Input operand planes in_hi/in_lo [B,T,C]; scratch dp_f, dp_hi/lo.
+int run_duration_predictor(efts_ctx* c, cudaStream_t st, const __half* in_hi, const __half* in_lo, int B,
+                           int T, float* dp_f, __half* dp_hi, __half* dp_lo, const int* lens, int mode,
+                           void* out) {
+  const int C = c->cfg.n_channels;
+  const size_t rows = static_cast<size_t>(B) * T;
+  const int nl = c->cfg.n_duration_layer;
+  const __half* ahi = in_hi;
+  const __half* alo = in_lo;
+  for (int l = 0; l < nl; ++l) {
+    GemmParams p = gemm_defaults();
+    p.N = C;
+    p.ntaps = c->dp[l].Z;
+    p.pad = (c->dp[l].Z - 1) / 2;
+    p.act = ACT_RELU;
+    p.bias = c->dp[l].bias;
+    p.out = dp_f; p.ld_out = C;
+    TRY(launch_gemm(c, st, OpA{ahi, alo, B, T, C, C}, weight_op(c->dp[l]), p));
+    const int wpb = 8;
+    const unsigned grid = static_cast<unsigned>((rows + wpb - 1) / wpb);
+    if (l < nl - 1) {
+      layernorm_kernel<0><<<grid, wpb * 32, 0, st>>>(dp_f, rows, T, c->ln_g[l], c->ln_b[l], dp_hi, dp_lo,
+                                                     nullptr, nullptr, nullptr, 0, 0.0f, nullptr);
+    } else {
+      layernorm_kernel<1><<<grid, wpb * 32, 0, st>>>(dp_f, rows, T, c->ln_g[l], c->ln_b[l], nullptr, nullptr,
+                                                     c->head_w, c->head_b, lens, mode,
+                                                     c->cfg.duration_offset, out);
+    }
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+    ahi = dp_hi; alo = dp_lo;
+  }
+  return EFTS_OK;
+}
+
+// Gaussian reconstruction + expansion (models/efficient_tts.py:184-194 / :270-280):
+// e [B,T1] -> reconst_alpha [B,T1,T2] and expanded value at frame rate (fp32 + planes).
+int run_reconstruct_expand(efts_ctx* c, cudaStream_t st, const float* e, const int* tl, const int* sl, int B,
+                           int T1, int T2, int T1p, __half* R_hi, __half* R_lo, const __half* valT_hi,
+                           const __half* valT_lo, float* reconst_alpha, float* out_f, __half* out_hi,
+                           __half* out_lo) {
+  const int C = c->cfg.n_channels;
+  {
+    dim3 grid((T2 + 127) / 128, B);
+    const float neg_sigma = -1.0f * c->cfg.sigma;
+    reconstruct_alignment_kernel<<<grid, 128, T1 * sizeof(float), st>>>(e, tl, sl, T1, T2, T1p, neg_sigma,
+                                                                        reconst_alpha, R_hi, R_lo);
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+  }
+  GemmParams p = gemm_defaults();
+  p.N = C;
+  p.b_batched = 1;
+  p.lens = sl;
+  p.out = out_f; p.ld_out = C;
+  p.out_hi = out_hi; p.out_lo = out_lo; p.ld_pl = C;
+  if (sl != nullptr && c->skip_pad_tiles) {
+    p.skip_lens = sl;
+    p.skip_halo = ((c->cfg.k_size - 1) / 2) * c->cfg.n_decoder_layer;
+  }
+  return launch_gemm(c, st, OpA{R_hi, R_lo, B, T2, T1p, T1p}, OpB{valT_hi, valT_lo, B, C, T1p, T1p}, p);
+}
+
+// Energy -> softmax/expectation -> scan -> aligned positions (models/efficient_tts.py:167-178).
+int run_imv(efts_ctx* c, cudaStream_t st, const __half* q_hi, const __half* q_lo, const __half* key_hi,
+            const __half* key_lo, const int* tl, const int* sl, int B, int T1, int T2, int T1p, float* S,
+            float* imv_raw, float* imv, float* e) {
+  const int C = c->cfg.n_channels;
+  GemmParams p = gemm_defaults();
+  p.N = T1p;
+  p.b_batched = 1;
+  p.divisor = static_cast<float>(std::sqrt(static_cast<double>(C)));   // np.sqrt(float(D)), :390
+  p.out = S; p.ld_out = T1p;
+  if (c->skip_pad_tiles) { p.skip_lens = sl; p.skip_halo = 0; }
+  TRY(launch_gemm(c, st, OpA{q_hi, q_lo, B, T2, C, C}, OpB{key_hi, key_lo, B, T1, C, C}, p));
+  const size_t rows = static_cast<size_t>(B) * T2;
+  energy_softmax_expect_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, st>>>(S, T1p, tl, sl, T2, rows,
+                                                                                       imv_raw);
+  CUDA_TRY(cudaGetLastError());
+  imv_scan_kernel<<<(B + 3) / 4, 128, 0, st>>>(imv_raw, tl, sl, B, T2, imv);
+  CUDA_TRY(cudaGetLastError());
+  aligned_positions_kernel<<<dim3((T1 + 7) / 8, B), 256, 0, st>>>(imv, tl, sl, T1, T2, c->cfg.sigma_e, e);
+  CUDA_TRY(cudaGetLastError());
+  c->launches += 3;
+  return EFTS_OK;
+}
+
+int check_ready(const efts_ctx* c) {
+  if (c == nullptr) return fail(EFTS_ERR_ARG, "null context");
+  if (!c->finalized) return fail(EFTS_ERR_STATE, "weights not finalised (call efts_finalize_weights)");
+  return EFTS_OK;
+}
+
+int split_planes(efts_ctx* c, cudaStream_t st, const float* x, size_t n, __half* hi, __half* lo) {
+  if (n % 4 != 0) return fail(EFTS_ERR_ARG, "split_planes: element count must be a multiple of 4");
+  const size_t n4 = n / 4;
+  const unsigned grid = static_cast<unsigned>(std::min<size_t>((n4 + 255) / 256, 148 * 16));
+  split_planes_kernel<<<grid ? grid : 1, 256, 0, st>>>(x, n4, hi, lo);
+  CUDA_TRY(cudaGetLastError());
+  c->launches++;
+  return EFTS_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+const char* efts_last_error(void) { return g_err; }
+const char* efts_version(void) { return "efts_b200 0.1 (sm_100a, split-fp16 tcgen05)"; }
+
+int efts_create(const efts_config* cfg, efts_ctx** out) {
+  if (cfg == nullptr || out == nullptr) return fail(EFTS_ERR_ARG, "null argument");
+  if (cfg->n_channels != 512) return fail(EFTS_ERR_UNSUPPORTED, "n_channels=%d (kernels are built for 512)", cfg->n_channels);
+  if (cfg->k_size != 5 && cfg->k_size != 3 && cfg->k_size != 1)
+    return fail(EFTS_ERR_UNSUPPORTED, "k_size=%d (supported: 1, 3, 5)", cfg->k_size);
+  if (cfg->duration_kernel_size != 3 && cfg->duration_kernel_size != 1 && cfg->duration_kernel_size != 5)
+    return fail(EFTS_ERR_UNSUPPORTED, "duration_kernel_size=%d", cfg->duration_kernel_size);
+  if (cfg->odim % 8 != 0 || cfg->odim <= 0 || cfg->odim > 256) return fail(EFTS_ERR_UNSUPPORTED, "odim=%d must be a multiple of 8, <= 256", cfg->odim);
+  if (cfg->n_text_encoder_layer < 1 || cfg->n_text_encoder_layer > 16 || cfg->n_mel_encoder_layer < 1 ||
+      cfg->n_mel_encoder_layer > 16 || cfg->n_decoder_layer < 1 || cfg->n_decoder_layer > 16 ||
+      cfg->n_duration_layer < 1 || cfg->n_duration_layer > 4)
+    return fail(EFTS_ERR_UNSUPPORTED, "layer counts out of range");
+  if (cfg->leaky_relu_slope != 0.1f) return fail(EFTS_ERR_UNSUPPORTED, "leaky_relu_slope must be 0.1");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(EFTS_ERR_CUDA, "no CUDA device: %s (this library has no CPU path)", cudaGetErrorString(e));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(EFTS_ERR_ARG, "device %d out of range", cfg->device);
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10)
+    return fail(EFTS_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", cfg->device,
+                prop.major, prop.minor);
+  CUDA_TRY(cudaSetDevice(cfg->device));
+  efts_ctx* c = new efts_ctx();
+  c->cfg = *cfg;
+  c->sm_count = prop.multiProcessorCount;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess) {
+    delete c;
+    return fail(EFTS_ERR_CUDA, "cuTensorMapEncodeTiled unavailable: %s", cudaGetErrorString(e));
+  }
+  c->encode = reinterpret_cast<EncodeTiledFn>(fn);
+  *out = c;
+  return EFTS_OK;
+}
+
+void efts_destroy(efts_ctx* c) {
+  if (c == nullptr) return;
+  for (void* p : c->device_allocs) cudaFree(p);
+  delete c;
+}
+
+int efts_set_weight(efts_ctx* c, const char* name, const float* data_host, const int64_t* shape, int32_t ndim) {
+  if (c == nullptr || name == nullptr || data_host == nullptr || shape == nullptr || ndim < 1 || ndim > 4)
+    return fail(EFTS_ERR_ARG, "bad argument to efts_set_weight");
+  if (c->finalized) return fail(EFTS_ERR_STATE, "weights already finalised");
+  size_t n = 1;
+  std::vector<int64_t> sh(shape, shape + ndim);
+  for (auto v : sh) n *= static_cast<size_t>(v);
+  c->raw[name].assign(data_host, data_host + n);
+  c->raw_shape[name] = sh;
+  return EFTS_OK;
+}
+
+int efts_finalize_weights(efts_ctx* c) {
+  if (c == nullptr) return fail(EFTS_ERR_ARG, "null context");
+  if (c->finalized) return fail(EFTS_ERR_STATE, "weights already finalised");
+  CUDA_TRY(cudaSetDevice(c->cfg.device));
+  const efts_config& g = c->cfg;
+  const int C = g.n_channels;
+  TRY(upload_vec(c, "text_embedding_table.weight", {g.num_symbols, C}, &c->emb));
+  struct { const char* name; int n; PackedW* dst; } stacks[3] = {
+      {"text_encoder", g.n_text_encoder_layer, c->text},
+      {"mel_encoder", g.n_mel_encoder_layer, c->mel},
+      {"decoder", g.n_decoder_layer, c->dec}};
+  for (auto& s : stacks)
+    for (int i = 0; i < s.n; ++i) {
+      const std::string p = std::string(s.name) + ".layers." + std::to_string(i) + ".conv.0.";
+      TRY(pack_weight(c, p + "weight", p + "bias", C, C, g.k_size, &s.dst[i]));
+    }
+  TRY(pack_weight(c, "text_encoder_key.weight", "text_encoder_key.bias", C, C, 1, &c->key));
+  TRY(pack_weight(c, "text_encoder_value.weight", "text_encoder_value.bias", C, C, 1, &c->value));
+  TRY(pack_weight(c, "mel_prenet.0.weight", "mel_prenet.0.bias", C, g.odim, 1, &c->prenet));
+  TRY(pack_weight(c, "mel_output_layer.weight", "mel_output_layer.bias", g.odim, C, 1, &c->melout));
+  for (int i = 0; i < g.n_duration_layer; ++i) {
+    const std::string p = "duration_predictor.conv." + std::to_string(i);
+    TRY(pack_weight(c, p + ".0.weight", p + ".0.bias", C, C, g.duration_kernel_size, &c->dp[i]));
+    TRY(upload_vec(c, p + ".2.weight", {C}, &c->ln_g[i]));
+    TRY(upload_vec(c, p + ".2.bias", {C}, &c->ln_b[i]));
+  }
+  TRY(upload_vec(c, "duration_predictor.linear.weight", {1, C}, &c->head_w));
+  TRY(upload_vec(c, "duration_predictor.linear.bias", {1}, &c->head_b));
+  c->raw.clear();
+  c->raw_shape.clear();
+  c->finalized = true;
+  return EFTS_OK;
+}
+
+size_t efts_workspace_bytes(const efts_ctx* c, int32_t B, int32_t T1, int32_t T2) {
+  if (c == nullptr || B < 1 || T1 < 1 || T2 < 1) return 0;
+  Arena a(nullptr, ~static_cast<size_t>(0));
+  FwdWs w;
+  carve_text(a, w, B, T1, c->cfg.n_channels);
+  carve_mel(a, w, B, T2, c->cfg.n_channels, c->cfg.odim, true);
+  // efts_alignment_fwd additionally stages key / value / query planes (3 text-sized, 1 mel-sized)
+  const size_t extra = (static_cast<size_t>(B) * T1 * 3 + static_cast<size_t>(B) * T2) * c->cfg.n_channels * 4 + 4096;
+  return a.off + extra + 4096;
+}
+
+int efts_set_option(efts_ctx* c, const char* name, int32_t value) {
+  if (c == nullptr || name == nullptr) return fail(EFTS_ERR_ARG, "null argument");
+  if (strcmp(name, "amode") == 0) {
+    if (value < 0 || value > 2) return fail(EFTS_ERR_ARG, "amode must be 0, 1 or 2");
+    c->amode = value;
+    return EFTS_OK;
+  }
+  if (strcmp(name, "skip_pad_tiles") == 0) { c->skip_pad_tiles = value != 0; return EFTS_OK; }
+  return fail(EFTS_ERR_ARG, "unknown option '%s'", name);
+}
+
+int64_t efts_launch_count(const efts_ctx* c) { return c ? c->launches : 0; }
+
+// ------------------------------------------------------------------------------------------------
+int efts_forward(efts_ctx* c, const int64_t* text, const int64_t* text_lengths, const float* speech,
+                 const int64_t* speech_lengths, int32_t B, int32_t T1, int32_t T2, float* imv,
+                 float* reconst_alpha, float* mel_pred, float* scalars, void* workspace, size_t workspace_bytes,
+                 void* stream) {
+  TRY(check_ready(c));
+  if (!text || !text_lengths || !speech || !speech_lengths || !imv || !reconst_alpha || !mel_pred || !scalars ||
+      !workspace)
+    return fail(EFTS_ERR_ARG, "efts_forward: null pointer");
+  if (B < 1 || T1 < 1 || T2 < 1) return fail(EFTS_ERR_ARG, "efts_forward: bad sizes B=%d T1=%d T2=%d", B, T1, T2);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const efts_config& g = c->cfg;
+  const int C = g.n_channels;
+  Arena a(workspace, workspace_bytes);
+  FwdWs w;
+  carve_text(a, w, B, T1, C);
+  carve_mel(a, w, B, T2, C, g.odim, true);
+  if (!a.ok) return fail(EFTS_ERR_WORKSPACE, "workspace too small: need %zu, have %zu", a.off, workspace_bytes);
+  const size_t m1 = static_cast<size_t>(B) * T1, m2 = static_cast<size_t>(B) * T2;
+
+  // 0. lengths, flags, accumulators
+  CUDA_TRY(cudaMemsetAsync(w.flags, 0, 4 * sizeof(int), st));
+  CUDA_TRY(cudaMemsetAsync(w.acc, 0, 2 * sizeof(double), st));
+  prep_lengths_kernel<<<1, 256, 0, st>>>(text_lengths, speech_lengths, B, T1, T2, w.tl32, w.sl32, w.flags);
+  CUDA_TRY(cudaGetLastError());
+  // 1. embedding (:144) -> text encoder (:148)
+  embed_kernel<<<static_cast<unsigned>(m1), C / 4, 0, st>>>(text, c->emb, g.num_symbols, C, w.xt_f[0], w.xt_hi[0],
+                                                            w.xt_lo[0], w.flags);
+  CUDA_TRY(cudaGetLastError());
+  c->launches += 2;
+  int cur = 0;
+  TRY(run_conv_stack(c, st, c->text, g.n_text_encoder_layer, B, T1, w.xt_f, w.xt_hi, w.xt_lo, nullptr, nullptr,
+                     w.tl32, &cur));
+  // 2. key / value projections, zero at pad tokens (:149-157)
+  {
+    GemmParams p = gemm_defaults();
+    p.N = C; p.bias = c->key.bias; p.lens = w.tl32;
+    p.out_hi = w.key_hi; p.out_lo = w.key_lo; p.ld_pl = C;
+    TRY(launch_gemm(c, st, OpA{w.xt_hi[cur], w.xt_lo[cur], B, T1, C, C}, weight_op(c->key), p));
+    p.bias = c->value.bias;
+    p.out_hi = w.val_hi; p.out_lo = w.val_lo;
+    p.outT_hi = w.valT_hi; p.outT_lo = w.valT_lo; p.ld_t = w.T1p;
+    if (w.T1p != T1) {   // K padding of the expansion GEMM must be finite (it multiplies zeros)
+      CUDA_TRY(cudaMemsetAsync(w.valT_hi, 0, static_cast<size_t>(B) * C * w.T1p * sizeof(__half), st));
+      CUDA_TRY(cudaMemsetAsync(w.valT_lo, 0, static_cast<size_t>(B) * C * w.T1p * sizeof(__half), st));
+    }
+    TRY(launch_gemm(c, st, OpA{w.xt_hi[cur], w.xt_lo[cur], B, T1, C, C}, weight_op(c->value), p));
+  }
+  // 3. mel prenet (:161) -> mel encoder (:162)
+  TRY(split_planes(c, st, speech, m2 * g.odim, w.sp_hi, w.sp_lo));
+  {
+    GemmParams p = gemm_defaults();
+    p.N = C; p.bias = c->prenet.bias; p.act = ACT_LRELU;
+    p.out = w.xm_f[0]; p.ld_out = C;
+    p.out_hi = w.xm_hi[0]; p.out_lo = w.xm_lo[0]; p.ld_pl = C;
+    if (c->skip_pad_tiles) {
+      p.skip_lens = w.sl32;
+      p.skip_halo = ((g.k_size - 1) / 2) * g.n_mel_encoder_layer;
+    }
+    TRY(launch_gemm(c, st, OpA{w.sp_hi, w.sp_lo, B, T2, g.odim, g.odim}, weight_op(c->prenet), p));
+  }
+  int curm = 0;
+  TRY(run_conv_stack(c, st, c->mel, g.n_mel_encoder_layer, B, T2, w.xm_f, w.xm_hi, w.xm_lo, nullptr, nullptr,
+                     w.sl32, &curm));
+  // 4. alignment: energy/softmax/expectation, scan, aligned positions (:167-178)
+  TRY(run_imv(c, st, w.xm_hi[curm], w.xm_lo[curm], w.key_hi, w.key_lo, w.tl32, w.sl32, B, T1, T2, w.T1p, w.S,
+              w.imv_raw, imv, w.e));
+  // 5. Gaussian reconstruction + expansion (:184-194) into mel buffer set 0
+  TRY(run_reconstruct_expand(c, st, w.e, w.tl32, w.sl32, B, T1, T2, w.T1p, w.R_hi, w.R_lo, w.valT_hi, w.valT_lo,
+                             reconst_alpha, w.xm_f[0], w.xm_hi[0], w.xm_lo[0]));
+  // 6. decoder (:197) and mel head (:198-200)
+  curm = 0;
+  TRY(run_conv_stack(c, st, c->dec, g.n_decoder_layer, B, T2, w.xm_f, w.xm_hi, w.xm_lo, nullptr, nullptr, w.sl32,
+                     &curm));
+  {
+    GemmParams p = gemm_defaults();
+    p.N = g.odim; p.bias = c->melout.bias; p.lens = w.sl32;
+    p.out = mel_pred; p.ld_out = g.odim;
+    TRY(launch_gemm(c, st, OpA{w.xm_hi[curm], w.xm_lo[curm], B, T2, C, C}, weight_op(c->melout), p));
+  }
+  // 7. duration predictor on value (:219), log domain, zero at pad tokens
+  TRY(run_duration_predictor(c, st, w.val_hi, w.val_lo, B, T1, w.dp_f, w.dp_hi, w.dp_lo, w.tl32, 0, w.dur));
+  // 8. losses (:220-227)
+  loss_partial_kernel<<<c->sm_count * 4, 256, 0, st>>>(mel_pred, speech, w.sl32, T2, g.odim, w.dur, w.e, w.tl32,
+                                                       T1, B, g.duration_offset, g.use_masking, w.acc);
+  CUDA_TRY(cudaGetLastError());
+  loss_finalize_kernel<<<1, 32, 0, st>>>(w.acc, w.tl32, w.sl32, B, T1, T2, g.odim, g.use_masking, w.flags, scalars);
+  CUDA_TRY(cudaGetLastError());
+  c->launches += 2;
+  return EFTS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+int efts_inference_phase1(efts_ctx* c, const int64_t* text, int32_t T1, int32_t* t2_dev, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  TRY(check_ready(c));
+  if (!text || !t2_dev || !workspace || T1 < 1) return fail(EFTS_ERR_ARG, "efts_inference_phase1: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const efts_config& g = c->cfg;
+  const int C = g.n_channels;
+  Arena a(workspace, workspace_bytes);
+  FwdWs w;
+  carve_text(a, w, 1, T1, C);
+  if (!a.ok) return fail(EFTS_ERR_WORKSPACE, "workspace too small: need %zu, have %zu", a.off, workspace_bytes);
+  CUDA_TRY(cudaMemsetAsync(t2_dev, 0, 2 * sizeof(int), st));
+  embed_kernel<<<T1, C / 4, 0, st>>>(text, c->emb, g.num_symbols, C, w.xt_f[0], w.xt_hi[0], w.xt_lo[0], t2_dev + 1);
+  CUDA_TRY(cudaGetLastError());
+  c->launches++;
+  int cur = 0;
+  TRY(run_conv_stack(c, st, c->text, g.n_text_encoder_layer, 1, T1, w.xt_f, w.xt_hi, w.xt_lo, nullptr, nullptr,
+                     nullptr, &cur));
+  {   // value only: the key projection at :251 is computed by the reference but never used
+    GemmParams p = gemm_defaults();
+    p.N = C; p.bias = c->value.bias;
+    p.out_hi = w.val_hi; p.out_lo = w.val_lo; p.ld_pl = C;
+    p.outT_hi = w.valT_hi; p.outT_lo = w.valT_lo; p.ld_t = w.T1p;
+    if (w.T1p != T1) {
+      CUDA_TRY(cudaMemsetAsync(w.valT_hi, 0, static_cast<size_t>(C) * w.T1p * sizeof(__half), st));
+      CUDA_TRY(cudaMemsetAsync(w.valT_lo, 0, static_cast<size_t>(C) * w.T1p * sizeof(__half), st));
+    }
+    TRY(launch_gemm(c, st, OpA{w.xt_hi[cur], w.xt_lo[cur], 1, T1, C, C}, weight_op(c->value), p));
+  }
+  // durations clamp(exp(x) - offset, 0) (:258) and their cumsum (:260); T2 = round(e[-1]) (:361)
+  TRY(run_duration_predictor(c, st, w.val_hi, w.val_lo, 1, T1, w.dp_f, w.dp_hi, w.dp_lo, nullptr, 1, w.dur));
+  duration_cumsum_kernel<<<1, 32, 0, st>>>(w.dur, T1, w.e, t2_dev);
+  CUDA_TRY(cudaGetLastError());
+  c->launches++;
+  return EFTS_OK;
+}
+
+int efts_inference_phase2(efts_ctx* c, int32_t T1, int32_t T2, float* mel_pred, float* reconst_alpha,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+  TRY(check_ready(c));
+  if (!mel_pred || !reconst_alpha || !workspace || T1 < 1) return fail(EFTS_ERR_ARG, "efts_inference_phase2: bad argument");
+  if (T2 < 1)
+    return fail(EFTS_ERR_DATA, "predicted length T2=%d: the reference's decoder conv fails on an empty sequence", T2);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const efts_config& g = c->cfg;
+  const int C = g.n_channels;
+  Arena a(workspace, workspace_bytes);
+  FwdWs w;
+  carve_text(a, w, 1, T1, C);
+  carve_mel(a, w, 1, T2, C, g.odim, false);
+  if (!a.ok) return fail(EFTS_ERR_WORKSPACE, "workspace too small: need %zu, have %zu", a.off, workspace_bytes);
+  TRY(run_reconstruct_expand(c, st, w.e, nullptr, nullptr, 1, T1, T2, w.T1p, w.R_hi, w.R_lo, w.valT_hi, w.valT_lo,
+                             reconst_alpha, w.xm_f[0], w.xm_hi[0], w.xm_lo[0]));
+  int curm = 0;
+  TRY(run_conv_stack(c, st, c->dec, g.n_decoder_layer, 1, T2, w.xm_f, w.xm_hi, w.xm_lo, nullptr, nullptr, nullptr,
+                     &curm));
+  GemmParams p = gemm_defaults();
+  p.N = g.odim; p.bias = c->melout.bias;
+  p.out = mel_pred; p.ld_out = g.odim;
+  return launch_gemm(c, st, OpA{w.xm_hi[curm], w.xm_lo[curm], 1, T2, C, C}, weight_op(c->melout), p);
+}
+
+// ------------------------------------------------------------------------------------------------
+int efts_conv_stack_fwd(efts_ctx* c, int32_t stack, const float* x, float* y, int32_t B, int32_t T, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  TRY(check_ready(c));
+  if (!x || !y || !workspace || B < 1 || T < 1) return fail(EFTS_ERR_ARG, "efts_conv_stack_fwd: bad argument");
+  const PackedW* layers;
+  int n;
+  if (stack == 0) { layers = c->text; n = c->cfg.n_text_encoder_layer; }
+  else if (stack == 1) { layers = c->mel; n = c->cfg.n_mel_encoder_layer; }
+  else if (stack == 2) { layers = c->dec; n = c->cfg.n_decoder_layer; }
+  else return fail(EFTS_ERR_ARG, "stack must be 0 (text), 1 (mel) or 2 (decoder)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int C = c->cfg.n_channels;
+  const size_t m = static_cast<size_t>(B) * T;
+  Arena a(workspace, workspace_bytes);
+  float* f[2]; __half* hi[2]; __half* lo[2];
+  for (int i = 0; i < 2; ++i) {
+    f[i] = a.get<float>(m * C);
+    hi[i] = a.get<__half>(m * C);
+    lo[i] = a.get<__half>(m * C);
+  }
+  if (!a.ok) return fail(EFTS_ERR_WORKSPACE, "workspace too small: need %zu, have %zu", a.off, workspace_bytes);
+  TRY(split_planes(c, st, x, m * C, hi[0], lo[0]));
+  int cur = 0;
+  return run_conv_stack(c, st, layers, n, B, T, f, hi, lo, x, y, nullptr, &cur);
+}
+
+int efts_duration_predictor_fwd(efts_ctx* c, const float* x, const int32_t* lengths, int32_t B, int32_t T,
+                                int32_t mode, void* out, void* workspace, size_t workspace_bytes, void* stream) {
+  TRY(check_ready(c));
+  if (!x || !out || !workspace || B < 1 || T < 1 || mode < 0 || mode > 2)
+    return fail(EFTS_ERR_ARG, "efts_duration_predictor_fwd: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int C = c->cfg.n_channels;
+  const size_t m = static_cast<size_t>(B) * T;
+  Arena a(workspace, workspace_bytes);
+  __half* in_hi = a.get<__half>(m * C);
+  __half* in_lo = a.get<__half>(m * C);
+  float* dp_f = a.get<float>(m * C);
+  __half* dp_hi = a.get<__half>(m * C);
+  __half* dp_lo = a.get<__half>(m * C);
+  if (!a.ok) return fail(EFTS_ERR_WORKSPACE, "workspace too small: need %zu, have %zu", a.off, workspace_bytes);
+  TRY(split_planes(c, st, x, m * C, in_hi, in_lo));
+  return run_duration_predictor(c, st, in_hi, in_lo, B, T, dp_f, dp_hi, dp_lo, lengths, mode, out);
+}
+
+int efts_tap_gemm(efts_ctx* c, const float* x, const float* wgt, float* out, int32_t B, int32_t T, int32_t K,
+                  int32_t N, int32_t ntaps, int32_t pad, int32_t batched, void* workspace, size_t workspace_bytes,
+                  void* stream) {
+  if (c == nullptr) return fail(EFTS_ERR_ARG, "null context");
+  if (!x || !wgt || !out || !workspace || B < 1 || T < 1 || K < 8 || N < 8 || K % 8 || N % 8 || ntaps < 1)
+    return fail(EFTS_ERR_ARG, "efts_tap_gemm: bad argument");
+  if (batched && ntaps != 1) return fail(EFTS_ERR_ARG, "efts_tap_gemm: batched requires ntaps == 1");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int Z = batched ? B : ntaps;
+  const size_t nx = static_cast<size_t>(B) * T * K, nw = static_cast<size_t>(Z) * N * K;
+  Arena a(workspace, workspace_bytes);
+  __half* xh = a.get<__half>(nx); __half* xl = a.get<__half>(nx);
+  __half* wh = a.get<__half>(nw); __half* wl = a.get<__half>(nw);
+  if (!a.ok) return fail(EFTS_ERR_WORKSPACE, "workspace too small: need %zu, have %zu", a.off, workspace_bytes);
+  TRY(split_planes(c, st, x, nx, xh, xl));
+  TRY(split_planes(c, st, wgt, nw, wh, wl));
+  GemmParams p = gemm_defaults();
+  p.N = N; p.ntaps = ntaps; p.pad = pad; p.b_batched = batched;
+  p.out = out; p.ld_out = N;
+  return launch_gemm(c, st, OpA{xh, xl, B, T, K, K}, OpB{wh, wl, Z, N, K, K}, p);
+}
+
+int efts_alignment_fwd(efts_ctx* c, const float* mel_h, const float* key, const float* value,
+                       const int32_t* text_lengths, const int32_t* speech_lengths, int32_t B, int32_t T1, int32_t T2,
+                       float* imv, float* e, float* reconst_alpha, float* expanded, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+  if (c == nullptr) return fail(EFTS_ERR_ARG, "null context");
+  if (!mel_h || !key || !value || !text_lengths || !speech_lengths || !imv || !e || !reconst_alpha || !expanded ||
+      !workspace || B < 1 || T1 < 1 || T2 < 1)
+    return fail(EFTS_ERR_ARG, "efts_alignment_fwd: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int C = c->cfg.n_channels;
+  const int T1p = round8(T1);
+  const size_t m1 = static_cast<size_t>(B) * T1, m2 = static_cast<size_t>(B) * T2;
+  Arena a(workspace, workspace_bytes);
+  __half* q_hi = a.get<__half>(m2 * C); __half* q_lo = a.get<__half>(m2 * C);
+  __half* k_hi = a.get<__half>(m1 * C); __half* k_lo = a.get<__half>(m1 * C);
+  __half* vT_hi = a.get<__half>(static_cast<size_t>(B) * C * T1p);
+  __half* vT_lo = a.get<__half>(static_cast<size_t>(B) * C * T1p);
+  float* S = a.get<float>(m2 * T1p);
+  float* imv_raw = a.get<float>(m2);
+  __half* R_hi = a.get<__half>(m2 * T1p); __half* R_lo = a.get<__half>(m2 * T1p);
+  __half* x_hi = a.get<__half>(m2 * C); __half* x_lo = a.get<__half>(m2 * C);
+  if (!a.ok) return fail(EFTS_ERR_WORKSPACE, "workspace too small: need %zu, have %zu", a.off, workspace_bytes);
+  TRY(split_planes(c, st, mel_h, m2 * C, q_hi, q_lo));
+  TRY(split_planes(c, st, key, m1 * C, k_hi, k_lo));
+  split_transpose_kernel<<<dim3((T1p + 31) / 32, C / 32, B), dim3(32, 8), 0, st>>>(value, T1, C, T1p, vT_hi, vT_lo);
+  CUDA_TRY(cudaGetLastError());
+  c->launches++;
+  TRY(run_imv(c, st, q_hi, q_lo, k_hi, k_lo, text_lengths, speech_lengths, B, T1, T2, T1p, S, imv_raw, imv, e));
+  return run_reconstruct_expand(c, st, e, text_lengths, speech_lengths, B, T1, T2, T1p, R_hi, R_lo, vT_hi, vT_lo,
+                                reconst_alpha, expanded, x_hi, x_lo);
+}
+
+// ------------------------------------------------------------------------------------------------
+int efts_length_regulator_plan(int64_t* ds, const int64_t* ilens, float alpha, int32_t B, int32_t T1,
+                               int64_t* ds_eff, int64_t* out_lens, int64_t* plan, void* stream) {
+  if (!ds || !ilens || !ds_eff || !out_lens || !plan || B < 1 || T1 < 1)
+    return fail(EFTS_ERR_ARG, "efts_length_regulator_plan: bad argument");
+  if (!(alpha > 0.0f)) return fail(EFTS_ERR_ARG, "alpha must be > 0 (layers/length_regulator.py:48)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(cudaMemsetAsync(plan, 0, 2 * sizeof(int64_t), st));
+  length_regulator_plan_kernel<<<(B + 3) / 4, 128, 0, st>>>(
+      reinterpret_cast<long long*>(ds), reinterpret_cast<const long long*>(ilens), alpha, alpha == 1.0f ? 1 : 0, B,
+      T1, reinterpret_cast<long long*>(ds_eff), reinterpret_cast<long long*>(out_lens),
+      reinterpret_cast<long long*>(plan));
+  CUDA_TRY(cudaGetLastError());
+  return EFTS_OK;
+}
+
+int efts_length_regulator_fwd(const float* xs, const int64_t* ds_eff, const int64_t* ilens, const int64_t* out_lens,
+                              int32_t B, int32_t T1, int32_t D, int64_t Tout, float pad_value, float* out,
+                              int64_t* idx, void* stream) {
+  if (!xs || !ds_eff || !ilens || !out_lens || !out || B < 1 || T1 < 1 || D < 1 || Tout < 0)
+    return fail(EFTS_ERR_ARG, "efts_length_regulator_fwd: bad argument");
+  if (Tout == 0) return EFTS_OK;
+  if (B > 65535) return fail(EFTS_ERR_ARG, "B too large");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t smem = static_cast<size_t>(T1) * sizeof(long long);
+  if (smem > 200 * 1024) return fail(EFTS_ERR_ARG, "T1=%d too long for the shared-memory scan", T1);
+  if (smem > 48 * 1024)
+    CUDA_TRY(cudaFuncSetAttribute(length_regulator_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(smem)));
+  dim3 grid(static_cast<unsigned>((Tout + LR_FRAMES - 1) / LR_FRAMES), B);
+  length_regulator_fwd_kernel<<<grid, 256, smem, st>>>(
+      xs, reinterpret_cast<const long long*>(ds_eff), reinterpret_cast<const long long*>(ilens),
+      reinterpret_cast<const long long*>(out_lens), T1, D, Tout, pad_value, out, reinterpret_cast<long long*>(idx));
+  CUDA_TRY(cudaGetLastError());
+  return EFTS_OK;
+}
+
+}  // extern "C"

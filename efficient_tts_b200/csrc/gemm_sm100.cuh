@@ -45,6 +45,8 @@ struct GemmParams {
   const float* bias;     // [N] or nullptr
   const float* resid;    // fp32 [B, T, ld_out] added after the activation, or nullptr
   const int* lens;       // [B] or nullptr: rows with t >= lens[b] are written as zeros
+  const int* skip_lens;  // [B] or nullptr: tiles with t0 >= skip_lens[b] + skip_halo are not computed
+  int skip_halo;         //   (their rows cannot reach a valid output; SURVEY.md 7, hard part 2)
   float* out;            // fp32 [B, T, ld_out] or nullptr
   int ld_out;
   __half* out_hi;        // fp16 planes [B, T, ld_pl] or nullptr
@@ -62,7 +64,7 @@ struct GemmCfg {
   static constexpr int A_ROWS = AMODE == 0 ? GEMM_BM : GEMM_AROWS_SHIFT;
   static constexpr int A_PLANE = A_ROWS * 128;
   static constexpr int B_PLANE = BN * 128;
-  static constexpr int B_STAGES = BN == 256 ? 2 : (BN == 128 ? (AMODE == 0 ? 3 : 4) : 6);
+  static constexpr int B_STAGES = BN == 256 ? 2 : (BN == 128 ? (AMODE == 0 ? 3 : 4) : (AMODE == 0 ? 4 : 6));
   static constexpr int A_STAGES = AMODE == 0 ? B_STAGES : 2;
   static constexpr int SMEM_TILES = A_STAGES * 2 * A_PLANE + B_STAGES * 2 * B_PLANE;
   static constexpr int SMEM_BYTES = SMEM_TILES + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -104,11 +106,13 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int tiles_per_b = (p.T + GEMM_BM - 1) / GEMM_BM;
-  const int b = blockIdx.x / tiles_per_b;
-  const int t0 = (blockIdx.x % tiles_per_b) * GEMM_BM;
-  const int n0 = blockIdx.y * BN;
+  // grid.x = n-tiles (fastest, so the CTAs sharing one A tile run together), grid.y = row tiles
+  // of one utterance, grid.z = utterance.
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.y * GEMM_BM;
+  const int n0 = blockIdx.x * BN;
   const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
+  if (p.skip_lens != nullptr && t0 >= p.skip_lens[b] + p.skip_halo) return;   // CTA-uniform
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::A_STAGES; ++s) { ptx::mbar_init(fullA(s), 1); ptx::mbar_init(emptyA(s), 1); }
@@ -221,6 +225,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       if (n0 + c0 >= p.N) break;                  // warp-uniform
+      __syncwarp();                               // tcgen05.ld is .aligned: reconverge after waits / skips
       uint32_t r0[32], r1[32];
       ptx::tmem_ld_32x32(lane_addr + c0, r0);
       ptx::tmem_ld_32x32(lane_addr + BN + c0, r1);

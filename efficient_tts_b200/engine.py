@@ -1,0 +1,255 @@
+"""Thin Python owner of one ``efts_ctx``: weight marshalling, workspace caching and raw-pointer calls.
+
+PyTorch is used for device memory and streams only; every computation below is a call into
+``libefts_b200.so``.  Reference citations are relative to /root/reference/nntts.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+N_CHANNELS = 512
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def fold_state_dict(state_dict):
+    """Reference ``state_dict`` -> folded fp32 CPU tensors keyed like ``remove_weight_norm()``
+    leaves them (layers/efts_modules.py:81-99): ``*.weight_g`` / ``*.weight_v`` pairs become
+    ``*.weight`` through torch's own ``_weight_norm`` so the effective weights are bit-identical
+    to the ones the reference convolves with."""
+    out = {}
+    for k, v in state_dict.items():
+        if k.endswith(".weight_g"):
+            p = k[: -len(".weight_g")]
+            g = v.detach().to("cpu", torch.float32)
+            w = state_dict[p + ".weight_v"].detach().to("cpu", torch.float32)
+            out[p + ".weight"] = torch._weight_norm(w, g, 0).contiguous()
+        elif k.endswith(".weight_v"):
+            continue
+        elif k.endswith("parametrizations.weight.original0") or k.endswith("parametrizations.weight.original1"):
+            raise NotImplementedError("parametrize-style weight norm checkpoints are not supported; "
+                                      "use torch.nn.utils.weight_norm keys (weight_g / weight_v)")
+        else:
+            out[k] = v.detach().to("cpu", torch.float32).contiguous()
+    return out
+
+
+class Engine:
+    """One prepacked model on one CUDA device."""
+
+    def __init__(self, device, state_dict, *, num_symbols, odim=80, n_channels=N_CHANNELS, k_size=5,
+                 n_text_encoder_layer=5, n_mel_encoder_layer=3, n_decoder_layer=6, n_duration_layer=2,
+                 duration_kernel_size=3, sigma=0.01, sigma_e=0.5, duration_offset=1.0,
+                 leaky_relu_slope=0.1, use_masking=True):
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("efts_b200 runs on CUDA (sm_100a) devices only; got %s" % (self.device,))
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", idx)
+        self.odim, self.C = int(odim), int(n_channels)
+        cfg = _lib.EftsConfig(int(num_symbols), int(odim), int(n_channels), int(k_size),
+                              int(n_text_encoder_layer), int(n_mel_encoder_layer), int(n_decoder_layer),
+                              int(n_duration_layer), int(duration_kernel_size), float(sigma),
+                              float(sigma_e), float(duration_offset), float(leaky_relu_slope),
+                              int(bool(use_masking)), idx)
+        h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.efts_create(ctypes.byref(cfg), ctypes.byref(h)))
+            self._h = h
+            folded = fold_state_dict(state_dict)
+            for name, t in folded.items():
+                shape = (ctypes.c_int64 * t.dim())(*t.shape)
+                _lib.check(self.lib.efts_set_weight(self._h, name.encode(), _ptr(t), shape, t.dim()))
+            _lib.check(self.lib.efts_finalize_weights(self._h))
+        self._ws = None
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self.lib.efts_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def set_option(self, name, value):
+        _lib.check(self.lib.efts_set_option(self._h, name.encode(), int(value)))
+
+    def launch_count(self):
+        return int(self.lib.efts_launch_count(self._h))
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def workspace(self, nbytes):
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = None
+            self._ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def workspace_for(self, B, T1, T2):
+        n = int(self.lib.efts_workspace_bytes(self._h, int(B), int(T1), int(T2)))
+        return self.workspace(n), n
+
+    def _f32(self, t, name):
+        if t.device != self.device:
+            raise RuntimeError("%s is on %s but the model is on %s" % (name, t.device, self.device))
+        return t.to(torch.float32).contiguous()
+
+    def _i64(self, t, name):
+        if t.device != self.device:
+            raise RuntimeError("%s is on %s but the model is on %s" % (name, t.device, self.device))
+        return t.to(torch.int64).contiguous()
+
+    # ------------------------------------------------------------------ model-level calls
+    def forward(self, text, text_lengths, speech, speech_lengths):
+        """models/efficient_tts.py:120-228.  Returns (imv, reconst_alpha, mel_pred, scalars[8])."""
+        text = self._i64(text, "text")
+        tl = self._i64(text_lengths, "text_lengths")
+        speech = self._f32(speech, "speech")
+        sl = self._i64(speech_lengths, "speech_lengths")
+        B, T1 = text.shape
+        T2 = speech.shape[1]
+        if speech.shape[0] != B or speech.shape[2] != self.odim or tl.numel() != B or sl.numel() != B:
+            raise RuntimeError("inconsistent batch shapes: text %s speech %s lengths %s %s" % (
+                tuple(text.shape), tuple(speech.shape), tuple(tl.shape), tuple(sl.shape)))
+        with torch.cuda.device(self.device):
+            imv = torch.empty(B, T2, dtype=torch.float32, device=self.device)
+            ra = torch.empty(B, T1, T2, dtype=torch.float32, device=self.device)
+            mel = torch.empty(B, T2, self.odim, dtype=torch.float32, device=self.device)
+            scal = torch.empty(8, dtype=torch.float32, device=self.device)
+            ws, n = self.workspace_for(B, T1, T2)
+            _lib.check(self.lib.efts_forward(self._h, _ptr(text), _ptr(tl), _ptr(speech), _ptr(sl), B, T1, T2,
+                                             _ptr(imv), _ptr(ra), _ptr(mel), _ptr(scal), _ptr(ws), n,
+                                             self._stream()))
+        return imv, ra, mel, scal
+
+    def inference(self, text, max_t2=None):
+        """models/efficient_tts.py:230-285, B = 1.  Returns (mel_pred[1,T2,odim], reconst_alpha[1,T1,T2])."""
+        text = self._i64(text, "text")
+        if text.dim() != 2 or text.shape[0] != 1:
+            # the reference's `.item()` at models/efficient_tts.py:361 only works for one utterance
+            raise RuntimeError("a Tensor with %d elements cannot be converted to Scalar (inference is "
+                               "B=1 like the reference, models/efficient_tts.py:361)" % text.shape[0])
+        T1 = text.shape[1]
+        with torch.cuda.device(self.device):
+            t2_dev = torch.empty(2, dtype=torch.int32, device=self.device)
+            # phase 1 only touches the text-sized part of the workspace
+            ws, n = self.workspace_for(1, T1, 1)
+            _lib.check(self.lib.efts_inference_phase1(self._h, _ptr(text), T1, _ptr(t2_dev), _ptr(ws), n,
+                                                      self._stream()))
+            t2, flags = (int(v) for v in t2_dev.cpu())        # the reference's .item() sync (:361)
+            if flags & 4:
+                raise IndexError("index out of range in self")   # embedding lookup, :246
+            if t2 < 1:
+                raise RuntimeError("predicted length T2=%d; the reference's decoder conv rejects an "
+                                   "empty sequence" % t2)
+            need = int(self.lib.efts_workspace_bytes(self._h, 1, T1, t2))
+            if need > ws.numel():
+                # grow, keeping phase 1's results (they live at the front of the buffer)
+                big = torch.empty(need, dtype=torch.uint8, device=self.device)
+                big[: ws.numel()].copy_(ws)
+                self._ws = ws = big
+            mel = torch.empty(1, t2, self.odim, dtype=torch.float32, device=self.device)
+            ra = torch.empty(1, T1, t2, dtype=torch.float32, device=self.device)
+            _lib.check(self.lib.efts_inference_phase2(self._h, T1, t2, _ptr(mel), _ptr(ra), _ptr(ws),
+                                                      ws.numel(), self._stream()))
+        return mel, ra
+
+    # ------------------------------------------------------------------ layer-level calls
+    def conv_stack(self, stack, x_btc):
+        x = self._f32(x_btc, "x")
+        B, T, C = x.shape
+        if C != self.C:
+            raise RuntimeError("expected %d channels, got %d" % (self.C, C))
+        with torch.cuda.device(self.device):
+            y = torch.empty_like(x)
+            ws, n = self.workspace_for(B, T, T)
+            _lib.check(self.lib.efts_conv_stack_fwd(self._h, int(stack), _ptr(x), _ptr(y), B, T, _ptr(ws), n,
+                                                    self._stream()))
+        return y
+
+    def duration_predictor(self, x_btc, lengths=None, mode=0):
+        x = self._f32(x_btc, "xs")
+        B, T, C = x.shape
+        if C != self.C:
+            raise RuntimeError("expected %d channels, got %d" % (self.C, C))
+        with torch.cuda.device(self.device):
+            out = torch.empty(B, T, dtype=torch.int64 if mode == 2 else torch.float32, device=self.device)
+            lens = None if lengths is None else lengths.to(self.device, torch.int32).contiguous()
+            ws, n = self.workspace_for(B, T, T)
+            _lib.check(self.lib.efts_duration_predictor_fwd(self._h, _ptr(x), _ptr(lens), B, T, int(mode),
+                                                            _ptr(out), _ptr(ws), n, self._stream()))
+        return out
+
+    def tap_gemm(self, x, w, ntaps=1, pad=0, batched=False):
+        x = self._f32(x, "x")
+        w = self._f32(w, "w")
+        B, T, K = x.shape
+        Z, N, K2 = w.shape
+        assert K == K2 and Z == (B if batched else ntaps)
+        with torch.cuda.device(self.device):
+            out = torch.empty(B, T, N, dtype=torch.float32, device=self.device)
+            n = (x.numel() + w.numel()) * 4 + 8192
+            ws = self.workspace(n)
+            _lib.check(self.lib.efts_tap_gemm(self._h, _ptr(x), _ptr(w), _ptr(out), B, T, K, N, int(ntaps),
+                                              int(pad), int(bool(batched)), _ptr(ws), ws.numel(),
+                                              self._stream()))
+        return out
+
+    def alignment(self, mel_h, key, value, text_lengths, speech_lengths):
+        mel_h, key, value = self._f32(mel_h, "mel_h"), self._f32(key, "key"), self._f32(value, "value")
+        B, T2, C = mel_h.shape
+        T1 = key.shape[1]
+        with torch.cuda.device(self.device):
+            tl = text_lengths.to(self.device, torch.int32).contiguous()
+            sl = speech_lengths.to(self.device, torch.int32).contiguous()
+            imv = torch.empty(B, T2, dtype=torch.float32, device=self.device)
+            e = torch.empty(B, T1, dtype=torch.float32, device=self.device)
+            ra = torch.empty(B, T1, T2, dtype=torch.float32, device=self.device)
+            ex = torch.empty(B, T2, C, dtype=torch.float32, device=self.device)
+            ws, n = self.workspace_for(B, T1, T2)
+            _lib.check(self.lib.efts_alignment_fwd(self._h, _ptr(mel_h), _ptr(key), _ptr(value), _ptr(tl),
+                                                   _ptr(sl), B, T1, T2, _ptr(imv), _ptr(e), _ptr(ra), _ptr(ex),
+                                                   _ptr(ws), n, self._stream()))
+        return imv, e, ra, ex
+
+
+def length_regulator(xs, ds, ilens, alpha=1.0, pad_value=0.0, return_index=False):
+    """layers/length_regulator.py:35-79 on the GPU (context-free entry points)."""
+    lib = _lib.load()
+    if xs.device.type != "cuda":
+        raise RuntimeError("efts_b200 length regulator runs on CUDA tensors only")
+    dev = xs.device
+    x = xs.to(torch.float32).contiguous()
+    B, T1 = ds.shape
+    D = x[0, 0].numel()
+    if ds.dtype != torch.int64 or not ds.is_contiguous() or ds.device != dev:
+        if alpha == 1.0:
+            raise RuntimeError("ds must be a contiguous int64 tensor on the same device as xs")
+        ds = ds.to(dev, torch.int64).contiguous()
+    il = ilens.to(dev, torch.int64).contiguous()
+    with torch.cuda.device(dev):
+        st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        ds_eff = torch.empty_like(ds)
+        out_lens = torch.empty(B, dtype=torch.int64, device=dev)
+        plan = torch.empty(2, dtype=torch.int64, device=dev)
+        _lib.check(lib.efts_length_regulator_plan(_ptr(ds), _ptr(il), float(alpha), B, T1, _ptr(ds_eff),
+                                                  _ptr(out_lens), _ptr(plan), st))
+        tout, flags = (int(v) for v in plan.cpu())
+        if flags & 1:
+            raise RuntimeError("Trying to create tensor with negative dimension (negative duration)")
+        out = torch.empty((B, tout) + tuple(x.shape[2:]), dtype=torch.float32, device=dev)
+        idx = torch.empty(B, tout, dtype=torch.int64, device=dev) if return_index else None
+        _lib.check(lib.efts_length_regulator_fwd(_ptr(x), _ptr(ds_eff), _ptr(il), _ptr(out_lens), B, T1, D,
+                                                 tout, float(pad_value), _ptr(out), _ptr(idx), st))
+    out = out.to(xs.dtype)
+    return (out, idx) if return_index else out

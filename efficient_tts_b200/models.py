@@ -1,0 +1,110 @@
+"""Drop-in for ``nntts.models.EfficientTTSCNN`` (``/root/reference/nntts/models/efficient_tts.py``).
+
+The reference resolves its model by name -- ``getattr(nntts.models, config["model_name"])(**params)``
+(bin/train.py:173-185, bin/inference.py:63-75) -- then uses ``load_state_dict``,
+``remove_weight_norm()``, ``.eval().to(device)``, ``model(text=, text_lengths=, speech=,
+speech_lengths=)`` and ``model.inference(text)``.  This class keeps that surface (constructor
+kwargs, parameter names, return tuples) and runs the forward path in ``libefts_b200.so``.
+"""
+import torch
+
+from .layers import DurationPredictor, ResConvBlock, _EngineOwner
+
+
+class EfficientTTSCNN(_EngineOwner):
+    """EFTS-CNN, forward path on B200.  Constructor: models/efficient_tts.py:26-49."""
+
+    def __init__(self, num_symbols, odim=80, symbol_embedding_dim=512, n_channels=512,
+                 n_text_encoder_layer=5, n_mel_encoder_layer=3, n_decoder_layer=6, n_duration_layer=2,
+                 k_size=5, nonlinear_activation="LeakyReLU",
+                 nonlinear_activation_params={"negative_slope": 0.1}, use_weight_norm=True,
+                 dropout_rate=0.1, use_masking=False, use_weighted_masking=False, duration_offset=1.0,
+                 sigma=0.01, sigma_e=0.5, delta_e_method_1=True, share_text_encoder_key_value=False,
+                 use_mel_query_fc=False):
+        super().__init__()
+        # configurations outside the production recipe are rejected, never approximated
+        if share_text_encoder_key_value:
+            raise NotImplementedError("share_text_encoder_key_value=True is outside the B200 path")
+        if use_mel_query_fc:
+            raise NotImplementedError("use_mel_query_fc=True is outside the B200 path")
+        if not delta_e_method_1:
+            raise NotImplementedError("delta_e_method_1=False is outside the B200 path")
+        if use_weighted_masking:
+            raise NotImplementedError("use_weighted_masking=True is outside the B200 path (the LJ recipe, "
+                                      "egs/lj/conf/efficient_tts_cnn_phnseq_noDropout.v1.yaml:21, disables it)")
+        if symbol_embedding_dim != n_channels:
+            raise NotImplementedError("symbol_embedding_dim must equal n_channels")
+        self.num_symbols, self.odim, self.n_channels, self.k_size = num_symbols, odim, n_channels, k_size
+        self.use_masking = bool(use_masking)
+        self.duration_offset = duration_offset
+        self.sigma = sigma
+        self.sigma_e = sigma_e
+        self.delta_e_method_1 = delta_e_method_1
+        self.share_text_encoder_key_value = share_text_encoder_key_value
+        blk = dict(n_channels=n_channels, k_size=k_size, nonlinear_activation=nonlinear_activation,
+                   nonlinear_activation_params=nonlinear_activation_params, dropout_rate=dropout_rate,
+                   use_weight_norm=use_weight_norm)
+        # same construction order as the reference, so a seeded default init gives the same weights
+        self.text_embedding_table = torch.nn.Embedding(num_symbols, symbol_embedding_dim)
+        self.text_encoder = ResConvBlock(num_layers=n_text_encoder_layer, **blk)
+        self.text_encoder_key = torch.nn.Linear(n_channels, n_channels)
+        self.text_encoder_value = torch.nn.Linear(n_channels, n_channels)
+        self.mel_prenet = torch.nn.Sequential(
+            torch.nn.Linear(odim, n_channels),
+            getattr(torch.nn, nonlinear_activation)(**nonlinear_activation_params),
+            torch.nn.Dropout(dropout_rate))
+        self.mel_encoder = ResConvBlock(num_layers=n_mel_encoder_layer, **blk)
+        self.mel_query_fc = None
+        self.decoder = ResConvBlock(num_layers=n_decoder_layer, **blk)
+        self.mel_output_layer = torch.nn.Linear(n_channels, odim)
+        self.duration_predictor = DurationPredictor(idim=n_channels, n_layers=n_duration_layer,
+                                                    n_chans=n_channels, offset=duration_offset)
+
+    # ------------------------------------------------------------------ engine plumbing
+    def _engine_kwargs(self):
+        return dict(num_symbols=self.num_symbols, odim=self.odim, n_channels=self.n_channels,
+                    k_size=self.k_size, n_text_encoder_layer=self.text_encoder.num_layers,
+                    n_mel_encoder_layer=self.mel_encoder.num_layers, n_decoder_layer=self.decoder.num_layers,
+                    n_duration_layer=self.duration_predictor.n_layers,
+                    duration_kernel_size=self.duration_predictor.kernel_size, sigma=self.sigma,
+                    sigma_e=self.sigma_e, duration_offset=self.duration_offset,
+                    use_masking=self.use_masking)
+
+    def _engine_state(self):
+        return self.state_dict()
+
+    def _get_engine(self):
+        eng = super()._get_engine()
+        # sub-modules share this context's fingerprinted lifetime; nothing else to do
+        return eng
+
+    # ------------------------------------------------------------------ reference surface
+    def forward(self, text, text_lengths, speech, speech_lengths):
+        """models/efficient_tts.py:120-228 ->
+        ``(loss, stats, imv, reconst_alpha, mel_pred, speech)``."""
+        self._require_eval()
+        eng = self._get_engine()
+        imv, reconst_alpha, mel_pred, scal = eng.forward(text, text_lengths, speech, speech_lengths)
+        host = scal.cpu()                      # the reference's three .item() syncs (:225-227) in one
+        flags = int(host[7])
+        if flags & 4:
+            raise IndexError("index out of range in self")          # torch.nn.Embedding, :144
+        if flags & 3:
+            which = "text" if flags & 1 else "speech"
+            raise RuntimeError("The padded %s length must equal max(%s_lengths) (the reference builds its "
+                               "masks with maxlen = max(lengths), utils/nets_utils.py:148)" % (which, which))
+        stats = dict(loss=float(host[0]), mel_loss=float(host[1]), duration_loss=float(host[2]))
+        return scal[0], stats, imv, reconst_alpha, mel_pred, speech
+
+    def inference(self, text, text_lengths=None):
+        """models/efficient_tts.py:230-285 -> ``(mel_pred[1,T2,odim], reconst_alpha[1,T1,T2])``."""
+        self._require_eval()
+        return self._get_engine().inference(text)
+
+    def remove_weight_norm(self):
+        for m in (self.text_encoder, self.mel_encoder, self.decoder):
+            m.remove_weight_norm()
+
+    def apply_weight_norm(self):
+        for m in (self.text_encoder, self.mel_encoder, self.decoder):
+            m.apply_weight_norm()

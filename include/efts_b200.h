@@ -1,0 +1,158 @@
+/*
+ * efts_b200 -- C ABI of the B200-native EFTS-CNN forward path.
+ *
+ * The reference (liusongxiang/efficient_tts, package `nntts`) has no FFI of its own: the boundary it
+ * offers is the Python `torch.nn.Module` contract of `nntts.models.EfficientTTSCNN` and the
+ * `nntts.layers` modules.  This header is the C surface a binding for that contract
+ * calls; every entry point names the reference interface it replaces (paths relative to
+ * /root/reference/nntts).  `efficient_tts_b200/_lib.py` is the ctypes binding, INTEGRATION.md shows
+ * the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C types only; every tensor argument is a DEVICE pointer unless its name ends in `_host`.
+ *   - activations are channels-last: [B, T, C] fp32, contiguous.
+ *   - the caller owns every input, output and workspace buffer; the library owns only the
+ *     prepacked weights inside `efts_ctx` and never allocates or synchronises inside a call
+ *     (except `efts_inference`, which must read T2 back exactly like the reference does, and the
+ *     weight upload in `efts_finalize_weights`).
+ *   - `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy default stream).
+ *   - return value 0 = OK, negative = `efts_status`; `efts_last_error()` gives the text.
+ *     There is no CPU fallback: a missing device / wrong architecture is an error.
+ */
+#ifndef EFTS_B200_H_
+#define EFTS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct efts_ctx efts_ctx;
+
+typedef enum {
+  EFTS_OK = 0,
+  EFTS_ERR_ARG = -1,         /* bad shape / null pointer / unknown name            */
+  EFTS_ERR_UNSUPPORTED = -2, /* config outside the production path (see efts_create) */
+  EFTS_ERR_CUDA = -3,        /* CUDA runtime / driver error                         */
+  EFTS_ERR_STATE = -4,       /* weights missing / not finalised                     */
+  EFTS_ERR_WORKSPACE = -5,   /* workspace too small                                 */
+  EFTS_ERR_DATA = -6         /* data-dependent failure the reference also raises    */
+} efts_status;
+
+/* Constructor arguments of EfficientTTSCNN (models/efficient_tts.py:26-49).  Values outside the
+ * production configuration (egs/lj/conf/efficient_tts_cnn_phnseq_noDropout.v1.yaml:16-22 plus the
+ * ctor defaults) are rejected with EFTS_ERR_UNSUPPORTED, never emulated on another path. */
+typedef struct {
+  int32_t num_symbols;          /* rows of text_embedding_table                                   */
+  int32_t odim;                 /* mel bins (80)                                                  */
+  int32_t n_channels;           /* 512; the kernels are specialised for it                        */
+  int32_t k_size;               /* 5 (ResConv1d kernel size, layers/efts_modules.py:24)           */
+  int32_t n_text_encoder_layer; /* 5 */
+  int32_t n_mel_encoder_layer;  /* 3 */
+  int32_t n_decoder_layer;      /* 6 */
+  int32_t n_duration_layer;     /* 2 */
+  int32_t duration_kernel_size; /* 3 (layers/duration_predictor.py:24)                            */
+  float sigma;                  /* 0.01: Gaussian re-alignment width (models/...:369)             */
+  float sigma_e;                /* 0.5 : aligned-position softmax width (models/...:338)          */
+  float duration_offset;        /* 1.0 (models/...:215, layers/duration_predictor.py:81-83)       */
+  float leaky_relu_slope;       /* 0.1 */
+  int32_t use_masking;          /* FastSpeechLoss(use_masking) (losses/fastspeech_loss.py:54-61): 1 = means over
+                                   valid frames / tokens only, 0 = over the whole padded batch          */
+  int32_t device;               /* CUDA device ordinal                                            */
+} efts_config;
+
+/* ---- life cycle: replaces EfficientTTSCNN.__init__ / load_state_dict / remove_weight_norm ---- */
+int efts_create(const efts_config* cfg, efts_ctx** out);
+void efts_destroy(efts_ctx* ctx);
+
+/* One call per tensor of the reference `state_dict` (key list: SURVEY.md 8b) with the weight-norm
+ * pair already folded (`*.conv.0.weight` as left by remove_weight_norm(), models/...:400-409,
+ * layers/efts_modules.py:92-99).  `data_host` is fp32, row-major, in the reference's own shape. */
+int efts_set_weight(efts_ctx* ctx, const char* name, const float* data_host, const int64_t* shape,
+                    int32_t ndim);
+/* Checks that every tensor arrived, prepacks (tap-major fp16 hi/lo operand planes) and uploads. */
+int efts_finalize_weights(efts_ctx* ctx);
+
+/* Bytes of scratch a call with these padded sizes needs (max over all entry points). */
+size_t efts_workspace_bytes(const efts_ctx* ctx, int32_t B, int32_t T1, int32_t T2);
+
+/* ---- EfficientTTSCNN.forward (models/efficient_tts.py:120-228), eval mode ----
+ * text int64 [B,T1]; text_lengths int64 [B]; speech fp32 [B,T2,odim]; speech_lengths int64 [B].
+ * Outputs: imv fp32 [B,T2]; reconst_alpha fp32 [B,T1,T2]; mel_pred fp32 [B,T2,odim];
+ * scalars fp32 [8] = {loss, mel_loss, duration_loss, sum_sq, n_mel, sum_abs, n_tok, flags}
+ *   flags (as float-encoded int): bit0 max(text_lengths) != T1, bit1 max(speech_lengths) != T2,
+ *   bit2 a text id outside [0, num_symbols)  -- the conditions the reference raises on
+ *   (utils/nets_utils.py:148-156 size mismatch, embedding IndexError); the binding checks them
+ *   when it reads the scalars back (the read-back the reference does with .item(), :225-227). */
+int efts_forward(efts_ctx* ctx, const int64_t* text, const int64_t* text_lengths, const float* speech,
+                 const int64_t* speech_lengths, int32_t B, int32_t T1, int32_t T2, float* imv,
+                 float* reconst_alpha, float* mel_pred, float* scalars, void* workspace,
+                 size_t workspace_bytes, void* stream);
+
+/* ---- EfficientTTSCNN.inference (models/efficient_tts.py:230-285), B = 1 like the reference ----
+ * Phase 1 runs text encoder, value projection, duration predictor and the duration cumsum; it
+ * leaves e[T1] in the workspace and writes T2 = round_half_even(e[T1-1]) (models/...:361) to
+ * `t2_dev` (device int32[2]: T2, flags).  The caller reads T2 back (the reference's .item()),
+ * allocates the outputs and calls phase 2: Gaussian reconstruction, expansion, decoder, mel head.
+ * The workspace must be the same buffer for both phases, sized for (1, T1, T2max). */
+int efts_inference_phase1(efts_ctx* ctx, const int64_t* text, int32_t T1, int32_t* t2_dev,
+                          void* workspace, size_t workspace_bytes, void* stream);
+int efts_inference_phase2(efts_ctx* ctx, int32_t T1, int32_t T2, float* mel_pred,
+                          float* reconst_alpha, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- ResConvBlock.forward (layers/efts_modules.py:54-79) on channels-last data ----
+ * stack: 0 = text_encoder, 1 = mel_encoder, 2 = decoder.  x, y fp32 [B,T,C]; may alias. */
+int efts_conv_stack_fwd(efts_ctx* ctx, int32_t stack, const float* x, float* y, int32_t B, int32_t T,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- DurationPredictor.forward / .inference (layers/duration_predictor.py:66-113) ----
+ * x fp32 [B,T,C]; lengths int32 [B] or NULL (no mask).  mode 0: log-domain fp32 out (forward);
+ * mode 1: clamp(exp(x)-offset, 0) fp32 (inference, to_round=False); mode 2: clamp(round(exp(x)-offset),0)
+ * int64 out (inference, to_round=True).  Positions t >= lengths[b] are written as 0. */
+int efts_duration_predictor_fwd(efts_ctx* ctx, const float* x, const int32_t* lengths, int32_t B,
+                                int32_t T, int32_t mode, void* out, void* workspace,
+                                size_t workspace_bytes, void* stream);
+
+/* ---- LengthRegulator.forward (layers/length_regulator.py:35-79; pad_list utils/nets_utils.py:28-55)
+ * plan: ds int64 [B,T1] (rewritten in place only for the all-zero fix-up when alpha == 1, like the
+ * reference's view semantics :52,76-78); ilens int64 [B].  Writes ds_eff int64 [B,T1] (rounded /
+ * fixed-up durations actually used), out_lens int64 [B] and plan int64 [2] = {max_b out_lens, flags}
+ * (flags bit0: a negative duration -- torch.repeat raises).  The caller reads `plan` back to size
+ * the output, then calls fwd: xs fp32 [B,T1,D] -> out fp32 [B,Tout,D] (pad_value beyond out_lens),
+ * idx int64 [B,Tout] (source token of every output frame, -1 on padding; may be NULL). */
+int efts_length_regulator_plan(int64_t* ds, const int64_t* ilens, float alpha, int32_t B, int32_t T1,
+                               int64_t* ds_eff, int64_t* out_lens, int64_t* plan, void* stream);
+int efts_length_regulator_fwd(const float* xs, const int64_t* ds_eff, const int64_t* ilens,
+                              const int64_t* out_lens, int32_t B, int32_t T1, int32_t D, int64_t Tout,
+                              float pad_value, float* out, int64_t* idx, void* stream);
+
+/* ---- building blocks exposed for parity tests (same kernels the calls above launch) ----
+ * Tap-GEMM on the tensor cores: out[b,t,n] = sum_tap sum_k x[b,t+tap-pad,k] * w[z,n,k]
+ * (z = tap, or z = b when `batched`), fp32 in / fp32 out through the split-fp16 operand planes.
+ * x [B,T,K], w [Z,N,K], out [B,T,N]; K and N multiples of 8. */
+int efts_tap_gemm(efts_ctx* ctx, const float* x, const float* w, float* out, int32_t B, int32_t T,
+                  int32_t K, int32_t N, int32_t ntaps, int32_t pad, int32_t batched, void* workspace,
+                  size_t workspace_bytes, void* stream);
+/* The alignment block alone (models/efficient_tts.py:167-194): mel_h fp32 [B,T2,C] (mel-encoder
+ * output), key/value fp32 [B,T1,C] (already zero at pad tokens), lengths int32.  Outputs imv
+ * [B,T2], e [B,T1], reconst_alpha [B,T1,T2], expanded [B,T2,C] (value at frame rate, zero at pad). */
+int efts_alignment_fwd(efts_ctx* ctx, const float* mel_h, const float* key, const float* value,
+                       const int32_t* text_lengths, const int32_t* speech_lengths, int32_t B,
+                       int32_t T1, int32_t T2, float* imv, float* e, float* reconst_alpha,
+                       float* expanded, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- introspection ---- */
+/* Options: "amode" (A-operand staging of the tap-GEMM: 0 one TMA box per tap, 1 one shifted box
+ * per k-block), "skip_pad_tiles" (0/1).  Returns EFTS_ERR_ARG for an unknown name. */
+int efts_set_option(efts_ctx* ctx, const char* name, int32_t value);
+/* Kernels launched by this context since creation (bench.py's `gpu_launches`). */
+int64_t efts_launch_count(const efts_ctx* ctx);
+const char* efts_last_error(void);
+const char* efts_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EFTS_B200_H_ */

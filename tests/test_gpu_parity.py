@@ -1,0 +1,331 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded
+inputs, against the committed golden fixtures, and through size-independent properties.
+
+Tolerances (stated by BASELINE.json's north_star): mel spectrogram <= 1e-4 abs vs the fp32
+reference; length-regulator indices bit-exact.  The other returned tensors are held to the same
+fp32-noise scale: reconst_alpha (values in [0,1]) <= 1e-4 abs; imv (values in [0, T1-1]) <= 2e-6
+relative to its range, i.e. 4e-4 abs at T1 = 200 -- the reference's own fp32-vs-fp64 noise on imv is
+7.5e-5 at that size.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import efts_oracle as orc
+from tests.cases import make_forward_inputs, make_inference_inputs
+
+pytestmark = pytest.mark.gpu
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+MEL_TOL = 1e-4
+RA_TOL = 1e-4
+
+
+def imv_tol(t1):
+    return max(1e-4, 2e-6 * t1)
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda", 0)
+
+
+def build_model(weights, dev):
+    import efficient_tts_b200 as E
+    m = E.EfficientTTSCNN(num_symbols=76, dropout_rate=0.0, use_masking=True, use_weighted_masking=False,
+                          sigma=0.01)
+    missing = m.load_state_dict(weights, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    return m.eval().to(dev)
+
+
+@pytest.fixture(scope="module")
+def model(dev):
+    return build_model(orc.make_weights(seed=1234), dev)
+
+
+def run_both(model, dev, seed, t1, t2):
+    w = orc.make_weights(seed=1234)
+    text, tl, speech, sl = make_forward_inputs(seed, t1, t2)
+    with torch.no_grad():
+        ref = orc.forward(w, text, tl, speech, sl)
+        out = model(text=text.to(dev), text_lengths=tl.to(dev), speech=speech.to(dev),
+                    speech_lengths=sl.to(dev))
+    return ref, out, (text, tl, speech, sl)
+
+
+def check_forward(ref, out, t1max):
+    loss_r, stats_r, imv_r, ra_r, mel_r, _ = ref
+    loss, stats, imv, ra, mel, _ = out
+    d_mel = (mel.cpu() - mel_r).abs().max().item()
+    d_ra = (ra.cpu() - ra_r).abs().max().item()
+    d_imv = (imv.cpu() - imv_r).abs().max().item()
+    print("max-abs: mel %.3e  reconst_alpha %.3e  imv %.3e  loss %.3e" %
+          (d_mel, d_ra, d_imv, abs(float(loss) - float(loss_r))))
+    assert d_mel <= MEL_TOL
+    assert d_ra <= RA_TOL
+    assert d_imv <= imv_tol(t1max)
+    for k in ("loss", "mel_loss", "duration_loss"):
+        assert abs(stats[k] - stats_r[k]) <= 1e-4 * max(1.0, abs(stats_r[k])), k
+    assert abs(float(loss) - float(loss_r)) <= 1e-4 * max(1.0, abs(float(loss_r)))
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [
+    dict(B=1, T=128, K=64, N=64, ntaps=1),
+    dict(B=2, T=200, K=512, N=512, ntaps=1),
+    dict(B=3, T=77, K=80, N=512, ntaps=1),          # K tail zero-filled by TMA (mel prenet shape)
+    dict(B=2, T=300, K=512, N=80, ntaps=1),         # N tail (mel head shape)
+    dict(B=2, T=260, K=512, N=512, ntaps=5),        # conv layer, tiles cross the utterance end
+    dict(B=2, T=50, K=512, N=512, ntaps=3),         # duration-predictor conv
+])
+@pytest.mark.parametrize("amode", [0, 1])
+def test_tap_gemm_against_float64(model, dev, shape, amode):
+    """The tensor-core tap-GEMM (split-fp16, 3 MMAs) reproduces an fp64 evaluation to fp32 level."""
+    if shape["ntaps"] == 1 and amode != 0:
+        pytest.skip("amode only changes multi-tap staging")
+    eng = model._get_engine()
+    eng.set_option("amode", amode)
+    try:
+        g = torch.Generator().manual_seed(5)
+        B, T, K, N, nt = shape["B"], shape["T"], shape["K"], shape["N"], shape["ntaps"]
+        x = torch.randn(B, T, K, generator=g)
+        w = torch.randn(nt, N, K, generator=g) / np.sqrt(K * nt)
+        out = eng.tap_gemm(x.to(dev), w.to(dev), ntaps=nt, pad=(nt - 1) // 2).cpu()
+        xp = torch.nn.functional.pad(x.double(), (0, 0, (nt - 1) // 2, (nt - 1) // 2))
+        ref = sum(xp[:, j:j + T] @ w[j].double().T for j in range(nt))
+        err = (out.double() - ref).abs().max().item()
+        print("tap_gemm", shape, "amode", amode, "max-abs err %.3e" % err)
+        assert err <= 2e-5
+    finally:
+        eng.set_option("amode", 0)
+
+
+def test_batched_gemm_against_float64(model, dev):
+    eng = model._get_engine()
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(3, 150, 512, generator=g)
+    w = torch.randn(3, 40, 512, generator=g) / np.sqrt(512)
+    out = eng.tap_gemm(x.to(dev), w.to(dev), batched=True).cpu()
+    ref = torch.bmm(x.double(), w.double().transpose(1, 2))
+    assert (out.double() - ref).abs().max().item() <= 2e-5
+
+
+@pytest.mark.parametrize("stack,name,n", [(0, "text_encoder", 5), (1, "mel_encoder", 3), (2, "decoder", 6)])
+def test_conv_stack_matches_oracle(model, dev, stack, name, n):
+    """ResConvBlock.forward (layers/efts_modules.py:77-79) incl. the non-inert padding region."""
+    w = orc.make_weights(seed=1234)
+    g = torch.Generator().manual_seed(stack)
+    x = torch.randn(2, 512, 300, generator=g)
+    with torch.no_grad():
+        ref = orc.res_conv_stack(x, w, name, n)
+    out = model._get_engine().conv_stack(stack, x.transpose(1, 2).contiguous().to(dev)).cpu().transpose(1, 2)
+    err = (out - ref).abs().max().item()
+    print(name, "max-abs err %.3e (|ref| max %.2f)" % (err, ref.abs().max().item()))
+    assert err <= 1e-4
+
+
+def test_resconvblock_module_matches_oracle(dev):
+    """The stand-alone layer mirror, [B, C, T] in and out like the reference module."""
+    from efficient_tts_b200.layers import ResConvBlock
+    torch.manual_seed(3)
+    blk = ResConvBlock(3).eval()
+    w = {"blk." + k: v for k, v in blk.state_dict().items()}
+    x = torch.randn(2, 512, 80)
+    with torch.no_grad():
+        ref = orc.res_conv_stack(x, w, "blk", 3)
+    out = blk.to(dev)(x.to(dev)).cpu()
+    assert out.shape == ref.shape
+    assert (out - ref).abs().max().item() <= 1e-4
+
+
+def test_duration_predictor_matches_golden_and_oracle(dev):
+    from efficient_tts_b200.layers import DurationPredictor
+    z = np.load(os.path.join(G, "dur_small.npz"))
+    w = orc.make_weights(seed=1234, dur_bias=1.2)
+    dp = DurationPredictor(idim=512, n_layers=2, n_chans=512, offset=1.0)
+    dp.load_state_dict({k[len("duration_predictor."):]: v for k, v in w.items()
+                        if k.startswith("duration_predictor.")})
+    dp = dp.eval().to(dev)
+    xs = torch.from_numpy(z["xs"]).to(dev)
+    masks = (~orc.non_pad_mask(torch.from_numpy(z["lens"]))).to(dev)
+    log_d = dp(xs, masks).cpu().numpy()
+    d_float = dp.inference(xs, None, to_round=False).cpu().numpy()
+    d_round = dp.inference(xs, masks).cpu()
+    np.testing.assert_allclose(log_d, z["log_d"], atol=1e-4, rtol=0)
+    np.testing.assert_allclose(d_float, z["d_float"], atol=1e-4, rtol=1e-4)
+    assert d_round.dtype == torch.int64
+    flips = d_round.numpy() != z["d_round"]
+    frac = np.abs((np.exp(z["log_d"]) - 1.0) % 1.0 - 0.5)
+    assert (~flips | (frac < 1e-3)).all()
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["fwd_small", "fwd_pad_heavy"])
+def test_forward_matches_golden(model, dev, name):
+    """Whole forward() against outputs of the unmodified reference (tests/golden/make_golden.py)."""
+    z = np.load(os.path.join(G, name + ".npz"))
+    text, tl, speech, sl = make_forward_inputs(int(z["seed"]), z["t1"], z["t2"])
+    loss, stats, imv, ra, mel, sp = model(text=text.to(dev), text_lengths=tl.to(dev), speech=speech.to(dev),
+                                          speech_lengths=sl.to(dev))
+    assert (mel.cpu().numpy() - z["mel_pred"]).__abs__().max() <= MEL_TOL
+    assert (ra.cpu().numpy() - z["reconst_alpha"]).__abs__().max() <= RA_TOL
+    assert (imv.cpu().numpy() - z["imv"]).__abs__().max() <= imv_tol(int(max(z["t1"])))
+    np.testing.assert_allclose([stats["loss"], stats["mel_loss"], stats["duration_loss"]], z["stats"],
+                               rtol=1e-4, atol=1e-4)
+    # pad regions are exactly zero (models/efficient_tts.py:186,199)
+    for b in range(len(z["t1"])):
+        assert not mel[b, int(z["t2"][b]):].any()
+        assert not ra[b, int(z["t1"][b]):].any() and not ra[b, :, int(z["t2"][b]):].any()
+        assert not imv[b, int(z["t2"][b]):].any()
+
+
+@pytest.mark.parametrize("case", [
+    dict(seed=11, t1=[30, 22, 8, 1], t2=[200, 131, 47, 9]),          # ragged, a 1-token utterance
+    dict(seed=12, t1=[129], t2=[1025]),                              # B=1, tile boundaries + 1
+    dict(seed=13, t1=[64, 64, 50], t2=[384, 256, 384]),              # lengths on tile boundaries
+    dict(seed=14, t1=[200, 50], t2=[1200, 300]),                     # C3-like extremes in one batch
+])
+def test_forward_matches_oracle(model, dev, case):
+    ref, out, _ = run_both(model, dev, case["seed"], case["t1"], case["t2"])
+    check_forward(ref, out, max(case["t1"]))
+
+
+def test_forward_long_form_shape(model, dev):
+    """C5-like shape (T1 = 300 needs two column tiles in the energy GEMM), B reduced to 2."""
+    ref, out, _ = run_both(model, dev, 15, [300, 280], [2000, 1900])
+    check_forward(ref, out, 300)
+
+
+def test_padding_is_not_inert_but_batch_independent(model, dev):
+    """An utterance's outputs depend on its padded length but not on what else is in
+    the batch: run it alone and inside a batch with the same padded dims -> bitwise identical."""
+    text, tl, speech, sl = make_forward_inputs(21, [40, 17, 25], [240, 100, 150])
+    a = model(text=text.to(dev), text_lengths=tl.to(dev), speech=speech.to(dev), speech_lengths=sl.to(dev))
+    # same utterances in reversed order, same padded dims
+    idx = torch.tensor([2, 1, 0])
+    b = model(text=text[idx].to(dev), text_lengths=tl[idx].to(dev), speech=speech[idx].to(dev),
+              speech_lengths=sl[idx].to(dev))
+    for k in (2, 3, 4):
+        assert torch.equal(a[k][idx], b[k])
+
+
+def test_skip_pad_tiles_does_not_change_results(model, dev):
+    text, tl, speech, sl = make_forward_inputs(22, [60, 20], [700, 130])
+    args = dict(text=text.to(dev), text_lengths=tl.to(dev), speech=speech.to(dev), speech_lengths=sl.to(dev))
+    eng = model._get_engine()
+    a = model(**args)
+    eng.set_option("skip_pad_tiles", 0)
+    try:
+        b = model(**args)
+    finally:
+        eng.set_option("skip_pad_tiles", 1)
+    for k in (2, 3, 4):
+        assert torch.equal(a[k], b[k])
+    assert abs(a[1]["loss"] - b[1]["loss"]) <= 1e-6 * max(1.0, abs(a[1]["loss"]))
+
+
+def test_forward_rejects_what_the_reference_rejects(model, dev):
+    text, tl, speech, sl = make_forward_inputs(23, [12, 9], [60, 40])
+    with pytest.raises(RuntimeError):       # padded dim != max(lengths): nets_utils.py:148 broadcast error
+        model(text=text.to(dev), text_lengths=(tl - 1).to(dev), speech=speech.to(dev), speech_lengths=sl.to(dev))
+    bad = text.clone()
+    bad[0, 0] = 76
+    with pytest.raises(IndexError):         # embedding index out of range
+        model(text=bad.to(dev), text_lengths=tl.to(dev), speech=speech.to(dev), speech_lengths=sl.to(dev))
+    with pytest.raises(RuntimeError):       # forward-only engine
+        model.train()(text=text.to(dev), text_lengths=tl.to(dev), speech=speech.to(dev), speech_lengths=sl.to(dev))
+    model.eval()
+
+
+# ------------------------------------------------------------------------------------------------
+def test_inference_matches_golden(dev):
+    z = np.load(os.path.join(G, "inf_small.npz"))
+    m = build_model(orc.make_weights(seed=1234, dur_bias=float(z["dur_bias"]), dur_weight_scale=0.05), dev)
+    text = make_inference_inputs(int(z["seed"]), int(z["t1"]))
+    mel, ra = m.inference(text.to(dev))
+    assert tuple(mel.shape) == z["mel_pred"].shape and tuple(ra.shape) == z["reconst_alpha"].shape
+    assert np.abs(mel.cpu().numpy() - z["mel_pred"]).max() <= MEL_TOL
+    assert np.abs(ra.cpu().numpy() - z["reconst_alpha"]).max() <= RA_TOL
+    # weight norm folded (bin/inference.py:80) gives the same answer
+    m.remove_weight_norm()
+    assert "decoder.layers.0.conv.0.weight" in m.state_dict()
+    mel2, _ = m.inference(text.to(dev))
+    assert torch.equal(mel, mel2)
+
+
+def test_inference_c1_shape_matches_oracle(dev):
+    """BASELINE configs[0]: batch 1, 64 phonemes -> ~80 x 512 mel."""
+    w = orc.make_weights(seed=1234, dur_bias=float(np.log(9.0)), dur_weight_scale=0.05)
+    m = build_model(w, dev)
+    text = make_inference_inputs(0, 64)
+    with torch.no_grad():
+        (mel_r, ra_r), inter = orc.inference(w, text, return_intermediates=True)
+    e_last = float(inter["e"][0, -1])
+    assert abs(e_last - np.floor(e_last) - 0.5) > 0.01, "T2 rounding margin too small for a stable test"
+    mel, ra = m.inference(text.to(dev))
+    assert mel.shape == mel_r.shape and 400 < mel.shape[1] < 640
+    assert (mel.cpu() - mel_r).abs().max().item() <= MEL_TOL
+    assert (ra.cpu() - ra_r).abs().max().item() <= RA_TOL
+    with pytest.raises(RuntimeError):        # B > 1: the reference's .item() at :361 raises
+        m.inference(torch.zeros(2, 5, dtype=torch.long, device=dev))
+
+
+# ------------------------------------------------------------------------------------------------
+def test_length_regulator_bit_exact(dev):
+    from efficient_tts_b200.engine import length_regulator
+    from efficient_tts_b200.layers import LengthRegulator
+    z = np.load(os.path.join(G, "lr_cases.npz"))
+    lr = LengthRegulator()
+    out = lr(torch.tensor([[[1.0], [2.0], [3.0]]], device=dev), torch.tensor([[1, 2, 3]], device=dev),
+             torch.tensor([3], device=dev))
+    assert np.array_equal(out.cpu().numpy(), z["doc_out"])                # docstring example :60-73
+    xs, ilens = torch.from_numpy(z["xs"]).to(dev), torch.from_numpy(z["ilens"]).to(dev)
+    ds = torch.from_numpy(z["ds_in"].copy()).to(dev)
+    out = lr(xs, ds, ilens)
+    assert np.array_equal(out.cpu().numpy(), z["out_a1"])
+    assert np.array_equal(ds.cpu().numpy(), z["ds_after_a1"])             # in-place all-zero fix-up
+    for alpha, key in ((1.3, "out_a13"), (0.5, "out_a05")):
+        ds = torch.from_numpy(z["ds_in"].copy()).to(dev)
+        assert np.array_equal(lr(xs, ds, ilens, alpha=alpha).cpu().numpy(), z[key])
+        assert np.array_equal(ds.cpu().numpy(), z["ds_in"])
+    out = LengthRegulator(pad_value=-9.0)(xs, torch.from_numpy(z["ds_in"].copy()).to(dev), ilens)
+    assert np.array_equal(out.cpu().numpy(), z["out_pad9"])
+    # indices against the oracle on a larger ragged batch, incl. empty rows and zero durations
+    g = torch.Generator().manual_seed(31)
+    B, T1, D = 37, 200, 512
+    xs = torch.randn(B, T1, D, generator=g)
+    ds = torch.randint(0, 12, (B, T1), generator=g)
+    ilens = torch.randint(1, T1 + 1, (B,), generator=g)
+    ds[5] = 0
+    ref_out, ref_idx = orc.length_regulator(xs, ds.clone(), ilens)
+    out, idx = length_regulator(xs.to(dev), ds.clone().to(dev), ilens.to(dev), return_index=True)
+    assert torch.equal(idx.cpu(), ref_idx)                                # bit-exact index contract
+    assert torch.equal(out.cpu(), ref_out)
+    with pytest.raises(RuntimeError):
+        bad = ds.clone()
+        bad[0, 0] = -1
+        length_regulator(xs.to(dev), bad.to(dev), ilens.to(dev))
+
+
+def test_length_regulator_full_size_properties(dev):
+    """BASELINE-size check through properties: frame counts, monotone indices, gather identity."""
+    from efficient_tts_b200.engine import length_regulator
+    g = torch.Generator(device="cpu").manual_seed(32)
+    B, T1, D = 256, 200, 512
+    xs = torch.randn(B, T1, D, generator=g).to(dev)
+    ds = torch.randint(0, 13, (B, T1), generator=g).to(dev)
+    ilens = torch.randint(50, T1 + 1, (B,), generator=g).to(dev)
+    out, idx = length_regulator(xs, ds.clone(), ilens, return_index=True)
+    valid = torch.arange(T1, device=dev)[None] < ilens[:, None]
+    lens = (ds * valid).sum(1)
+    assert out.shape[1] == int(lens.max())
+    live = idx >= 0
+    assert torch.equal(live.sum(1), lens)
+    assert bool(((idx[:, 1:] >= idx[:, :-1]) | ~live[:, 1:]).all())       # sorted
+    counts = torch.zeros(B, T1, dtype=torch.int64, device=dev).scatter_add_(1, idx.clamp(min=0), live.long())
+    assert torch.equal(counts, ds * valid)                                # histogram of idx == durations
+    gathered = torch.gather(xs, 1, idx.clamp(min=0)[..., None].expand(-1, -1, D)) * live[..., None]
+    assert torch.equal(gathered, out)
