@@ -101,9 +101,35 @@ struct efts_ctx {
   float* ln_b[4] = {nullptr, nullptr, nullptr, nullptr};
   float* head_w = nullptr;
   float* head_b = nullptr;
+  // measurement hooks (efts_profile_*): CUDA-event pairs around tagged launches
+  struct ProfRec { cudaEvent_t a, b; int tag; };
+  std::vector<ProfRec> prof;
+  size_t prof_used = 0;
+  uint32_t profile_mask = 0;
 };
 
 namespace {
+
+// Records an event pair around the launches issued while it is alive (only when the tag is enabled).
+struct ProfScope {
+  efts_ctx* c; cudaStream_t st; int idx = -1;
+  ProfScope(efts_ctx* c_, cudaStream_t st_, int tag) : c(c_), st(st_) {
+    if (!(c->profile_mask & (1u << tag))) return;
+    if (c->prof_used == c->prof.size()) {
+      efts_ctx::ProfRec r;
+      r.tag = tag;
+      if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+      c->prof.push_back(r);
+    }
+    idx = static_cast<int>(c->prof_used++);
+    c->prof[idx].tag = tag;
+    cudaEventRecord(c->prof[idx].a, st);
+  }
+  ~ProfScope() { if (idx >= 0) cudaEventRecord(c->prof[idx].b, st); }
+};
+enum ProfTag { TAG_TEXT_CONV = 0, TAG_MEL_CONV = 1, TAG_DEC_CONV = 2, TAG_LINEAR = 3, TAG_ENERGY = 4,
+               TAG_SOFTMAX = 5, TAG_SCAN = 6, TAG_ALIGNED = 7, TAG_RECONSTRUCT = 8, TAG_EXPAND = 9,
+               TAG_DURATION = 10, TAG_LOSS = 11, TAG_PREP = 12 };
 
 // ------------------------------------------------------------------------------------------------
 // tensor maps
@@ -303,7 +329,7 @@ void carve_mel(Arena& a, FwdWs& w, int B, int T2, int C, int odim, bool teacher_
 // is non-null the last layer writes its fp32 result there instead (planes still go to the set).
 int run_conv_stack(efts_ctx* c, cudaStream_t st, const PackedW* layers, int n, int B, int T, float* f[2],
                    __half* hi[2], __half* lo[2], const float* first_resid, float* final_f,
-                   const int* skip_lens, int* cur_io) {
+                   const int* skip_lens, int* cur_io, int tag) {
   const int C = c->cfg.n_channels;
   int cur = *cur_io;
   for (int l = 0; l < n; ++l) {
@@ -322,7 +348,10 @@ int run_conv_stack(efts_ctx* c, cudaStream_t st, const PackedW* layers, int n, i
       p.skip_lens = skip_lens;
       p.skip_halo = p.pad * (n - 1 - l);
     }
-    TRY(launch_gemm(c, st, OpA{hi[cur], lo[cur], B, T, C, C}, weight_op(layers[l]), p));
+    {
+      ProfScope ps(c, st, tag);
+      TRY(launch_gemm(c, st, OpA{hi[cur], lo[cur], B, T, C, C}, weight_op(layers[l]), p));
+    }
     cur = nxt;
   }
   *cur_io = cur;
@@ -339,6 +368,7 @@ int run_duration_predictor(efts_ctx* c, cudaStream_t st, const __half* in_hi, co
   const int nl = c->cfg.n_duration_layer;
   const __half* ahi = in_hi;
   const __half* alo = in_lo;
+  ProfScope ps(c, st, TAG_DURATION);
   for (int l = 0; l < nl; ++l) {
     GemmParams p = gemm_defaults();
     p.N = C;
@@ -373,6 +403,7 @@ int run_reconstruct_expand(efts_ctx* c, cudaStream_t st, const float* e, const i
                            __half* out_lo) {
   const int C = c->cfg.n_channels;
   {
+    ProfScope ps(c, st, TAG_RECONSTRUCT);
     dim3 grid((T2 + 127) / 128, B);
     const float neg_sigma = -1.0f * c->cfg.sigma;
     reconstruct_alignment_kernel<<<grid, 128, T1 * sizeof(float), st>>>(e, tl, sl, T1, T2, T1p, neg_sigma,
@@ -390,6 +421,7 @@ int run_reconstruct_expand(efts_ctx* c, cudaStream_t st, const float* e, const i
     p.skip_lens = sl;
     p.skip_halo = ((c->cfg.k_size - 1) / 2) * c->cfg.n_decoder_layer;
   }
+  ProfScope ps(c, st, TAG_EXPAND);
   return launch_gemm(c, st, OpA{R_hi, R_lo, B, T2, T1p, T1p}, OpB{valT_hi, valT_lo, B, C, T1p, T1p}, p);
 }
 
@@ -404,15 +436,27 @@ int run_imv(efts_ctx* c, cudaStream_t st, const __half* q_hi, const __half* q_lo
   p.divisor = static_cast<float>(std::sqrt(static_cast<double>(C)));   // np.sqrt(float(D)), :390
   p.out = S; p.ld_out = T1p;
   if (c->skip_pad_tiles) { p.skip_lens = sl; p.skip_halo = 0; }
-  TRY(launch_gemm(c, st, OpA{q_hi, q_lo, B, T2, C, C}, OpB{key_hi, key_lo, B, T1, C, C}, p));
+  {
+    ProfScope ps(c, st, TAG_ENERGY);
+    TRY(launch_gemm(c, st, OpA{q_hi, q_lo, B, T2, C, C}, OpB{key_hi, key_lo, B, T1, C, C}, p));
+  }
   const size_t rows = static_cast<size_t>(B) * T2;
-  energy_softmax_expect_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, st>>>(S, T1p, tl, sl, T2, rows,
-                                                                                       imv_raw);
-  CUDA_TRY(cudaGetLastError());
-  imv_scan_kernel<<<(B + 3) / 4, 128, 0, st>>>(imv_raw, tl, sl, B, T2, imv);
-  CUDA_TRY(cudaGetLastError());
-  aligned_positions_kernel<<<dim3((T1 + 7) / 8, B), 256, 0, st>>>(imv, tl, sl, T1, T2, c->cfg.sigma_e, e);
-  CUDA_TRY(cudaGetLastError());
+  {
+    ProfScope ps(c, st, TAG_SOFTMAX);
+    energy_softmax_expect_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, st>>>(S, T1p, tl, sl, T2, rows,
+                                                                                         imv_raw);
+    CUDA_TRY(cudaGetLastError());
+  }
+  {
+    ProfScope ps(c, st, TAG_SCAN);
+    imv_scan_kernel<<<(B + 3) / 4, 128, 0, st>>>(imv_raw, tl, sl, B, T2, imv);
+    CUDA_TRY(cudaGetLastError());
+  }
+  {
+    ProfScope ps(c, st, TAG_ALIGNED);
+    aligned_positions_kernel<<<dim3((T1 + 7) / 8, B), 256, 0, st>>>(imv, tl, sl, T1, T2, c->cfg.sigma_e, e);
+    CUDA_TRY(cudaGetLastError());
+  }
   c->launches += 3;
   return EFTS_OK;
 }
@@ -483,6 +527,7 @@ int efts_create(const efts_config* cfg, efts_ctx** out) {
 void efts_destroy(efts_ctx* c) {
   if (c == nullptr) return;
   for (void* p : c->device_allocs) cudaFree(p);
+  for (auto& r : c->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   delete c;
 }
 
@@ -556,6 +601,30 @@ int efts_set_option(efts_ctx* c, const char* name, int32_t value) {
 
 int64_t efts_launch_count(const efts_ctx* c) { return c ? c->launches : 0; }
 
+int efts_profile_enable(efts_ctx* c, uint32_t tag_mask) {
+  if (c == nullptr) return fail(EFTS_ERR_ARG, "null context");
+  c->profile_mask = tag_mask;
+  c->prof_used = 0;
+  return EFTS_OK;
+}
+
+int efts_profile_read(efts_ctx* c, int32_t tag, double* total_ms, int64_t* count) {
+  if (c == nullptr || total_ms == nullptr || count == nullptr) return fail(EFTS_ERR_ARG, "null argument");
+  double ms = 0.0;
+  int64_t n = 0;
+  for (size_t i = 0; i < c->prof_used; ++i) {
+    if (c->prof[i].tag != tag) continue;
+    CUDA_TRY(cudaEventSynchronize(c->prof[i].b));
+    float t = 0.0f;
+    CUDA_TRY(cudaEventElapsedTime(&t, c->prof[i].a, c->prof[i].b));
+    ms += t;
+    ++n;
+  }
+  *total_ms = ms;
+  *count = n;
+  return EFTS_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 int efts_forward(efts_ctx* c, const int64_t* text, const int64_t* text_lengths, const float* speech,
                  const int64_t* speech_lengths, int32_t B, int32_t T1, int32_t T2, float* imv,
@@ -588,7 +657,7 @@ int efts_forward(efts_ctx* c, const int64_t* text, const int64_t* text_lengths, 
   c->launches += 2;
   int cur = 0;
   TRY(run_conv_stack(c, st, c->text, g.n_text_encoder_layer, B, T1, w.xt_f, w.xt_hi, w.xt_lo, nullptr, nullptr,
-                     w.tl32, &cur));
+                     w.tl32, &cur, TAG_TEXT_CONV));
   // 2. key / value projections, zero at pad tokens (:149-157)
   {
     GemmParams p = gemm_defaults();
@@ -619,7 +688,7 @@ int efts_forward(efts_ctx* c, const int64_t* text, const int64_t* text_lengths, 
   }
   int curm = 0;
   TRY(run_conv_stack(c, st, c->mel, g.n_mel_encoder_layer, B, T2, w.xm_f, w.xm_hi, w.xm_lo, nullptr, nullptr,
-                     w.sl32, &curm));
+                     w.sl32, &curm, TAG_MEL_CONV));
   // 4. alignment: energy/softmax/expectation, scan, aligned positions (:167-178)
   TRY(run_imv(c, st, w.xm_hi[curm], w.xm_lo[curm], w.key_hi, w.key_lo, w.tl32, w.sl32, B, T1, T2, w.T1p, w.S,
               w.imv_raw, imv, w.e));
@@ -629,7 +698,7 @@ int efts_forward(efts_ctx* c, const int64_t* text, const int64_t* text_lengths, 
   // 6. decoder (:197) and mel head (:198-200)
   curm = 0;
   TRY(run_conv_stack(c, st, c->dec, g.n_decoder_layer, B, T2, w.xm_f, w.xm_hi, w.xm_lo, nullptr, nullptr, w.sl32,
-                     &curm));
+                     &curm, TAG_DEC_CONV));
   {
     GemmParams p = gemm_defaults();
     p.N = g.odim; p.bias = c->melout.bias; p.lens = w.sl32;
@@ -666,7 +735,7 @@ int efts_inference_phase1(efts_ctx* c, const int64_t* text, int32_t T1, int32_t*
   c->launches++;
   int cur = 0;
   TRY(run_conv_stack(c, st, c->text, g.n_text_encoder_layer, 1, T1, w.xt_f, w.xt_hi, w.xt_lo, nullptr, nullptr,
-                     nullptr, &cur));
+                     nullptr, &cur, TAG_TEXT_CONV));
   {   // value only: the key projection at :251 is computed by the reference but never used
     GemmParams p = gemm_defaults();
     p.N = C; p.bias = c->value.bias;
@@ -704,7 +773,7 @@ int efts_inference_phase2(efts_ctx* c, int32_t T1, int32_t T2, float* mel_pred, 
                              reconst_alpha, w.xm_f[0], w.xm_hi[0], w.xm_lo[0]));
   int curm = 0;
   TRY(run_conv_stack(c, st, c->dec, g.n_decoder_layer, 1, T2, w.xm_f, w.xm_hi, w.xm_lo, nullptr, nullptr, nullptr,
-                     &curm));
+                     &curm, TAG_DEC_CONV));
   GemmParams p = gemm_defaults();
   p.N = g.odim; p.bias = c->melout.bias;
   p.out = mel_pred; p.ld_out = g.odim;
@@ -735,7 +804,7 @@ int efts_conv_stack_fwd(efts_ctx* c, int32_t stack, const float* x, float* y, in
   if (!a.ok) return fail(EFTS_ERR_WORKSPACE, "workspace too small: need %zu, have %zu", a.off, workspace_bytes);
   TRY(split_planes(c, st, x, m * C, hi[0], lo[0]));
   int cur = 0;
-  return run_conv_stack(c, st, layers, n, B, T, f, hi, lo, x, y, nullptr, &cur);
+  return run_conv_stack(c, st, layers, n, B, T, f, hi, lo, x, y, nullptr, &cur, stack);
 }
 
 int efts_duration_predictor_fwd(efts_ctx* c, const float* x, const int32_t* lengths, int32_t B, int32_t T,

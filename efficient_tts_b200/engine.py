@@ -86,6 +86,16 @@ class Engine:
     def launch_count(self):
         return int(self.lib.efts_launch_count(self._h))
 
+    def profile_enable(self, tag_mask):
+        """Bracket launches of the tagged kinds with CUDA events (include/efts_b200.h)."""
+        _lib.check(self.lib.efts_profile_enable(self._h, int(tag_mask)))
+
+    def profile_read(self, tag):
+        """(total milliseconds, launches) recorded for one tag since ``profile_enable``."""
+        ms, n = ctypes.c_double(), ctypes.c_int64()
+        _lib.check(self.lib.efts_profile_read(self._h, int(tag), ctypes.byref(ms), ctypes.byref(n)))
+        return ms.value, n.value
+
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 

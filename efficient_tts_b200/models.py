@@ -96,6 +96,13 @@ class EfficientTTSCNN(_EngineOwner):
         stats = dict(loss=float(host[0]), mel_loss=float(host[1]), duration_loss=float(host[2]))
         return scal[0], stats, imv, reconst_alpha, mel_pred, speech
 
+    def forward_shard(self, text, text_lengths, speech, speech_lengths):
+        """One data-parallel shard of a larger batch: the tensors keep the GLOBAL padded dims, so the
+        max(lengths) == padded-dim check of ``forward`` does not apply; nothing is read back.
+        Returns ``(imv, reconst_alpha, mel_pred, scalars[8])`` on the device (include/efts_b200.h)."""
+        self._require_eval()
+        return self._get_engine().forward(text, text_lengths, speech, speech_lengths)
+
     def inference(self, text, text_lengths=None):
         """models/efficient_tts.py:230-285 -> ``(mel_pred[1,T2,odim], reconst_alpha[1,T1,T2])``."""
         self._require_eval()

@@ -147,6 +147,14 @@ int efts_alignment_fwd(efts_ctx* ctx, const float* mel_h, const float* key, cons
 /* Options: "amode" (A-operand staging of the tap-GEMM: 0 one TMA box per tap, 1 one shifted box
  * per k-block), "skip_pad_tiles" (0/1).  Returns EFTS_ERR_ARG for an unknown name. */
 int efts_set_option(efts_ctx* ctx, const char* name, int32_t value);
+/* Measurement hooks: while a tag's bit is set in `tag_mask`, every launch of that kind is bracketed
+ * by a CUDA-event pair on the caller's stream (no extra synchronisation).  Tags: 0 text-encoder conv
+ * layer, 1 mel-encoder conv layer, 2 decoder conv layer, 3 linear, 4 energy GEMM, 5 softmax-expectation,
+ * 6 IMV scan, 7 aligned positions, 8 Gaussian reconstruction, 9 expansion GEMM, 10 duration predictor.
+ * `efts_profile_read` waits for the recorded events and returns their summed duration and count;
+ * `efts_profile_enable` also clears what was recorded. */
+int efts_profile_enable(efts_ctx* ctx, uint32_t tag_mask);
+int efts_profile_read(efts_ctx* ctx, int32_t tag, double* total_ms, int64_t* count);
 /* Kernels launched by this context since creation (bench.py's `gpu_launches`). */
 int64_t efts_launch_count(const efts_ctx* ctx);
 const char* efts_last_error(void);

@@ -1,46 +1,4 @@
-"""Seeded synthetic inputs for the parity tests, golden fixtures and bench.py.
-
-Shapes follow the reference's collate output (datasets/taco2_data.py:95-139): ``text``
-int64 [B, T1] padded with id 0, ``speech`` float32 [B, T2, 80] padded with zeros, and
-the padded dims equal ``max(lengths)`` (utils/nets_utils.py:148).
-Config recipes C1..C5 are the ones in SURVEY.md 8d / BASELINE.md 3.
-"""
-import numpy as np
-import torch
-
-NUM_SYMBOLS = 76
-ODIM = 80
-
-
-def make_forward_inputs(seed, t1_lens, t2_lens):
-    t1_lens = [int(x) for x in t1_lens]
-    t2_lens = [int(x) for x in t2_lens]
-    B, T1, T2 = len(t1_lens), max(t1_lens), max(t2_lens)
-    g = torch.Generator().manual_seed(int(seed))
-    text = torch.randint(0, NUM_SYMBOLS, (B, T1), generator=g)
-    speech = torch.randn(B, T2, ODIM, generator=g) * 1.5 - 4.0        # log-mel-like
-    tl = torch.tensor(t1_lens, dtype=torch.int64)
-    sl = torch.tensor(t2_lens, dtype=torch.int64)
-    text = text * (torch.arange(T1).unsqueeze(0) < tl.unsqueeze(1))
-    speech = speech * (torch.arange(T2).unsqueeze(0) < sl.unsqueeze(1)).unsqueeze(-1)
-    return text, tl, speech, sl
-
-
-def make_inference_inputs(seed, t1):
-    g = torch.Generator().manual_seed(int(seed))
-    return torch.randint(0, NUM_SYMBOLS, (1, int(t1)), generator=g)
-
-
-def config_lengths(name, seed=0):
-    """(t1_lens, t2_lens) of the named BASELINE.json config."""
-    if name == "C2":
-        return [100] * 16, [800] * 16
-    if name == "C3":
-        t1 = np.random.default_rng(seed).integers(50, 201, 256)
-        if seed == 0:
-            assert int(t1.sum()) == 32825
-        # the reference requires padded dim == max(lengths); pin the maxima like the survey draw
-        return t1.tolist(), (6 * t1).tolist()
-    if name == "C5":
-        return [300] * 32, [2000] * 32
-    raise KeyError(name)
+"""Seeded synthetic inputs for the parity tests and golden fixtures (see
+``efficient_tts_b200/workloads.py``, which bench.py shares)."""
+from efficient_tts_b200.workloads import (NUM_SYMBOLS, ODIM, config_lengths,  # noqa: F401
+                                          make_forward_inputs, make_inference_inputs)

@@ -243,17 +243,24 @@ def test_forward_rejects_what_the_reference_rejects(model, dev):
 # ------------------------------------------------------------------------------------------------
 def test_inference_matches_golden(dev):
     z = np.load(os.path.join(G, "inf_small.npz"))
-    m = build_model(orc.make_weights(seed=1234, dur_bias=float(z["dur_bias"]), dur_weight_scale=0.05), dev)
+    w = orc.make_weights(seed=1234, dur_bias=float(z["dur_bias"]), dur_weight_scale=0.05)
+    m = build_model(w, dev)
     text = make_inference_inputs(int(z["seed"]), int(z["t1"]))
     mel, ra = m.inference(text.to(dev))
     assert tuple(mel.shape) == z["mel_pred"].shape and tuple(ra.shape) == z["reconst_alpha"].shape
     assert np.abs(mel.cpu().numpy() - z["mel_pred"]).max() <= MEL_TOL
     assert np.abs(ra.cpu().numpy() - z["reconst_alpha"]).max() <= RA_TOL
-    # weight norm folded (bin/inference.py:80) gives the same answer
-    m.remove_weight_norm()
-    assert "decoder.layers.0.conv.0.weight" in m.state_dict()
-    mel2, _ = m.inference(text.to(dev))
-    assert torch.equal(mel, mel2)
+    # the reference's loading order (bin/inference.py:77-83): load_state_dict, remove_weight_norm()
+    # on the CPU, then .eval().to(device) -- folded weights give bit-identical results
+    import efficient_tts_b200 as E
+    m2 = E.EfficientTTSCNN(num_symbols=76, dropout_rate=0.0, use_masking=True, sigma=0.01)
+    m2.load_state_dict(w)
+    m2.remove_weight_norm()
+    assert "decoder.layers.0.conv.0.weight" in m2.state_dict()
+    assert "decoder.layers.0.conv.0.weight_g" not in m2.state_dict()
+    m2 = m2.eval().to(dev)
+    mel2, ra2 = m2.inference(text.to(dev))
+    assert torch.equal(mel, mel2) and torch.equal(ra, ra2)
 
 
 def test_inference_c1_shape_matches_oracle(dev):

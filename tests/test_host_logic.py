@@ -1,0 +1,199 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol the header declares, the
+product never touches the oracle, the drop-in mirrors the reference's parameter contract, and the
+data-parallel split / reduce / gather logic works across 2 gloo ranks."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "efts_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(efts_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_builds_loads_and_exports_the_header():
+    from efficient_tts_b200 import _lib
+    lib = _lib.load()
+    names = header_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), "missing export " + n
+    assert sorted(_lib.SIGNATURES) == names          # the ctypes binding types exactly the header
+    assert b"sm_100a" in lib.efts_version()
+
+
+def test_no_device_is_an_error_not_a_fallback():
+    """Without a GPU (or on the wrong architecture) the library refuses; nothing computes on the CPU."""
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    from efficient_tts_b200 import _lib
+    lib = _lib.load()
+    cfg = _lib.EftsConfig(76, 80, 512, 5, 5, 3, 6, 2, 3, 0.01, 0.5, 1.0, 0.1, 1, 0)
+    h = ctypes.c_void_p()
+    rc = lib.efts_create(ctypes.byref(cfg), ctypes.byref(h))
+    assert rc == -3 and b"no CPU path" in lib.efts_last_error()
+    import efficient_tts_b200 as E
+    from efficient_tts_b200 import workloads as wl
+    m = E.EfficientTTSCNN(**wl.MODEL_KWARGS).eval()
+    text, tl, speech, sl = wl.make_forward_inputs(0, [5], [20])
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m(text=text, text_lengths=tl, speech=speech, speech_lengths=sl)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m.inference(text)
+
+
+def test_create_rejects_unsupported_configs():
+    from efficient_tts_b200 import _lib
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    bad = _lib.EftsConfig(76, 80, 384, 5, 5, 3, 6, 2, 3, 0.01, 0.5, 1.0, 0.1, 1, 0)       # n_channels
+    assert lib.efts_create(ctypes.byref(bad), ctypes.byref(h)) == -2
+    bad = _lib.EftsConfig(76, 80, 512, 7, 5, 3, 6, 2, 3, 0.01, 0.5, 1.0, 0.1, 1, 0)       # k_size
+    assert lib.efts_create(ctypes.byref(bad), ctypes.byref(h)) == -2
+    bad = _lib.EftsConfig(76, 80, 512, 5, 5, 3, 6, 2, 3, 0.01, 0.5, 1.0, 0.2, 1, 0)       # activation slope
+    assert lib.efts_create(ctypes.byref(bad), ctypes.byref(h)) == -2
+    assert lib.efts_create(None, ctypes.byref(h)) == -1
+    import efficient_tts_b200 as E
+    for kw in (dict(share_text_encoder_key_value=True), dict(use_mel_query_fc=True),
+               dict(delta_e_method_1=False), dict(use_weighted_masking=True),
+               dict(nonlinear_activation="ReLU", nonlinear_activation_params={})):
+        with pytest.raises(NotImplementedError):
+            E.EfficientTTSCNN(76, **kw)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "efficient_tts_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.lower(), "product file mentions the oracle: " + f
+    code = "import sys; import efficient_tts_b200, efficient_tts_b200.engine, efficient_tts_b200.data_parallel; " \
+           "assert not any(m.startswith('oracle') for m in sys.modules); assert 'nntts' not in sys.modules"
+    subprocess.run([sys.executable, "-c", code], check=True, cwd=ROOT)
+
+
+def test_dropin_parameter_contract_matches_oracle_key_list():
+    """state_dict keys/shapes == the reference's (the oracle's make_weights mirrors
+    them and is pinned to the reference by tests/golden); load_state_dict(strict) round-trips;
+    remove_weight_norm() folds to `.weight` exactly like torch's own fold."""
+    from oracle import efts_oracle as orc
+    import efficient_tts_b200 as E
+    from efficient_tts_b200 import workloads as wl
+    from efficient_tts_b200.engine import fold_state_dict
+    warnings.filterwarnings("ignore")
+    w = orc.make_weights(seed=1234)
+    m = E.EfficientTTSCNN(**wl.MODEL_KWARGS)
+    sd = m.state_dict()
+    assert list(sd) == sorted(sd, key=list(sd).index) and set(sd) == set(w)
+    for k in w:
+        assert tuple(sd[k].shape) == tuple(w[k].shape), k
+    m.load_state_dict(w, strict=True)
+    folded = fold_state_dict(m.state_dict())
+    m.remove_weight_norm()
+    sd2 = m.state_dict()
+    assert "decoder.layers.5.conv.0.weight" in sd2 and not any(k.endswith("weight_g") for k in sd2)
+    for k, v in sd2.items():
+        assert torch.equal(folded[k], v), k
+        if k.endswith("conv.0.weight") and "duration" not in k:
+            assert torch.equal(v, orc.conv_weight(w, k[: -len(".weight")]))
+    m.apply_weight_norm()
+    assert "decoder.layers.5.conv.0.weight_g" in m.state_dict()
+
+
+def test_layer_mirrors_keep_reference_signatures():
+    from efficient_tts_b200.layers import DurationPredictor, LengthRegulator, ResConvBlock
+    blk = ResConvBlock(num_layers=2, n_channels=512, k_size=5, dropout_rate=0.0, use_weight_norm=True)
+    assert list(blk.state_dict()) == ["layers.0.conv.0.bias", "layers.0.conv.0.weight_g", "layers.0.conv.0.weight_v",
+                                      "layers.1.conv.0.bias", "layers.1.conv.0.weight_g", "layers.1.conv.0.weight_v"]
+    dp = DurationPredictor(idim=512, n_layers=2, n_chans=512, kernel_size=3, dropout_rate=0.1, offset=1.0)
+    assert "conv.1.2.weight" in dp.state_dict() and dp.state_dict()["linear.weight"].shape == (1, 512)
+    assert dp.conv[0][2].eps == 1e-12                                    # layers/layer_norm.py:16
+    assert LengthRegulator(pad_value=1.5).pad_value == 1.5
+    with pytest.raises(NotImplementedError):
+        DurationPredictor(idim=512, n_chans=512, spk_embed_dim=64, num_spks=4)
+
+
+def test_workload_recipes():
+    from efficient_tts_b200 import workloads as wl
+    t1, t2 = wl.config_lengths("C3")
+    assert len(t1) == 256 and sum(t1) == 32825 and max(t1) == 200 and min(t1) >= 50 and sum(t2) == 196950
+    for seed in range(1, 8):
+        a, b = wl.config_lengths("C3", seed=seed)
+        assert max(a) == 200 and max(b) == 1200
+    text, tl, speech, sl = wl.make_forward_inputs(0, [5, 3], [20, 9])
+    assert text.shape == (2, 5) and speech.shape == (2, 20, 80)
+    assert not text[1, 3:].any() and not speech[1, 9:].any()
+
+
+# ------------------------------------------------------------------------------------------------
+DP_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %(root)r)
+from efficient_tts_b200.data_parallel import DataParallelForward, shard_range, combine_loss_partials
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%(port)d", rank=rank, world_size=world)
+B, T1, T2 = 5, 4, 6
+g = torch.Generator().manual_seed(0)
+text = torch.randint(0, 9, (B, T1), generator=g)
+tl = torch.tensor([4, 2, 3, 1, 4]); sl = torch.tensor([6, 3, 5, 2, 6])
+speech = torch.randn(B, T2, 2, generator=g)
+def fake_forward(text, tl, speech, sl):       # stand-in with the device path's return contract
+    mm = (torch.arange(T2)[None] < sl[:, None]).float()
+    tm = (torch.arange(T1)[None] < tl[:, None]).float()
+    mel = speech * 0.5 * mm[..., None]
+    imv = mm * text.float().sum(1, keepdim=True)
+    ra = tm[:, :, None] * mm[:, None, :]
+    sq = (((mel - speech) ** 2) * mm[..., None]).sum()
+    ab = (tm * text.float()).sum()
+    scal = torch.stack([sq * 0, sq * 0, sq * 0, sq, mm.sum() * 2, ab, tm.sum(), sq * 0])
+    return imv, ra, mel, scal
+dp = DataParallelForward(fake_forward)
+loss, stats, imv, ra, mel = dp(text, tl, speech, sl, gather_outputs=True)
+ref = fake_forward(text, tl, speech, sl)
+want = combine_loss_partials(ref[3][3:7].tolist())
+assert abs(loss - want[0]) < 1e-6 and abs(stats["mel_loss"] - want[1]) < 1e-6, (loss, want)
+assert torch.equal(imv, ref[0]) and torch.equal(ra, ref[1]) and torch.equal(mel, ref[2])
+lo, hi = shard_range(B, rank, world)
+_, _, imv_s, _, _ = dp(text, tl, speech, sl)             # outputs stay sharded by default
+assert torch.equal(imv_s, ref[0][lo:hi])
+dist.barrier(); dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_data_parallel_split_reduce_gather_gloo_world2():
+    from efficient_tts_b200.data_parallel import shard_range
+    assert [shard_range(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
+    assert [shard_range(2048, r, 8) for r in range(8)][3] == (768, 1024)
+    port = 29500 + os.getpid() % 2000
+    code = DP_WORKER % dict(root=ROOT, port=port)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        out, _ = p.communicate(timeout=180)
+        assert p.returncode == 0, out
+        assert "ok" in out
+
+
+def test_bench_reference_arm_prints_contract_line():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "1", "--cpu-sample", "2"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr
+    import json
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "mel_frames/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
