@@ -16,6 +16,7 @@
 
 #include "../../include/efts_b200.h"
 #include "gemm_sm100.cuh"
+#include "gemm2_sm100.cuh"
 #include "path_kernels.cuh"
 
 namespace {
@@ -88,6 +89,9 @@ struct efts_ctx {
   int sm_count = 0;
   int amode = 0;
   int skip_pad_tiles = 1;
+  int gemm_version = 2;      // 1: gemm_sm100.cuh, 2: gemm2_sm100.cuh (persistent, flushed accumulator)
+  int pair = 1;              // v2: CTA pairs (cta_group::2) for the weight GEMMs
+  int chunk_kb = 1;          // v2: k-blocks per main-accumulator flush
   int64_t launches = 0;
   bool finalized = false;
   EncodeTiledFn encode = nullptr;
@@ -172,10 +176,54 @@ int launch_gemm_t(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, cons
   return EFTS_OK;
 }
 
+template <int CG>
+int launch_gemm2_t(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, const GemmParams& p) {
+  using Cfg = G2Cfg<CG>;
+  static bool attr_set = false;
+  auto kern = gemm2_kernel<CG>;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  alignas(64) CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  TRY(make_map(c, &ma_hi, a.hi, a.K, a.T, a.B, a.ld, G2_A_ROWS));
+  TRY(make_map(c, &ma_lo, a.lo, a.K, a.T, a.B, a.ld, G2_A_ROWS));
+  TRY(make_map(c, &mb_hi, b.hi, b.K, b.N, b.Z, b.ld, Cfg::B_ROWS));
+  TRY(make_map(c, &mb_lo, b.lo, b.K, b.N, b.Z, b.ld, Cfg::B_ROWS));
+  // persistent: one CTA per SM (CTA pairs when CG == 2), never more than there are tiles
+  const long long n_rt = static_cast<long long>(p.B) * ((p.T + G2_BM - 1) / G2_BM);
+  const long long work = ((n_rt + CG - 1) / CG) * ((p.N + G2_BN - 1) / G2_BN);
+  long long ctas = std::min<long long>(c->sm_count / CG, work) * CG;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(static_cast<unsigned>(ctas));
+  cfg.blockDim = dim3(G2_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ma_hi, ma_lo, mb_hi, mb_lo, p));
+  c->launches++;
+  return EFTS_OK;
+}
+
 int launch_gemm(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, GemmParams p) {
   p.B = a.B; p.T = a.T; p.K = a.K;
   if (a.K != b.K) return fail(EFTS_ERR_ARG, "gemm K mismatch %d vs %d", a.K, b.K);
   if (p.N % 8 != 0) return fail(EFTS_ERR_ARG, "gemm N=%d must be a multiple of 8", p.N);
+  if (c->gemm_version == 2) {
+    if (p.ntaps > 9) return fail(EFTS_ERR_ARG, "at most 9 taps");
+    p.chunk_kb = c->chunk_kb;
+    if (!c->skip_pad_tiles) { p.tile_list = nullptr; p.tile_count = nullptr; p.skip_lens = nullptr; }
+    if (c->pair && !p.b_batched) return launch_gemm2_t<2>(c, st, a, b, p);
+    return launch_gemm2_t<1>(c, st, a, b, p);
+  }
+  p.tile_list = nullptr; p.tile_count = nullptr;
   if (p.B > 65535 || (p.T + GEMM_BM - 1) / GEMM_BM > 65535) return fail(EFTS_ERR_ARG, "grid too large");
   const long row_tiles = static_cast<long>(p.B) * ((p.T + GEMM_BM - 1) / GEMM_BM);
   int bn = p.N <= 64 ? 64 : (p.N <= 128 ? 128 : 256);
@@ -279,8 +327,13 @@ struct FwdWs {
   float* xm_f[2]; __half *xm_hi[2], *xm_lo[2];
   float *S, *imv_raw;
   __half *R_hi, *R_lo;
+  int2 *list_t, *list_m;      // compacted live row tiles (text side / mel side)
+  int *cnt_t, *cnt_m;
   int T1p;
 };
+
+// Which rows of a padded batch can still reach a valid output: lengths + (optional) compacted tiles.
+struct Skip { const int* lens; const int2* list; const int* count; };
 
 void carve_text(Arena& a, FwdWs& w, int B, int T1, int C) {
   const size_t m1 = static_cast<size_t>(B) * T1;
@@ -302,6 +355,8 @@ void carve_text(Arena& a, FwdWs& w, int B, int T1, int C) {
   w.dp_hi = a.get<__half>(m1 * C); w.dp_lo = a.get<__half>(m1 * C);
   w.dur = a.get<float>(m1);
   w.e = a.get<float>(m1);
+  w.list_t = a.get<int2>(static_cast<size_t>(B) * ((T1 + G2_BM - 1) / G2_BM));
+  w.cnt_t = a.get<int>(4);
 }
 
 void carve_mel(Arena& a, FwdWs& w, int B, int T2, int C, int odim, bool teacher_forced) {
@@ -313,6 +368,8 @@ void carve_mel(Arena& a, FwdWs& w, int B, int T2, int C, int odim, bool teacher_
   }
   w.R_hi = a.get<__half>(m2 * w.T1p);
   w.R_lo = a.get<__half>(m2 * w.T1p);
+  w.list_m = a.get<int2>(static_cast<size_t>(B) * ((T2 + G2_BM - 1) / G2_BM));
+  w.cnt_m = a.get<int>(4);
   if (teacher_forced) {
     w.sp_hi = a.get<__half>(m2 * odim);
     w.sp_lo = a.get<__half>(m2 * odim);
@@ -329,7 +386,7 @@ void carve_mel(Arena& a, FwdWs& w, int B, int T2, int C, int odim, bool teacher_
 // is non-null the last layer writes its fp32 result there instead (planes still go to the set).
 int run_conv_stack(efts_ctx* c, cudaStream_t st, const PackedW* layers, int n, int B, int T, float* f[2],
                    __half* hi[2], __half* lo[2], const float* first_resid, float* final_f,
-                   const int* skip_lens, int* cur_io, int tag) {
+                   const Skip* skip, int* cur_io, int tag) {
   const int C = c->cfg.n_channels;
   int cur = *cur_io;
   for (int l = 0; l < n; ++l) {
@@ -344,8 +401,8 @@ int run_conv_stack(efts_ctx* c, cudaStream_t st, const PackedW* layers, int n, i
     p.out = (l == n - 1 && final_f != nullptr) ? final_f : f[nxt];
     p.ld_out = C;
     p.out_hi = hi[nxt]; p.out_lo = lo[nxt]; p.ld_pl = C;
-    if (skip_lens != nullptr && c->skip_pad_tiles) {
-      p.skip_lens = skip_lens;
+    if (skip != nullptr && c->skip_pad_tiles) {
+      p.skip_lens = skip->lens; p.tile_list = skip->list; p.tile_count = skip->count;
       p.skip_halo = p.pad * (n - 1 - l);
     }
     {
@@ -397,11 +454,12 @@ int run_duration_predictor(efts_ctx* c, cudaStream_t st, const __half* in_hi, co
 
 // Gaussian reconstruction + expansion (models/efficient_tts.py:184-194 / :270-280):
 // e [B,T1] -> reconst_alpha [B,T1,T2] and expanded value at frame rate (fp32 + planes).
-int run_reconstruct_expand(efts_ctx* c, cudaStream_t st, const float* e, const int* tl, const int* sl, int B,
+int run_reconstruct_expand(efts_ctx* c, cudaStream_t st, const float* e, const int* tl, const Skip* mel, int B,
                            int T1, int T2, int T1p, __half* R_hi, __half* R_lo, const __half* valT_hi,
                            const __half* valT_lo, float* reconst_alpha, float* out_f, __half* out_hi,
                            __half* out_lo) {
   const int C = c->cfg.n_channels;
+  const int* sl = mel != nullptr ? mel->lens : nullptr;
   {
     ProfScope ps(c, st, TAG_RECONSTRUCT);
     dim3 grid((T2 + 127) / 128, B);
@@ -417,8 +475,8 @@ int run_reconstruct_expand(efts_ctx* c, cudaStream_t st, const float* e, const i
   p.lens = sl;
   p.out = out_f; p.ld_out = C;
   p.out_hi = out_hi; p.out_lo = out_lo; p.ld_pl = C;
-  if (sl != nullptr && c->skip_pad_tiles) {
-    p.skip_lens = sl;
+  if (mel != nullptr && c->skip_pad_tiles) {
+    p.skip_lens = mel->lens; p.tile_list = mel->list; p.tile_count = mel->count;
     p.skip_halo = ((c->cfg.k_size - 1) / 2) * c->cfg.n_decoder_layer;
   }
   ProfScope ps(c, st, TAG_EXPAND);
@@ -427,15 +485,16 @@ int run_reconstruct_expand(efts_ctx* c, cudaStream_t st, const float* e, const i
 
 // Energy -> softmax/expectation -> scan -> aligned positions (models/efficient_tts.py:167-178).
 int run_imv(efts_ctx* c, cudaStream_t st, const __half* q_hi, const __half* q_lo, const __half* key_hi,
-            const __half* key_lo, const int* tl, const int* sl, int B, int T1, int T2, int T1p, float* S,
+            const __half* key_lo, const int* tl, const Skip* mel, int B, int T1, int T2, int T1p, float* S,
             float* imv_raw, float* imv, float* e) {
   const int C = c->cfg.n_channels;
+  const int* sl = mel->lens;
   GemmParams p = gemm_defaults();
   p.N = T1p;
   p.b_batched = 1;
   p.divisor = static_cast<float>(std::sqrt(static_cast<double>(C)));   // np.sqrt(float(D)), :390
   p.out = S; p.ld_out = T1p;
-  if (c->skip_pad_tiles) { p.skip_lens = sl; p.skip_halo = 0; }
+  if (c->skip_pad_tiles) { p.skip_lens = mel->lens; p.tile_list = mel->list; p.tile_count = mel->count; p.skip_halo = 0; }
   {
     ProfScope ps(c, st, TAG_ENERGY);
     TRY(launch_gemm(c, st, OpA{q_hi, q_lo, B, T2, C, C}, OpB{key_hi, key_lo, B, T1, C, C}, p));
@@ -596,6 +655,17 @@ int efts_set_option(efts_ctx* c, const char* name, int32_t value) {
     return EFTS_OK;
   }
   if (strcmp(name, "skip_pad_tiles") == 0) { c->skip_pad_tiles = value != 0; return EFTS_OK; }
+  if (strcmp(name, "gemm_version") == 0) {
+    if (value != 1 && value != 2) return fail(EFTS_ERR_ARG, "gemm_version must be 1 or 2");
+    c->gemm_version = value;
+    return EFTS_OK;
+  }
+  if (strcmp(name, "pair") == 0) { c->pair = value != 0; return EFTS_OK; }
+  if (strcmp(name, "chunk_kb") == 0) {
+    if (value < 0 || value > 64) return fail(EFTS_ERR_ARG, "chunk_kb out of range");
+    c->chunk_kb = value;
+    return EFTS_OK;
+  }
   return fail(EFTS_ERR_ARG, "unknown option '%s'", name);
 }
 
@@ -650,6 +720,16 @@ int efts_forward(efts_ctx* c, const int64_t* text, const int64_t* text_lengths, 
   CUDA_TRY(cudaMemsetAsync(w.acc, 0, 2 * sizeof(double), st));
   prep_lengths_kernel<<<1, 256, 0, st>>>(text_lengths, speech_lengths, B, T1, T2, w.tl32, w.sl32, w.flags);
   CUDA_TRY(cudaGetLastError());
+  // live row tiles of both sides (largest halo any launch uses; launches re-check their own halo)
+  const int pad_k = (g.k_size - 1) / 2;
+  build_tile_list_kernel<<<1, 256, 0, st>>>(w.tl32, B, T1, pad_k * g.n_text_encoder_layer, w.list_t, w.cnt_t);
+  CUDA_TRY(cudaGetLastError());
+  build_tile_list_kernel<<<1, 256, 0, st>>>(w.sl32, B, T2, pad_k * std::max(g.n_mel_encoder_layer, g.n_decoder_layer),
+                                            w.list_m, w.cnt_m);
+  CUDA_TRY(cudaGetLastError());
+  c->launches += 2;
+  const Skip skip_t{w.tl32, w.list_t, w.cnt_t};
+  const Skip skip_m{w.sl32, w.list_m, w.cnt_m};
   // 1. embedding (:144) -> text encoder (:148)
   embed_kernel<<<static_cast<unsigned>(m1), C / 4, 0, st>>>(text, c->emb, g.num_symbols, C, w.xt_f[0], w.xt_hi[0],
                                                             w.xt_lo[0], w.flags);
@@ -657,7 +737,7 @@ int efts_forward(efts_ctx* c, const int64_t* text, const int64_t* text_lengths, 
   c->launches += 2;
   int cur = 0;
   TRY(run_conv_stack(c, st, c->text, g.n_text_encoder_layer, B, T1, w.xt_f, w.xt_hi, w.xt_lo, nullptr, nullptr,
-                     w.tl32, &cur, TAG_TEXT_CONV));
+                     &skip_t, &cur, TAG_TEXT_CONV));
   // 2. key / value projections, zero at pad tokens (:149-157)
   {
     GemmParams p = gemm_defaults();
@@ -681,23 +761,23 @@ int efts_forward(efts_ctx* c, const int64_t* text, const int64_t* text_lengths, 
     p.out = w.xm_f[0]; p.ld_out = C;
     p.out_hi = w.xm_hi[0]; p.out_lo = w.xm_lo[0]; p.ld_pl = C;
     if (c->skip_pad_tiles) {
-      p.skip_lens = w.sl32;
-      p.skip_halo = ((g.k_size - 1) / 2) * g.n_mel_encoder_layer;
+      p.skip_lens = skip_m.lens; p.tile_list = skip_m.list; p.tile_count = skip_m.count;
+      p.skip_halo = pad_k * g.n_mel_encoder_layer;
     }
     TRY(launch_gemm(c, st, OpA{w.sp_hi, w.sp_lo, B, T2, g.odim, g.odim}, weight_op(c->prenet), p));
   }
   int curm = 0;
   TRY(run_conv_stack(c, st, c->mel, g.n_mel_encoder_layer, B, T2, w.xm_f, w.xm_hi, w.xm_lo, nullptr, nullptr,
-                     w.sl32, &curm, TAG_MEL_CONV));
+                     &skip_m, &curm, TAG_MEL_CONV));
   // 4. alignment: energy/softmax/expectation, scan, aligned positions (:167-178)
-  TRY(run_imv(c, st, w.xm_hi[curm], w.xm_lo[curm], w.key_hi, w.key_lo, w.tl32, w.sl32, B, T1, T2, w.T1p, w.S,
+  TRY(run_imv(c, st, w.xm_hi[curm], w.xm_lo[curm], w.key_hi, w.key_lo, w.tl32, &skip_m, B, T1, T2, w.T1p, w.S,
               w.imv_raw, imv, w.e));
   // 5. Gaussian reconstruction + expansion (:184-194) into mel buffer set 0
-  TRY(run_reconstruct_expand(c, st, w.e, w.tl32, w.sl32, B, T1, T2, w.T1p, w.R_hi, w.R_lo, w.valT_hi, w.valT_lo,
+  TRY(run_reconstruct_expand(c, st, w.e, w.tl32, &skip_m, B, T1, T2, w.T1p, w.R_hi, w.R_lo, w.valT_hi, w.valT_lo,
                              reconst_alpha, w.xm_f[0], w.xm_hi[0], w.xm_lo[0]));
   // 6. decoder (:197) and mel head (:198-200)
   curm = 0;
-  TRY(run_conv_stack(c, st, c->dec, g.n_decoder_layer, B, T2, w.xm_f, w.xm_hi, w.xm_lo, nullptr, nullptr, w.sl32,
+  TRY(run_conv_stack(c, st, c->dec, g.n_decoder_layer, B, T2, w.xm_f, w.xm_hi, w.xm_lo, nullptr, nullptr, &skip_m,
                      &curm, TAG_DEC_CONV));
   {
     GemmParams p = gemm_defaults();
@@ -875,8 +955,9 @@ int efts_alignment_fwd(efts_ctx* c, const float* mel_h, const float* key, const 
   split_transpose_kernel<<<dim3((T1p + 31) / 32, C / 32, B), dim3(32, 8), 0, st>>>(value, T1, C, T1p, vT_hi, vT_lo);
   CUDA_TRY(cudaGetLastError());
   c->launches++;
-  TRY(run_imv(c, st, q_hi, q_lo, k_hi, k_lo, text_lengths, speech_lengths, B, T1, T2, T1p, S, imv_raw, imv, e));
-  return run_reconstruct_expand(c, st, e, text_lengths, speech_lengths, B, T1, T2, T1p, R_hi, R_lo, vT_hi, vT_lo,
+  const Skip mel{speech_lengths, nullptr, nullptr};
+  TRY(run_imv(c, st, q_hi, q_lo, k_hi, k_lo, text_lengths, &mel, B, T1, T2, T1p, S, imv_raw, imv, e));
+  return run_reconstruct_expand(c, st, e, text_lengths, &mel, B, T1, T2, T1p, R_hi, R_lo, vT_hi, vT_lo,
                                 reconst_alpha, expanded, x_hi, x_lo);
 }
 

@@ -1,0 +1,379 @@
+// Second-generation tap-GEMM: persistent, CTA-pair (tcgen05 cta_group::2) capable, with the main
+// accumulator flushed to fp32 registers every few k-blocks.
+//
+// Same contraction and epilogue as gemm_sm100.cuh (see there for the split-fp16 scheme), but
+//   * one 136-row A box per k-block serves all taps through row-shifted UMMA descriptors;
+//   * CG = 2: two CTAs (one TPC) form a 256-row x 128-column tile; each loads its own 128 A rows and
+//     half of the W tile, so weight traffic from L2 halves;
+//   * persistent CTAs walk a (compacted) list of live row tiles; TMEM holds two 128-column main
+//     accumulators and two correction accumulators, so MMAs of the next chunk / tile overlap the
+//     drain and the epilogue of the previous one;
+//   * tensor-core fp32 accumulation truncates (measured on B200: the error of a 160-step chain is
+//     biased towards zero and 16x the noise of an fp32 FMA chain).  The main hi*hi accumulator is
+//     therefore restarted every `chunk_kb` k-blocks and the partial sums are added in round-to-nearest
+//     fp32 on the CUDA cores; the correction accumulator is 2^-11 down and needs no flushing.
+#pragma once
+#include <cuda_fp16.h>
+
+#include "gemm_sm100.cuh"
+#include "sm100_ptx.cuh"
+
+namespace efts {
+
+constexpr int G2_BM = 128;
+constexpr int G2_BN = 128;
+constexpr int G2_BK = 64;
+constexpr int G2_A_ROWS = 136;
+constexpr int G2_A_PLANE = G2_A_ROWS * 128;
+constexpr int G2_A_STAGE = 2 * G2_A_PLANE;
+constexpr int G2_THREADS = 192;
+
+template <int CG>
+struct G2Cfg {
+  static constexpr int B_ROWS = G2_BN / CG;
+  static constexpr int B_PLANE = B_ROWS * 128;
+  static constexpr int B_STAGE = 2 * B_PLANE;
+  static constexpr int A_STAGES = CG == 2 ? 3 : 2;
+  static constexpr int B_STAGES = CG == 2 ? 6 : 4;
+  static constexpr int SMEM_TILES = A_STAGES * G2_A_STAGE + B_STAGES * B_STAGE;
+  static constexpr int SMEM_BYTES = SMEM_TILES + 1024 + 512;
+  static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB");
+};
+
+// Compacts the row tiles that can reach a valid output: utterance b keeps ceil(min(T, L_b + halo) / 128).
+__global__ void build_tile_list_kernel(const int* __restrict__ lens, int B, int T, int halo,
+                                       int2* __restrict__ list, int* __restrict__ count) {
+  __shared__ int warp_tot[32];
+  __shared__ int carry_s;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < B; base += blockDim.x) {
+    const int b = base + threadIdx.x;
+    int n = 0;
+    if (b < B) {
+      const int lim = min(T, max(lens[b], 0) + halo);
+      n = (lim + G2_BM - 1) / G2_BM;
+    }
+    int v = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += u;
+    }
+    if (lane == 31) warp_tot[w] = v;
+    __syncthreads();
+    int pre = carry_s;
+    for (int k = 0; k < w; ++k) pre += warp_tot[k];
+    const int start = pre + v - n;
+    for (int j = 0; j < n; ++j) list[start + j] = make_int2(b, j * G2_BM);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int k = 0; k < nw; ++k) tot += warp_tot[k];
+      carry_s += tot;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *count = carry_s;
+}
+
+template <int CG>
+__global__ void __launch_bounds__(G2_THREADS, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+             const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+             const GemmParams p) {
+  using Cfg = G2Cfg<CG>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = smem_base;
+  const uint32_t sB = sA + Cfg::A_STAGES * G2_A_STAGE;
+  const uint32_t sBar = sB + Cfg::B_STAGES * Cfg::B_STAGE;
+  auto fullA = [&](int s) { return sBar + 8u * s; };               // [4]
+  auto emptyA = [&](int s) { return sBar + 32u + 8u * s; };        // [4]
+  auto fullB = [&](int s) { return sBar + 64u + 8u * s; };         // [8]
+  auto emptyB = [&](int s) { return sBar + 128u + 8u * s; };       // [8]
+  auto acc0_full = [&](int s) { return sBar + 192u + 8u * s; };    // [2]
+  auto acc0_empty = [&](int s) { return sBar + 208u + 8u * s; };   // [2]
+  auto acc1_full = [&](int s) { return sBar + 224u + 8u * s; };    // [2]
+  auto acc1_empty = [&](int s) { return sBar + 240u + 8u * s; };   // [2]
+  const uint32_t tmem_slot = sBar + 256u;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = CG == 2 ? ptx::cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::A_STAGES; ++s) { ptx::mbar_init(fullA(s), 1); ptx::mbar_init(emptyA(s), 1); }
+    for (int s = 0; s < Cfg::B_STAGES; ++s) { ptx::mbar_init(fullB(s), 1); ptx::mbar_init(emptyB(s), 1); }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(acc0_full(s), 1);
+      ptx::mbar_init(acc1_full(s), 1);
+      ptx::mbar_init(acc0_empty(s), 4 * CG);     // one arrival per epilogue warp of every CTA in the pair
+      ptx::mbar_init(acc1_empty(s), 4 * CG);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    if (CG == 2) ptx::tmem_alloc_pair(tmem_slot, 512); else ptx::tmem_alloc(tmem_slot, 512);
+  }
+  ptx::tc_fence_before();
+  if (CG == 2) ptx::cluster_sync(); else __syncthreads();
+  ptx::tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  // ---- work list (identical in every role) ----
+  const int n_nt = (p.N + G2_BN - 1) / G2_BN;
+  const int tiles_per_b = (p.T + G2_BM - 1) / G2_BM;
+  const int n_rt = p.tile_list != nullptr ? *p.tile_count : p.B * tiles_per_b;
+  const int n_prt = (n_rt + CG - 1) / CG;
+  const long long total = static_cast<long long>(n_prt) * n_nt;
+  const int cid = blockIdx.x / CG, ncl = gridDim.x / CG;
+  const int num_kb = (p.K + G2_BK - 1) / G2_BK;
+  const int chunk_kb = p.chunk_kb < 1 ? num_kb : p.chunk_kb;
+
+  auto locate = [&](long long w, int& b, int& t0, int& n0, bool& valid) {
+    const int nt = static_cast<int>(w % n_nt);
+    const int rt = static_cast<int>(w / n_nt) * CG + static_cast<int>(rank);
+    n0 = nt * G2_BN;
+    valid = rt < n_rt;
+    if (!valid) { b = p.B; t0 = 0; return; }                 // b == B: every TMA row is out of range -> zeros
+    if (p.tile_list != nullptr) {
+      const int2 e = p.tile_list[rt];
+      b = e.x; t0 = e.y;
+    } else {
+      b = rt / tiles_per_b; t0 = (rt % tiles_per_b) * G2_BM;
+    }
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (every CTA)
+    if (lane == 0) {
+      ptx::prefetch_tensormap(&tmA_hi); ptx::prefetch_tensormap(&tmA_lo);
+      ptx::prefetch_tensormap(&tmB_hi); ptx::prefetch_tensormap(&tmB_lo);
+      uint32_t ia = 0, ib = 0;
+      for (long long w = cid; w < total; w += ncl) {
+        int b, t0, n0; bool valid;
+        locate(w, b, t0, n0, valid);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          {
+            const int s = ia % Cfg::A_STAGES; const uint32_t ph = (ia / Cfg::A_STAGES) & 1;
+            ptx::mbar_wait(emptyA(s), ph ^ 1u);
+            const uint32_t dst = sA + s * G2_A_STAGE;
+            if (CG == 2) {
+              const uint32_t bar = ptx::map_to_cta(fullA(s), 0);
+              if (leader) ptx::mbar_expect_tx(fullA(s), 2 * G2_A_STAGE);
+              ptx::tma_load_3d_pair(&tmA_hi, bar, dst, kb * G2_BK, t0 - p.pad, b);
+              ptx::tma_load_3d_pair(&tmA_lo, bar, dst + G2_A_PLANE, kb * G2_BK, t0 - p.pad, b);
+            } else {
+              ptx::mbar_expect_tx(fullA(s), G2_A_STAGE);
+              ptx::tma_load_3d(&tmA_hi, fullA(s), dst, kb * G2_BK, t0 - p.pad, b);
+              ptx::tma_load_3d(&tmA_lo, fullA(s), dst + G2_A_PLANE, kb * G2_BK, t0 - p.pad, b);
+            }
+            ++ia;
+          }
+          for (int tap = 0; tap < p.ntaps; ++tap) {
+            const int s = ib % Cfg::B_STAGES; const uint32_t ph = (ib / Cfg::B_STAGES) & 1;
+            ptx::mbar_wait(emptyB(s), ph ^ 1u);
+            const uint32_t dst = sB + s * Cfg::B_STAGE;
+            const int z = p.b_batched ? b : tap;
+            const int nrow = n0 + static_cast<int>(rank) * Cfg::B_ROWS;
+            if (CG == 2) {
+              const uint32_t bar = ptx::map_to_cta(fullB(s), 0);
+              if (leader) ptx::mbar_expect_tx(fullB(s), 2 * Cfg::B_STAGE);
+              ptx::tma_load_3d_pair(&tmB_hi, bar, dst, kb * G2_BK, nrow, z);
+              ptx::tma_load_3d_pair(&tmB_lo, bar, dst + Cfg::B_PLANE, kb * G2_BK, nrow, z);
+            } else {
+              ptx::mbar_expect_tx(fullB(s), Cfg::B_STAGE);
+              ptx::tma_load_3d(&tmB_hi, fullB(s), dst, kb * G2_BK, nrow, z);
+              ptx::tma_load_3d(&tmB_lo, fullB(s), dst + Cfg::B_PLANE, kb * G2_BK, nrow, z);
+            }
+            ++ib;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA, one thread)
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = ptx::make_idesc_f16(G2_BM * CG, G2_BN);
+      auto commit = [&](uint32_t bar) {
+        if (CG == 2) ptx::tc_commit_pair(bar, 3); else ptx::tc_commit(bar);
+      };
+      uint32_t ia = 0, ib = 0, g = 0, it = 0;
+      for (long long w = cid; w < total; w += ncl) {
+        const uint32_t tb = it & 1u;
+        ptx::mbar_wait(acc1_empty(tb), ((it >> 1) & 1u) ^ 1u);
+        const uint32_t acc1 = tmem_base + 256u + tb * G2_BN;
+        uint32_t first1 = 1;
+        for (int kb0 = 0; kb0 < num_kb; kb0 += chunk_kb) {
+          const uint32_t buf = g & 1u;
+          ptx::mbar_wait(acc0_empty(buf), ((g >> 1) & 1u) ^ 1u);
+          ptx::tc_fence_after();
+          const uint32_t acc0 = tmem_base + buf * G2_BN;
+          uint32_t first0 = 1;
+          const int kb1 = min(kb0 + chunk_kb, num_kb);
+          for (int kb = kb0; kb < kb1; ++kb) {
+            const int sa = ia % Cfg::A_STAGES;
+            ptx::mbar_wait(fullA(sa), (ia / Cfg::A_STAGES) & 1);
+            ++ia;
+            for (int tap = 0; tap < p.ntaps; ++tap) {
+              const int sb = ib % Cfg::B_STAGES;
+              ptx::mbar_wait(fullB(sb), (ib / Cfg::B_STAGES) & 1);
+              ++ib;
+              ptx::tc_fence_after();
+              const uint32_t a_addr = sA + sa * G2_A_STAGE + tap * 128;     // row shift = tap
+              const uint32_t b_addr = sB + sb * Cfg::B_STAGE;
+              const uint64_t dAh = ptx::make_desc_sw128(a_addr, 0);
+              const uint64_t dAl = ptx::make_desc_sw128(a_addr + G2_A_PLANE, 0);
+              const uint64_t dBh = ptx::make_desc_sw128(b_addr, 0);
+              const uint64_t dBl = ptx::make_desc_sw128(b_addr + Cfg::B_PLANE, 0);
+#pragma unroll
+              for (int k = 0; k < G2_BK / 16; ++k) {
+                const uint64_t ko = static_cast<uint64_t>(k * 2);
+                if (CG == 2) {
+                  ptx::mma_f16_ss_pair(acc0, dAh + ko, dBh + ko, idesc, first0 ? 0u : 1u);
+                  ptx::mma_f16_ss_pair(acc1, dAh + ko, dBl + ko, idesc, first1 ? 0u : 1u);
+                  ptx::mma_f16_ss_pair(acc1, dAl + ko, dBh + ko, idesc, 1u);
+                } else {
+                  ptx::mma_f16_ss(acc0, dAh + ko, dBh + ko, idesc, first0 ? 0u : 1u);
+                  ptx::mma_f16_ss(acc1, dAh + ko, dBl + ko, idesc, first1 ? 0u : 1u);
+                  ptx::mma_f16_ss(acc1, dAl + ko, dBh + ko, idesc, 1u);
+                }
+                first0 = 0; first1 = 0;
+              }
+              commit(emptyB(sb));
+            }
+            commit(emptyA(sa));
+          }
+          commit(acc0_full(buf));
+          ++g;
+        }
+        commit(acc1_full(tb));
+        ++it;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ accumulate + epilogue (warps 2..5)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    auto release = [&](uint32_t bar) {            // one arrival per warp, on the leader's barrier
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (CG == 2) ptx::mbar_arrive_cluster(ptx::map_to_cta(bar, 0)); else ptx::mbar_arrive(bar);
+      }
+    };
+    uint32_t g = 0, it = 0;
+    for (long long w = cid; w < total; w += ncl) {
+      int b, t0, n0; bool valid;
+      locate(w, b, t0, n0, valid);
+      const int t = t0 + row;
+      const bool tile_live = valid && !(p.skip_lens != nullptr && t0 >= p.skip_lens[b] + p.skip_halo);
+      const bool row_ok = tile_live && t < p.T;
+      const bool row_live = row_ok && (p.lens == nullptr || t < p.lens[b]);
+      const size_t m = row_ok ? static_cast<size_t>(b) * p.T + t : 0;
+      float sum[G2_BN];
+#pragma unroll
+      for (int j = 0; j < G2_BN; ++j) sum[j] = 0.0f;
+      for (int kb0 = 0; kb0 < num_kb; kb0 += chunk_kb) {
+        const uint32_t buf = g & 1u;
+        ptx::mbar_wait(acc0_full(buf), (g >> 1) & 1u);
+        ptx::tc_fence_after();
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < G2_BN / 32; ++c) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(lane_addr + buf * G2_BN + c * 32, r);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sum[c * 32 + j] = __fadd_rn(sum[c * 32 + j], __uint_as_float(r[j]));
+        }
+        release(acc0_empty(buf));
+        ++g;
+      }
+      const uint32_t tb = it & 1u;
+      ptx::mbar_wait(acc1_full(tb), (it >> 1) & 1u);
+      ptx::tc_fence_after();
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < G2_BN / 32; ++c) {
+        uint32_t r[32];
+        __syncwarp();                               // tcgen05.ld is .aligned: reconverge after the stores
+        ptx::tmem_ld_32x32(lane_addr + 256u + tb * G2_BN + c * 32, r);
+        ptx::tmem_ld_wait();
+        if (c == G2_BN / 32 - 1) release(acc1_empty(tb));
+        const int c0 = c * 32;
+        if (n0 + c0 >= p.N || !row_ok) continue;      // warp-divergent only around plain loads/stores
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float a = __fadd_rn(sum[c0 + j], __uint_as_float(r[j]) * SPLIT_INV_SCALE);
+          if (p.divisor != 1.0f) a = __fdiv_rn(a, p.divisor);
+          v[j] = a;
+        }
+#pragma unroll
+        for (int gq = 0; gq < 4; ++gq) {
+          const int n = n0 + c0 + gq * 8;
+          if (n >= p.N) break;
+          float* vv = v + gq * 8;
+          if (p.bias != nullptr) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
+            vv[0] += b0.x; vv[1] += b0.y; vv[2] += b0.z; vv[3] += b0.w;
+            vv[4] += b1.x; vv[5] += b1.y; vv[6] += b1.z; vv[7] += b1.w;
+          }
+          if (p.act == ACT_LRELU) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) vv[j] = vv[j] > 0.0f ? vv[j] : vv[j] * 0.1f;
+          } else if (p.act == ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) vv[j] = fmaxf(vv[j], 0.0f);
+          }
+          if (p.resid != nullptr) {
+            const float* rp = p.resid + m * p.ld_out + n;
+            const float4 x0 = *reinterpret_cast<const float4*>(rp);
+            const float4 x1 = *reinterpret_cast<const float4*>(rp + 4);
+            vv[0] = x0.x + vv[0]; vv[1] = x0.y + vv[1]; vv[2] = x0.z + vv[2]; vv[3] = x0.w + vv[3];
+            vv[4] = x1.x + vv[4]; vv[5] = x1.y + vv[5]; vv[6] = x1.z + vv[6]; vv[7] = x1.w + vv[7];
+          }
+          if (!row_live) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) vv[j] = 0.0f;
+          }
+          if (p.out != nullptr) {
+            float* op = p.out + m * p.ld_out + n;
+            *reinterpret_cast<float4*>(op) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+            *reinterpret_cast<float4*>(op + 4) = make_float4(vv[4], vv[5], vv[6], vv[7]);
+          }
+          if (p.out_hi != nullptr) {
+            split_store8(p.out_hi + m * p.ld_pl + n, p.out_lo + m * p.ld_pl + n, vv);
+          }
+          if (p.outT_hi != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const size_t o = (static_cast<size_t>(b) * p.N + (n + j)) * p.ld_t + t;
+              const __half h = __float2half_rn(vv[j]);
+              p.outT_hi[o] = h;
+              p.outT_lo[o] = __float2half_rn((vv[j] - __half2float(h)) * SPLIT_SCALE);
+            }
+          }
+        }
+      }
+      ++it;
+    }
+  }
+
+  // ---- teardown: nobody may leave while the pair can still touch this CTA's smem / TMEM ----
+  __syncwarp();
+  ptx::tc_fence_before();
+  if (CG == 2) ptx::cluster_sync(); else __syncthreads();
+  if (warp == 1) {
+    if (CG == 2) ptx::tmem_dealloc_pair(tmem_base, 512); else ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace efts

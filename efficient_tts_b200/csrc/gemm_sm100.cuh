@@ -55,6 +55,10 @@ struct GemmParams {
   __half* outT_hi;       // transposed fp16 planes [B, N, ld_t] (t contiguous) or nullptr
   __half* outT_lo;
   int ld_t;
+  // second-generation kernel only (gemm2_sm100.cuh)
+  const int2* tile_list; // compacted live row tiles (b, t0), or nullptr = all B * ceil(T/128)
+  const int* tile_count; // device count of tile_list entries
+  int chunk_kb;          // k-blocks per main-accumulator flush (0 = never flush)
 };
 
 template <int BN, int AMODE>

@@ -19,7 +19,8 @@ cfg = %(cfg)r
 dev = torch.device("cuda", 0)
 m = E.EfficientTTSCNN(num_symbols=76, dropout_rate=0.0, use_masking=True, sigma=0.01)
 m.load_state_dict(orc.make_weights(seed=1234)); m = m.eval().to(dev)
-eng = m._get_engine(); eng.set_option("amode", cfg["amode"])
+eng = m._get_engine()
+for k, v in cfg.get("opts", {}).items(): eng.set_option(k, v)
 g = torch.Generator().manual_seed(5)
 B, T, K, N, nt = cfg["B"], cfg["T"], cfg["K"], cfg["N"], cfg["ntaps"]
 x = torch.randn(B, T, K, generator=g); w = torch.randn(nt, N, K, generator=g) / np.sqrt(K * nt)
@@ -33,16 +34,22 @@ print("RESULT " + json.dumps(dict(cfg=cfg, max_err=float(err.max()), mean_err=fl
       ref_absmax=float(ref.abs().max()), nan=int(torch.isnan(out).sum()))))
 '''
 
-CASES = [
-    dict(B=1, T=128, K=64, N=64, ntaps=1, amode=0),
-    dict(B=1, T=128, K=512, N=256, ntaps=1, amode=0),
-    dict(B=2, T=200, K=512, N=512, ntaps=1, amode=0),
-    dict(B=3, T=77, K=80, N=512, ntaps=1, amode=0),
-    dict(B=2, T=300, K=512, N=80, ntaps=1, amode=0),
-    dict(B=2, T=260, K=512, N=512, ntaps=5, amode=0),
-    dict(B=2, T=260, K=512, N=512, ntaps=5, amode=1),
-    dict(B=2, T=260, K=512, N=512, ntaps=5, amode=2),
-    dict(B=64, T=1200, K=512, N=512, ntaps=5, amode=0),
+V1 = dict(gemm_version=1, amode=0)
+V2S = dict(gemm_version=2, pair=0, chunk_kb=1)
+V2P = dict(gemm_version=2, pair=1, chunk_kb=1)
+SHAPES = [
+    dict(B=1, T=128, K=64, N=64, ntaps=1),
+    dict(B=1, T=128, K=512, N=256, ntaps=1),
+    dict(B=3, T=77, K=80, N=512, ntaps=1),
+    dict(B=2, T=300, K=512, N=80, ntaps=1),
+    dict(B=2, T=260, K=512, N=512, ntaps=5),
+    dict(B=3, T=50, K=512, N=512, ntaps=3),
+    dict(B=64, T=1200, K=512, N=512, ntaps=5),
+]
+CASES = [dict(sh, opts=o) for o in (V2S, V2P) for sh in SHAPES] + [
+    dict(B=64, T=1200, K=512, N=512, ntaps=5, opts=dict(gemm_version=2, pair=1, chunk_kb=2)),
+    dict(B=64, T=1200, K=512, N=512, ntaps=5, opts=dict(gemm_version=2, pair=1, chunk_kb=0)),
+    dict(B=64, T=1200, K=512, N=512, ntaps=5, opts=V1),
 ]
 
 

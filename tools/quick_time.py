@@ -15,8 +15,7 @@ import efficient_tts_b200 as E  # noqa: E402
 
 def main():
     name = sys.argv[1] if len(sys.argv) > 1 else "C3"
-    amode = int(sys.argv[2]) if len(sys.argv) > 2 else 0
-    skip = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+    opts = dict(kv.split("=") for kv in sys.argv[2].split(",")) if len(sys.argv) > 2 and sys.argv[2] else {}
     dev = torch.device("cuda", 0)
     m = E.EfficientTTSCNN(num_symbols=76, dropout_rate=0.0, use_masking=True, sigma=0.01)
     m.load_state_dict(orc.make_weights(seed=1234))
@@ -24,8 +23,8 @@ def main():
     t1, t2 = config_lengths(name)
     text, tl, speech, sl = (x.to(dev) for x in make_forward_inputs(0, t1, t2))
     eng = m._get_engine()
-    eng.set_option("amode", amode)
-    eng.set_option("skip_pad_tiles", skip)
+    for k, v in opts.items():
+        eng.set_option(k, int(v))
     for _ in range(3):
         out = m(text=text, text_lengths=tl, speech=speech, speech_lengths=sl)
     torch.cuda.synchronize()
@@ -38,7 +37,7 @@ def main():
     torch.cuda.synchronize()
     ms = ev[0].elapsed_time(ev[1]) / n
     frames = int(sl.sum())
-    print("QUICK " + json.dumps(dict(config=name, amode=amode, skip=skip, ms=ms, valid_frames=frames,
+    print("QUICK " + json.dumps(dict(config=name, opts=opts, ms=ms, valid_frames=frames,
                                      frames_per_s=frames / ms * 1e3, stats=out[1],
                                      launches=eng.launch_count())))
 
