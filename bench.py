@@ -240,7 +240,7 @@ def run_ours(args, rank, local_rank, world):
                 traffic = json.load(open(tp)).get("decoder_conv_dram_bytes_per_launch")
             except Exception:
                 traffic = None
-        roof = {"bound": "tensor", "kernel": "gemm_split_kernel<256,*> decoder Conv1d layer (k=5, 512->512)",
+        roof = {"bound": "tensor", "kernel": "gemm2_kernel<2> (CTA-pair tcgen05 tap-GEMM) on the decoder Conv1d layers (k=5, 512->512)",
                 "achieved": ach, "peak": peaks["tf"], "unit": "TFLOP/s", "frac": (ach / peaks["tf"]) if ach else None,
                 "traffic": traffic, "peak_source": peaks["src"], "passes": 3,
                 "executed_frac": (3 * ach / peaks["tf"]) if ach else None,

@@ -91,7 +91,7 @@ struct efts_ctx {
   int skip_pad_tiles = 1;
   int gemm_version = 2;      // 1: gemm_sm100.cuh, 2: gemm2_sm100.cuh (persistent, flushed accumulator)
   int pair = 1;              // v2: CTA pairs (cta_group::2) for the weight GEMMs
-  int chunk_kb = 1;          // v2: k-blocks per main-accumulator flush
+  int chunk_kb = 2;          // v2: k-blocks per main-accumulator flush (1 = most accurate, 0 = never)
   int64_t launches = 0;
   bool finalized = false;
   EncodeTiledFn encode = nullptr;

@@ -26,7 +26,9 @@ constexpr int G2_BK = 64;
 constexpr int G2_A_ROWS = 136;
 constexpr int G2_A_PLANE = G2_A_ROWS * 128;
 constexpr int G2_A_STAGE = 2 * G2_A_PLANE;
-constexpr int G2_THREADS = 192;
+constexpr int G2_EPI_WARPS = 8;                    // two per TMEM lane quadrant, 64 columns each
+constexpr int G2_EPI_COLS = G2_BN * 4 / G2_EPI_WARPS;
+constexpr int G2_THREADS = 64 + 32 * G2_EPI_WARPS;
 
 template <int CG>
 struct G2Cfg {
@@ -110,8 +112,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(acc0_full(s), 1);
       ptx::mbar_init(acc1_full(s), 1);
-      ptx::mbar_init(acc0_empty(s), 4 * CG);     // one arrival per epilogue warp of every CTA in the pair
-      ptx::mbar_init(acc1_empty(s), 4 * CG);
+      ptx::mbar_init(acc0_empty(s), G2_EPI_WARPS * CG);   // one arrival per epilogue warp of every CTA in the pair
+      ptx::mbar_init(acc1_empty(s), G2_EPI_WARPS * CG);
     }
     ptx::fence_barrier_init();
   }
@@ -256,8 +258,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       }
     }
   } else {
-    // ------------------------------------------------------------ accumulate + epilogue (warps 2..5)
+    // ------------------------------------------------------------ accumulate + epilogue (warps 2..9)
+    // warp w may touch TMEM lanes (w % 4) * 32 ..; the two warps of a quadrant split the columns.
     const int q = warp & 3;
+    const int cbase = ((warp - 2) >> 2) * G2_EPI_COLS;
     const int row = q * 32 + lane;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     auto release = [&](uint32_t bar) {            // one arrival per warp, on the leader's barrier
@@ -276,18 +280,18 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       const bool row_ok = tile_live && t < p.T;
       const bool row_live = row_ok && (p.lens == nullptr || t < p.lens[b]);
       const size_t m = row_ok ? static_cast<size_t>(b) * p.T + t : 0;
-      float sum[G2_BN];
+      float sum[G2_EPI_COLS];
 #pragma unroll
-      for (int j = 0; j < G2_BN; ++j) sum[j] = 0.0f;
+      for (int j = 0; j < G2_EPI_COLS; ++j) sum[j] = 0.0f;
       for (int kb0 = 0; kb0 < num_kb; kb0 += chunk_kb) {
         const uint32_t buf = g & 1u;
         ptx::mbar_wait(acc0_full(buf), (g >> 1) & 1u);
         ptx::tc_fence_after();
         __syncwarp();
 #pragma unroll
-        for (int c = 0; c < G2_BN / 32; ++c) {
+        for (int c = 0; c < G2_EPI_COLS / 32; ++c) {
           uint32_t r[32];
-          ptx::tmem_ld_32x32(lane_addr + buf * G2_BN + c * 32, r);
+          ptx::tmem_ld_32x32(lane_addr + buf * G2_BN + cbase + c * 32, r);
           ptx::tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) sum[c * 32 + j] = __fadd_rn(sum[c * 32 + j], __uint_as_float(r[j]));
@@ -300,18 +304,18 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       ptx::tc_fence_after();
       __syncwarp();
 #pragma unroll
-      for (int c = 0; c < G2_BN / 32; ++c) {
+      for (int c = 0; c < G2_EPI_COLS / 32; ++c) {
         uint32_t r[32];
         __syncwarp();                               // tcgen05.ld is .aligned: reconverge after the stores
-        ptx::tmem_ld_32x32(lane_addr + 256u + tb * G2_BN + c * 32, r);
+        ptx::tmem_ld_32x32(lane_addr + 256u + tb * G2_BN + cbase + c * 32, r);
         ptx::tmem_ld_wait();
-        if (c == G2_BN / 32 - 1) release(acc1_empty(tb));
-        const int c0 = c * 32;
+        if (c == G2_EPI_COLS / 32 - 1) release(acc1_empty(tb));
+        const int c0 = cbase + c * 32;
         if (n0 + c0 >= p.N || !row_ok) continue;      // warp-divergent only around plain loads/stores
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          float a = __fadd_rn(sum[c0 + j], __uint_as_float(r[j]) * SPLIT_INV_SCALE);
+          float a = __fadd_rn(sum[c * 32 + j], __uint_as_float(r[j]) * SPLIT_INV_SCALE);
           if (p.divisor != 1.0f) a = __fdiv_rn(a, p.divisor);
           v[j] = a;
         }

@@ -160,7 +160,9 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+  // default semantics (.release at CTA scope): the waiter only needs this warp's tcgen05.ld to have
+  // completed (tcgen05.wait::ld + fence::before_thread_sync), not a GPU-scope memory barrier
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 // TMA load issued by either CTA of a pair; the transaction bytes are credited to `cluster_bar`
 // (a shared::cluster mbarrier address, normally the leader CTA's).

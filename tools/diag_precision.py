@@ -24,6 +24,9 @@ def main():
     m.load_state_dict(w)
     m = m.eval().to(dev)
     eng = m._get_engine()
+    for kv in os.environ.get("EFTS_OPTS", "").split(","):
+        if kv:
+            eng.set_option(kv.split("=")[0], int(kv.split("=")[1]))
     res = {}
     if "bias" in which:
         g = torch.Generator().manual_seed(5)
@@ -59,6 +62,21 @@ def main():
             diff = (a.cpu() - b).abs()
             d[key] = dict(max=float(diff.max()), p9999=float(diff.flatten().kthvalue(int(diff.numel() * 0.9999)).values),
                           rms=float(diff.pow(2).mean().sqrt()), n_over_1e4=int((diff > 1e-4).sum()), numel=diff.numel())
+        if "fp64" in which and name == "C5":
+            # the reference's own conditioning: its fp64 restatement vs its fp32 run, and ours vs fp64
+            w64 = {k: v.double() for k, v in w.items()}
+            _f = torch.Tensor.float
+            torch.Tensor.float = lambda self, *a, **k: self.double()
+            try:
+                with torch.no_grad():
+                    r64 = orc.forward(w64, text, tl, speech.double(), sl)
+            finally:
+                torch.Tensor.float = _f
+            for key, i in (("imv", 2), ("reconst_alpha", 3), ("mel", 4)):
+                d[key]["ours_vs_fp64_max"] = float((out[i].cpu().double() - r64[i]).abs().max())
+                d[key]["ref32_vs_fp64_max"] = float((ref[i].double() - r64[i]).abs().max())
+                d[key]["ours_vs_fp64_rms"] = float((out[i].cpu().double() - r64[i]).pow(2).mean().sqrt())
+                d[key]["ref32_vs_fp64_rms"] = float((ref[i].double() - r64[i]).pow(2).mean().sqrt())
         d["loss"] = [out[1]["loss"], ref[1]["loss"]]
         d["cpu_oracle_seconds"] = cpu_s
         d["cpu_threads"] = torch.get_num_threads()
