@@ -731,9 +731,12 @@ int efts_forward(efts_ctx* c, const int64_t* text, const int64_t* text_lengths, 
   const Skip skip_t{w.tl32, w.list_t, w.cnt_t};
   const Skip skip_m{w.sl32, w.list_m, w.cnt_m};
   // 1. embedding (:144) -> text encoder (:148)
-  embed_kernel<<<static_cast<unsigned>(m1), C / 4, 0, st>>>(text, c->emb, g.num_symbols, C, w.xt_f[0], w.xt_hi[0],
-                                                            w.xt_lo[0], w.flags);
-  CUDA_TRY(cudaGetLastError());
+  {
+    ProfScope ps(c, st, TAG_PREP);
+    embed_kernel<<<static_cast<unsigned>(m1), C / 4, 0, st>>>(text, c->emb, g.num_symbols, C, w.xt_f[0], w.xt_hi[0],
+                                                              w.xt_lo[0], w.flags);
+    CUDA_TRY(cudaGetLastError());
+  }
   c->launches += 2;
   int cur = 0;
   TRY(run_conv_stack(c, st, c->text, g.n_text_encoder_layer, B, T1, w.xt_f, w.xt_hi, w.xt_lo, nullptr, nullptr,
@@ -743,7 +746,7 @@ int efts_forward(efts_ctx* c, const int64_t* text, const int64_t* text_lengths, 
     GemmParams p = gemm_defaults();
     p.N = C; p.bias = c->key.bias; p.lens = w.tl32;
     p.out_hi = w.key_hi; p.out_lo = w.key_lo; p.ld_pl = C;
-    TRY(launch_gemm(c, st, OpA{w.xt_hi[cur], w.xt_lo[cur], B, T1, C, C}, weight_op(c->key), p));
+    { ProfScope ps(c, st, TAG_LINEAR); TRY(launch_gemm(c, st, OpA{w.xt_hi[cur], w.xt_lo[cur], B, T1, C, C}, weight_op(c->key), p)); }
     p.bias = c->value.bias;
     p.out_hi = w.val_hi; p.out_lo = w.val_lo;
     p.outT_hi = w.valT_hi; p.outT_lo = w.valT_lo; p.ld_t = w.T1p;
@@ -751,10 +754,10 @@ int efts_forward(efts_ctx* c, const int64_t* text, const int64_t* text_lengths, 
       CUDA_TRY(cudaMemsetAsync(w.valT_hi, 0, static_cast<size_t>(B) * C * w.T1p * sizeof(__half), st));
       CUDA_TRY(cudaMemsetAsync(w.valT_lo, 0, static_cast<size_t>(B) * C * w.T1p * sizeof(__half), st));
     }
-    TRY(launch_gemm(c, st, OpA{w.xt_hi[cur], w.xt_lo[cur], B, T1, C, C}, weight_op(c->value), p));
+    { ProfScope ps(c, st, TAG_LINEAR); TRY(launch_gemm(c, st, OpA{w.xt_hi[cur], w.xt_lo[cur], B, T1, C, C}, weight_op(c->value), p)); }
   }
   // 3. mel prenet (:161) -> mel encoder (:162)
-  TRY(split_planes(c, st, speech, m2 * g.odim, w.sp_hi, w.sp_lo));
+  { ProfScope ps(c, st, TAG_PREP); TRY(split_planes(c, st, speech, m2 * g.odim, w.sp_hi, w.sp_lo)); }
   {
     GemmParams p = gemm_defaults();
     p.N = C; p.bias = c->prenet.bias; p.act = ACT_LRELU;
@@ -764,7 +767,7 @@ int efts_forward(efts_ctx* c, const int64_t* text, const int64_t* text_lengths, 
       p.skip_lens = skip_m.lens; p.tile_list = skip_m.list; p.tile_count = skip_m.count;
       p.skip_halo = pad_k * g.n_mel_encoder_layer;
     }
-    TRY(launch_gemm(c, st, OpA{w.sp_hi, w.sp_lo, B, T2, g.odim, g.odim}, weight_op(c->prenet), p));
+    { ProfScope ps(c, st, TAG_LINEAR); TRY(launch_gemm(c, st, OpA{w.sp_hi, w.sp_lo, B, T2, g.odim, g.odim}, weight_op(c->prenet), p)); }
   }
   int curm = 0;
   TRY(run_conv_stack(c, st, c->mel, g.n_mel_encoder_layer, B, T2, w.xm_f, w.xm_hi, w.xm_lo, nullptr, nullptr,
@@ -783,11 +786,12 @@ int efts_forward(efts_ctx* c, const int64_t* text, const int64_t* text_lengths, 
     GemmParams p = gemm_defaults();
     p.N = g.odim; p.bias = c->melout.bias; p.lens = w.sl32;
     p.out = mel_pred; p.ld_out = g.odim;
-    TRY(launch_gemm(c, st, OpA{w.xm_hi[curm], w.xm_lo[curm], B, T2, C, C}, weight_op(c->melout), p));
+    { ProfScope ps(c, st, TAG_LINEAR); TRY(launch_gemm(c, st, OpA{w.xm_hi[curm], w.xm_lo[curm], B, T2, C, C}, weight_op(c->melout), p)); }
   }
   // 7. duration predictor on value (:219), log domain, zero at pad tokens
   TRY(run_duration_predictor(c, st, w.val_hi, w.val_lo, B, T1, w.dp_f, w.dp_hi, w.dp_lo, w.tl32, 0, w.dur));
   // 8. losses (:220-227)
+  ProfScope ps_loss(c, st, TAG_LOSS);
   loss_partial_kernel<<<c->sm_count * 4, 256, 0, st>>>(mel_pred, speech, w.sl32, T2, g.odim, w.dur, w.e, w.tl32,
                                                        T1, B, g.duration_offset, g.use_masking, w.acc);
   CUDA_TRY(cudaGetLastError());

@@ -26,9 +26,10 @@ constexpr int G2_BK = 64;
 constexpr int G2_A_ROWS = 136;
 constexpr int G2_A_PLANE = G2_A_ROWS * 128;
 constexpr int G2_A_STAGE = 2 * G2_A_PLANE;
-constexpr int G2_EPI_WARPS = 8;                    // two per TMEM lane quadrant, 64 columns each
-constexpr int G2_EPI_COLS = G2_BN * 4 / G2_EPI_WARPS;
-constexpr int G2_THREADS = 64 + 32 * G2_EPI_WARPS;
+constexpr int G2_EPI_WARPS = 8;                    // two groups of four (one warp per TMEM lane quadrant)
+constexpr int G2_THREADS = 128 + 32 * G2_EPI_WARPS;   // warpgroup 0: TMA, MMA, 2 idle warps; warpgroups 1, 2: epilogue groups
+constexpr int G2_REGS_CTRL = 72;                     // setmaxnreg budgets: 3 warps per SM sub-partition,
+constexpr int G2_REGS_EPI = 216;                     // 32 * (72 + 2 * 216) = 16128 <= 16384 registers
 
 template <int CG>
 struct G2Cfg {
@@ -95,11 +96,13 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
   auto emptyA = [&](int s) { return sBar + 32u + 8u * s; };        // [4]
   auto fullB = [&](int s) { return sBar + 64u + 8u * s; };         // [8]
   auto emptyB = [&](int s) { return sBar + 128u + 8u * s; };       // [8]
-  auto acc0_full = [&](int s) { return sBar + 192u + 8u * s; };    // [2]
-  auto acc0_empty = [&](int s) { return sBar + 208u + 8u * s; };   // [2]
-  auto acc1_full = [&](int s) { return sBar + 224u + 8u * s; };    // [2]
-  auto acc1_empty = [&](int s) { return sBar + 240u + 8u * s; };   // [2]
-  const uint32_t tmem_slot = sBar + 256u;
+  // acc0_full is per (epilogue group, buffer): a group only ever waits on its own barriers, so it is
+  // never more than one phase away from them even though it idles through the other group's tiles.
+  auto acc0_full = [&](int grp, int s) { return sBar + 192u + 8u * (grp * 2 + s); };   // [2][2]
+  auto acc0_empty = [&](int s) { return sBar + 224u + 8u * s; };   // [2]
+  auto acc1_full = [&](int s) { return sBar + 240u + 8u * s; };    // [2] (buffer == owning group)
+  auto acc1_empty = [&](int s) { return sBar + 256u + 8u * s; };   // [2]
+  const uint32_t tmem_slot = sBar + 272u;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -110,10 +113,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
     for (int s = 0; s < Cfg::A_STAGES; ++s) { ptx::mbar_init(fullA(s), 1); ptx::mbar_init(emptyA(s), 1); }
     for (int s = 0; s < Cfg::B_STAGES; ++s) { ptx::mbar_init(fullB(s), 1); ptx::mbar_init(emptyB(s), 1); }
     for (int s = 0; s < 2; ++s) {
-      ptx::mbar_init(acc0_full(s), 1);
+      ptx::mbar_init(acc0_full(0, s), 1);
+      ptx::mbar_init(acc0_full(1, s), 1);
       ptx::mbar_init(acc1_full(s), 1);
-      ptx::mbar_init(acc0_empty(s), G2_EPI_WARPS * CG);   // one arrival per epilogue warp of every CTA in the pair
-      ptx::mbar_init(acc1_empty(s), G2_EPI_WARPS * CG);
+      ptx::mbar_init(acc0_empty(s), 4 * CG);     // one arrival per warp of the owning group, per CTA
+      ptx::mbar_init(acc1_empty(s), 4 * CG);
     }
     ptx::fence_barrier_init();
   }
@@ -152,6 +156,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (every CTA)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(G2_REGS_CTRL));
     if (lane == 0) {
       ptx::prefetch_tensormap(&tmA_hi); ptx::prefetch_tensormap(&tmA_lo);
       ptx::prefetch_tensormap(&tmB_hi); ptx::prefetch_tensormap(&tmB_lo);
@@ -199,6 +204,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (leader CTA, one thread)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(G2_REGS_CTRL));
     if (lane == 0 && leader) {
       constexpr uint32_t idesc = ptx::make_idesc_f16(G2_BM * CG, G2_BN);
       auto commit = [&](uint32_t bar) {
@@ -250,20 +256,26 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
             }
             commit(emptyA(sa));
           }
-          commit(acc0_full(buf));
+          commit(acc0_full(static_cast<int>(it & 1u), static_cast<int>(buf)));
           ++g;
         }
         commit(acc1_full(tb));
         ++it;
       }
     }
+  } else if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(G2_REGS_CTRL));   // idle warps of warpgroup 0
   } else {
-    // ------------------------------------------------------------ accumulate + epilogue (warps 2..9)
-    // warp w may touch TMEM lanes (w % 4) * 32 ..; the two warps of a quadrant split the columns.
+    // ------------------------------------------------------------ accumulate + epilogue (warps 4..11)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(G2_REGS_EPI));
+    // Two groups of four warps (one warp per TMEM lane quadrant, warp w may touch lanes (w % 4) * 32 ..)
+    // take alternate tiles: while one group runs the store-heavy epilogue of tile i, the other drains
+    // the chunks of tile i + 1 as soon as the MMAs commit them, so the tensor pipe never waits for stores.
     const int q = warp & 3;
-    const int cbase = ((warp - 2) >> 2) * G2_EPI_COLS;
+    const uint32_t grp = static_cast<uint32_t>(warp - 4) >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t nchunks = static_cast<uint32_t>((num_kb + chunk_kb - 1) / chunk_kb);
     auto release = [&](uint32_t bar) {            // one arrival per warp, on the leader's barrier
       ptx::tc_fence_before();
       __syncwarp();
@@ -272,7 +284,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       }
     };
     uint32_t g = 0, it = 0;
-    for (long long w = cid; w < total; w += ncl) {
+    uint32_t uses0 = 0u, uses1 = 0u;              // completed waits on this group's acc0_full[buf]
+    for (long long w = cid; w < total; w += ncl, ++it) {
+      if ((it & 1u) != grp) { g += nchunks; continue; }
       int b, t0, n0; bool valid;
       locate(w, b, t0, n0, valid);
       const int t = t0 + row;
@@ -280,94 +294,93 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       const bool row_ok = tile_live && t < p.T;
       const bool row_live = row_ok && (p.lens == nullptr || t < p.lens[b]);
       const size_t m = row_ok ? static_cast<size_t>(b) * p.T + t : 0;
-      float sum[G2_EPI_COLS];
+      float sum[G2_BN];
 #pragma unroll
-      for (int j = 0; j < G2_EPI_COLS; ++j) sum[j] = 0.0f;
-      for (int kb0 = 0; kb0 < num_kb; kb0 += chunk_kb) {
+      for (int j = 0; j < G2_BN; ++j) sum[j] = 0.0f;
+      for (uint32_t ch = 0; ch < nchunks; ++ch, ++g) {
         const uint32_t buf = g & 1u;
-        ptx::mbar_wait(acc0_full(buf), (g >> 1) & 1u);
+        ptx::mbar_wait(acc0_full(static_cast<int>(grp), static_cast<int>(buf)), (buf ? uses1 : uses0) & 1u);
+        if (buf) ++uses1; else ++uses0;
         ptx::tc_fence_after();
         __syncwarp();
 #pragma unroll
-        for (int c = 0; c < G2_EPI_COLS / 32; ++c) {
-          uint32_t r[32];
-          ptx::tmem_ld_32x32(lane_addr + buf * G2_BN + cbase + c * 32, r);
+        for (int c = 0; c < G2_BN / 16; ++c) {
+          uint32_t r[16];
+          ptx::tmem_ld_32x16(lane_addr + buf * G2_BN + c * 16, r);
           ptx::tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) sum[c * 32 + j] = __fadd_rn(sum[c * 32 + j], __uint_as_float(r[j]));
+          for (int j = 0; j < 16; ++j) sum[c * 16 + j] = __fadd_rn(sum[c * 16 + j], __uint_as_float(r[j]));
         }
         release(acc0_empty(buf));
-        ++g;
       }
+      // fold the correction accumulator in and hand its TMEM back before the stores start
       const uint32_t tb = it & 1u;
       ptx::mbar_wait(acc1_full(tb), (it >> 1) & 1u);
       ptx::tc_fence_after();
       __syncwarp();
 #pragma unroll
-      for (int c = 0; c < G2_EPI_COLS / 32; ++c) {
-        uint32_t r[32];
-        __syncwarp();                               // tcgen05.ld is .aligned: reconverge after the stores
-        ptx::tmem_ld_32x32(lane_addr + 256u + tb * G2_BN + cbase + c * 32, r);
+      for (int c = 0; c < G2_BN / 16; ++c) {
+        uint32_t r[16];
+        ptx::tmem_ld_32x16(lane_addr + 256u + tb * G2_BN + c * 16, r);
         ptx::tmem_ld_wait();
-        if (c == G2_EPI_COLS / 32 - 1) release(acc1_empty(tb));
-        const int c0 = cbase + c * 32;
-        if (n0 + c0 >= p.N || !row_ok) continue;      // warp-divergent only around plain loads/stores
-        float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float a = __fadd_rn(sum[c * 32 + j], __uint_as_float(r[j]) * SPLIT_INV_SCALE);
-          if (p.divisor != 1.0f) a = __fdiv_rn(a, p.divisor);
-          v[j] = a;
+        for (int j = 0; j < 16; ++j)
+          sum[c * 16 + j] = __fadd_rn(sum[c * 16 + j], __uint_as_float(r[j]) * SPLIT_INV_SCALE);
+      }
+      release(acc1_empty(tb));
+      if (!row_ok) continue;
+#pragma unroll
+      for (int c8 = 0; c8 < G2_BN / 8; ++c8) {
+        const int n = n0 + c8 * 8;
+        if (n >= p.N) break;
+        float vv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          vv[j] = sum[c8 * 8 + j];
+          if (p.divisor != 1.0f) vv[j] = __fdiv_rn(vv[j], p.divisor);
         }
+        if (p.bias != nullptr) {
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
+          vv[0] += b0.x; vv[1] += b0.y; vv[2] += b0.z; vv[3] += b0.w;
+          vv[4] += b1.x; vv[5] += b1.y; vv[6] += b1.z; vv[7] += b1.w;
+        }
+        if (p.act == ACT_LRELU) {
 #pragma unroll
-        for (int gq = 0; gq < 4; ++gq) {
-          const int n = n0 + c0 + gq * 8;
-          if (n >= p.N) break;
-          float* vv = v + gq * 8;
-          if (p.bias != nullptr) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
-            vv[0] += b0.x; vv[1] += b0.y; vv[2] += b0.z; vv[3] += b0.w;
-            vv[4] += b1.x; vv[5] += b1.y; vv[6] += b1.z; vv[7] += b1.w;
-          }
-          if (p.act == ACT_LRELU) {
+          for (int j = 0; j < 8; ++j) vv[j] = vv[j] > 0.0f ? vv[j] : vv[j] * 0.1f;
+        } else if (p.act == ACT_RELU) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) vv[j] = vv[j] > 0.0f ? vv[j] : vv[j] * 0.1f;
-          } else if (p.act == ACT_RELU) {
+          for (int j = 0; j < 8; ++j) vv[j] = fmaxf(vv[j], 0.0f);
+        }
+        if (p.resid != nullptr) {
+          const float* rp = p.resid + m * p.ld_out + n;
+          const float4 x0 = *reinterpret_cast<const float4*>(rp);
+          const float4 x1 = *reinterpret_cast<const float4*>(rp + 4);
+          vv[0] = x0.x + vv[0]; vv[1] = x0.y + vv[1]; vv[2] = x0.z + vv[2]; vv[3] = x0.w + vv[3];
+          vv[4] = x1.x + vv[4]; vv[5] = x1.y + vv[5]; vv[6] = x1.z + vv[6]; vv[7] = x1.w + vv[7];
+        }
+        if (!row_live) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) vv[j] = fmaxf(vv[j], 0.0f);
-          }
-          if (p.resid != nullptr) {
-            const float* rp = p.resid + m * p.ld_out + n;
-            const float4 x0 = *reinterpret_cast<const float4*>(rp);
-            const float4 x1 = *reinterpret_cast<const float4*>(rp + 4);
-            vv[0] = x0.x + vv[0]; vv[1] = x0.y + vv[1]; vv[2] = x0.z + vv[2]; vv[3] = x0.w + vv[3];
-            vv[4] = x1.x + vv[4]; vv[5] = x1.y + vv[5]; vv[6] = x1.z + vv[6]; vv[7] = x1.w + vv[7];
-          }
-          if (!row_live) {
+          for (int j = 0; j < 8; ++j) vv[j] = 0.0f;
+        }
+        if (p.out != nullptr) {
+          float* op = p.out + m * p.ld_out + n;
+          *reinterpret_cast<float4*>(op) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+          *reinterpret_cast<float4*>(op + 4) = make_float4(vv[4], vv[5], vv[6], vv[7]);
+        }
+        if (p.out_hi != nullptr) {
+          split_store8(p.out_hi + m * p.ld_pl + n, p.out_lo + m * p.ld_pl + n, vv);
+        }
+        if (p.outT_hi != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) vv[j] = 0.0f;
-          }
-          if (p.out != nullptr) {
-            float* op = p.out + m * p.ld_out + n;
-            *reinterpret_cast<float4*>(op) = make_float4(vv[0], vv[1], vv[2], vv[3]);
-            *reinterpret_cast<float4*>(op + 4) = make_float4(vv[4], vv[5], vv[6], vv[7]);
-          }
-          if (p.out_hi != nullptr) {
-            split_store8(p.out_hi + m * p.ld_pl + n, p.out_lo + m * p.ld_pl + n, vv);
-          }
-          if (p.outT_hi != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const size_t o = (static_cast<size_t>(b) * p.N + (n + j)) * p.ld_t + t;
-              const __half h = __float2half_rn(vv[j]);
-              p.outT_hi[o] = h;
-              p.outT_lo[o] = __float2half_rn((vv[j] - __half2float(h)) * SPLIT_SCALE);
-            }
+          for (int j = 0; j < 8; ++j) {
+            const size_t o = (static_cast<size_t>(b) * p.N + (n + j)) * p.ld_t + t;
+            const __half h = __float2half_rn(vv[j]);
+            p.outT_hi[o] = h;
+            p.outT_lo[o] = __float2half_rn((vv[j] - __half2float(h)) * SPLIT_SCALE);
           }
         }
       }
-      ++it;
     }
   }
 

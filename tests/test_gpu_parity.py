@@ -80,11 +80,13 @@ def check_forward(ref, out, t1max):
     dict(B=2, T=300, K=512, N=80, ntaps=1),         # N tail (mel head shape)
     dict(B=2, T=260, K=512, N=512, ntaps=5),        # conv layer, tiles cross the utterance end
     dict(B=2, T=50, K=512, N=512, ntaps=3),         # duration-predictor conv
+    dict(B=48, T=1100, K=512, N=512, ntaps=5),      # several tiles per persistent CTA (both epilogue groups)
 ])
 @pytest.mark.parametrize("variant", ["v2_pair", "v2_single", "v1_amode0", "v1_amode1"])
 def test_tap_gemm_against_float64(model, dev, shape, variant):
     """The tensor-core tap-GEMM (split-fp16, 3 MMAs) reproduces an fp64 evaluation to fp32 level.
-    v2 (flushed accumulator) must stay within 4e-6; v1 (one 160-step truncating chain) within 2e-5."""
+    v2 (accumulator flushed every 2 k-blocks) must stay within 8e-6; v1 (one 160-step truncating chain)
+    within 3e-5."""
     opts = {"v2_pair": dict(gemm_version=2, pair=1), "v2_single": dict(gemm_version=2, pair=0),
             "v1_amode0": dict(gemm_version=1, amode=0), "v1_amode1": dict(gemm_version=1, amode=1)}[variant]
     if variant == "v1_amode1" and shape["ntaps"] == 1:
@@ -102,7 +104,7 @@ def test_tap_gemm_against_float64(model, dev, shape, variant):
         ref = sum(xp[:, j:j + T] @ w[j].double().T for j in range(nt))
         err = (out.double() - ref).abs().max().item()
         print("tap_gemm", shape, variant, "max-abs err %.3e" % err)
-        assert err <= (4e-6 if variant.startswith("v2") else 2e-5)
+        assert err <= (8e-6 if variant.startswith("v2") else 3e-5)
     finally:
         for k, v in dict(gemm_version=2, pair=1, amode=0).items():
             eng.set_option(k, v)
