@@ -161,6 +161,9 @@ def run_ours(args, rank, local_rank, world):
     state = {k: v.clone() for k, v in model.state_dict().items()}
     model = model.to(dev)
     eng = model._get_engine()
+    for kv in os.environ.get("EFTS_BENCH_OPTS", "").split(","):     # A/B switches for experiments
+        if kv:
+            eng.set_option(kv.split("=")[0], int(kv.split("=")[1]))
 
     t1, t2 = wl.config_lengths("C3", seed=rank)
     host = [t.pin_memory() for t in wl.make_forward_inputs(rank, t1, t2)]

@@ -91,6 +91,7 @@ struct efts_ctx {
   int skip_pad_tiles = 1;
   int gemm_version = 2;      // 1: gemm_sm100.cuh, 2: gemm2_sm100.cuh (persistent, flushed accumulator)
   int pair = 1;              // v2: CTA pairs (cta_group::2) for the weight GEMMs
+  int debug_mask = 0;        // timing experiments only
   int chunk_kb = 2;          // v2: k-blocks per main-accumulator flush (1 = most accurate, 0 = never)
   int64_t launches = 0;
   bool finalized = false;
@@ -219,6 +220,7 @@ int launch_gemm(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, GemmPa
   if (c->gemm_version == 2) {
     if (p.ntaps > 9) return fail(EFTS_ERR_ARG, "at most 9 taps");
     p.chunk_kb = c->chunk_kb;
+    p.debug_mask = c->debug_mask;
     if (!c->skip_pad_tiles) { p.tile_list = nullptr; p.tile_count = nullptr; p.skip_lens = nullptr; }
     if (c->pair && !p.b_batched) return launch_gemm2_t<2>(c, st, a, b, p);
     return launch_gemm2_t<1>(c, st, a, b, p);
@@ -462,10 +464,23 @@ int run_reconstruct_expand(efts_ctx* c, cudaStream_t st, const float* e, const i
   const int* sl = mel != nullptr ? mel->lens : nullptr;
   {
     ProfScope ps(c, st, TAG_RECONSTRUCT);
-    dim3 grid((T2 + 127) / 128, B);
     const float neg_sigma = -1.0f * c->cfg.sigma;
-    reconstruct_alignment_kernel<<<grid, 128, T1 * sizeof(float), st>>>(e, tl, sl, T1, T2, T1p, neg_sigma,
-                                                                        reconst_alpha, R_hi, R_lo);
+    const size_t smem = (static_cast<size_t>(T1p) * (RT_FRAMES + 1) + T1) * sizeof(float);
+    if (T1 <= 32 * RT_KMAX && smem <= 200 * 1024) {
+      static size_t attr_smem = 0;
+      if (smem > 48 * 1024 && smem > attr_smem) {
+        CUDA_TRY(cudaFuncSetAttribute(reconstruct_alignment_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(smem)));
+        attr_smem = smem;
+      }
+      dim3 grid((T2 + RT_FRAMES - 1) / RT_FRAMES, B);
+      reconstruct_alignment_tiled_kernel<<<grid, 256, smem, st>>>(e, tl, sl, T1, T2, T1p, neg_sigma, reconst_alpha,
+                                                                 R_hi, R_lo);
+    } else {
+      dim3 grid((T2 + 127) / 128, B);
+      reconstruct_alignment_kernel<<<grid, 128, T1 * sizeof(float), st>>>(e, tl, sl, T1, T2, T1p, neg_sigma,
+                                                                          reconst_alpha, R_hi, R_lo);
+    }
     CUDA_TRY(cudaGetLastError());
     c->launches++;
   }
@@ -493,14 +508,23 @@ int run_imv(efts_ctx* c, cudaStream_t st, const __half* q_hi, const __half* q_lo
   p.N = T1p;
   p.b_batched = 1;
   p.divisor = static_cast<float>(std::sqrt(static_cast<double>(C)));   // np.sqrt(float(D)), :390
-  p.out = S; p.ld_out = T1p;
+  // v2 kernel: the token softmax runs in the GEMM epilogue and only (max, sum, weighted sum) per column
+  // tile reaches memory (the buffer S is reused for them); v1 writes the scores and a separate kernel reads them.
+  const bool fused = c->gemm_version == 2;
+  const int n_part = (T1p + G2_BN - 1) / G2_BN;
+  if (fused) {
+    p.softmax_part = reinterpret_cast<float4*>(S);
+    p.col_lens = tl;
+  } else {
+    p.out = S; p.ld_out = T1p;
+  }
   if (c->skip_pad_tiles) { p.skip_lens = mel->lens; p.tile_list = mel->list; p.tile_count = mel->count; p.skip_halo = 0; }
   {
     ProfScope ps(c, st, TAG_ENERGY);
     TRY(launch_gemm(c, st, OpA{q_hi, q_lo, B, T2, C, C}, OpB{key_hi, key_lo, B, T1, C, C}, p));
   }
   const size_t rows = static_cast<size_t>(B) * T2;
-  {
+  if (!fused) {
     ProfScope ps(c, st, TAG_SOFTMAX);
     energy_softmax_expect_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, st>>>(S, T1p, tl, sl, T2, rows,
                                                                                          imv_raw);
@@ -508,7 +532,8 @@ int run_imv(efts_ctx* c, cudaStream_t st, const __half* q_hi, const __half* q_lo
   }
   {
     ProfScope ps(c, st, TAG_SCAN);
-    imv_scan_kernel<<<(B + 3) / 4, 128, 0, st>>>(imv_raw, tl, sl, B, T2, imv);
+    imv_scan_kernel<<<(B + 3) / 4, 128, 0, st>>>(imv_raw, fused ? reinterpret_cast<const float4*>(S) : nullptr, n_part,
+                                                 tl, sl, B, T2, imv);
     CUDA_TRY(cudaGetLastError());
   }
   {
@@ -661,6 +686,7 @@ int efts_set_option(efts_ctx* c, const char* name, int32_t value) {
     return EFTS_OK;
   }
   if (strcmp(name, "pair") == 0) { c->pair = value != 0; return EFTS_OK; }
+  if (strcmp(name, "debug_mask") == 0) { c->debug_mask = value; return EFTS_OK; }
   if (strcmp(name, "chunk_kb") == 0) {
     if (value < 0 || value > 64) return fail(EFTS_ERR_ARG, "chunk_kb out of range");
     c->chunk_kb = value;

@@ -14,6 +14,7 @@
 //     fp32 on the CUDA cores; the correction accumulator is 2^-11 down and needs no flushing.
 #pragma once
 #include <cuda_fp16.h>
+#include <math_constants.h>
 
 #include "gemm_sm100.cuh"
 #include "sm100_ptx.cuh"
@@ -28,6 +29,7 @@ constexpr int G2_A_PLANE = G2_A_ROWS * 128;
 constexpr int G2_A_STAGE = 2 * G2_A_PLANE;
 constexpr int G2_EPI_WARPS = 8;                    // two groups of four (one warp per TMEM lane quadrant)
 constexpr int G2_THREADS = 128 + 32 * G2_EPI_WARPS;   // warpgroup 0: TMA, MMA, 2 idle warps; warpgroups 1, 2: epilogue groups
+constexpr int G2_BIAS_MAX = 1024;                     // columns whose bias is staged in shared memory
 constexpr int G2_REGS_CTRL = 72;                     // setmaxnreg budgets: 3 warps per SM sub-partition,
 constexpr int G2_REGS_EPI = 216;                     // 32 * (72 + 2 * 216) = 16128 <= 16384 registers
 
@@ -39,7 +41,7 @@ struct G2Cfg {
   static constexpr int A_STAGES = CG == 2 ? 3 : 2;
   static constexpr int B_STAGES = CG == 2 ? 6 : 4;
   static constexpr int SMEM_TILES = A_STAGES * G2_A_STAGE + B_STAGES * B_STAGE;
-  static constexpr int SMEM_BYTES = SMEM_TILES + 1024 + 512;
+  static constexpr int SMEM_BYTES = SMEM_TILES + 1024 + 512 + 4 * G2_BIAS_MAX;
   static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB");
 };
 
@@ -103,6 +105,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
   auto acc1_full = [&](int s) { return sBar + 240u + 8u * s; };    // [2] (buffer == owning group)
   auto acc1_empty = [&](int s) { return sBar + 256u + 8u * s; };   // [2]
   const uint32_t tmem_slot = sBar + 272u;
+  const uint32_t sBias = sBar + 512u;              // [G2_BIAS_MAX] fp32 copy of the bias (epilogue reads it per row)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -123,6 +126,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
   }
   if (warp == 1) {
     if (CG == 2) ptx::tmem_alloc_pair(tmem_slot, 512); else ptx::tmem_alloc(tmem_slot, 512);
+  }
+  const bool bias_smem = p.bias != nullptr && p.N <= G2_BIAS_MAX;
+  if (bias_smem) {
+    for (int i = threadIdx.x; i < p.N; i += G2_THREADS)
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(sBias + 4u * i), "f"(__ldg(p.bias + i)) : "memory");
   }
   ptx::tc_fence_before();
   if (CG == 2) ptx::cluster_sync(); else __syncthreads();
@@ -304,12 +312,16 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
         ptx::tc_fence_after();
         __syncwarp();
 #pragma unroll
-        for (int c = 0; c < G2_BN / 16; ++c) {
-          uint32_t r[16];
-          ptx::tmem_ld_32x16(lane_addr + buf * G2_BN + c * 16, r);
+        for (int c = 0; c < G2_BN / 32; ++c) {     // two TMEM loads in flight per wait
+          uint32_t r0[16], r1[16];
+          ptx::tmem_ld_32x16(lane_addr + buf * G2_BN + c * 32, r0);
+          ptx::tmem_ld_32x16(lane_addr + buf * G2_BN + c * 32 + 16, r1);
           ptx::tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) sum[c * 16 + j] = __fadd_rn(sum[c * 16 + j], __uint_as_float(r[j]));
+          for (int j = 0; j < 16; ++j) {
+            sum[c * 32 + j] = __fadd_rn(sum[c * 32 + j], __uint_as_float(r0[j]));
+            sum[c * 32 + 16 + j] = __fadd_rn(sum[c * 32 + 16 + j], __uint_as_float(r1[j]));
+          }
         }
         release(acc0_empty(buf));
       }
@@ -319,16 +331,53 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       ptx::tc_fence_after();
       __syncwarp();
 #pragma unroll
-      for (int c = 0; c < G2_BN / 16; ++c) {
-        uint32_t r[16];
-        ptx::tmem_ld_32x16(lane_addr + 256u + tb * G2_BN + c * 16, r);
+      for (int c = 0; c < G2_BN / 32; ++c) {
+        uint32_t r0[16], r1[16];
+        ptx::tmem_ld_32x16(lane_addr + 256u + tb * G2_BN + c * 32, r0);
+        ptx::tmem_ld_32x16(lane_addr + 256u + tb * G2_BN + c * 32 + 16, r1);
         ptx::tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          sum[c * 16 + j] = __fadd_rn(sum[c * 16 + j], __uint_as_float(r[j]) * SPLIT_INV_SCALE);
+        for (int j = 0; j < 16; ++j) {
+          sum[c * 32 + j] = __fadd_rn(sum[c * 32 + j], __uint_as_float(r0[j]) * SPLIT_INV_SCALE);
+          sum[c * 32 + 16 + j] = __fadd_rn(sum[c * 32 + 16 + j], __uint_as_float(r1[j]) * SPLIT_INV_SCALE);
+        }
       }
       release(acc1_empty(tb));
       if (!row_ok) continue;
+      if (p.softmax_part != nullptr) {
+        // scaled-dot-product softmax over tokens, one partial per column tile (models/efficient_tts.py:390-398):
+        // the scores never leave the SM; imv_scan_kernel merges the partials into the position expectation.
+        const int L = p.col_lens[b];
+        float mx = -CUDART_INF_F;
+#pragma unroll
+        for (int j = 0; j < G2_BN; ++j) {
+          sum[j] = __fdiv_rn(sum[j], p.divisor);
+          if (n0 + j < L) mx = fmaxf(mx, sum[j]);
+        }
+        float den = 0.0f, num = 0.0f;
+#pragma unroll
+        for (int j = 0; j < G2_BN; ++j) {
+          if (n0 + j < L) {
+            const float ev = expf(sum[j] - mx);
+            den += ev;
+            num = fmaf(ev, static_cast<float>(n0 + j), num);
+          }
+        }
+        p.softmax_part[m * n_nt + n0 / G2_BN] = make_float4(mx, den, num, 0.0f);
+        continue;
+      }
+      // residual rows are prefetched two 8-column groups ahead: the stores in between may alias for all
+      // the compiler knows, so without this every group would wait a full memory round trip
+      const float* rp = p.resid != nullptr ? p.resid + m * p.ld_out + n0 : nullptr;
+      float4 rx[2][2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        rx[k][0] = rx[k][1] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (rp != nullptr && n0 + k * 8 < p.N) {
+          rx[k][0] = *reinterpret_cast<const float4*>(rp + k * 8);
+          rx[k][1] = *reinterpret_cast<const float4*>(rp + k * 8 + 4);
+        }
+      }
 #pragma unroll
       for (int c8 = 0; c8 < G2_BN / 8; ++c8) {
         const int n = n0 + c8 * 8;
@@ -340,8 +389,16 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
           if (p.divisor != 1.0f) vv[j] = __fdiv_rn(vv[j], p.divisor);
         }
         if (p.bias != nullptr) {
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-          const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
+          float4 b0, b1;
+          if (bias_smem) {
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b0.x), "=f"(b0.y), "=f"(b0.z), "=f"(b0.w)
+                         : "r"(sBias + 4u * n));
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b1.x), "=f"(b1.y), "=f"(b1.z), "=f"(b1.w)
+                         : "r"(sBias + 4u * n + 16u));
+          } else {
+            b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+            b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
+          }
           vv[0] += b0.x; vv[1] += b0.y; vv[2] += b0.z; vv[3] += b0.w;
           vv[4] += b1.x; vv[5] += b1.y; vv[6] += b1.z; vv[7] += b1.w;
         }
@@ -353,9 +410,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
           for (int j = 0; j < 8; ++j) vv[j] = fmaxf(vv[j], 0.0f);
         }
         if (p.resid != nullptr) {
-          const float* rp = p.resid + m * p.ld_out + n;
-          const float4 x0 = *reinterpret_cast<const float4*>(rp);
-          const float4 x1 = *reinterpret_cast<const float4*>(rp + 4);
+          const float4 x0 = rx[c8 & 1][0];
+          const float4 x1 = rx[c8 & 1][1];
+          if (n + 16 < p.N) {
+            rx[c8 & 1][0] = *reinterpret_cast<const float4*>(rp + c8 * 8 + 16);
+            rx[c8 & 1][1] = *reinterpret_cast<const float4*>(rp + c8 * 8 + 20);
+          }
           vv[0] = x0.x + vv[0]; vv[1] = x0.y + vv[1]; vv[2] = x0.z + vv[2]; vv[3] = x0.w + vv[3];
           vv[4] = x1.x + vv[4]; vv[5] = x1.y + vv[5]; vv[6] = x1.z + vv[6]; vv[7] = x1.w + vv[7];
         }
@@ -363,12 +423,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
 #pragma unroll
           for (int j = 0; j < 8; ++j) vv[j] = 0.0f;
         }
-        if (p.out != nullptr) {
+        if (p.out != nullptr && !(p.debug_mask & 1)) {
           float* op = p.out + m * p.ld_out + n;
           *reinterpret_cast<float4*>(op) = make_float4(vv[0], vv[1], vv[2], vv[3]);
           *reinterpret_cast<float4*>(op + 4) = make_float4(vv[4], vv[5], vv[6], vv[7]);
         }
-        if (p.out_hi != nullptr) {
+        if (p.out_hi != nullptr && !(p.debug_mask & 2)) {
           split_store8(p.out_hi + m * p.ld_pl + n, p.out_lo + m * p.ld_pl + n, vv);
         }
         if (p.outT_hi != nullptr) {

@@ -59,6 +59,11 @@ struct GemmParams {
   const int2* tile_list; // compacted live row tiles (b, t0), or nullptr = all B * ceil(T/128)
   const int* tile_count; // device count of tile_list entries
   int chunk_kb;          // k-blocks per main-accumulator flush (0 = never flush)
+  // softmax-partial epilogue (energy GEMM): instead of storing the scores, every 128-column tile writes
+  // (max, sum exp, sum exp * column, 0) over its columns n < col_lens[b] to softmax_part[(b*T + t) * n_tiles + tile]
+  float4* softmax_part;
+  const int* col_lens;
+  int debug_mask;        // timing experiments only (results become wrong): 1 = no fp32 store, 2 = no plane stores
 };
 
 template <int BN, int AMODE>

@@ -169,20 +169,44 @@ __global__ void energy_softmax_expect_kernel(const float* __restrict__ S, int ld
 // B2: imv_generator tail (models/efficient_tts.py:314-323): Delta = relu(diff), Delta[0] = 0;
 // prefix sum over frames accumulated in double and rounded to fp32 per prefix (what torch's CPU
 // cumsum does for fp32); * mel_mask; / clamp(max, 1e-8); * (T1_b - 1).  One warp per utterance.
-__global__ void imv_scan_kernel(const float* __restrict__ imv_raw, const int* __restrict__ tl,
-                                const int* __restrict__ sl, int B, int T2, float* __restrict__ imv) {
+// The position expectation imv'[t] comes either from `imv_raw` or, when `part` is given, from the
+// per-column-tile softmax partials the energy GEMM epilogue wrote (max, sum exp, sum exp * i).
+__global__ void imv_scan_kernel(const float* __restrict__ imv_raw, const float4* __restrict__ part, int n_part,
+                                const int* __restrict__ tl, const int* __restrict__ sl, int B, int T2,
+                                float* __restrict__ imv) {
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= B) return;
-  const float* x = imv_raw + static_cast<size_t>(b) * T2;
   float* y = imv + static_cast<size_t>(b) * T2;
   const int L2 = sl[b];
   double carry = 0.0;
   float vmax = -CUDART_INF_F;
+  float prev_last = 0.0f;
   for (int base = 0; base < T2; base += 32) {
     const int t = base + lane;
+    float r = 0.0f;
+    if (t < T2) {
+      if (part == nullptr) {
+        r = imv_raw[static_cast<size_t>(b) * T2 + t];
+      } else if (t < L2) {                       // pad frames: alpha is zeroed (:168) -> expectation 0
+        const float4* pp = part + (static_cast<size_t>(b) * T2 + t) * n_part;
+        float mx = -CUDART_INF_F;
+        for (int k = 0; k < n_part; ++k) mx = fmaxf(mx, pp[k].x);
+        float den = 0.0f, num = 0.0f;
+        for (int k = 0; k < n_part; ++k) {
+          const float4 v = pp[k];
+          const float sc = expf(v.x - mx);
+          den = fmaf(v.y, sc, den);
+          num = fmaf(v.z, sc, num);
+        }
+        r = __fdiv_rn(num, den);
+      }
+    }
+    float prev = __shfl_up_sync(0xffffffffu, r, 1);
+    if (lane == 0) prev = prev_last;
+    prev_last = __shfl_sync(0xffffffffu, r, 31);
     float d = 0.0f;
-    if (t > 0 && t < T2) d = fmaxf(__fsub_rn(x[t], x[t - 1]), 0.0f);
+    if (t > 0 && t < T2) d = fmaxf(__fsub_rn(r, prev), 0.0f);
     double s = static_cast<double>(d);
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -288,6 +312,88 @@ __global__ void reconstruct_alignment_kernel(const float* __restrict__ e, const 
     }
     *reinterpret_cast<uint4*>(ph + i0) = *reinterpret_cast<const uint4*>(h);
     *reinterpret_cast<uint4*>(pl + i0) = *reinterpret_cast<const uint4*>(l);
+  }
+}
+
+// B4, tiled: same arithmetic as reconstruct_alignment_kernel, organised so that both output layouts are
+// written with full coalescing.  One block per (utterance, 64-frame tile): each warp evaluates the
+// token-softmax of 8 frames with the tokens spread over its lanes (one expf per element, the exps stay
+// in registers between the sum and the normalisation), the 64 x T1 tile is staged in shared memory
+// (row stride 65 words: conflict-free both ways) and then stored as rows of the returned fp32 matrix
+// [B,T1,T2] (256 B per row segment) and as K-major fp16 hi/lo operand rows [B,T2,ldp] (half2 per lane).
+// Frames t >= L2 get zeros in the fp32 matrix; their operand rows are not written (the expansion GEMM
+// masks those rows by select).  Requires T1 <= 32 * RT_KMAX.
+constexpr int RT_FRAMES = 64;
+constexpr int RT_KMAX = 16;
+__global__ void __launch_bounds__(256)
+reconstruct_alignment_tiled_kernel(const float* __restrict__ e, const int* __restrict__ tl,
+                                   const int* __restrict__ sl, int T1, int T2, int ldp, float neg_sigma,
+                                   float* __restrict__ R, __half* __restrict__ p_hi, __half* __restrict__ p_lo) {
+  extern __shared__ float rt_smem[];
+  float* tile = rt_smem;                                   // [ldp][65]
+  float* se = rt_smem + static_cast<size_t>(ldp) * (RT_FRAMES + 1);
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * RT_FRAMES;
+  const int L1 = tl != nullptr ? tl[b] : T1;
+  const int L2 = sl != nullptr ? sl[b] : T2;
+  const int nt = min(RT_FRAMES, T2 - t0);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* Rb = R + static_cast<size_t>(b) * T1 * T2 + t0;
+  if (t0 >= L2) {                                          // whole tile is padding
+    for (int i = warp; i < T1; i += 8)
+      for (int tt = lane; tt < nt; tt += 32) Rb[static_cast<size_t>(i) * T2 + tt] = 0.0f;
+    return;
+  }
+  for (int i = threadIdx.x; i < T1; i += 256) se[i] = e[static_cast<size_t>(b) * T1 + i];
+  __syncthreads();
+  for (int tt = warp; tt < RT_FRAMES; tt += 8) {
+    const int t = t0 + tt;
+    const bool live = t < L2;
+    const float q = live ? static_cast<float>(t) : 0.0f;
+    float h[RT_KMAX];
+    float m = -CUDART_INF_F;
+#pragma unroll
+    for (int k = 0; k < RT_KMAX; ++k) {
+      const int i = lane + 32 * k;
+      h[k] = -CUDART_INF_F;
+      if (i < L1) {
+        const float d = __fsub_rn(q, se[i]);
+        h[k] = __fmul_rn(neg_sigma, __fmul_rn(d, d));
+        m = fmaxf(m, h[k]);
+      }
+    }
+    m = warp_max(m);
+    float den = 0.0f;
+#pragma unroll
+    for (int k = 0; k < RT_KMAX; ++k) {
+      const int i = lane + 32 * k;
+      if (i < L1) {
+        h[k] = expf(h[k] - m);
+        den += h[k];
+      }
+    }
+    den = warp_sum(den);
+#pragma unroll
+    for (int k = 0; k < RT_KMAX; ++k) {
+      const int i = lane + 32 * k;
+      if (i < ldp) tile[i * (RT_FRAMES + 1) + tt] = (live && i < L1) ? __fdiv_rn(h[k], den) : 0.0f;
+    }
+  }
+  __syncthreads();
+  for (int i = warp; i < T1; i += 8)
+    for (int tt = lane; tt < nt; tt += 32) Rb[static_cast<size_t>(i) * T2 + tt] = tile[i * (RT_FRAMES + 1) + tt];
+  const int nlive = min(nt, L2 - t0);
+  for (int tt = warp; tt < nlive; tt += 8) {
+    const size_t o = (static_cast<size_t>(b) * T2 + t0 + tt) * ldp;
+    for (int i2 = lane; 2 * i2 < ldp; i2 += 32) {
+      const float a = tile[(2 * i2) * (RT_FRAMES + 1) + tt];
+      const float c = tile[(2 * i2 + 1) * (RT_FRAMES + 1) + tt];
+      const __half ah = __float2half_rn(a), ch = __float2half_rn(c);
+      const __half al = __float2half_rn((a - __half2float(ah)) * kSplitScale);
+      const __half cl = __float2half_rn((c - __half2float(ch)) * kSplitScale);
+      *reinterpret_cast<__half2*>(p_hi + o + 2 * i2) = __halves2half2(ah, ch);
+      *reinterpret_cast<__half2*>(p_lo + o + 2 * i2) = __halves2half2(al, cl);
+    }
   }
 }
 
