@@ -197,18 +197,36 @@ def run_ours(args, rank, local_rank, world):
     eng.profile_enable(0)
     clocks = sampler.stop()
 
-    # ---- end to end through the public API: pinned host inputs -> H2D -> forward -> stats read-back
-    def e2e_step():
-        d = [t.to(dev, non_blocking=True) for t in host]
-        loss, stats, imv, ra, mel, _ = model(text=d[0], text_lengths=d[1], speech=d[2], speech_lengths=d[3])
+    # ---- end to end through the public API: pinned host inputs -> H2D -> forward -> stats read-back.
+    # Like a prefetching loader (the reference trains with pin_memory + non_blocking copies), the copy of
+    # step i + 1 is issued on a second stream while step i computes; every step's inputs cross PCIe inside
+    # the timed region and every step ends with the host reading its loss statistics.
+    copy_stream = torch.cuda.Stream(dev)
+    dbuf = [[torch.empty_like(t, device=dev) for t in host] for _ in range(2)]
+
+    def issue_copy(slot):
+        with torch.cuda.stream(copy_stream):
+            for d, h in zip(dbuf[slot], host):
+                d.copy_(h, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return ev
+
+    def e2e_run(n):
+        stats = None
+        ready = issue_copy(0)
+        for i in range(n):
+            torch.cuda.current_stream(dev).wait_event(ready)
+            d = dbuf[i % 2]
+            if i + 1 < n:
+                ready = issue_copy((i + 1) % 2)      # slot (i+1)%2 was released by step i-1's read-back
+            loss, stats, imv, ra, mel, _ = model(text=d[0], text_lengths=d[1], speech=d[2], speech_lengths=d[3])
         return stats
-    for _ in range(2):
-        e2e_step()
+    e2e_run(2)
     barrier()
     ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev2.record()
-    for _ in range(args.steps):
-        stats = e2e_step()
+    stats = e2e_run(args.steps)
     ev3.record()
     barrier()
     ms_e2e = ev2.elapsed_time(ev3)
@@ -255,13 +273,23 @@ def run_ours(args, rank, local_rank, world):
         names = ["text_conv", "mel_conv", "dec_conv", "linear", "energy_gemm", "softmax_expect", "imv_scan",
                  "aligned_pos", "reconstruct", "expand_gemm", "duration", "loss", "embed_split"]
         breakdown = {names[k]: round(v[0] / args.steps, 4) for k, v in prof.items()}
-        # IMV (HBM-bound) kernels: algorithmic bytes per forward against measured HBM peak
-        m2, m1 = B * T2p, B * T1p
-        imv_bytes = 4 * (m2 * round8(T1p) + m2) + 4 * (2 * m2) + 4 * (m2 + m1) + (4 * m1 + 4 * B * T1p * T2p + 4 * m2 * round8(T1p))
+        # IMV (HBM-bound) kernels: algorithmic bytes per forward against measured HBM peak.
+        # The token softmax is fused into the energy GEMM epilogue (16 B per row and column tile reach memory).
+        m2, m1r = B * T2p, B * T1p
+        live2 = float(sum(t2))
+        n_part = -(-round8(T1p) // 128)
+        scan_bytes = 16 * n_part * live2 + 4 * m2 + 8 * m2
+        aligned_bytes = 4 * live2 + 4 * m1r
+        recon_bytes = 4 * m1r + 4 * B * T1p * T2p + 4 * live2 * round8(T1p)
+        imv_bytes = scan_bytes + aligned_bytes + recon_bytes
         imv_ms = sum(prof[k][0] for k in (5, 6, 7, 8)) / args.steps
-        hbm = {"kernels": "softmax_expect + imv_scan + aligned_pos + reconstruct", "bytes_per_step": imv_bytes,
+        rec_ms = prof[8][0] / args.steps
+        hbm = {"kernels": "imv_scan + aligned_positions + reconstruct_alignment_tiled", "bytes_per_step": imv_bytes,
                "ms_per_step": imv_ms, "achieved_gbs": imv_bytes / (imv_ms * 1e-3) / 1e9 if imv_ms else None,
-               "peak_gbs": peaks["hbm"], "frac": (imv_bytes / (imv_ms * 1e-3) / 1e9 / peaks["hbm"]) if imv_ms else None}
+               "peak_gbs": peaks["hbm"], "frac": (imv_bytes / (imv_ms * 1e-3) / 1e9 / peaks["hbm"]) if imv_ms else None,
+               "reconstruct": {"bytes": recon_bytes, "ms": rec_ms,
+                               "achieved_gbs": recon_bytes / (rec_ms * 1e-3) / 1e9 if rec_ms else None,
+                               "frac": (recon_bytes / (rec_ms * 1e-3) / 1e9 / peaks["hbm"]) if rec_ms else None}}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32 (split-fp16 tensor-core operands, fp32 accumulate)",
@@ -271,7 +299,8 @@ def run_ours(args, rank, local_rank, world):
                            "parallelism": "dp%d (utterance shards, no data-path collective)" % world},
                 "clocks": clocks, "gpu_launches": launches,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": ms_e2e / args.steps, "stats": stats},
+                        "ms_per_step": ms_e2e / args.steps, "stats": stats,
+                        "pipeline": "H2D of step i+1 on a copy stream overlaps step i; loss read back every step"},
                 "roofline": roof, "roofline_hbm_imv": hbm, "kernel_ms_per_step": breakdown}
     # ---- extras on rank 0 at N = 1: RTF at batch 1 (C1) and the CPU baseline ----------------------
     if rank == 0 and world == 1:

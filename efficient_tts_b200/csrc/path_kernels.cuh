@@ -346,6 +346,7 @@ reconstruct_alignment_tiled_kernel(const float* __restrict__ e, const int* __res
   }
   for (int i = threadIdx.x; i < T1; i += 256) se[i] = e[static_cast<size_t>(b) * T1 + i];
   __syncthreads();
+  const int kcount = (L1 + 31) >> 5;                       // lane-strided token chunks that hold valid tokens
   for (int tt = warp; tt < RT_FRAMES; tt += 8) {
     const int t = t0 + tt;
     const bool live = t < L2;
@@ -354,11 +355,11 @@ reconstruct_alignment_tiled_kernel(const float* __restrict__ e, const int* __res
     float m = -CUDART_INF_F;
 #pragma unroll
     for (int k = 0; k < RT_KMAX; ++k) {
-      const int i = lane + 32 * k;
-      h[k] = -CUDART_INF_F;
-      if (i < L1) {
-        const float d = __fsub_rn(q, se[i]);
-        h[k] = __fmul_rn(neg_sigma, __fmul_rn(d, d));
+      h[k] = 0.0f;
+      if (k < kcount) {                                    // warp-uniform
+        const int i = lane + 32 * k;
+        const float d = __fsub_rn(q, se[min(i, T1 - 1)]);
+        h[k] = i < L1 ? __fmul_rn(neg_sigma, __fmul_rn(d, d)) : -CUDART_INF_F;
         m = fmaxf(m, h[k]);
       }
     }
@@ -366,17 +367,19 @@ reconstruct_alignment_tiled_kernel(const float* __restrict__ e, const int* __res
     float den = 0.0f;
 #pragma unroll
     for (int k = 0; k < RT_KMAX; ++k) {
-      const int i = lane + 32 * k;
-      if (i < L1) {
-        h[k] = expf(h[k] - m);
+      if (k < kcount) {
+        h[k] = expf(h[k] - m);                             // exp(-inf) = 0 on pad tokens
         den += h[k];
       }
     }
     den = warp_sum(den);
+    // one correctly rounded reciprocal per frame instead of a division per element (differs from
+    // exp / sum by at most one ulp of a value <= 1)
+    const float inv = live ? __frcp_rn(den) : 0.0f;
 #pragma unroll
     for (int k = 0; k < RT_KMAX; ++k) {
       const int i = lane + 32 * k;
-      if (i < ldp) tile[i * (RT_FRAMES + 1) + tt] = (live && i < L1) ? __fdiv_rn(h[k], den) : 0.0f;
+      if (i < ldp) tile[i * (RT_FRAMES + 1) + tt] = (k < kcount) ? __fmul_rn(h[k], inv) : 0.0f;
     }
   }
   __syncthreads();
