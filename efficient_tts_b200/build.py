@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libefts_b200.so")
 SOURCES = [os.path.join(CSRC, "efts_api.cu")]
-HEADERS = [os.path.join(CSRC, f) for f in ("gemm_sm100.cuh", "sm100_ptx.cuh", "path_kernels.cuh")] + [
+HEADERS = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [
     os.path.join(os.path.dirname(HERE), "include", "efts_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]

@@ -91,6 +91,7 @@ struct efts_ctx {
   int skip_pad_tiles = 1;
   int gemm_version = 2;      // 1: gemm_sm100.cuh, 2: gemm2_sm100.cuh (persistent, flushed accumulator)
   int pair = 1;              // v2: CTA pairs (cta_group::2) for the weight GEMMs
+  int cur_tag = 15;          // ProfTag of the launch being issued (diagnostics)
   int debug_mask = 0;        // timing experiments only
   int chunk_kb = 2;          // v2: k-blocks per main-accumulator flush (1 = most accurate, 0 = never)
   int64_t launches = 0;
@@ -106,6 +107,7 @@ struct efts_ctx {
   float* ln_b[4] = {nullptr, nullptr, nullptr, nullptr};
   float* head_w = nullptr;
   float* head_b = nullptr;
+  int* err_flag = nullptr;   // device word: bit 3 = activation outside the fp16 operand range
   // measurement hooks (efts_profile_*): CUDA-event pairs around tagged launches
   struct ProfRec { cudaEvent_t a, b; int tag; };
   std::vector<ProfRec> prof;
@@ -119,6 +121,7 @@ namespace {
 struct ProfScope {
   efts_ctx* c; cudaStream_t st; int idx = -1;
   ProfScope(efts_ctx* c_, cudaStream_t st_, int tag) : c(c_), st(st_) {
+    c->cur_tag = tag;
     if (!(c->profile_mask & (1u << tag))) return;
     if (c->prof_used == c->prof.size()) {
       efts_ctx::ProfRec r;
@@ -159,12 +162,7 @@ int make_map(efts_ctx* c, CUtensorMap* m, const __half* ptr, int inner, int rows
 template <int BN, int AMODE>
 int launch_gemm_t(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, const GemmParams& p) {
   using Cfg = GemmCfg<BN, AMODE>;
-  static bool attr_set = false;
   auto kern = gemm_split_kernel<BN, AMODE>;
-  if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
   alignas(64) CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   TRY(make_map(c, &ma_hi, a.hi, a.K, a.T, a.B, a.ld, Cfg::A_ROWS));
   TRY(make_map(c, &ma_lo, a.lo, a.K, a.T, a.B, a.ld, Cfg::A_ROWS));
@@ -180,12 +178,7 @@ int launch_gemm_t(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, cons
 template <int CG>
 int launch_gemm2_t(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, const GemmParams& p) {
   using Cfg = G2Cfg<CG>;
-  static bool attr_set = false;
   auto kern = gemm2_kernel<CG>;
-  if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
   alignas(64) CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   TRY(make_map(c, &ma_hi, a.hi, a.K, a.T, a.B, a.ld, G2_A_ROWS));
   TRY(make_map(c, &ma_lo, a.lo, a.K, a.T, a.B, a.ld, G2_A_ROWS));
@@ -221,6 +214,8 @@ int launch_gemm(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, GemmPa
     if (p.ntaps > 9) return fail(EFTS_ERR_ARG, "at most 9 taps");
     p.chunk_kb = c->chunk_kb;
     p.debug_mask = c->debug_mask;
+    p.err_flag = c->err_flag;
+    p.err_code = 1 << (8 + c->cur_tag);
     if (!c->skip_pad_tiles) { p.tile_list = nullptr; p.tile_count = nullptr; p.skip_lens = nullptr; }
     if (c->pair && !p.b_batched) return launch_gemm2_t<2>(c, st, a, b, p);
     return launch_gemm2_t<1>(c, st, a, b, p);
@@ -242,6 +237,26 @@ int launch_gemm(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, GemmPa
   if (bn == 128) { EFTS_DISPATCH(128) }
   EFTS_DISPATCH(64)
 #undef EFTS_DISPATCH
+}
+
+constexpr size_t kReconstructSmemMax = 200 * 1024;
+
+// Opt every kernel that needs more than 48 KB of dynamic shared memory in, once per context (the attribute
+// is per device, so it is not cached in a process-wide static).
+template <int BN, int AMODE>
+cudaError_t opt_in_v1() {
+  return cudaFuncSetAttribute(gemm_split_kernel<BN, AMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              GemmCfg<BN, AMODE>::SMEM_BYTES);
+}
+int set_kernel_attributes() {
+  CUDA_TRY((opt_in_v1<64, 0>()));  CUDA_TRY((opt_in_v1<64, 1>()));  CUDA_TRY((opt_in_v1<64, 2>()));
+  CUDA_TRY((opt_in_v1<128, 0>())); CUDA_TRY((opt_in_v1<128, 1>())); CUDA_TRY((opt_in_v1<128, 2>()));
+  CUDA_TRY((opt_in_v1<256, 0>())); CUDA_TRY((opt_in_v1<256, 1>())); CUDA_TRY((opt_in_v1<256, 2>()));
+  CUDA_TRY(cudaFuncSetAttribute(gemm2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2Cfg<1>::SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(gemm2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2Cfg<2>::SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(reconstruct_alignment_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(kReconstructSmemMax)));
+  return EFTS_OK;
 }
 
 GemmParams gemm_defaults() {
@@ -466,13 +481,7 @@ int run_reconstruct_expand(efts_ctx* c, cudaStream_t st, const float* e, const i
     ProfScope ps(c, st, TAG_RECONSTRUCT);
     const float neg_sigma = -1.0f * c->cfg.sigma;
     const size_t smem = (static_cast<size_t>(T1p) * (RT_FRAMES + 1) + T1) * sizeof(float);
-    if (T1 <= 32 * RT_KMAX && smem <= 200 * 1024) {
-      static size_t attr_smem = 0;
-      if (smem > 48 * 1024 && smem > attr_smem) {
-        CUDA_TRY(cudaFuncSetAttribute(reconstruct_alignment_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      static_cast<int>(smem)));
-        attr_smem = smem;
-      }
+    if (T1 <= 32 * RT_KMAX && smem <= kReconstructSmemMax) {
       dim3 grid((T2 + RT_FRAMES - 1) / RT_FRAMES, B);
       reconstruct_alignment_tiled_kernel<<<grid, 256, smem, st>>>(e, tl, sl, T1, T2, T1p, neg_sigma, reconst_alpha,
                                                                  R_hi, R_lo);
@@ -555,7 +564,7 @@ int split_planes(efts_ctx* c, cudaStream_t st, const float* x, size_t n, __half*
   if (n % 4 != 0) return fail(EFTS_ERR_ARG, "split_planes: element count must be a multiple of 4");
   const size_t n4 = n / 4;
   const unsigned grid = static_cast<unsigned>(std::min<size_t>((n4 + 255) / 256, 148 * 16));
-  split_planes_kernel<<<grid ? grid : 1, 256, 0, st>>>(x, n4, hi, lo);
+  split_planes_kernel<<<grid ? grid : 1, 256, 0, st>>>(x, n4, hi, lo, c->err_flag);
   CUDA_TRY(cudaGetLastError());
   c->launches++;
   return EFTS_OK;
@@ -593,6 +602,7 @@ int efts_create(const efts_config* cfg, efts_ctx** out) {
     return fail(EFTS_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", cfg->device,
                 prop.major, prop.minor);
   CUDA_TRY(cudaSetDevice(cfg->device));
+  TRY(set_kernel_attributes());
   efts_ctx* c = new efts_ctx();
   c->cfg = *cfg;
   c->sm_count = prop.multiProcessorCount;
@@ -604,6 +614,12 @@ int efts_create(const efts_config* cfg, efts_ctx** out) {
     return fail(EFTS_ERR_CUDA, "cuTensorMapEncodeTiled unavailable: %s", cudaGetErrorString(e));
   }
   c->encode = reinterpret_cast<EncodeTiledFn>(fn);
+  if (cudaMalloc(reinterpret_cast<void**>(&c->err_flag), sizeof(int)) != cudaSuccess ||
+      cudaMemset(c->err_flag, 0, sizeof(int)) != cudaSuccess) {
+    delete c;
+    return fail(EFTS_ERR_CUDA, "cudaMalloc failed");
+  }
+  c->device_allocs.push_back(c->err_flag);
   *out = c;
   return EFTS_OK;
 }
@@ -697,6 +713,14 @@ int efts_set_option(efts_ctx* c, const char* name, int32_t value) {
 
 int64_t efts_launch_count(const efts_ctx* c) { return c ? c->launches : 0; }
 
+int efts_error_flags(efts_ctx* c, void* stream, int32_t* flags_host) {
+  if (c == nullptr || flags_host == nullptr) return fail(EFTS_ERR_ARG, "null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(cudaMemcpyAsync(flags_host, c->err_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return EFTS_OK;
+}
+
 int efts_profile_enable(efts_ctx* c, uint32_t tag_mask) {
   if (c == nullptr) return fail(EFTS_ERR_ARG, "null context");
   c->profile_mask = tag_mask;
@@ -744,6 +768,7 @@ int efts_forward(efts_ctx* c, const int64_t* text, const int64_t* text_lengths, 
   // 0. lengths, flags, accumulators
   CUDA_TRY(cudaMemsetAsync(w.flags, 0, 4 * sizeof(int), st));
   CUDA_TRY(cudaMemsetAsync(w.acc, 0, 2 * sizeof(double), st));
+  CUDA_TRY(cudaMemsetAsync(c->err_flag, 0, sizeof(int), st));
   prep_lengths_kernel<<<1, 256, 0, st>>>(text_lengths, speech_lengths, B, T1, T2, w.tl32, w.sl32, w.flags);
   CUDA_TRY(cudaGetLastError());
   // live row tiles of both sides (largest halo any launch uses; launches re-check their own halo)
@@ -821,7 +846,8 @@ int efts_forward(efts_ctx* c, const int64_t* text, const int64_t* text_lengths, 
   loss_partial_kernel<<<c->sm_count * 4, 256, 0, st>>>(mel_pred, speech, w.sl32, T2, g.odim, w.dur, w.e, w.tl32,
                                                        T1, B, g.duration_offset, g.use_masking, w.acc);
   CUDA_TRY(cudaGetLastError());
-  loss_finalize_kernel<<<1, 32, 0, st>>>(w.acc, w.tl32, w.sl32, B, T1, T2, g.odim, g.use_masking, w.flags, scalars);
+  loss_finalize_kernel<<<1, 32, 0, st>>>(w.acc, w.tl32, w.sl32, B, T1, T2, g.odim, g.use_masking, w.flags, c->err_flag,
+                                         scalars);
   CUDA_TRY(cudaGetLastError());
   c->launches += 2;
   return EFTS_OK;
@@ -840,6 +866,7 @@ int efts_inference_phase1(efts_ctx* c, const int64_t* text, int32_t T1, int32_t*
   carve_text(a, w, 1, T1, C);
   if (!a.ok) return fail(EFTS_ERR_WORKSPACE, "workspace too small: need %zu, have %zu", a.off, workspace_bytes);
   CUDA_TRY(cudaMemsetAsync(t2_dev, 0, 2 * sizeof(int), st));
+  CUDA_TRY(cudaMemsetAsync(c->err_flag, 0, sizeof(int), st));
   embed_kernel<<<T1, C / 4, 0, st>>>(text, c->emb, g.num_symbols, C, w.xt_f[0], w.xt_hi[0], w.xt_lo[0], t2_dev + 1);
   CUDA_TRY(cudaGetLastError());
   c->launches++;

@@ -301,6 +301,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       const bool tile_live = valid && !(p.skip_lens != nullptr && t0 >= p.skip_lens[b] + p.skip_halo);
       const bool row_ok = tile_live && t < p.T;
       const bool row_live = row_ok && (p.lens == nullptr || t < p.lens[b]);
+      // rows past L_b + halo of a live tile may be fed by never-written workspace: they cannot reach a valid
+      // output, so their values are not range-checked
+      const bool row_checked = row_ok && (p.skip_lens == nullptr || t < p.skip_lens[b] + p.skip_halo);
       const size_t m = row_ok ? static_cast<size_t>(b) * p.T + t : 0;
       float sum[G2_BN];
 #pragma unroll
@@ -429,6 +432,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
           *reinterpret_cast<float4*>(op + 4) = make_float4(vv[4], vv[5], vv[6], vv[7]);
         }
         if (p.out_hi != nullptr && !(p.debug_mask & 2)) {
+          const float amax = fmaxf(fmaxf(fmaxf(fabsf(vv[0]), fabsf(vv[1])), fmaxf(fabsf(vv[2]), fabsf(vv[3]))),
+                                   fmaxf(fmaxf(fabsf(vv[4]), fabsf(vv[5])), fmaxf(fabsf(vv[6]), fabsf(vv[7]))));
+          const float asum = ((fabsf(vv[0]) + fabsf(vv[1])) + (fabsf(vv[2]) + fabsf(vv[3]))) +
+                             ((fabsf(vv[4]) + fabsf(vv[5])) + (fabsf(vv[6]) + fabsf(vv[7])));   // NaN / inf propagate
+          if (row_checked && (amax > 65504.0f || !(asum < CUDART_INF_F)) && p.err_flag != nullptr)
+            atomicOr(p.err_flag, 8 | p.err_code);   // outside the fp16 operand range (or already non-finite)
           split_store8(p.out_hi + m * p.ld_pl + n, p.out_lo + m * p.ld_pl + n, vv);
         }
         if (p.outT_hi != nullptr) {

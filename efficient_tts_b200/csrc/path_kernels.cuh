@@ -89,6 +89,8 @@ __global__ void embed_kernel(const int64_t* __restrict__ text, const float* __re
   const int c = threadIdx.x * 4;
   if (c >= C) return;
   const float4 v = __ldg(reinterpret_cast<const float4*>(table + static_cast<size_t>(id) * C + c));
+  if (!(fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))) <= 65504.0f))
+    atomicOr(flags, 8);                           // outside the fp16 operand range
   *reinterpret_cast<float4*>(out + row * C + c) = v;
   uint2 h, l;
   split4(v, &h, &l);
@@ -98,10 +100,12 @@ __global__ void embed_kernel(const int64_t* __restrict__ text, const float* __re
 
 // fp32 [n] -> operand planes; n multiple of 4.
 __global__ void split_planes_kernel(const float* __restrict__ x, size_t n4, __half* __restrict__ hi,
-                                    __half* __restrict__ lo) {
+                                    __half* __restrict__ lo, int* __restrict__ err_flag) {
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    if (fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))) > 65504.0f && err_flag != nullptr)
+      atomicOr(err_flag, 8);                      // outside the fp16 operand range
     uint2 h, l;
     split4(v, &h, &l);
     reinterpret_cast<uint2*>(hi)[i] = h;
@@ -535,7 +539,7 @@ __global__ void loss_partial_kernel(const float* __restrict__ mel_pred, const fl
 __global__ void loss_finalize_kernel(const double* __restrict__ acc, const int* __restrict__ tl,
                                      const int* __restrict__ sl, int B, int T1, int T2, int odim,
                                      int use_masking, const int* __restrict__ flags,
-                                     float* __restrict__ scalars) {
+                                     const int* __restrict__ err_flag, float* __restrict__ scalars) {
   double nt = 0.0, nm = 0.0;
   for (int b = threadIdx.x; b < B; b += 32) {
     nt += use_masking ? tl[b] : T1;
@@ -553,7 +557,7 @@ __global__ void loss_finalize_kernel(const double* __restrict__ acc, const int* 
     scalars[4] = static_cast<float>(nm);
     scalars[5] = static_cast<float>(acc[1]);
     scalars[6] = static_cast<float>(nt);
-    scalars[7] = static_cast<float>(flags[0]);
+    scalars[7] = static_cast<float>(flags[0] | err_flag[0]);
   }
 }
 

@@ -10,6 +10,8 @@ import torch
 from . import _lib
 
 N_CHANNELS = 512
+RANGE_MESSAGE = ("an activation left the fp16 operand range (|x| > 65504): the split-fp16 tensor-core "
+                 "scheme cannot represent it (include/efts_b200.h, flags bit 3)")
 
 
 def _ptr(t):
@@ -142,7 +144,7 @@ class Engine:
                                              self._stream()))
         return imv, ra, mel, scal
 
-    def inference(self, text, max_t2=None):
+    def inference(self, text, check_numerics=True):
         """models/efficient_tts.py:230-285, B = 1.  Returns (mel_pred[1,T2,odim], reconst_alpha[1,T1,T2])."""
         text = self._i64(text, "text")
         if text.dim() != 2 or text.shape[0] != 1:
@@ -172,7 +174,17 @@ class Engine:
             ra = torch.empty(1, T1, t2, dtype=torch.float32, device=self.device)
             _lib.check(self.lib.efts_inference_phase2(self._h, T1, t2, _ptr(mel), _ptr(ra), _ptr(ws),
                                                       ws.numel(), self._stream()))
+            if check_numerics:
+                self.check_error_flags()
         return mel, ra
+
+    def check_error_flags(self):
+        """Synchronising read of the kernels' data-dependent error bits (include/efts_b200.h)."""
+        flags = ctypes.c_int32(0)
+        _lib.check(self.lib.efts_error_flags(self._h, self._stream(), ctypes.byref(flags)))
+        if flags.value & 8:
+            raise FloatingPointError(RANGE_MESSAGE)
+        return flags.value
 
     # ------------------------------------------------------------------ layer-level calls
     def conv_stack(self, stack, x_btc):

@@ -89,6 +89,9 @@ class EfficientTTSCNN(_EngineOwner):
         flags = int(host[7])
         if flags & 4:
             raise IndexError("index out of range in self")          # torch.nn.Embedding, :144
+        if flags & 8:
+            from .engine import RANGE_MESSAGE
+            raise FloatingPointError(RANGE_MESSAGE + " [flags 0x%x]" % flags)
         if flags & 3:
             which = "text" if flags & 1 else "speech"
             raise RuntimeError("The padded %s length must equal max(%s_lengths) (the reference builds its "

@@ -83,7 +83,9 @@ size_t efts_workspace_bytes(const efts_ctx* ctx, int32_t B, int32_t T1, int32_t 
  * Outputs: imv fp32 [B,T2]; reconst_alpha fp32 [B,T1,T2]; mel_pred fp32 [B,T2,odim];
  * scalars fp32 [8] = {loss, mel_loss, duration_loss, sum_sq, n_mel, sum_abs, n_tok, flags}
  *   flags (as float-encoded int): bit0 max(text_lengths) != T1, bit1 max(speech_lengths) != T2,
- *   bit2 a text id outside [0, num_symbols)  -- the conditions the reference raises on
+ *   bit2 a text id outside [0, num_symbols), bit3 an activation left the fp16 operand range
+ *   (|x| > 65504: the split-fp16 tensor-core scheme cannot represent it; nothing in the reference
+ *   corresponds to this, it is reported instead of returning inf/NaN)  -- bits 0-2 are the conditions the reference raises on
  *   (utils/nets_utils.py:148-156 size mismatch, embedding IndexError); the binding checks them
  *   when it reads the scalars back (the read-back the reference does with .item(), :225-227). */
 int efts_forward(efts_ctx* ctx, const int64_t* text, const int64_t* text_lengths, const float* speech,
@@ -155,6 +157,10 @@ int efts_set_option(efts_ctx* ctx, const char* name, int32_t value);
  * `efts_profile_enable` also clears what was recorded. */
 int efts_profile_enable(efts_ctx* ctx, uint32_t tag_mask);
 int efts_profile_read(efts_ctx* ctx, int32_t tag, double* total_ms, int64_t* count);
+/* Data-dependent error bits raised by the kernels of the calls issued on `stream` since the last
+ * efts_forward / efts_inference_phase1 (bit 3: activation outside the fp16 operand range).
+ * Synchronises the stream (4-byte read-back); efts_forward reports the same bits in scalars[7]. */
+int efts_error_flags(efts_ctx* ctx, void* stream, int32_t* flags_host);
 /* Kernels launched by this context since creation (bench.py's `gpu_launches`). */
 int64_t efts_launch_count(const efts_ctx* ctx);
 const char* efts_last_error(void);

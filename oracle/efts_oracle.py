@@ -202,7 +202,7 @@ def reconstruct_alignment(e, delta, mel_mask=None, text_mask=None):
 
 # --------------------------------------------------------------------------- model
 def forward(w: Weights, text, text_lengths, speech, speech_lengths, sigma=0.01, sigma_e=0.5,
-            duration_offset=1.0, return_intermediates=False):
+            duration_offset=1.0, return_intermediates=False, use_masking=True):
     """Teacher-forced pass, models/efficient_tts.py:120-228, eval mode, production
     flags (``use_masking=True``, ``delta_e_method_1=True``, separate key/value, no
     mel-query fc).  Returns ``(loss, stats, imv, reconst_alpha, mel_pred, speech)``."""
@@ -238,10 +238,14 @@ def forward(w: Weights, text, text_lengths, speech, speech_lengths, sigma=0.01, 
     log_delta_e = torch.log(delta_e + duration_offset).masked_fill(~text_mask, 0.0)
     dur_pred = duration_predictor_forward(value, ~text_mask, w)
 
-    # losses/fastspeech_loss.py:54-67 with use_masking=True
-    mel_loss = F.mse_loss(mel_pred.masked_select(mel_mask.unsqueeze(-1)),
-                          speech.masked_select(mel_mask.unsqueeze(-1)))
-    dur_loss = F.l1_loss(dur_pred.masked_select(text_mask), log_delta_e.masked_select(text_mask))
+    # losses/fastspeech_loss.py:54-67: masked_select under use_masking=True, plain means otherwise
+    if use_masking:
+        mel_loss = F.mse_loss(mel_pred.masked_select(mel_mask.unsqueeze(-1)),
+                              speech.masked_select(mel_mask.unsqueeze(-1)))
+        dur_loss = F.l1_loss(dur_pred.masked_select(text_mask), log_delta_e.masked_select(text_mask))
+    else:
+        mel_loss = F.mse_loss(mel_pred, speech)
+        dur_loss = F.l1_loss(dur_pred, log_delta_e)
     loss = mel_loss + dur_loss
     stats = dict(loss=loss.item(), mel_loss=mel_loss.item(), duration_loss=dur_loss.item())
     if return_intermediates:

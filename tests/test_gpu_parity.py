@@ -247,6 +247,62 @@ def test_forward_rejects_what_the_reference_rejects(model, dev):
     model.eval()
 
 
+def test_forward_without_loss_masking(dev):
+    """FastSpeechLoss(use_masking=False) (the reference's constructor default): means over the padded batch."""
+    import efficient_tts_b200 as E
+    w = orc.make_weights(seed=1234)
+    m = E.EfficientTTSCNN(num_symbols=76, dropout_rate=0.0, use_masking=False, sigma=0.01)
+    m.load_state_dict(w)
+    m = m.eval().to(dev)
+    text, tl, speech, sl = make_forward_inputs(24, [20, 11], [120, 70])
+    with torch.no_grad():
+        ref = orc.forward(w, text, tl, speech, sl, use_masking=False)
+    out = m(text=text.to(dev), text_lengths=tl.to(dev), speech=speech.to(dev), speech_lengths=sl.to(dev))
+    for k in ("loss", "mel_loss", "duration_loss"):
+        assert abs(out[1][k] - ref[1][k]) <= 1e-4 * max(1.0, abs(ref[1][k])), k
+    assert (out[4].cpu() - ref[4]).abs().max().item() <= MEL_TOL
+
+
+def test_forward_on_a_side_stream_and_with_long_text(model, dev):
+    """Caller's stream is honoured; T1 > 512 takes the generic reconstruction kernel."""
+    ref, _, (text, tl, speech, sl) = run_both(model, dev, 25, [530, 300], [700, 400])
+    s = torch.cuda.Stream(dev)
+    args = [t.to(dev) for t in (text, tl, speech, sl)]
+    torch.cuda.synchronize(dev)
+    with torch.cuda.stream(s):
+        out = model(text=args[0], text_lengths=args[1], speech=args[2], speech_lengths=args[3])
+    s.synchronize()
+    check_forward(ref, out, 530)
+
+
+def test_shard_keeps_global_padded_dims(model, dev):
+    """forward_shard: a data-parallel shard whose own max length is below the global padded dims gives the
+    same per-utterance outputs as the full batch, and its loss partials add up."""
+    text, tl, speech, sl = make_forward_inputs(26, [33, 12, 25, 7], [210, 80, 160, 50])
+    d = [t.to(dev) for t in (text, tl, speech, sl)]
+    full = model.forward_shard(*d)
+    parts = [model.forward_shard(*(t[lo:hi] for t in d)) for lo, hi in ((0, 2), (2, 4))]
+    for k in range(3):
+        assert torch.equal(torch.cat([p[k] for p in parts]), full[k])
+    s = sum(p[3][3:7].cpu().double() for p in parts)
+    f = full[3][3:7].cpu().double()
+    assert torch.allclose(s, f, rtol=1e-6)
+    with pytest.raises(RuntimeError):          # the reference-style call does check max(lengths) == padded dim
+        model(text=d[0][2:], text_lengths=d[1][2:], speech=d[2][2:], speech_lengths=d[3][2:])
+
+
+def test_fp16_range_violation_is_reported(dev):
+    """Activations beyond the fp16 operand range are reported, not turned into inf/NaN silently."""
+    w = orc.make_weights(seed=1234)
+    w["text_embedding_table.weight"] = w["text_embedding_table.weight"] * 3e4
+    m = build_model(w, dev)
+    text, tl, speech, sl = make_forward_inputs(27, [12, 9], [60, 40])
+    with pytest.raises(FloatingPointError):
+        m(text=text.to(dev), text_lengths=tl.to(dev), speech=speech.to(dev), speech_lengths=sl.to(dev))
+    with pytest.raises(FloatingPointError):
+        m.inference(text[:1, :12].to(dev))
+
+
 # ------------------------------------------------------------------------------------------------
 def test_inference_matches_golden(dev):
     z = np.load(os.path.join(G, "inf_small.npz"))
