@@ -34,6 +34,10 @@ SIGNATURES = {
     "efts_inference_phase1": (c_i32, [c_void_p, c_void_p, c_i32, c_void_p, c_void_p, c_size_t, c_void_p]),
     "efts_inference_phase2": (c_i32, [c_void_p, c_i32, c_i32, c_void_p, c_void_p, c_void_p, c_size_t,
                                       c_void_p]),
+    "efts_inference_batch_phase1": (c_i32, [c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_void_p, c_void_p,
+                                            c_size_t, c_void_p]),
+    "efts_inference_batch_phase2": (c_i32, [c_void_p, c_i32, c_i32, c_i32, c_void_p, c_void_p, c_void_p, c_void_p,
+                                            c_size_t, c_void_p]),
     "efts_conv_stack_fwd": (c_i32, [c_void_p, c_i32, c_void_p, c_void_p, c_i32, c_i32, c_void_p,
                                     c_size_t, c_void_p]),
     "efts_duration_predictor_fwd": (c_i32, [c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_void_p,

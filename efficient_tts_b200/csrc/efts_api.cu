@@ -403,7 +403,7 @@ void carve_mel(Arena& a, FwdWs& w, int B, int T2, int C, int odim, bool teacher_
 // is non-null the last layer writes its fp32 result there instead (planes still go to the set).
 int run_conv_stack(efts_ctx* c, cudaStream_t st, const PackedW* layers, int n, int B, int T, float* f[2],
                    __half* hi[2], __half* lo[2], const float* first_resid, float* final_f,
-                   const Skip* skip, int* cur_io, int tag) {
+                   const Skip* skip, int* cur_io, int tag, bool ragged = false) {
   const int C = c->cfg.n_channels;
   int cur = *cur_io;
   for (int l = 0; l < n; ++l) {
@@ -420,8 +420,11 @@ int run_conv_stack(efts_ctx* c, cudaStream_t st, const PackedW* layers, int n, i
     p.out_hi = hi[nxt]; p.out_lo = lo[nxt]; p.ld_pl = C;
     if (skip != nullptr && c->skip_pad_tiles) {
       p.skip_lens = skip->lens; p.tile_list = skip->list; p.tile_count = skip->count;
-      p.skip_halo = p.pad * (n - 1 - l);
+      p.skip_halo = ragged ? p.pad : p.pad * (n - 1 - l);
     }
+    // ragged synthesis: every layer's rows t >= L_b are written as zeros, so utterance b convolves against
+    // the zero padding it would see alone (tiles within `pad` rows of L_b are computed to produce those zeros)
+    if (ragged) p.lens = skip->lens;
     {
       ProfScope ps(c, st, tag);
       TRY(launch_gemm(c, st, OpA{hi[cur], lo[cur], B, T, C, C}, weight_op(layers[l]), p));
@@ -436,7 +439,7 @@ int run_conv_stack(efts_ctx* c, cudaStream_t st, const PackedW* layers, int n, i
 // Input operand planes in_hi/in_lo [B,T,C]; scratch dp_f, dp_hi/lo.
 int run_duration_predictor(efts_ctx* c, cudaStream_t st, const __half* in_hi, const __half* in_lo, int B,
                            int T, float* dp_f, __half* dp_hi, __half* dp_lo, const int* lens, int mode,
-                           void* out) {
+                           void* out, bool mask_hidden = false) {
   const int C = c->cfg.n_channels;
   const size_t rows = static_cast<size_t>(B) * T;
   const int nl = c->cfg.n_duration_layer;
@@ -456,7 +459,8 @@ int run_duration_predictor(efts_ctx* c, cudaStream_t st, const __half* in_hi, co
     const unsigned grid = static_cast<unsigned>((rows + wpb - 1) / wpb);
     if (l < nl - 1) {
       layernorm_kernel<0><<<grid, wpb * 32, 0, st>>>(dp_f, rows, T, c->ln_g[l], c->ln_b[l], dp_hi, dp_lo,
-                                                     nullptr, nullptr, nullptr, 0, 0.0f, nullptr);
+                                                     nullptr, nullptr, mask_hidden ? lens : nullptr, 0, 0.0f,
+                                                     nullptr);
     } else {
       layernorm_kernel<1><<<grid, wpb * 32, 0, st>>>(dp_f, rows, T, c->ln_g[l], c->ln_b[l], nullptr, nullptr,
                                                      c->head_w, c->head_b, lens, mode,
@@ -785,7 +789,7 @@ int efts_forward(efts_ctx* c, const int64_t* text, const int64_t* text_lengths, 
   {
     ProfScope ps(c, st, TAG_PREP);
     embed_kernel<<<static_cast<unsigned>(m1), C / 4, 0, st>>>(text, c->emb, g.num_symbols, C, w.xt_f[0], w.xt_hi[0],
-                                                              w.xt_lo[0], w.flags);
+                                                              w.xt_lo[0], w.flags, nullptr, T1);
     CUDA_TRY(cudaGetLastError());
   }
   c->launches += 2;
@@ -867,7 +871,8 @@ int efts_inference_phase1(efts_ctx* c, const int64_t* text, int32_t T1, int32_t*
   if (!a.ok) return fail(EFTS_ERR_WORKSPACE, "workspace too small: need %zu, have %zu", a.off, workspace_bytes);
   CUDA_TRY(cudaMemsetAsync(t2_dev, 0, 2 * sizeof(int), st));
   CUDA_TRY(cudaMemsetAsync(c->err_flag, 0, sizeof(int), st));
-  embed_kernel<<<T1, C / 4, 0, st>>>(text, c->emb, g.num_symbols, C, w.xt_f[0], w.xt_hi[0], w.xt_lo[0], t2_dev + 1);
+  embed_kernel<<<T1, C / 4, 0, st>>>(text, c->emb, g.num_symbols, C, w.xt_f[0], w.xt_hi[0], w.xt_lo[0], t2_dev + 1,
+                                     nullptr, T1);
   CUDA_TRY(cudaGetLastError());
   c->launches++;
   int cur = 0;
@@ -915,6 +920,88 @@ int efts_inference_phase2(efts_ctx* c, int32_t T1, int32_t T2, float* mel_pred, 
   p.N = g.odim; p.bias = c->melout.bias;
   p.out = mel_pred; p.ld_out = g.odim;
   return launch_gemm(c, st, OpA{w.xm_hi[curm], w.xm_lo[curm], 1, T2, C, C}, weight_op(c->melout), p);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Ragged batched synthesis.  Every utterance is computed as if it were alone and unpadded:
+// rows beyond its length are zero after every layer, exactly the zero padding the B = 1 path convolves against.
+int efts_inference_batch_phase1(efts_ctx* c, const int64_t* text, const int64_t* text_lengths, int32_t B, int32_t T1,
+                                int32_t* t2_dev, void* workspace, size_t workspace_bytes, void* stream) {
+  TRY(check_ready(c));
+  if (!text || !text_lengths || !t2_dev || !workspace || B < 1 || T1 < 1 || B > 65535)
+    return fail(EFTS_ERR_ARG, "efts_inference_batch_phase1: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const efts_config& g = c->cfg;
+  const int C = g.n_channels;
+  const int pad_k = (g.k_size - 1) / 2;
+  Arena a(workspace, workspace_bytes);
+  FwdWs w;
+  carve_text(a, w, B, T1, C);
+  if (!a.ok) return fail(EFTS_ERR_WORKSPACE, "workspace too small: need %zu, have %zu", a.off, workspace_bytes);
+  const size_t m1 = static_cast<size_t>(B) * T1;
+  CUDA_TRY(cudaMemsetAsync(t2_dev, 0, (B + 1) * sizeof(int), st));
+  CUDA_TRY(cudaMemsetAsync(c->err_flag, 0, sizeof(int), st));
+  prep_lengths_kernel<<<1, 256, 0, st>>>(text_lengths, nullptr, B, T1, 0, w.tl32, w.sl32, t2_dev + B);
+  CUDA_TRY(cudaGetLastError());
+  build_tile_list_kernel<<<1, 256, 0, st>>>(w.tl32, B, T1, pad_k, w.list_t, w.cnt_t);
+  CUDA_TRY(cudaGetLastError());
+  embed_kernel<<<static_cast<unsigned>(m1), C / 4, 0, st>>>(text, c->emb, g.num_symbols, C, w.xt_f[0], w.xt_hi[0],
+                                                            w.xt_lo[0], t2_dev + B, w.tl32, T1);
+  CUDA_TRY(cudaGetLastError());
+  c->launches += 3;
+  const Skip skip_t{w.tl32, w.list_t, w.cnt_t};
+  int cur = 0;
+  TRY(run_conv_stack(c, st, c->text, g.n_text_encoder_layer, B, T1, w.xt_f, w.xt_hi, w.xt_lo, nullptr, nullptr,
+                     &skip_t, &cur, TAG_TEXT_CONV, true));
+  {
+    GemmParams p = gemm_defaults();
+    p.N = C; p.bias = c->value.bias; p.lens = w.tl32;
+    p.out_hi = w.val_hi; p.out_lo = w.val_lo; p.ld_pl = C;
+    p.outT_hi = w.valT_hi; p.outT_lo = w.valT_lo; p.ld_t = w.T1p;
+    if (w.T1p != T1) {
+      CUDA_TRY(cudaMemsetAsync(w.valT_hi, 0, static_cast<size_t>(B) * C * w.T1p * sizeof(__half), st));
+      CUDA_TRY(cudaMemsetAsync(w.valT_lo, 0, static_cast<size_t>(B) * C * w.T1p * sizeof(__half), st));
+    }
+    ProfScope ps(c, st, TAG_LINEAR);
+    TRY(launch_gemm(c, st, OpA{w.xt_hi[cur], w.xt_lo[cur], B, T1, C, C}, weight_op(c->value), p));
+  }
+  TRY(run_duration_predictor(c, st, w.val_hi, w.val_lo, B, T1, w.dp_f, w.dp_hi, w.dp_lo, w.tl32, 1, w.dur, true));
+  duration_cumsum_batch_kernel<<<(B + 3) / 4, 128, 0, st>>>(w.dur, w.tl32, B, T1, w.e, t2_dev);
+  CUDA_TRY(cudaGetLastError());
+  c->launches++;
+  return EFTS_OK;
+}
+
+int efts_inference_batch_phase2(efts_ctx* c, int32_t B, int32_t T1, int32_t T2max, const int32_t* t2_dev,
+                                float* mel_pred, float* reconst_alpha, void* workspace, size_t workspace_bytes,
+                                void* stream) {
+  TRY(check_ready(c));
+  if (!t2_dev || !mel_pred || !reconst_alpha || !workspace || B < 1 || T1 < 1 || T2max < 1 || B > 65535)
+    return fail(EFTS_ERR_ARG, "efts_inference_batch_phase2: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const efts_config& g = c->cfg;
+  const int C = g.n_channels;
+  const int pad_k = (g.k_size - 1) / 2;
+  Arena a(workspace, workspace_bytes);
+  FwdWs w;
+  carve_text(a, w, B, T1, C);
+  carve_mel(a, w, B, T2max, C, g.odim, false);
+  if (!a.ok) return fail(EFTS_ERR_WORKSPACE, "workspace too small: need %zu, have %zu", a.off, workspace_bytes);
+  const int* t2 = t2_dev;                         // per-utterance frame counts are the mel-side lengths
+  build_tile_list_kernel<<<1, 256, 0, st>>>(t2, B, T2max, pad_k, w.list_m, w.cnt_m);
+  CUDA_TRY(cudaGetLastError());
+  c->launches++;
+  const Skip skip_m{t2, w.list_m, w.cnt_m};
+  TRY(run_reconstruct_expand(c, st, w.e, w.tl32, &skip_m, B, T1, T2max, w.T1p, w.R_hi, w.R_lo, w.valT_hi,
+                             w.valT_lo, reconst_alpha, w.xm_f[0], w.xm_hi[0], w.xm_lo[0]));
+  int curm = 0;
+  TRY(run_conv_stack(c, st, c->dec, g.n_decoder_layer, B, T2max, w.xm_f, w.xm_hi, w.xm_lo, nullptr, nullptr,
+                     &skip_m, &curm, TAG_DEC_CONV, true));
+  GemmParams p = gemm_defaults();
+  p.N = g.odim; p.bias = c->melout.bias; p.lens = t2;
+  p.out = mel_pred; p.ld_out = g.odim;
+  ProfScope ps(c, st, TAG_LINEAR);
+  return launch_gemm(c, st, OpA{w.xm_hi[curm], w.xm_lo[curm], B, T2max, C, C}, weight_op(c->melout), p);
 }
 
 // ------------------------------------------------------------------------------------------------

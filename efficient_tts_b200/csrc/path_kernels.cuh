@@ -77,10 +77,22 @@ __global__ void prep_lengths_kernel(const int64_t* __restrict__ tl, const int64_
 // ------------------------------------------------------------------------------------------------
 // Embedding gather (models/efficient_tts.py:144,246; no padding_idx: id 0 is a real row).
 // One block of C/4 threads per (b, i); writes the fp32 master and the operand planes.
+// `lens` (ragged batched synthesis only): rows i >= lens[b] are written as zeros, so that an utterance
+// sees the same zero padding it would see when run alone and unpadded.
 __global__ void embed_kernel(const int64_t* __restrict__ text, const float* __restrict__ table,
                              int num_symbols, int C, float* __restrict__ out, __half* __restrict__ hi,
-                             __half* __restrict__ lo, int* __restrict__ flags) {
+                             __half* __restrict__ lo, int* __restrict__ flags, const int* __restrict__ lens,
+                             int T) {
   const size_t row = blockIdx.x;
+  if (lens != nullptr && static_cast<int>(row % T) >= lens[row / T]) {
+    const int c0 = threadIdx.x * 4;
+    if (c0 < C) {
+      *reinterpret_cast<float4*>(out + row * C + c0) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      *reinterpret_cast<uint2*>(hi + row * C + c0) = make_uint2(0u, 0u);
+      *reinterpret_cast<uint2*>(lo + row * C + c0) = make_uint2(0u, 0u);
+    }
+    return;
+  }
   long long id = text[row];
   if (id < 0 || id >= num_symbols) {
     if (threadIdx.x == 0) atomicOr(flags, 4);
@@ -451,6 +463,7 @@ __global__ void layernorm_kernel(const float* __restrict__ x, size_t rows, int T
     y.z = (v[j].z - mean) * rstd * g.z + bb.z;
     y.w = (v[j].w - mean) * rstd * g.w + bb.w;
     if (HEAD == 0) {
+      if (lens != nullptr && static_cast<int>(row % T) >= lens[row / T]) y = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
       uint2 h, l;
       split4(y, &h, &l);
       *reinterpret_cast<uint2*>(hi + row * C + c) = h;
@@ -564,6 +577,31 @@ __global__ void loss_finalize_kernel(const double* __restrict__ acc, const int* 
 // ------------------------------------------------------------------------------------------------
 // inference(): e = cumsum(durations) (models/efficient_tts.py:260; fp32 cumsum accumulated in
 // double like torch CPU) and T2 = round_half_even(e[T1-1]) (:361).  One warp, B = 1.
+// Batched form (ragged synthesis): one warp per utterance over its first lens[b] tokens; e beyond is 0.
+__global__ void duration_cumsum_batch_kernel(const float* __restrict__ d, const int* __restrict__ lens, int B,
+                                             int T1, float* __restrict__ e, int* __restrict__ t2_out) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const int L = min(max(lens[b], 0), T1);
+  const float* db = d + static_cast<size_t>(b) * T1;
+  float* eb = e + static_cast<size_t>(b) * T1;
+  double carry = 0.0;
+  for (int base = 0; base < T1; base += 32) {
+    const int i = base + lane;
+    double s = i < L ? static_cast<double>(db[i]) : 0.0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double n = __shfl_up_sync(0xffffffffu, s, o);
+      if (lane >= o) s += n;
+    }
+    s += carry;
+    carry = __shfl_sync(0xffffffffu, s, 31);
+    if (i < T1) eb[i] = i < L ? static_cast<float>(s) : 0.0f;
+  }
+  if (lane == 0) t2_out[b] = L > 0 ? static_cast<int>(rintf(static_cast<float>(carry))) : 0;
+}
+
 __global__ void duration_cumsum_kernel(const float* __restrict__ d, int T1, float* __restrict__ e,
                                        int* __restrict__ t2_out) {
   const int lane = threadIdx.x;

@@ -178,6 +178,49 @@ class Engine:
                 self.check_error_flags()
         return mel, ra
 
+    def inference_batch(self, text, text_lengths, check_numerics=True):
+        """Ragged batched synthesis (include/efts_b200.h, efts_inference_batch_*): utterance b is computed
+        exactly as ``inference(text[b:b+1, :text_lengths[b]])``.  Returns ``(mel_pred[B,T2max,odim],
+        mel_lengths int64 [B], reconst_alpha[B,T1,T2max])``; frames beyond ``mel_lengths[b]`` are zero."""
+        text = self._i64(text, "text")
+        tl = self._i64(text_lengths, "text_lengths")
+        if text.dim() != 2 or tl.numel() != text.shape[0]:
+            raise RuntimeError("text must be [B, T1] and text_lengths [B]")
+        B, T1 = text.shape
+        tl_host = tl.cpu()
+        if int(tl_host.min()) < 1 or int(tl_host.max()) > T1:
+            raise RuntimeError("text_lengths must lie in [1, %d]" % T1)
+        with torch.cuda.device(self.device):
+            t2_dev = torch.empty(B + 1, dtype=torch.int32, device=self.device)
+            ws, n = self.workspace_for(B, T1, 1)
+            _lib.check(self.lib.efts_inference_batch_phase1(self._h, _ptr(text), _ptr(tl), B, T1, _ptr(t2_dev), _ptr(ws),
+                                                            ws.numel(), self._stream()))
+            host = t2_dev.cpu()                            # one read-back for the whole batch
+            flags = int(host[B])
+            if flags & 4:
+                raise IndexError("index out of range in self")
+            if flags & 8:
+                raise FloatingPointError(RANGE_MESSAGE)
+            t2 = host[:B].to(torch.int64)
+            if int(t2.min()) < 1:
+                raise RuntimeError("utterance %d has predicted length %d; the reference's decoder conv rejects an "
+                                   "empty sequence" % (int(t2.argmin()), int(t2.min())))
+            t2max = int(t2.max())
+            need = int(self.lib.efts_workspace_bytes(self._h, B, T1, t2max))
+            if need > ws.numel():
+                big = torch.empty(need, dtype=torch.uint8, device=self.device)
+                big[: ws.numel()].copy_(ws)
+                self._ws = ws = big
+            mel = torch.empty(B, t2max, self.odim, dtype=torch.float32, device=self.device)
+            ra = torch.empty(B, T1, t2max, dtype=torch.float32, device=self.device)
+            _lib.check(self.lib.efts_inference_batch_phase2(self._h, B, T1, t2max, _ptr(t2_dev), _ptr(mel), _ptr(ra),
+                                                            _ptr(ws), ws.numel(), self._stream()))
+            # t2_dev must outlive the kernels that read it as the frame-length vector
+            mel._efts_keepalive = t2_dev
+            if check_numerics:
+                self.check_error_flags()
+        return mel, t2.to(self.device), ra
+
     def check_error_flags(self):
         """Synchronising read of the kernels' data-dependent error bits (include/efts_b200.h)."""
         flags = ctypes.c_int32(0)

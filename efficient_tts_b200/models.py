@@ -111,6 +111,14 @@ class EfficientTTSCNN(_EngineOwner):
         self._require_eval()
         return self._get_engine().inference(text)
 
+    def inference_batch(self, text, text_lengths):
+        """Batched variable-length synthesis (the reference stops at B = 1 because of the
+        ``.item()`` at models/efficient_tts.py:361).  ``text`` int64 [B, T1] (padded anyhow), ``text_lengths``
+        [B].  Returns ``(mel_pred[B, T2max, odim], mel_lengths[B], reconst_alpha[B, T1, T2max])`` where row b
+        equals ``inference(text[b:b+1, :text_lengths[b]])`` and is zero beyond its own length."""
+        self._require_eval()
+        return self._get_engine().inference_batch(text, text_lengths)
+
     def remove_weight_norm(self):
         for m in (self.text_encoder, self.mel_encoder, self.decoder):
             m.remove_weight_norm()

@@ -104,6 +104,23 @@ int efts_inference_phase1(efts_ctx* ctx, const int64_t* text, int32_t T1, int32_
 int efts_inference_phase2(efts_ctx* ctx, int32_t T1, int32_t T2, float* mel_pred,
                           float* reconst_alpha, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- batched variable-length synthesis (no counterpart in the reference, whose
+ * inference() is limited to B = 1 by the .item() at models/efficient_tts.py:361) ----
+ * Utterance b of a padded batch (text int64 [B,T1], text_lengths int64 [B]) is computed exactly as
+ * `inference(text[b:b+1, :text_lengths[b]])` would compute it: every layer writes zeros beyond the
+ * utterance's own length, so neighbours and padding cannot leak in.
+ * Phase 1 leaves e[B,T1] in the workspace and writes t2_dev int32 [B+1] = per-utterance frame counts
+ * T2_b = round_half_even(e[b, L1_b - 1]) followed by a flags word (bit2: token id out of range).
+ * The caller reads t2_dev back, allocates mel_pred [B,T2max,odim] and reconst_alpha [B,T1,T2max]
+ * (T2max = max_b T2_b; a T2_b < 1 is the caller's error to raise) and calls phase 2 with the same
+ * workspace (sized for (B, T1, T2max)); frames t >= T2_b are written as zeros. */
+int efts_inference_batch_phase1(efts_ctx* ctx, const int64_t* text, const int64_t* text_lengths, int32_t B,
+                                int32_t T1, int32_t* t2_dev, void* workspace, size_t workspace_bytes,
+                                void* stream);
+int efts_inference_batch_phase2(efts_ctx* ctx, int32_t B, int32_t T1, int32_t T2max, const int32_t* t2_dev,
+                                float* mel_pred, float* reconst_alpha, void* workspace,
+                                size_t workspace_bytes, void* stream);
+
 /* ---- ResConvBlock.forward (layers/efts_modules.py:54-79) on channels-last data ----
  * stack: 0 = text_encoder, 1 = mel_encoder, 2 = decoder.  x, y fp32 [B,T,C]; may alias. */
 int efts_conv_stack_fwd(efts_ctx* ctx, int32_t stack, const float* x, float* y, int32_t B, int32_t T,

@@ -247,6 +247,41 @@ def test_forward_rejects_what_the_reference_rejects(model, dev):
     model.eval()
 
 
+@pytest.mark.parametrize("name", ["C3", "C5"])
+def test_forward_full_size_properties(model, dev, name):
+    """BASELINE.json sizes (C3: B=256 mixed lengths padded to (200,1200); C5: B=32, T1=300, T2=2000), checked
+    through properties that need no CPU run: exact zeros on padding, monotone IMV ending at T1-1, alignment
+    columns that are probability vectors, losses that can be recomputed from the returned tensors, and
+    bitwise batch independence (a slice of the batch with the same padded dims gives identical outputs)."""
+    from tests.cases import config_lengths
+    t1, t2 = config_lengths(name)
+    text, tl, speech, sl = (t.to(dev) for t in make_forward_inputs(0, t1, t2))
+    loss, stats, imv, ra, mel, _ = model(text=text, text_lengths=tl, speech=speech, speech_lengths=sl)
+    B, T1, T2 = text.shape[0], text.shape[1], speech.shape[1]
+    tm = torch.arange(T1, device=dev)[None] < tl[:, None]
+    mm = torch.arange(T2, device=dev)[None] < sl[:, None]
+    assert torch.isfinite(mel).all() and torch.isfinite(ra).all() and torch.isfinite(imv).all()
+    assert not mel[~mm].any() and not imv[~mm].any()
+    assert not ra[~(tm[:, :, None] & mm[:, None, :])].any()
+    # imv_generator (models/efficient_tts.py:314-323): cumulative sum of ReLUs, normalised to T1_b - 1
+    d = imv[:, 1:] - imv[:, :-1]
+    assert bool((d[mm[:, 1:]] >= 0).all())
+    last = imv.gather(1, (sl - 1)[:, None]).squeeze(1)
+    assert torch.allclose(last, (tl - 1).float(), rtol=0, atol=1e-3)
+    # reconstruct_align_from_aligned_position (:366-375): softmax over tokens on every valid frame
+    col = ra.sum(1)
+    assert torch.allclose(col[mm], torch.ones_like(col[mm]), rtol=0, atol=2e-5)
+    assert float(ra.min()) >= 0.0
+    # FastSpeechLoss (losses/fastspeech_loss.py:54-67): the mel term is recomputable from the outputs
+    mel_loss = ((mel - speech) ** 2)[mm].double().mean().item()
+    assert abs(stats["mel_loss"] - mel_loss) <= 1e-5 * max(1.0, mel_loss)
+    assert abs(stats["loss"] - (stats["mel_loss"] + stats["duration_loss"])) <= 1e-5 * max(1.0, stats["loss"])
+    # batch independence: rows 3..10 alone, padded to the same (T1, T2)
+    idx = slice(3, 11)
+    sub = model.forward_shard(text[idx], tl[idx], speech[idx], sl[idx])
+    assert torch.equal(sub[0], imv[idx]) and torch.equal(sub[1], ra[idx]) and torch.equal(sub[2], mel[idx])
+
+
 def test_forward_without_loss_masking(dev):
     """FastSpeechLoss(use_masking=False) (the reference's constructor default): means over the padded batch."""
     import efficient_tts_b200 as E
@@ -341,6 +376,34 @@ def test_inference_c1_shape_matches_oracle(dev):
     assert (ra.cpu() - ra_r).abs().max().item() <= RA_TOL
     with pytest.raises(RuntimeError):        # B > 1: the reference's .item() at :361 raises
         m.inference(torch.zeros(2, 5, dtype=torch.long, device=dev))
+
+
+def test_batched_inference_equals_per_utterance_inference(dev):
+    """ragged batched synthesis.  Row b of the batch must be what the reference-shaped
+    B = 1 call returns for that utterance alone (bitwise on this path, <= 1e-4 vs the oracle)."""
+    w = orc.make_weights(seed=1234, dur_bias=float(np.log(7.0)), dur_weight_scale=0.05)
+    m = build_model(w, dev)
+    g = torch.Generator().manual_seed(41)
+    lens = [37, 64, 5, 128, 129, 1]
+    T1 = max(lens)
+    text = torch.randint(0, 76, (len(lens), T1), generator=g)
+    text = text * (torch.arange(T1)[None] < torch.tensor(lens)[:, None])       # id 0 on padding, any id works
+    mel, mel_lens, ra = m.inference_batch(text.to(dev), torch.tensor(lens).to(dev))
+    assert mel.shape[0] == len(lens) and mel.shape[1] == int(mel_lens.max()) and ra.shape[:2] == (len(lens), T1)
+    for b, L in enumerate(lens):
+        one_mel, one_ra = m.inference(text[b:b + 1, :L].to(dev))
+        n = int(mel_lens[b])
+        assert one_mel.shape[1] == n
+        assert torch.equal(mel[b, :n], one_mel[0]), "utterance %d differs from its B=1 run" % b
+        assert torch.equal(ra[b, :L, :n], one_ra[0])
+        assert not mel[b, n:].any() and not ra[b, L:].any() and not ra[b, :, n:].any()
+        with torch.no_grad():
+            rmel, rra = orc.inference(w, text[b:b + 1, :L])
+        assert rmel.shape[1] == n
+        assert (one_mel.cpu() - rmel).abs().max().item() <= MEL_TOL
+        assert (one_ra.cpu() - rra).abs().max().item() <= RA_TOL
+    with pytest.raises(RuntimeError):
+        m.inference_batch(text.to(dev), torch.tensor([0] + lens[1:]).to(dev))
 
 
 # ------------------------------------------------------------------------------------------------
