@@ -51,6 +51,16 @@ SIGNATURES = {
     "efts_alignment_fwd": (c_i32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i32,
                                    c_i32, c_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_size_t, c_void_p]),
+    "efts_mask_lengths": (c_i32, [c_void_p, c_i32, c_i32, c_void_p, c_void_p]),
+    "efts_index_vector": (c_i32, [c_void_p, c_i32, c_i32, c_void_p, c_void_p]),
+    "efts_attention_alpha": (c_i32, [c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_void_p, c_void_p,
+                                     c_size_t, c_void_p]),
+    "efts_imv_generator": (c_i32, [c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_void_p, c_void_p,
+                                   c_size_t, c_void_p]),
+    "efts_aligned_positions": (c_i32, [c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_f32, c_void_p,
+                                       c_void_p]),
+    "efts_reconstruct_alignment": (c_i32, [c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_f32, c_void_p,
+                                           c_void_p]),
     "efts_set_option": (c_i32, [c_void_p, c_char_p, c_i32]),
     "efts_launch_count": (c_i64, [c_void_p]),
     "efts_error_flags": (c_i32, [c_void_p, c_void_p, ctypes.POINTER(c_i32)]),

@@ -1106,6 +1106,99 @@ int efts_alignment_fwd(efts_ctx* c, const float* mel_h, const float* key, const 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Stand-alone helper methods of EfficientTTSCNN (models/efficient_tts.py:287-398).
+int efts_mask_lengths(const uint8_t* mask, int32_t B, int32_t T, int32_t* lengths, void* stream) {
+  if (!mask || !lengths || B < 1 || T < 1) return fail(EFTS_ERR_ARG, "efts_mask_lengths: bad argument");
+  mask_lengths_kernel<<<(B + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(mask, B, T, lengths);
+  CUDA_TRY(cudaGetLastError());
+  return EFTS_OK;
+}
+
+int efts_index_vector(const int32_t* text_lengths, int32_t B, int32_t T1, float* p, void* stream) {
+  if (!text_lengths || !p || B < 1 || T1 < 1) return fail(EFTS_ERR_ARG, "efts_index_vector: bad argument");
+  const size_t n = static_cast<size_t>(B) * T1;
+  index_vector_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      text_lengths, B, T1, p);
+  CUDA_TRY(cudaGetLastError());
+  return EFTS_OK;
+}
+
+int efts_attention_alpha(efts_ctx* c, const float* query, const float* key, const int32_t* text_lengths, int32_t B,
+                         int32_t T1, int32_t T2, float* alpha, void* workspace, size_t workspace_bytes, void* stream) {
+  if (c == nullptr) return fail(EFTS_ERR_ARG, "null context");
+  if (!query || !key || !text_lengths || !alpha || !workspace || B < 1 || T1 < 1 || T2 < 1 || B > 65535)
+    return fail(EFTS_ERR_ARG, "efts_attention_alpha: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int C = c->cfg.n_channels;
+  const int T1p = round8(T1);
+  const size_t m1 = static_cast<size_t>(B) * T1, m2 = static_cast<size_t>(B) * T2;
+  Arena a(workspace, workspace_bytes);
+  __half* q_hi = a.get<__half>(m2 * C); __half* q_lo = a.get<__half>(m2 * C);
+  __half* k_hi = a.get<__half>(m1 * C); __half* k_lo = a.get<__half>(m1 * C);
+  float* S = a.get<float>(m2 * T1p);
+  if (!a.ok) return fail(EFTS_ERR_WORKSPACE, "workspace too small: need %zu, have %zu", a.off, workspace_bytes);
+  TRY(split_planes(c, st, query, m2 * C, q_hi, q_lo));
+  TRY(split_planes(c, st, key, m1 * C, k_hi, k_lo));
+  GemmParams p = gemm_defaults();
+  p.N = T1p;
+  p.b_batched = 1;
+  p.divisor = static_cast<float>(std::sqrt(static_cast<double>(C)));
+  p.out = S; p.ld_out = T1p;
+  TRY(launch_gemm(c, st, OpA{q_hi, q_lo, B, T2, C, C}, OpB{k_hi, k_lo, B, T1, C, C}, p));
+  attention_alpha_kernel<<<static_cast<unsigned>((m2 + 7) / 8), 256, 0, st>>>(S, T1p, text_lengths, T1, T2, m2, alpha);
+  CUDA_TRY(cudaGetLastError());
+  c->launches++;
+  return EFTS_OK;
+}
+
+int efts_imv_generator(const float* alpha, const float* p, const int32_t* text_lengths, const int32_t* speech_lengths,
+                       int32_t B, int32_t T1, int32_t T2, float* imv, void* workspace, size_t workspace_bytes,
+                       void* stream) {
+  if (!alpha || !p || !text_lengths || !speech_lengths || !imv || !workspace || B < 1 || T1 < 1 || T2 < 1 || B > 65535)
+    return fail(EFTS_ERR_ARG, "efts_imv_generator: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Arena a(workspace, workspace_bytes);
+  float* raw = a.get<float>(static_cast<size_t>(B) * T2);
+  if (!a.ok) return fail(EFTS_ERR_WORKSPACE, "workspace too small: need %zu, have %zu", a.off, workspace_bytes);
+  alpha_expectation_kernel<<<dim3((T2 + 127) / 128, B), 128, 0, st>>>(alpha, p, T1, T2, raw);
+  CUDA_TRY(cudaGetLastError());
+  imv_scan_kernel<<<(B + 3) / 4, 128, 0, st>>>(raw, nullptr, 0, text_lengths, speech_lengths, B, T2, imv);
+  CUDA_TRY(cudaGetLastError());
+  return EFTS_OK;
+}
+
+int efts_aligned_positions(const float* imv, const float* p, const int32_t* text_lengths, const int32_t* speech_lengths,
+                           int32_t B, int32_t T1, int32_t T2, float sigma_e, float* e, void* stream) {
+  if (!imv || !text_lengths || !speech_lengths || !e || B < 1 || T1 < 1 || T2 < 1 || B > 65535)
+    return fail(EFTS_ERR_ARG, "efts_aligned_positions: bad argument");
+  aligned_positions_kernel<<<dim3((T1 + 7) / 8, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      imv, text_lengths, speech_lengths, T1, T2, sigma_e, e, p);
+  CUDA_TRY(cudaGetLastError());
+  return EFTS_OK;
+}
+
+int efts_reconstruct_alignment(const float* e, const int32_t* text_lengths, const int32_t* speech_lengths, int32_t B,
+                               int32_t T1, int32_t T2, float delta, float* reconst_alpha, void* stream) {
+  if (!e || !reconst_alpha || B < 1 || T1 < 1 || T2 < 1 || B > 65535)
+    return fail(EFTS_ERR_ARG, "efts_reconstruct_alignment: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int T1p = round8(T1);
+  const float neg_sigma = -1.0f * delta;
+  const size_t smem = (static_cast<size_t>(T1p) * (RT_FRAMES + 1) + T1) * sizeof(float);
+  if (T1 <= 32 * RT_KMAX && smem <= kReconstructSmemMax) {
+    CUDA_TRY(cudaFuncSetAttribute(reconstruct_alignment_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(kReconstructSmemMax)));
+    reconstruct_alignment_tiled_kernel<<<dim3((T2 + RT_FRAMES - 1) / RT_FRAMES, B), 256, smem, st>>>(
+        e, text_lengths, speech_lengths, T1, T2, T1p, neg_sigma, reconst_alpha, nullptr, nullptr);
+  } else {
+    reconstruct_alignment_kernel<<<dim3((T2 + 127) / 128, B), 128, T1 * sizeof(float), st>>>(
+        e, text_lengths, speech_lengths, T1, T2, T1p, neg_sigma, reconst_alpha, nullptr, nullptr);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return EFTS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 int efts_length_regulator_plan(int64_t* ds, const int64_t* ilens, float alpha, int32_t B, int32_t T1,
                                int64_t* ds_eff, int64_t* out_lens, int64_t* plan, void* stream) {
   if (!ds || !ilens || !ds_eff || !out_lens || !plan || B < 1 || T1 < 1)

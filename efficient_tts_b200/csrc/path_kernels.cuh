@@ -248,7 +248,7 @@ __global__ void imv_scan_kernel(const float* __restrict__ imv_raw, const float4*
 // e[b,i] = sum_t softmax_t(-(imv[t]-i)^2 * sigma_e over valid frames) * t.  One warp per (b, i).
 __global__ void aligned_positions_kernel(const float* __restrict__ imv, const int* __restrict__ tl,
                                          const int* __restrict__ sl, int T1, int T2, float sigma_e,
-                                         float* __restrict__ e) {
+                                         float* __restrict__ e, const float* __restrict__ pvec = nullptr) {
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.y;
   const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -259,7 +259,7 @@ __global__ void aligned_positions_kernel(const float* __restrict__ imv, const in
   }
   const float* x = imv + static_cast<size_t>(b) * T2;
   const int L2 = sl[b];
-  const float p = static_cast<float>(i);
+  const float p = pvec != nullptr ? pvec[static_cast<size_t>(b) * T1 + i] : static_cast<float>(i);
   float m = -CUDART_INF_F;
   for (int t = lane; t < L2; t += 32) {
     const float d = __fsub_rn(x[t], p);
@@ -326,8 +326,10 @@ __global__ void reconstruct_alignment_kernel(const float* __restrict__ e, const 
       h[j] = __float2half_rn(r);
       l[j] = __float2half_rn((r - __half2float(h[j])) * kSplitScale);
     }
-    *reinterpret_cast<uint4*>(ph + i0) = *reinterpret_cast<const uint4*>(h);
-    *reinterpret_cast<uint4*>(pl + i0) = *reinterpret_cast<const uint4*>(l);
+    if (p_hi != nullptr) {
+      *reinterpret_cast<uint4*>(ph + i0) = *reinterpret_cast<const uint4*>(h);
+      *reinterpret_cast<uint4*>(pl + i0) = *reinterpret_cast<const uint4*>(l);
+    }
   }
 }
 
@@ -401,7 +403,7 @@ reconstruct_alignment_tiled_kernel(const float* __restrict__ e, const int* __res
   __syncthreads();
   for (int i = warp; i < T1; i += 8)
     for (int tt = lane; tt < nt; tt += 32) Rb[static_cast<size_t>(i) * T2 + tt] = tile[i * (RT_FRAMES + 1) + tt];
-  const int nlive = min(nt, L2 - t0);
+  const int nlive = p_hi != nullptr ? min(nt, L2 - t0) : 0;
   for (int tt = warp; tt < nlive; tt += 8) {
     const size_t o = (static_cast<size_t>(b) * T2 + t0 + tt) * ldp;
     for (int i2 = lane; 2 * i2 < ldp; i2 += 32) {
@@ -414,6 +416,62 @@ reconstruct_alignment_tiled_kernel(const float* __restrict__ e, const int* __res
       *reinterpret_cast<__half2*>(p_lo + o + 2 * i2) = __halves2half2(al, cl);
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stand-alone forms of the reference's helper methods (models/efficient_tts.py:287-398); forward() itself
+// uses the fused kernels above.
+
+// bool prefix mask [B, T] -> int32 lengths (the reference only builds masks with make_non_pad_mask).
+__global__ void mask_lengths_kernel(const uint8_t* __restrict__ mask, int B, int T, int* __restrict__ lens) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  int n = 0;
+  for (int t = lane; t < T; t += 32) n += mask[static_cast<size_t>(b) * T + t] != 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+  if (lane == 0) lens[b] = n;
+}
+
+// generate_index_vector (:287-297): p[b, i] = i on valid tokens, 0 on padding.
+__global__ void index_vector_kernel(const int* __restrict__ tl, int B, int T1, float* __restrict__ p) {
+  const size_t k = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (k >= static_cast<size_t>(B) * T1) return;
+  const int b = static_cast<int>(k / T1), i = static_cast<int>(k % T1);
+  p[k] = i < tl[b] ? static_cast<float>(i) : 0.0f;
+}
+
+// scaled_dot_product_attention tail (:392-398): softmax over valid tokens of the (already scaled) scores
+// S[B*T2, ldS], zero on padding, written transposed as alpha[B, T1, T2].  One warp per (b, t).
+__global__ void attention_alpha_kernel(const float* __restrict__ S, int ldS, const int* __restrict__ tl, int T1,
+                                       int T2, size_t rows, float* __restrict__ alpha) {
+  const int lane = threadIdx.x & 31;
+  const size_t row = blockIdx.x * static_cast<size_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int b = static_cast<int>(row / T2), t = static_cast<int>(row % T2);
+  const int L = tl[b];
+  const float* s = S + row * ldS;
+  float m = -CUDART_INF_F;
+  for (int i = lane; i < L; i += 32) m = fmaxf(m, s[i]);
+  m = warp_max(m);
+  float den = 0.0f;
+  for (int i = lane; i < L; i += 32) den += expf(s[i] - m);
+  den = warp_sum(den);
+  float* a = alpha + static_cast<size_t>(b) * T1 * T2 + t;
+  for (int i = lane; i < T1; i += 32) a[static_cast<size_t>(i) * T2] = i < L ? __fdiv_rn(expf(s[i] - m), den) : 0.0f;
+}
+
+// imv_generator head (:312): imv'[b, t] = sum_i alpha[b, i, t] * p[b, i].  One thread per (b, t).
+__global__ void alpha_expectation_kernel(const float* __restrict__ alpha, const float* __restrict__ p, int T1,
+                                         int T2, float* __restrict__ out) {
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T2) return;
+  const float* a = alpha + static_cast<size_t>(b) * T1 * T2 + t;
+  float acc = 0.0f;
+  for (int i = 0; i < T1; ++i) acc = fmaf(a[static_cast<size_t>(i) * T2], p[static_cast<size_t>(b) * T1 + i], acc);
+  out[static_cast<size_t>(b) * T2 + t] = acc;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -270,6 +270,17 @@ class Engine:
                                               self._stream()))
         return out
 
+    def attention_alpha(self, query, key, text_lengths_i32):
+        query, key = self._f32(query, "query"), self._f32(key, "key")
+        B, T2, C = query.shape
+        T1 = key.shape[1]
+        with torch.cuda.device(self.device):
+            alpha = torch.empty(B, T1, T2, dtype=torch.float32, device=self.device)
+            ws, n = self.workspace_for(B, T1, T2)
+            _lib.check(self.lib.efts_attention_alpha(self._h, _ptr(query), _ptr(key), _ptr(text_lengths_i32), B, T1, T2,
+                                                     _ptr(alpha), _ptr(ws), n, self._stream()))
+        return alpha
+
     def alignment(self, mel_h, key, value, text_lengths, speech_lengths):
         mel_h, key, value = self._f32(mel_h, "mel_h"), self._f32(key, "key"), self._f32(value, "value")
         B, T2, C = mel_h.shape
@@ -286,6 +297,73 @@ class Engine:
                                                    _ptr(sl), B, T1, T2, _ptr(imv), _ptr(e), _ptr(ra), _ptr(ex),
                                                    _ptr(ws), n, self._stream()))
         return imv, e, ra, ex
+
+
+def _stream_of(dev):
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def mask_lengths(mask):
+    """bool prefix mask [B, T] (make_non_pad_mask output) -> int32 lengths [B], on the device."""
+    lib = _lib.load()
+    if mask.device.type != "cuda":
+        raise RuntimeError("efts_b200 helpers run on CUDA tensors only")
+    m = mask.to(torch.uint8).contiguous() if mask.dtype != torch.bool else mask.contiguous().view(torch.uint8)
+    B, T = m.shape
+    with torch.cuda.device(mask.device):
+        out = torch.empty(B, dtype=torch.int32, device=mask.device)
+        _lib.check(lib.efts_mask_lengths(_ptr(m), B, T, _ptr(out), _stream_of(mask.device)))
+    return out
+
+
+def index_vector(text_lengths_i32, T1):
+    lib = _lib.load()
+    dev = text_lengths_i32.device
+    B = text_lengths_i32.numel()
+    with torch.cuda.device(dev):
+        p = torch.empty(B, T1, dtype=torch.float32, device=dev)
+        _lib.check(lib.efts_index_vector(_ptr(text_lengths_i32), B, T1, _ptr(p), _stream_of(dev)))
+    return p
+
+
+def imv_generator(alpha, p, text_lengths_i32, speech_lengths_i32):
+    lib = _lib.load()
+    dev = alpha.device
+    alpha = alpha.to(torch.float32).contiguous()
+    p = p.to(torch.float32).contiguous()
+    B, T1, T2 = alpha.shape
+    with torch.cuda.device(dev):
+        imv = torch.empty(B, T2, dtype=torch.float32, device=dev)
+        ws = torch.empty(B * T2 * 4 + 1024, dtype=torch.uint8, device=dev)
+        _lib.check(lib.efts_imv_generator(_ptr(alpha), _ptr(p), _ptr(text_lengths_i32), _ptr(speech_lengths_i32), B, T1,
+                                          T2, _ptr(imv), _ptr(ws), ws.numel(), _stream_of(dev)))
+    return imv
+
+
+def aligned_positions(imv, p, text_lengths_i32, speech_lengths_i32, sigma_e):
+    lib = _lib.load()
+    dev = imv.device
+    imv = imv.to(torch.float32).contiguous()
+    p = p.to(torch.float32).contiguous()
+    B, T2 = imv.shape
+    T1 = p.shape[1]
+    with torch.cuda.device(dev):
+        e = torch.empty(B, T1, dtype=torch.float32, device=dev)
+        _lib.check(lib.efts_aligned_positions(_ptr(imv), _ptr(p), _ptr(text_lengths_i32), _ptr(speech_lengths_i32), B, T1,
+                                              T2, float(sigma_e), _ptr(e), _stream_of(dev)))
+    return e
+
+
+def reconstruct_alignment(e, delta, text_lengths_i32, speech_lengths_i32, T2):
+    lib = _lib.load()
+    dev = e.device
+    e = e.to(torch.float32).contiguous()
+    B, T1 = e.shape
+    with torch.cuda.device(dev):
+        out = torch.empty(B, T1, int(T2), dtype=torch.float32, device=dev)
+        _lib.check(lib.efts_reconstruct_alignment(_ptr(e), _ptr(text_lengths_i32), _ptr(speech_lengths_i32), B, T1,
+                                                  int(T2), float(delta), _ptr(out), _stream_of(dev)))
+    return out
 
 
 def length_regulator(xs, ds, ilens, alpha=1.0, pad_value=0.0, return_index=False):

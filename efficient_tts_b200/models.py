@@ -119,6 +119,38 @@ class EfficientTTSCNN(_EngineOwner):
         self._require_eval()
         return self._get_engine().inference_batch(text, text_lengths)
 
+    # ------------------------------------------------------------------ the reference's helper methods
+    # (models/efficient_tts.py:287-398).  forward() runs fused kernels; these stand-alone forms keep the
+    # public method surface.  Masks are the prefix masks make_non_pad_mask builds; they travel as lengths.
+    def generate_index_vector(self, text_mask):
+        from . import engine as E
+        return E.index_vector(E.mask_lengths(text_mask), text_mask.shape[1])
+
+    def imv_generator(self, alpha, p, mel_mask, text_length):
+        from . import engine as E
+        return E.imv_generator(alpha, p, text_length.to(alpha.device, torch.int32).contiguous(), E.mask_lengths(mel_mask))
+
+    def get_aligned_positions(self, imv, p, mel_mask, text_mask, sigma=0.5):
+        from . import engine as E
+        return E.aligned_positions(imv, p, E.mask_lengths(text_mask), E.mask_lengths(mel_mask), sigma)
+
+    def reconstruct_align_from_aligned_position(self, e, delta=0.1, mel_mask=None, text_mask=None, trim_e=False):
+        from . import engine as E
+        if trim_e:
+            raise NotImplementedError("trim_e is only reachable with delta_e_method_1=False (outside the B200 path)")
+        if mel_mask is None:
+            max_length = int(torch.round(e[:, -1]).squeeze().item())       # the reference's .item(), :361
+            sl = None
+        else:
+            max_length = mel_mask.size(-1)
+            sl = E.mask_lengths(mel_mask)
+        tl = E.mask_lengths(text_mask) if text_mask is not None else None
+        return E.reconstruct_alignment(e, delta, tl, sl, max_length)
+
+    def scaled_dot_product_attention(self, query, key, key_mask):
+        from . import engine as E
+        return self._get_engine().attention_alpha(query, key, E.mask_lengths(key_mask))
+
     def remove_weight_norm(self):
         for m in (self.text_encoder, self.mel_encoder, self.decoder):
             m.remove_weight_norm()

@@ -162,6 +162,30 @@ int efts_alignment_fwd(efts_ctx* ctx, const float* mel_h, const float* key, cons
                        int32_t T1, int32_t T2, float* imv, float* e, float* reconst_alpha,
                        float* expanded, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- stand-alone helper methods of EfficientTTSCNN (models/efficient_tts.py:287-398) ----
+ * The reference exposes the stages of its alignment block as public methods taking bool masks; masks
+ * built by make_non_pad_mask are prefix masks, which travel here as int32 lengths (efts_mask_lengths
+ * converts a bool [B,T] mask).  forward() uses fused kernels; these are for callers of the methods. */
+int efts_mask_lengths(const uint8_t* mask, int32_t B, int32_t T, int32_t* lengths, void* stream);
+/* generate_index_vector (:287-297): p fp32 [B,T1]. */
+int efts_index_vector(const int32_t* text_lengths, int32_t B, int32_t T1, float* p, void* stream);
+/* scaled_dot_product_attention (:377-398): query [B,T2,C], key [B,T1,C] -> alpha fp32 [B,T1,T2]. */
+int efts_attention_alpha(efts_ctx* ctx, const float* query, const float* key, const int32_t* text_lengths,
+                         int32_t B, int32_t T1, int32_t T2, float* alpha, void* workspace,
+                         size_t workspace_bytes, void* stream);
+/* imv_generator (:299-324): alpha [B,T1,T2], p [B,T1] -> imv [B,T2]. */
+int efts_imv_generator(const float* alpha, const float* p, const int32_t* text_lengths,
+                       const int32_t* speech_lengths, int32_t B, int32_t T1, int32_t T2, float* imv,
+                       void* workspace, size_t workspace_bytes, void* stream);
+/* get_aligned_positions (:326-345): imv [B,T2], p [B,T1] (NULL = index vector) -> e [B,T1]. */
+int efts_aligned_positions(const float* imv, const float* p, const int32_t* text_lengths,
+                           const int32_t* speech_lengths, int32_t B, int32_t T1, int32_t T2, float sigma_e,
+                           float* e, void* stream);
+/* reconstruct_align_from_aligned_position (:347-375): e [B,T1] -> fp32 [B,T1,T2]; NULL lengths = no mask. */
+int efts_reconstruct_alignment(const float* e, const int32_t* text_lengths, const int32_t* speech_lengths,
+                               int32_t B, int32_t T1, int32_t T2, float delta, float* reconst_alpha,
+                               void* stream);
+
 /* ---- introspection ---- */
 /* Options: "amode" (A-operand staging of the tap-GEMM: 0 one TMA box per tap, 1 one shifted box
  * per k-block), "skip_pad_tiles" (0/1).  Returns EFTS_ERR_ARG for an unknown name. */

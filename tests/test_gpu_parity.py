@@ -378,6 +378,41 @@ def test_inference_c1_shape_matches_oracle(dev):
         m.inference(torch.zeros(2, 5, dtype=torch.long, device=dev))
 
 
+def test_helper_methods_match_oracle(model, dev):
+    """The reference's public stage methods (models/efficient_tts.py:287-398) called one by one."""
+    w = orc.make_weights(seed=1234)
+    text, tl, speech, sl = make_forward_inputs(51, [30, 18, 7], [190, 120, 45])
+    with torch.no_grad():
+        _, inter = orc.forward(w, text, tl, speech, sl, return_intermediates=True)
+        text_mask, mel_mask = orc.non_pad_mask(tl), orc.non_pad_mask(sl)
+        p_r = orc.index_vector(text_mask)
+        alpha_r = orc.attention_alpha(inter["mel_h"], inter["key"], text_mask)
+        alpha_r = alpha_r.masked_fill(~(text_mask.unsqueeze(-1) & mel_mask.unsqueeze(1)), 0.0)
+        imv_r = orc.imv_from_alpha(alpha_r, p_r, mel_mask, tl)
+        e_r = orc.aligned_positions(imv_r, p_r, mel_mask, text_mask, 0.5)
+        ra_r = orc.reconstruct_alignment(e_r, 0.01, mel_mask, text_mask)
+    tmd, mmd = text_mask.to(dev), mel_mask.to(dev)
+    p = model.generate_index_vector(tmd)
+    assert torch.equal(p.cpu(), p_r)
+    alpha = model.scaled_dot_product_attention(inter["mel_h"].to(dev), inter["key"].to(dev), tmd)
+    assert alpha.shape == alpha_r.shape
+    live = mel_mask.unsqueeze(1).expand_as(alpha_r)
+    assert (alpha.cpu() - orc.attention_alpha(inter["mel_h"], inter["key"], text_mask))[live].abs().max().item() <= 1e-5
+    imv = model.imv_generator(alpha_r.to(dev), p, mmd, tl.to(dev))
+    assert (imv.cpu() - imv_r).abs().max().item() <= 1e-4
+    e = model.get_aligned_positions(imv_r.to(dev), p, mmd, tmd, sigma=0.5)
+    assert (e.cpu() - e_r).abs().max().item() <= 2e-3        # e spans [0, T2): fp32 noise of a 190-term expectation
+    ra = model.reconstruct_align_from_aligned_position(e_r.to(dev), delta=0.01, mel_mask=mmd, text_mask=tmd)
+    ra_ref = ra_r.masked_fill(~(text_mask.unsqueeze(-1) & mel_mask.unsqueeze(1)), 0.0)
+    assert (ra.cpu() - ra_ref).abs().max().item() <= 1e-5
+    # inference form: no masks, T2 = round(e[:, -1])
+    e1 = torch.cumsum(torch.full((1, 9), 4.3), dim=1)
+    with torch.no_grad():
+        r1 = orc.reconstruct_alignment(e1, 0.01)
+    g1 = model.reconstruct_align_from_aligned_position(e1.to(dev), delta=0.01)
+    assert g1.shape == r1.shape and (g1.cpu() - r1).abs().max().item() <= 1e-5
+
+
 def test_batched_inference_equals_per_utterance_inference(dev):
     """ragged batched synthesis.  Row b of the batch must be what the reference-shaped
     B = 1 call returns for that utterance alone (bitwise on this path, <= 1e-4 vs the oracle)."""
