@@ -91,6 +91,10 @@ struct efts_ctx {
   int skip_pad_tiles = 1;
   int gemm_version = 2;      // 1: gemm_sm100.cuh, 2: gemm2_sm100.cuh (persistent, flushed accumulator)
   int pair = 1;              // v2: CTA pairs (cta_group::2) for the weight GEMMs
+  int fp32_master = 1;       // 1: conv stacks keep an fp32 copy of every activation for the residual (always with the
+                             // v1 kernel).  0 takes the residual from the fp16 operand planes instead: half the HBM
+                             // traffic and +2.5 % speed, but a 22-bit residual stream pushes mel to 1.1e-4 at C3 --
+                             // outside the budget, so it is an experiment switch only.
   int cur_tag = 15;          // ProfTag of the launch being issued (diagnostics)
   int debug_mask = 0;        // timing experiments only
   int chunk_kb = 2;          // v2: k-blocks per main-accumulator flush (1 = most accurate, 0 = never)
@@ -414,8 +418,16 @@ int run_conv_stack(efts_ctx* c, cudaStream_t st, const PackedW* layers, int n, i
     p.pad = (layers[l].Z - 1) / 2;
     p.act = ACT_LRELU;
     p.bias = layers[l].bias;
-    p.resid = (l == 0 && first_resid != nullptr) ? first_resid : f[cur];
-    p.out = (l == n - 1 && final_f != nullptr) ? final_f : f[nxt];
+    // the residual is x itself: either its fp32 copy, or (v2 default) the operand planes the MMAs read, in
+    // which case no fp32 activations are stored between layers at all
+    const bool planes_only = c->gemm_version == 2 && !c->fp32_master;
+    if (planes_only) {
+      p.resid_hi = hi[cur]; p.resid_lo = lo[cur]; p.ld_res = C;
+      p.out = (l == n - 1 && final_f != nullptr) ? final_f : nullptr;
+    } else {
+      p.resid = (l == 0 && first_resid != nullptr) ? first_resid : f[cur];
+      p.out = (l == n - 1 && final_f != nullptr) ? final_f : f[nxt];
+    }
     p.ld_out = C;
     p.out_hi = hi[nxt]; p.out_lo = lo[nxt]; p.ld_pl = C;
     if (skip != nullptr && c->skip_pad_tiles) {
@@ -707,6 +719,7 @@ int efts_set_option(efts_ctx* c, const char* name, int32_t value) {
   }
   if (strcmp(name, "pair") == 0) { c->pair = value != 0; return EFTS_OK; }
   if (strcmp(name, "debug_mask") == 0) { c->debug_mask = value; return EFTS_OK; }
+  if (strcmp(name, "fp32_master") == 0) { c->fp32_master = value != 0; return EFTS_OK; }
   if (strcmp(name, "chunk_kb") == 0) {
     if (value < 0 || value > 64) return fail(EFTS_ERR_ARG, "chunk_kb out of range");
     c->chunk_kb = value;
@@ -816,7 +829,7 @@ int efts_forward(efts_ctx* c, const int64_t* text, const int64_t* text_lengths, 
   {
     GemmParams p = gemm_defaults();
     p.N = C; p.bias = c->prenet.bias; p.act = ACT_LRELU;
-    p.out = w.xm_f[0]; p.ld_out = C;
+    p.out = (c->gemm_version == 2 && !c->fp32_master) ? nullptr : w.xm_f[0]; p.ld_out = C;
     p.out_hi = w.xm_hi[0]; p.out_lo = w.xm_lo[0]; p.ld_pl = C;
     if (c->skip_pad_tiles) {
       p.skip_lens = skip_m.lens; p.tile_list = skip_m.list; p.tile_count = skip_m.count;
@@ -832,7 +845,8 @@ int efts_forward(efts_ctx* c, const int64_t* text, const int64_t* text_lengths, 
               w.imv_raw, imv, w.e));
   // 5. Gaussian reconstruction + expansion (:184-194) into mel buffer set 0
   TRY(run_reconstruct_expand(c, st, w.e, w.tl32, &skip_m, B, T1, T2, w.T1p, w.R_hi, w.R_lo, w.valT_hi, w.valT_lo,
-                             reconst_alpha, w.xm_f[0], w.xm_hi[0], w.xm_lo[0]));
+                             reconst_alpha, (c->gemm_version == 2 && !c->fp32_master) ? nullptr : w.xm_f[0], w.xm_hi[0],
+                             w.xm_lo[0]));
   // 6. decoder (:197) and mel head (:198-200)
   curm = 0;
   TRY(run_conv_stack(c, st, c->dec, g.n_decoder_layer, B, T2, w.xm_f, w.xm_hi, w.xm_lo, nullptr, nullptr, &skip_m,
@@ -912,7 +926,8 @@ int efts_inference_phase2(efts_ctx* c, int32_t T1, int32_t T2, float* mel_pred, 
   carve_mel(a, w, 1, T2, C, g.odim, false);
   if (!a.ok) return fail(EFTS_ERR_WORKSPACE, "workspace too small: need %zu, have %zu", a.off, workspace_bytes);
   TRY(run_reconstruct_expand(c, st, w.e, nullptr, nullptr, 1, T1, T2, w.T1p, w.R_hi, w.R_lo, w.valT_hi, w.valT_lo,
-                             reconst_alpha, w.xm_f[0], w.xm_hi[0], w.xm_lo[0]));
+                             reconst_alpha, (c->gemm_version == 2 && !c->fp32_master) ? nullptr : w.xm_f[0], w.xm_hi[0],
+                             w.xm_lo[0]));
   int curm = 0;
   TRY(run_conv_stack(c, st, c->dec, g.n_decoder_layer, 1, T2, w.xm_f, w.xm_hi, w.xm_lo, nullptr, nullptr, nullptr,
                      &curm, TAG_DEC_CONV));
@@ -993,7 +1008,8 @@ int efts_inference_batch_phase2(efts_ctx* c, int32_t B, int32_t T1, int32_t T2ma
   c->launches++;
   const Skip skip_m{t2, w.list_m, w.cnt_m};
   TRY(run_reconstruct_expand(c, st, w.e, w.tl32, &skip_m, B, T1, T2max, w.T1p, w.R_hi, w.R_lo, w.valT_hi,
-                             w.valT_lo, reconst_alpha, w.xm_f[0], w.xm_hi[0], w.xm_lo[0]));
+                             w.valT_lo, reconst_alpha, (c->gemm_version == 2 && !c->fp32_master) ? nullptr : w.xm_f[0], w.xm_hi[0],
+                             w.xm_lo[0]));
   int curm = 0;
   TRY(run_conv_stack(c, st, c->dec, g.n_decoder_layer, B, T2max, w.xm_f, w.xm_hi, w.xm_lo, nullptr, nullptr,
                      &skip_m, &curm, TAG_DEC_CONV, true));

@@ -357,29 +357,43 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
           sum[j] = __fdiv_rn(sum[j], p.divisor);
           if (n0 + j < L) mx = fmaxf(mx, sum[j]);
         }
-        float den = 0.0f, num = 0.0f;
+        // 128 sequential fp32 additions would cost ~1e-4 of absolute error on the position expectation (values up
+        // to T1); the two running sums are kept in double and rounded once
+        double den = 0.0, num = 0.0;
 #pragma unroll
         for (int j = 0; j < G2_BN; ++j) {
           if (n0 + j < L) {
-            const float ev = expf(sum[j] - mx);
+            const double ev = static_cast<double>(expf(sum[j] - mx));
             den += ev;
-            num = fmaf(ev, static_cast<float>(n0 + j), num);
+            num = fma(ev, static_cast<double>(n0 + j), num);
           }
         }
-        p.softmax_part[m * n_nt + n0 / G2_BN] = make_float4(mx, den, num, 0.0f);
+        p.softmax_part[m * n_nt + n0 / G2_BN] = make_float4(mx, static_cast<float>(den), static_cast<float>(num), 0.0f);
         continue;
       }
       // residual rows are prefetched two 8-column groups ahead: the stores in between may alias for all
       // the compiler knows, so without this every group would wait a full memory round trip
+      // The residual comes either from an fp32 tensor or from the input's own operand planes
+      // (x = hi + lo * 2^-11: what the MMAs consumed, so no fp32 copy of the activations has to exist).
+      const bool res_planes = p.resid == nullptr && p.resid_hi != nullptr;
+      const bool has_resid = p.resid != nullptr || res_planes;
       const float* rp = p.resid != nullptr ? p.resid + m * p.ld_out + n0 : nullptr;
+      const __half* rh = res_planes ? p.resid_hi + m * p.ld_res + n0 : nullptr;
+      const __half* rl = res_planes ? p.resid_lo + m * p.ld_res + n0 : nullptr;
+      auto load_resid = [&](int grp8, float4& a, float4& b) {
+        if (res_planes) {
+          a = *reinterpret_cast<const float4*>(rh + grp8 * 8);     // 8 hi halves
+          b = *reinterpret_cast<const float4*>(rl + grp8 * 8);     // 8 lo halves
+        } else {
+          a = *reinterpret_cast<const float4*>(rp + grp8 * 8);
+          b = *reinterpret_cast<const float4*>(rp + grp8 * 8 + 4);
+        }
+      };
       float4 rx[2][2];
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
         rx[k][0] = rx[k][1] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        if (rp != nullptr && n0 + k * 8 < p.N) {
-          rx[k][0] = *reinterpret_cast<const float4*>(rp + k * 8);
-          rx[k][1] = *reinterpret_cast<const float4*>(rp + k * 8 + 4);
-        }
+        if (has_resid && n0 + k * 8 < p.N) load_resid(k, rx[k][0], rx[k][1]);
       }
 #pragma unroll
       for (int c8 = 0; c8 < G2_BN / 8; ++c8) {
@@ -412,12 +426,23 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
 #pragma unroll
           for (int j = 0; j < 8; ++j) vv[j] = fmaxf(vv[j], 0.0f);
         }
-        if (p.resid != nullptr) {
-          const float4 x0 = rx[c8 & 1][0];
-          const float4 x1 = rx[c8 & 1][1];
-          if (n + 16 < p.N) {
-            rx[c8 & 1][0] = *reinterpret_cast<const float4*>(rp + c8 * 8 + 16);
-            rx[c8 & 1][1] = *reinterpret_cast<const float4*>(rp + c8 * 8 + 20);
+        if (has_resid) {
+          float4 x0 = rx[c8 & 1][0];
+          float4 x1 = rx[c8 & 1][1];
+          if (n + 16 < p.N) load_resid(c8 + 2, rx[c8 & 1][0], rx[c8 & 1][1]);
+          if (res_planes) {
+            const __half2* h2 = reinterpret_cast<const __half2*>(&x0);
+            const __half2* l2 = reinterpret_cast<const __half2*>(&x1);
+            float xr[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 hf = __half22float2(h2[j]);
+              const float2 lf = __half22float2(l2[j]);
+              xr[2 * j] = fmaf(lf.x, SPLIT_INV_SCALE, hf.x);
+              xr[2 * j + 1] = fmaf(lf.y, SPLIT_INV_SCALE, hf.y);
+            }
+            x0 = make_float4(xr[0], xr[1], xr[2], xr[3]);
+            x1 = make_float4(xr[4], xr[5], xr[6], xr[7]);
           }
           vv[0] = x0.x + vv[0]; vv[1] = x0.y + vv[1]; vv[2] = x0.z + vv[2]; vv[3] = x0.w + vv[3];
           vv[4] = x1.x + vv[4]; vv[5] = x1.y + vv[5]; vv[6] = x1.z + vv[6]; vv[7] = x1.w + vv[7];
@@ -434,9 +459,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
         if (p.out_hi != nullptr && !(p.debug_mask & 2)) {
           const float amax = fmaxf(fmaxf(fmaxf(fabsf(vv[0]), fabsf(vv[1])), fmaxf(fabsf(vv[2]), fabsf(vv[3]))),
                                    fmaxf(fmaxf(fabsf(vv[4]), fabsf(vv[5])), fmaxf(fabsf(vv[6]), fabsf(vv[7]))));
-          const float asum = ((fabsf(vv[0]) + fabsf(vv[1])) + (fabsf(vv[2]) + fabsf(vv[3]))) +
-                             ((fabsf(vv[4]) + fabsf(vv[5])) + (fabsf(vv[6]) + fabsf(vv[7])));   // NaN / inf propagate
-          if (row_checked && (amax > 65504.0f || !(asum < CUDART_INF_F)) && p.err_flag != nullptr)
+          // (a NaN can only follow an overflow, which is flagged where it first exceeds the range)
+          if (row_checked && amax > 65504.0f && p.err_flag != nullptr)
             atomicOr(p.err_flag, 8 | p.err_code);   // outside the fp16 operand range (or already non-finite)
           split_store8(p.out_hi + m * p.ld_pl + n, p.out_lo + m * p.ld_pl + n, vv);
         }

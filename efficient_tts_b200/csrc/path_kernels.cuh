@@ -208,14 +208,14 @@ __global__ void imv_scan_kernel(const float* __restrict__ imv_raw, const float4*
         const float4* pp = part + (static_cast<size_t>(b) * T2 + t) * n_part;
         float mx = -CUDART_INF_F;
         for (int k = 0; k < n_part; ++k) mx = fmaxf(mx, pp[k].x);
-        float den = 0.0f, num = 0.0f;
+        double den = 0.0, num = 0.0;
         for (int k = 0; k < n_part; ++k) {
           const float4 v = pp[k];
-          const float sc = expf(v.x - mx);
-          den = fmaf(v.y, sc, den);
-          num = fmaf(v.z, sc, num);
+          const double sc = static_cast<double>(expf(v.x - mx));
+          den = fma(static_cast<double>(v.y), sc, den);
+          num = fma(static_cast<double>(v.z), sc, num);
         }
-        r = __fdiv_rn(num, den);
+        r = static_cast<float>(num / den);
       }
     }
     float prev = __shfl_up_sync(0xffffffffu, r, 1);

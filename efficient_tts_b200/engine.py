@@ -161,6 +161,8 @@ class Engine:
             t2, flags = (int(v) for v in t2_dev.cpu())        # the reference's .item() sync (:361)
             if flags & 4:
                 raise IndexError("index out of range in self")   # embedding lookup, :246
+            if flags & 8:
+                raise FloatingPointError(RANGE_MESSAGE)
             if t2 < 1:
                 raise RuntimeError("predicted length T2=%d; the reference's decoder conv rejects an "
                                    "empty sequence" % t2)
