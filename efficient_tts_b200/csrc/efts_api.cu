@@ -91,10 +91,6 @@ struct efts_ctx {
   int skip_pad_tiles = 1;
   int gemm_version = 2;      // 1: gemm_sm100.cuh, 2: gemm2_sm100.cuh (persistent, flushed accumulator)
   int pair = 1;              // v2: CTA pairs (cta_group::2) for the weight GEMMs
-  int fp32_master = 1;       // 1: conv stacks keep an fp32 copy of every activation for the residual (always with the
-                             // v1 kernel).  0 takes the residual from the fp16 operand planes instead: half the HBM
-                             // traffic and +2.5 % speed, but a 22-bit residual stream pushes mel to 1.1e-4 at C3 --
-                             // outside the budget, so it is an experiment switch only.
   int cur_tag = 15;          // ProfTag of the launch being issued (diagnostics)
   int debug_mask = 0;        // timing experiments only
   int chunk_kb = 2;          // v2: k-blocks per main-accumulator flush (1 = most accurate, 0 = never)
@@ -179,10 +175,10 @@ int launch_gemm_t(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, cons
   return EFTS_OK;
 }
 
-template <int CG>
+template <int CG, int EPI>
 int launch_gemm2_t(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, const GemmParams& p) {
   using Cfg = G2Cfg<CG>;
-  auto kern = gemm2_kernel<CG>;
+  auto kern = gemm2_kernel<CG, EPI>;
   alignas(64) CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   TRY(make_map(c, &ma_hi, a.hi, a.K, a.T, a.B, a.ld, G2_A_ROWS));
   TRY(make_map(c, &ma_lo, a.lo, a.K, a.T, a.B, a.ld, G2_A_ROWS));
@@ -216,13 +212,18 @@ int launch_gemm(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, GemmPa
   if (p.N % 8 != 0) return fail(EFTS_ERR_ARG, "gemm N=%d must be a multiple of 8", p.N);
   if (c->gemm_version == 2) {
     if (p.ntaps > 9) return fail(EFTS_ERR_ARG, "at most 9 taps");
+    if (p.bias != nullptr && p.N > G2_BIAS_MAX) return fail(EFTS_ERR_ARG, "bias supports at most %d columns", G2_BIAS_MAX);
     p.chunk_kb = c->chunk_kb;
     p.debug_mask = c->debug_mask;
     p.err_flag = c->err_flag;
     p.err_code = 1 << (8 + c->cur_tag);
     if (!c->skip_pad_tiles) { p.tile_list = nullptr; p.tile_count = nullptr; p.skip_lens = nullptr; }
-    if (c->pair && !p.b_batched) return launch_gemm2_t<2>(c, st, a, b, p);
-    return launch_gemm2_t<1>(c, st, a, b, p);
+    const int epi = p.softmax_part != nullptr ? EPI_SOFTMAX
+                    : (p.divisor != 1.0f || p.outT_hi != nullptr) ? EPI_FULL : EPI_STD;
+    const bool pair = c->pair && !p.b_batched;
+    if (epi == EPI_STD) return pair ? launch_gemm2_t<2, EPI_STD>(c, st, a, b, p) : launch_gemm2_t<1, EPI_STD>(c, st, a, b, p);
+    if (epi == EPI_FULL) return pair ? launch_gemm2_t<2, EPI_FULL>(c, st, a, b, p) : launch_gemm2_t<1, EPI_FULL>(c, st, a, b, p);
+    return pair ? launch_gemm2_t<2, EPI_SOFTMAX>(c, st, a, b, p) : launch_gemm2_t<1, EPI_SOFTMAX>(c, st, a, b, p);
   }
   p.tile_list = nullptr; p.tile_count = nullptr;
   if (p.B > 65535 || (p.T + GEMM_BM - 1) / GEMM_BM > 65535) return fail(EFTS_ERR_ARG, "grid too large");
@@ -256,8 +257,11 @@ int set_kernel_attributes() {
   CUDA_TRY((opt_in_v1<64, 0>()));  CUDA_TRY((opt_in_v1<64, 1>()));  CUDA_TRY((opt_in_v1<64, 2>()));
   CUDA_TRY((opt_in_v1<128, 0>())); CUDA_TRY((opt_in_v1<128, 1>())); CUDA_TRY((opt_in_v1<128, 2>()));
   CUDA_TRY((opt_in_v1<256, 0>())); CUDA_TRY((opt_in_v1<256, 1>())); CUDA_TRY((opt_in_v1<256, 2>()));
-  CUDA_TRY(cudaFuncSetAttribute(gemm2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2Cfg<1>::SMEM_BYTES));
-  CUDA_TRY(cudaFuncSetAttribute(gemm2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2Cfg<2>::SMEM_BYTES));
+#define EFTS_OPT_IN_V2(CG_, EPI_) \
+  CUDA_TRY(cudaFuncSetAttribute(gemm2_kernel<CG_, EPI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2Cfg<CG_>::SMEM_BYTES))
+  EFTS_OPT_IN_V2(1, EPI_STD); EFTS_OPT_IN_V2(1, EPI_FULL); EFTS_OPT_IN_V2(1, EPI_SOFTMAX);
+  EFTS_OPT_IN_V2(2, EPI_STD); EFTS_OPT_IN_V2(2, EPI_FULL); EFTS_OPT_IN_V2(2, EPI_SOFTMAX);
+#undef EFTS_OPT_IN_V2
   CUDA_TRY(cudaFuncSetAttribute(reconstruct_alignment_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(kReconstructSmemMax)));
   return EFTS_OK;
@@ -418,16 +422,8 @@ int run_conv_stack(efts_ctx* c, cudaStream_t st, const PackedW* layers, int n, i
     p.pad = (layers[l].Z - 1) / 2;
     p.act = ACT_LRELU;
     p.bias = layers[l].bias;
-    // the residual is x itself: either its fp32 copy, or (v2 default) the operand planes the MMAs read, in
-    // which case no fp32 activations are stored between layers at all
-    const bool planes_only = c->gemm_version == 2 && !c->fp32_master;
-    if (planes_only) {
-      p.resid_hi = hi[cur]; p.resid_lo = lo[cur]; p.ld_res = C;
-      p.out = (l == n - 1 && final_f != nullptr) ? final_f : nullptr;
-    } else {
-      p.resid = (l == 0 && first_resid != nullptr) ? first_resid : f[cur];
-      p.out = (l == n - 1 && final_f != nullptr) ? final_f : f[nxt];
-    }
+    p.resid = (l == 0 && first_resid != nullptr) ? first_resid : f[cur];
+    p.out = (l == n - 1 && final_f != nullptr) ? final_f : f[nxt];
     p.ld_out = C;
     p.out_hi = hi[nxt]; p.out_lo = lo[nxt]; p.ld_pl = C;
     if (skip != nullptr && c->skip_pad_tiles) {
@@ -451,7 +447,7 @@ int run_conv_stack(efts_ctx* c, cudaStream_t st, const PackedW* layers, int n, i
 // Input operand planes in_hi/in_lo [B,T,C]; scratch dp_f, dp_hi/lo.
 int run_duration_predictor(efts_ctx* c, cudaStream_t st, const __half* in_hi, const __half* in_lo, int B,
                            int T, float* dp_f, __half* dp_hi, __half* dp_lo, const int* lens, int mode,
-                           void* out, bool mask_hidden = false) {
+                           void* out, bool mask_hidden = false, const Skip* skip = nullptr) {
   const int C = c->cfg.n_channels;
   const size_t rows = static_cast<size_t>(B) * T;
   const int nl = c->cfg.n_duration_layer;
@@ -466,6 +462,10 @@ int run_duration_predictor(efts_ctx* c, cudaStream_t st, const __half* in_hi, co
     p.act = ACT_RELU;
     p.bias = c->dp[l].bias;
     p.out = dp_f; p.ld_out = C;
+    if (skip != nullptr && c->skip_pad_tiles) {   // only rows that can reach a valid token's duration
+      p.skip_lens = skip->lens; p.tile_list = skip->list; p.tile_count = skip->count;
+      p.skip_halo = p.pad * (nl - 1 - l);
+    }
     TRY(launch_gemm(c, st, OpA{ahi, alo, B, T, C, C}, weight_op(c->dp[l]), p));
     const int wpb = 8;
     const unsigned grid = static_cast<unsigned>((rows + wpb - 1) / wpb);
@@ -719,7 +719,6 @@ int efts_set_option(efts_ctx* c, const char* name, int32_t value) {
   }
   if (strcmp(name, "pair") == 0) { c->pair = value != 0; return EFTS_OK; }
   if (strcmp(name, "debug_mask") == 0) { c->debug_mask = value; return EFTS_OK; }
-  if (strcmp(name, "fp32_master") == 0) { c->fp32_master = value != 0; return EFTS_OK; }
   if (strcmp(name, "chunk_kb") == 0) {
     if (value < 0 || value > 64) return fail(EFTS_ERR_ARG, "chunk_kb out of range");
     c->chunk_kb = value;
@@ -829,7 +828,7 @@ int efts_forward(efts_ctx* c, const int64_t* text, const int64_t* text_lengths, 
   {
     GemmParams p = gemm_defaults();
     p.N = C; p.bias = c->prenet.bias; p.act = ACT_LRELU;
-    p.out = (c->gemm_version == 2 && !c->fp32_master) ? nullptr : w.xm_f[0]; p.ld_out = C;
+    p.out = w.xm_f[0]; p.ld_out = C;
     p.out_hi = w.xm_hi[0]; p.out_lo = w.xm_lo[0]; p.ld_pl = C;
     if (c->skip_pad_tiles) {
       p.skip_lens = skip_m.lens; p.tile_list = skip_m.list; p.tile_count = skip_m.count;
@@ -845,8 +844,7 @@ int efts_forward(efts_ctx* c, const int64_t* text, const int64_t* text_lengths, 
               w.imv_raw, imv, w.e));
   // 5. Gaussian reconstruction + expansion (:184-194) into mel buffer set 0
   TRY(run_reconstruct_expand(c, st, w.e, w.tl32, &skip_m, B, T1, T2, w.T1p, w.R_hi, w.R_lo, w.valT_hi, w.valT_lo,
-                             reconst_alpha, (c->gemm_version == 2 && !c->fp32_master) ? nullptr : w.xm_f[0], w.xm_hi[0],
-                             w.xm_lo[0]));
+                             reconst_alpha, w.xm_f[0], w.xm_hi[0], w.xm_lo[0]));
   // 6. decoder (:197) and mel head (:198-200)
   curm = 0;
   TRY(run_conv_stack(c, st, c->dec, g.n_decoder_layer, B, T2, w.xm_f, w.xm_hi, w.xm_lo, nullptr, nullptr, &skip_m,
@@ -858,7 +856,8 @@ int efts_forward(efts_ctx* c, const int64_t* text, const int64_t* text_lengths, 
     { ProfScope ps(c, st, TAG_LINEAR); TRY(launch_gemm(c, st, OpA{w.xm_hi[curm], w.xm_lo[curm], B, T2, C, C}, weight_op(c->melout), p)); }
   }
   // 7. duration predictor on value (:219), log domain, zero at pad tokens
-  TRY(run_duration_predictor(c, st, w.val_hi, w.val_lo, B, T1, w.dp_f, w.dp_hi, w.dp_lo, w.tl32, 0, w.dur));
+  TRY(run_duration_predictor(c, st, w.val_hi, w.val_lo, B, T1, w.dp_f, w.dp_hi, w.dp_lo, w.tl32, 0, w.dur, false,
+                             &skip_t));
   // 8. losses (:220-227)
   ProfScope ps_loss(c, st, TAG_LOSS);
   loss_partial_kernel<<<c->sm_count * 4, 256, 0, st>>>(mel_pred, speech, w.sl32, T2, g.odim, w.dur, w.e, w.tl32,
@@ -926,8 +925,7 @@ int efts_inference_phase2(efts_ctx* c, int32_t T1, int32_t T2, float* mel_pred, 
   carve_mel(a, w, 1, T2, C, g.odim, false);
   if (!a.ok) return fail(EFTS_ERR_WORKSPACE, "workspace too small: need %zu, have %zu", a.off, workspace_bytes);
   TRY(run_reconstruct_expand(c, st, w.e, nullptr, nullptr, 1, T1, T2, w.T1p, w.R_hi, w.R_lo, w.valT_hi, w.valT_lo,
-                             reconst_alpha, (c->gemm_version == 2 && !c->fp32_master) ? nullptr : w.xm_f[0], w.xm_hi[0],
-                             w.xm_lo[0]));
+                             reconst_alpha, w.xm_f[0], w.xm_hi[0], w.xm_lo[0]));
   int curm = 0;
   TRY(run_conv_stack(c, st, c->dec, g.n_decoder_layer, 1, T2, w.xm_f, w.xm_hi, w.xm_lo, nullptr, nullptr, nullptr,
                      &curm, TAG_DEC_CONV));
@@ -1008,8 +1006,7 @@ int efts_inference_batch_phase2(efts_ctx* c, int32_t B, int32_t T1, int32_t T2ma
   c->launches++;
   const Skip skip_m{t2, w.list_m, w.cnt_m};
   TRY(run_reconstruct_expand(c, st, w.e, w.tl32, &skip_m, B, T1, T2max, w.T1p, w.R_hi, w.R_lo, w.valT_hi,
-                             w.valT_lo, reconst_alpha, (c->gemm_version == 2 && !c->fp32_master) ? nullptr : w.xm_f[0], w.xm_hi[0],
-                             w.xm_lo[0]));
+                             w.valT_lo, reconst_alpha, w.xm_f[0], w.xm_hi[0], w.xm_lo[0]));
   int curm = 0;
   TRY(run_conv_stack(c, st, c->dec, g.n_decoder_layer, B, T2max, w.xm_f, w.xm_hi, w.xm_lo, nullptr, nullptr,
                      &skip_m, &curm, TAG_DEC_CONV, true));

@@ -83,7 +83,12 @@ __global__ void build_tile_list_kernel(const int* __restrict__ lens, int B, int 
   if (threadIdx.x == 0) *count = carry_s;
 }
 
-template <int CG>
+// EPI selects how much epilogue is compiled in (the fully unrolled column loop makes every option cost
+// instruction-cache footprint in all launches): 0 = bias / activation / residual / fp32 + plane stores (conv and
+// Linear layers), 1 = also the divisor and the transposed plane store, 2 = token-softmax partials only.
+enum Gemm2Epi { EPI_STD = 0, EPI_FULL = 1, EPI_SOFTMAX = 2 };
+
+template <int CG, int EPI>
 __global__ void __launch_bounds__(G2_THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
              const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
@@ -127,8 +132,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
   if (warp == 1) {
     if (CG == 2) ptx::tmem_alloc_pair(tmem_slot, 512); else ptx::tmem_alloc(tmem_slot, 512);
   }
-  const bool bias_smem = p.bias != nullptr && p.N <= G2_BIAS_MAX;
-  if (bias_smem) {
+  if (p.bias != nullptr) {                         // launch_gemm guarantees N <= G2_BIAS_MAX when a bias is given
     for (int i = threadIdx.x; i < p.N; i += G2_THREADS)
       asm volatile("st.shared.f32 [%0], %1;" ::"r"(sBias + 4u * i), "f"(__ldg(p.bias + i)) : "memory");
   }
@@ -347,7 +351,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       }
       release(acc1_empty(tb));
       if (!row_ok) continue;
-      if (p.softmax_part != nullptr) {
+      if (EPI == EPI_SOFTMAX) {
         // scaled-dot-product softmax over tokens, one partial per column tile (models/efficient_tts.py:390-398):
         // the scores never leave the SM; imv_scan_kernel merges the partials into the position expectation.
         const int L = p.col_lens[b];
@@ -371,29 +375,21 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
         p.softmax_part[m * n_nt + n0 / G2_BN] = make_float4(mx, static_cast<float>(den), static_cast<float>(num), 0.0f);
         continue;
       }
+      if (EPI == EPI_SOFTMAX) continue;
       // residual rows are prefetched two 8-column groups ahead: the stores in between may alias for all
       // the compiler knows, so without this every group would wait a full memory round trip
-      // The residual comes either from an fp32 tensor or from the input's own operand planes
-      // (x = hi + lo * 2^-11: what the MMAs consumed, so no fp32 copy of the activations has to exist).
-      const bool res_planes = p.resid == nullptr && p.resid_hi != nullptr;
-      const bool has_resid = p.resid != nullptr || res_planes;
-      const float* rp = p.resid != nullptr ? p.resid + m * p.ld_out + n0 : nullptr;
-      const __half* rh = res_planes ? p.resid_hi + m * p.ld_res + n0 : nullptr;
-      const __half* rl = res_planes ? p.resid_lo + m * p.ld_res + n0 : nullptr;
-      auto load_resid = [&](int grp8, float4& a, float4& b) {
-        if (res_planes) {
-          a = *reinterpret_cast<const float4*>(rh + grp8 * 8);     // 8 hi halves
-          b = *reinterpret_cast<const float4*>(rl + grp8 * 8);     // 8 lo halves
-        } else {
-          a = *reinterpret_cast<const float4*>(rp + grp8 * 8);
-          b = *reinterpret_cast<const float4*>(rp + grp8 * 8 + 4);
-        }
-      };
+      // residual rows are prefetched two 8-column groups ahead: the stores in between may alias for all
+      // the compiler knows, so without this every group would wait a full memory round trip
+      const bool has_resid = p.resid != nullptr;
+      const float* rp = has_resid ? p.resid + m * p.ld_out + n0 : nullptr;
       float4 rx[2][2];
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
         rx[k][0] = rx[k][1] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        if (has_resid && n0 + k * 8 < p.N) load_resid(k, rx[k][0], rx[k][1]);
+        if (has_resid && n0 + k * 8 < p.N) {
+          rx[k][0] = *reinterpret_cast<const float4*>(rp + k * 8);
+          rx[k][1] = *reinterpret_cast<const float4*>(rp + k * 8 + 4);
+        }
       }
 #pragma unroll
       for (int c8 = 0; c8 < G2_BN / 8; ++c8) {
@@ -403,19 +399,14 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           vv[j] = sum[c8 * 8 + j];
-          if (p.divisor != 1.0f) vv[j] = __fdiv_rn(vv[j], p.divisor);
+          if (EPI == EPI_FULL && p.divisor != 1.0f) vv[j] = __fdiv_rn(vv[j], p.divisor);
         }
         if (p.bias != nullptr) {
           float4 b0, b1;
-          if (bias_smem) {
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b0.x), "=f"(b0.y), "=f"(b0.z), "=f"(b0.w)
-                         : "r"(sBias + 4u * n));
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b1.x), "=f"(b1.y), "=f"(b1.z), "=f"(b1.w)
-                         : "r"(sBias + 4u * n + 16u));
-          } else {
-            b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-            b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
-          }
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b0.x), "=f"(b0.y), "=f"(b0.z), "=f"(b0.w)
+                       : "r"(sBias + 4u * n));
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b1.x), "=f"(b1.y), "=f"(b1.z), "=f"(b1.w)
+                       : "r"(sBias + 4u * n + 16u));
           vv[0] += b0.x; vv[1] += b0.y; vv[2] += b0.z; vv[3] += b0.w;
           vv[4] += b1.x; vv[5] += b1.y; vv[6] += b1.z; vv[7] += b1.w;
         }
@@ -427,22 +418,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
           for (int j = 0; j < 8; ++j) vv[j] = fmaxf(vv[j], 0.0f);
         }
         if (has_resid) {
-          float4 x0 = rx[c8 & 1][0];
-          float4 x1 = rx[c8 & 1][1];
-          if (n + 16 < p.N) load_resid(c8 + 2, rx[c8 & 1][0], rx[c8 & 1][1]);
-          if (res_planes) {
-            const __half2* h2 = reinterpret_cast<const __half2*>(&x0);
-            const __half2* l2 = reinterpret_cast<const __half2*>(&x1);
-            float xr[8];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 hf = __half22float2(h2[j]);
-              const float2 lf = __half22float2(l2[j]);
-              xr[2 * j] = fmaf(lf.x, SPLIT_INV_SCALE, hf.x);
-              xr[2 * j + 1] = fmaf(lf.y, SPLIT_INV_SCALE, hf.y);
-            }
-            x0 = make_float4(xr[0], xr[1], xr[2], xr[3]);
-            x1 = make_float4(xr[4], xr[5], xr[6], xr[7]);
+          const float4 x0 = rx[c8 & 1][0];
+          const float4 x1 = rx[c8 & 1][1];
+          if (n + 16 < p.N) {
+            rx[c8 & 1][0] = *reinterpret_cast<const float4*>(rp + c8 * 8 + 16);
+            rx[c8 & 1][1] = *reinterpret_cast<const float4*>(rp + c8 * 8 + 20);
           }
           vv[0] = x0.x + vv[0]; vv[1] = x0.y + vv[1]; vv[2] = x0.z + vv[2]; vv[3] = x0.w + vv[3];
           vv[4] = x1.x + vv[4]; vv[5] = x1.y + vv[5]; vv[6] = x1.z + vv[6]; vv[7] = x1.w + vv[7];
@@ -464,7 +444,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
             atomicOr(p.err_flag, 8 | p.err_code);   // outside the fp16 operand range (or already non-finite)
           split_store8(p.out_hi + m * p.ld_pl + n, p.out_lo + m * p.ld_pl + n, vv);
         }
-        if (p.outT_hi != nullptr) {
+        if (EPI == EPI_FULL && p.outT_hi != nullptr) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const size_t o = (static_cast<size_t>(b) * p.N + (n + j)) * p.ld_t + t;

@@ -63,9 +63,6 @@ struct GemmParams {
   // (max, sum exp, sum exp * column, 0) over its columns n < col_lens[b] to softmax_part[(b*T + t) * n_tiles + tile]
   float4* softmax_part;
   const int* col_lens;
-  const __half* resid_hi; // alternative residual source: the operand planes of the input (x = hi + lo * 2^-11),
-  const __half* resid_lo; //   [B, T, ld_res]; used when `resid` is null (gemm2 only)
-  int ld_res;
   int err_code;          // extra bits OR-ed into err_flag with bit 3 (identifies the launch kind in diagnostics)
   int* err_flag;         // |= 8 when an activation leaves the fp16 operand range (|x| > 65504)
   int debug_mask;        // timing experiments only (results become wrong): 1 = no fp32 store, 2 = no plane stores
