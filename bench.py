@@ -292,7 +292,7 @@ def run_ours(args, rank, local_rank, world):
                                "frac": (recon_bytes / (rec_ms * 1e-3) / 1e9 / peaks["hbm"]) if rec_ms else None}}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32 (split-fp16 tensor-core operands, fp32 accumulate)",
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "dtype_note": "fp32 in/out; split-fp16 (hi/lo) tensor-core operands, fp32 accumulation",
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "utterances_per_gpu": B, "valid_frames_per_gpu": frames,
                            "padded": [T1p, T2p], "l2": "working set per step ~3.3 GB >> 126 MB L2 (no flush needed)",
@@ -322,6 +322,22 @@ def run_ours(args, rank, local_rank, world):
                                   "ms": dt * 1e3, "rtf_mel_only": dt / (mel.shape[1] * 256 / 22050.0),
                                   "frames_per_s": mel.shape[1] / dt,
                                   "note": "mel-only RTF; the reference's RTF also includes HiFi-GAN (bin/inference.py:100-111)"}
+            # batched variable-length synthesis: 64 utterances of 32-64 tokens in one call
+            g = torch.Generator().manual_seed(7)
+            lens = torch.randint(32, 65, (64,), generator=g)
+            btxt = torch.randint(0, wl.NUM_SYMBOLS, (64, 64), generator=g).to(dev)
+            for _ in range(2):
+                bmel, blen, _ = mc1.inference_batch(btxt, lens.to(dev))
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            n = 10
+            for _ in range(n):
+                bmel, blen, _ = mc1.inference_batch(btxt, lens.to(dev))
+            torch.cuda.synchronize(dev)
+            dt = (time.perf_counter() - t0) / n
+            line["inference_batch64"] = {"config": "inference_batch, 64 utterances x 32-64 tokens -> %d frames" % int(blen.sum()),
+                                         "ms": dt * 1e3, "frames_per_s": float(blen.sum()) / dt,
+                                         "rtf_mel_only": dt / (float(blen.sum()) * 256 / 22050.0)}
             del mc1
         except Exception as exc:  # the headline line must still print
             line["rtf_batch1"] = {"error": str(exc)[:200]}
