@@ -92,6 +92,7 @@ struct efts_ctx {
   int gemm_version = 2;      // 1: gemm_sm100.cuh, 2: gemm2_sm100.cuh (persistent, flushed accumulator)
   int pair = 1;              // v2: CTA pairs (cta_group::2) for the weight GEMMs
   int cur_tag = 15;          // ProfTag of the launch being issued (diagnostics)
+  int wide = 1;              // v2: short-reduction launches use the 16-epilogue-warp variant
   int debug_mask = 0;        // timing experiments only
   int chunk_kb = 2;          // v2: k-blocks per main-accumulator flush (1 = most accurate, 0 = never)
   int64_t launches = 0;
@@ -175,10 +176,10 @@ int launch_gemm_t(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, cons
   return EFTS_OK;
 }
 
-template <int CG, int EPI>
+template <int CG, int EPI, int WIDE>
 int launch_gemm2_t(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, const GemmParams& p) {
-  using Cfg = G2Cfg<CG>;
-  auto kern = gemm2_kernel<CG, EPI>;
+  using Cfg = G2Cfg<CG, WIDE>;
+  auto kern = gemm2_kernel<CG, EPI, WIDE>;
   alignas(64) CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   TRY(make_map(c, &ma_hi, a.hi, a.K, a.T, a.B, a.ld, G2_A_ROWS));
   TRY(make_map(c, &ma_lo, a.lo, a.K, a.T, a.B, a.ld, G2_A_ROWS));
@@ -191,7 +192,7 @@ int launch_gemm2_t(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, con
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(static_cast<unsigned>(ctas));
-  cfg.blockDim = dim3(G2_THREADS);
+  cfg.blockDim = dim3(WIDE ? G2_THREADS_WIDE : G2_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -221,9 +222,18 @@ int launch_gemm(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, GemmPa
     const int epi = p.softmax_part != nullptr ? EPI_SOFTMAX
                     : (p.divisor != 1.0f || p.outT_hi != nullptr) ? EPI_FULL : EPI_STD;
     const bool pair = c->pair && !p.b_batched;
-    if (epi == EPI_STD) return pair ? launch_gemm2_t<2, EPI_STD>(c, st, a, b, p) : launch_gemm2_t<1, EPI_STD>(c, st, a, b, p);
-    if (epi == EPI_FULL) return pair ? launch_gemm2_t<2, EPI_FULL>(c, st, a, b, p) : launch_gemm2_t<1, EPI_FULL>(c, st, a, b, p);
-    return pair ? launch_gemm2_t<2, EPI_SOFTMAX>(c, st, a, b, p) : launch_gemm2_t<1, EPI_SOFTMAX>(c, st, a, b, p);
+    // short reductions (<= 40 MMA steps: one accumulation chain is as accurate as a flushed one) are bound by
+    // their epilogue: they take the wide variant, which reads the single chunk straight from tensor memory
+    const int steps = p.ntaps * ((p.K + G2_BK - 1) / G2_BK) * (G2_BK / 16);
+    const bool wide = c->wide && epi != EPI_SOFTMAX && steps <= 40;
+    if (wide) {
+      p.chunk_kb = 0;
+      if (epi == EPI_STD) return pair ? launch_gemm2_t<2, EPI_STD, 1>(c, st, a, b, p) : launch_gemm2_t<1, EPI_STD, 1>(c, st, a, b, p);
+      return pair ? launch_gemm2_t<2, EPI_FULL, 1>(c, st, a, b, p) : launch_gemm2_t<1, EPI_FULL, 1>(c, st, a, b, p);
+    }
+    if (epi == EPI_STD) return pair ? launch_gemm2_t<2, EPI_STD, 0>(c, st, a, b, p) : launch_gemm2_t<1, EPI_STD, 0>(c, st, a, b, p);
+    if (epi == EPI_FULL) return pair ? launch_gemm2_t<2, EPI_FULL, 0>(c, st, a, b, p) : launch_gemm2_t<1, EPI_FULL, 0>(c, st, a, b, p);
+    return pair ? launch_gemm2_t<2, EPI_SOFTMAX, 0>(c, st, a, b, p) : launch_gemm2_t<1, EPI_SOFTMAX, 0>(c, st, a, b, p);
   }
   p.tile_list = nullptr; p.tile_count = nullptr;
   if (p.B > 65535 || (p.T + GEMM_BM - 1) / GEMM_BM > 65535) return fail(EFTS_ERR_ARG, "grid too large");
@@ -257,10 +267,12 @@ int set_kernel_attributes() {
   CUDA_TRY((opt_in_v1<64, 0>()));  CUDA_TRY((opt_in_v1<64, 1>()));  CUDA_TRY((opt_in_v1<64, 2>()));
   CUDA_TRY((opt_in_v1<128, 0>())); CUDA_TRY((opt_in_v1<128, 1>())); CUDA_TRY((opt_in_v1<128, 2>()));
   CUDA_TRY((opt_in_v1<256, 0>())); CUDA_TRY((opt_in_v1<256, 1>())); CUDA_TRY((opt_in_v1<256, 2>()));
-#define EFTS_OPT_IN_V2(CG_, EPI_) \
-  CUDA_TRY(cudaFuncSetAttribute(gemm2_kernel<CG_, EPI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2Cfg<CG_>::SMEM_BYTES))
-  EFTS_OPT_IN_V2(1, EPI_STD); EFTS_OPT_IN_V2(1, EPI_FULL); EFTS_OPT_IN_V2(1, EPI_SOFTMAX);
-  EFTS_OPT_IN_V2(2, EPI_STD); EFTS_OPT_IN_V2(2, EPI_FULL); EFTS_OPT_IN_V2(2, EPI_SOFTMAX);
+#define EFTS_OPT_IN_V2(CG_, EPI_, W_) \
+  CUDA_TRY(cudaFuncSetAttribute(gemm2_kernel<CG_, EPI_, W_>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2Cfg<CG_, W_>::SMEM_BYTES))
+  EFTS_OPT_IN_V2(1, EPI_STD, 0); EFTS_OPT_IN_V2(1, EPI_FULL, 0); EFTS_OPT_IN_V2(1, EPI_SOFTMAX, 0);
+  EFTS_OPT_IN_V2(2, EPI_STD, 0); EFTS_OPT_IN_V2(2, EPI_FULL, 0); EFTS_OPT_IN_V2(2, EPI_SOFTMAX, 0);
+  EFTS_OPT_IN_V2(1, EPI_STD, 1); EFTS_OPT_IN_V2(1, EPI_FULL, 1);
+  EFTS_OPT_IN_V2(2, EPI_STD, 1); EFTS_OPT_IN_V2(2, EPI_FULL, 1);
 #undef EFTS_OPT_IN_V2
   CUDA_TRY(cudaFuncSetAttribute(reconstruct_alignment_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(kReconstructSmemMax)));
@@ -719,6 +731,7 @@ int efts_set_option(efts_ctx* c, const char* name, int32_t value) {
   }
   if (strcmp(name, "pair") == 0) { c->pair = value != 0; return EFTS_OK; }
   if (strcmp(name, "debug_mask") == 0) { c->debug_mask = value; return EFTS_OK; }
+  if (strcmp(name, "wide") == 0) { c->wide = value != 0; return EFTS_OK; }
   if (strcmp(name, "chunk_kb") == 0) {
     if (value < 0 || value > 64) return fail(EFTS_ERR_ARG, "chunk_kb out of range");
     c->chunk_kb = value;

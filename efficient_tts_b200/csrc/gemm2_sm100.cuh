@@ -33,15 +33,19 @@ constexpr int G2_BIAS_MAX = 1024;                     // columns whose bias is s
 constexpr int G2_REGS_CTRL = 72;                     // setmaxnreg budgets: 3 warps per SM sub-partition,
 constexpr int G2_REGS_EPI = 216;                     // 32 * (72 + 2 * 216) = 16128 <= 16384 registers
 
-template <int CG>
+constexpr int G2_STAGE_ROW_BYTES = 144;               // wide epilogue staging: 32 fp32 + pad per row (conflict-free v4 stores)
+constexpr int G2_STAGE_WARP_BYTES = 32 * G2_STAGE_ROW_BYTES;
+
+template <int CG, int WIDE = 0>
 struct G2Cfg {
   static constexpr int B_ROWS = G2_BN / CG;
   static constexpr int B_PLANE = B_ROWS * 128;
   static constexpr int B_STAGE = 2 * B_PLANE;
-  static constexpr int A_STAGES = CG == 2 ? 3 : 2;
-  static constexpr int B_STAGES = CG == 2 ? 6 : 4;
+  // the wide (short-reduction) variant trades pipeline depth for 16 per-warp transposition buffers
+  static constexpr int A_STAGES = WIDE ? 2 : (CG == 2 ? 3 : 2);
+  static constexpr int B_STAGES = WIDE ? (CG == 2 ? 4 : 2) : (CG == 2 ? 6 : 4);
   static constexpr int SMEM_TILES = A_STAGES * G2_A_STAGE + B_STAGES * B_STAGE;
-  static constexpr int SMEM_BYTES = SMEM_TILES + 1024 + 512 + 4 * G2_BIAS_MAX;
+  static constexpr int SMEM_BYTES = SMEM_TILES + 1024 + 512 + 4 * G2_BIAS_MAX + (WIDE ? 16 * G2_STAGE_WARP_BYTES : 0);
   static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB");
 };
 
@@ -88,12 +92,18 @@ __global__ void build_tile_list_kernel(const int* __restrict__ lens, int B, int 
 // Linear layers), 1 = also the divisor and the transposed plane store, 2 = token-softmax partials only.
 enum Gemm2Epi { EPI_STD = 0, EPI_FULL = 1, EPI_SOFTMAX = 2 };
 
-template <int CG, int EPI>
-__global__ void __launch_bounds__(G2_THREADS, 1)
+// WIDE = 1 is the variant for short reductions (a single accumulation chunk: Linear layers, mel prenet, the
+// expansion matmul), whose cost is the epilogue, not the MMAs: sixteen epilogue warps instead of eight (two per
+// TMEM lane quadrant and group, 64 columns each) read the finished accumulators straight from tensor memory 16
+// columns at a time -- no running sums, 96 registers per thread, twice the warps to hide the store latency.
+constexpr int G2_THREADS_WIDE = 128 + 32 * 16;
+
+template <int CG, int EPI, int WIDE>
+__global__ void __launch_bounds__(WIDE ? G2_THREADS_WIDE : G2_THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
              const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
              const GemmParams p) {
-  using Cfg = G2Cfg<CG>;
+  using Cfg = G2Cfg<CG, WIDE>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = smem_base;
@@ -111,6 +121,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
   auto acc1_empty = [&](int s) { return sBar + 256u + 8u * s; };   // [2]
   const uint32_t tmem_slot = sBar + 272u;
   const uint32_t sBias = sBar + 512u;              // [G2_BIAS_MAX] fp32 copy of the bias (epilogue reads it per row)
+  const uint32_t sStage = sBias + 4u * G2_BIAS_MAX; // wide variant: [16 warps][32 rows][144 B]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -124,8 +135,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       ptx::mbar_init(acc0_full(0, s), 1);
       ptx::mbar_init(acc0_full(1, s), 1);
       ptx::mbar_init(acc1_full(s), 1);
-      ptx::mbar_init(acc0_empty(s), 4 * CG);     // one arrival per warp of the owning group, per CTA
-      ptx::mbar_init(acc1_empty(s), 4 * CG);
+      ptx::mbar_init(acc0_empty(s), (WIDE ? 8 : 4) * CG);   // one arrival per warp of the owning group, per CTA
+      ptx::mbar_init(acc1_empty(s), (WIDE ? 8 : 4) * CG);
     }
     ptx::fence_barrier_init();
   }
@@ -133,7 +144,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
     if (CG == 2) ptx::tmem_alloc_pair(tmem_slot, 512); else ptx::tmem_alloc(tmem_slot, 512);
   }
   if (p.bias != nullptr) {                         // launch_gemm guarantees N <= G2_BIAS_MAX when a bias is given
-    for (int i = threadIdx.x; i < p.N; i += G2_THREADS)
+    for (int i = threadIdx.x; i < p.N; i += blockDim.x)
       asm volatile("st.shared.f32 [%0], %1;" ::"r"(sBias + 4u * i), "f"(__ldg(p.bias + i)) : "memory");
   }
   ptx::tc_fence_before();
@@ -168,7 +179,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (every CTA)
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(G2_REGS_CTRL));
+    if (!WIDE) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(G2_REGS_CTRL));
     if (lane == 0) {
       ptx::prefetch_tensormap(&tmA_hi); ptx::prefetch_tensormap(&tmA_lo);
       ptx::prefetch_tensormap(&tmB_hi); ptx::prefetch_tensormap(&tmB_lo);
@@ -216,7 +227,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (leader CTA, one thread)
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(G2_REGS_CTRL));
+    if (!WIDE) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(G2_REGS_CTRL));
     if (lane == 0 && leader) {
       constexpr uint32_t idesc = ptx::make_idesc_f16(G2_BM * CG, G2_BN);
       auto commit = [&](uint32_t bar) {
@@ -276,7 +287,128 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       }
     }
   } else if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(G2_REGS_CTRL));   // idle warps of warpgroup 0
+    if (!WIDE) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(G2_REGS_CTRL));   // idle warps of warpgroup 0
+  } else if (WIDE) {
+    // ------------------------------------------------------------ direct epilogue (warps 4..19), one chunk per tile
+    // Scattered 16-byte stores (one row per thread) cost the LSU two cycles per row and instruction and are
+    // what bounds these launches, so each warp transposes its 32 x 32 block through shared memory: eight lanes
+    // then write one row's 128 contiguous bytes, four rows per instruction.
+    const int q = warp & 3;
+    const uint32_t ew = static_cast<uint32_t>(warp - 4);
+    const uint32_t grp = ew >> 3;
+    const int cbase = static_cast<int>((ew >> 2) & 1u) * (G2_BN / 2);
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t stg = sStage + ew * G2_STAGE_WARP_BYTES;
+    const int sub_row = lane >> 3, sub_col = (lane & 7) * 4;
+    auto release = [&](uint32_t bar) {
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (CG == 2) ptx::mbar_arrive_cluster(ptx::map_to_cta(bar, 0)); else ptx::mbar_arrive(bar);
+      }
+    };
+    uint32_t g = 0, it = 0, uses0 = 0u, uses1 = 0u;
+    for (long long w = cid; w < total; w += ncl, ++it, ++g) {       // exactly one chunk per tile
+      if ((it & 1u) != grp) continue;
+      int b, t0, n0; bool valid;
+      locate(w, b, t0, n0, valid);
+      const int t = t0 + row;
+      const bool tile_live = valid && !(p.skip_lens != nullptr && t0 >= p.skip_lens[b] + p.skip_halo);
+      const bool row_ok = tile_live && t < p.T;
+      const bool row_live = row_ok && (p.lens == nullptr || t < p.lens[b]);
+      const int lens_b = (valid && p.lens != nullptr) ? p.lens[b] : p.T;
+      const int check_b = (valid && p.skip_lens != nullptr) ? p.skip_lens[b] + p.skip_halo : p.T;
+      const uint32_t buf = g & 1u, tb = it & 1u;
+      ptx::mbar_wait(acc0_full(static_cast<int>(grp), static_cast<int>(buf)), (buf ? uses1 : uses0) & 1u);
+      if (buf) ++uses1; else ++uses0;
+      ptx::mbar_wait(acc1_full(tb), (it >> 1) & 1u);
+      ptx::tc_fence_after();
+#pragma unroll
+      for (int c32 = 0; c32 < G2_BN / 64; ++c32) {
+        const int n = n0 + cbase + c32 * 32;
+        __syncwarp();                               // previous block's transposed reads are done; ld is .aligned
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t r0[16], r1[16];
+          ptx::tmem_ld_32x16(lane_addr + buf * G2_BN + cbase + c32 * 32 + h * 16, r0);
+          ptx::tmem_ld_32x16(lane_addr + 256u + tb * G2_BN + cbase + c32 * 32 + h * 16, r1);
+          ptx::tmem_ld_wait();
+          if (c32 == G2_BN / 64 - 1 && h == 1) {    // everything this warp needs has left tensor memory
+            release(acc0_empty(buf));
+            release(acc1_empty(tb));
+          }
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const int nn = n + h * 16 + k4 * 4;
+            float vv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              vv[j] = __fadd_rn(__uint_as_float(r0[k4 * 4 + j]), __uint_as_float(r1[k4 * 4 + j]) * SPLIT_INV_SCALE);
+              if (EPI == EPI_FULL && p.divisor != 1.0f) vv[j] = __fdiv_rn(vv[j], p.divisor);
+            }
+            if (p.bias != nullptr && nn < p.N) {
+              float4 bb;
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(bb.x), "=f"(bb.y), "=f"(bb.z), "=f"(bb.w)
+                           : "r"(sBias + 4u * nn));
+              vv[0] += bb.x; vv[1] += bb.y; vv[2] += bb.z; vv[3] += bb.w;
+            }
+            if (p.act == ACT_LRELU) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) vv[j] = vv[j] > 0.0f ? vv[j] : vv[j] * 0.1f;
+            } else if (p.act == ACT_RELU) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) vv[j] = fmaxf(vv[j], 0.0f);
+            }
+            if (EPI == EPI_FULL && p.outT_hi != nullptr && row_ok && nn < p.N) {   // t-contiguous planes: thread = row
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float x = row_live ? vv[j] : 0.0f;
+                const size_t o = (static_cast<size_t>(b) * p.N + (nn + j)) * p.ld_t + t;
+                const __half hh = __float2half_rn(x);
+                p.outT_hi[o] = hh;
+                p.outT_lo[o] = __float2half_rn((x - __half2float(hh)) * SPLIT_SCALE);
+              }
+            }
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * G2_STAGE_ROW_BYTES + h * 64 + k4 * 16),
+                         "f"(vv[0]), "f"(vv[1]), "f"(vv[2]), "f"(vv[3]) : "memory");
+          }
+        }
+        __syncwarp();
+        if (!tile_live) continue;                   // warp-uniform
+#pragma unroll
+        for (int itr = 0; itr < 8; ++itr) {
+          const int rr = itr * 4 + sub_row;
+          const int tr = t0 + q * 32 + rr;
+          const int nn = n + sub_col;
+          float4 v;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                       : "r"(stg + rr * G2_STAGE_ROW_BYTES + sub_col * 4) : "memory");
+          if (tr < p.T && nn < p.N) {
+            const size_t mr = static_cast<size_t>(b) * p.T + tr;
+            if (p.resid != nullptr) {
+              const float4 x = *reinterpret_cast<const float4*>(p.resid + mr * p.ld_out + nn);
+              v.x = x.x + v.x; v.y = x.y + v.y; v.z = x.z + v.z; v.w = x.w + v.w;
+            }
+            if (tr >= lens_b) v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (p.out != nullptr && !(p.debug_mask & 1)) *reinterpret_cast<float4*>(p.out + mr * p.ld_out + nn) = v;
+            if (p.out_hi != nullptr && !(p.debug_mask & 2)) {
+              const float amax = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+              if (tr < check_b && amax > 65504.0f && p.err_flag != nullptr) atomicOr(p.err_flag, 8 | p.err_code);
+              const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
+              const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+              const __half2 l01 = __floats2half2_rn((v.x - f01.x) * SPLIT_SCALE, (v.y - f01.y) * SPLIT_SCALE);
+              const __half2 l23 = __floats2half2_rn((v.z - f23.x) * SPLIT_SCALE, (v.w - f23.y) * SPLIT_SCALE);
+              uint2 ph, pl;
+              ph.x = *reinterpret_cast<const uint32_t*>(&h01); ph.y = *reinterpret_cast<const uint32_t*>(&h23);
+              pl.x = *reinterpret_cast<const uint32_t*>(&l01); pl.y = *reinterpret_cast<const uint32_t*>(&l23);
+              *reinterpret_cast<uint2*>(p.out_hi + mr * p.ld_pl + nn) = ph;
+              *reinterpret_cast<uint2*>(p.out_lo + mr * p.ld_pl + nn) = pl;
+            }
+          }
+        }
+      }
+    }
   } else {
     // ------------------------------------------------------------ accumulate + epilogue (warps 4..11)
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(G2_REGS_EPI));
