@@ -84,8 +84,8 @@ def load():
     with _lock:
         if _lib is not None:
             return _lib
-        path = _build.LIB_PATH
-        if _build.is_stale():
+        path = os.environ.get("EFTS_B200_LIB") or _build.LIB_PATH     # A/B experiments: alternate build
+        if path == _build.LIB_PATH and _build.is_stale():
             try:
                 _build.build_library()
             except Exception as exc:  # no nvcc on this machine: use a prebuilt library if present

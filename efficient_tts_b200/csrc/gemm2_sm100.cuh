@@ -43,9 +43,10 @@ struct G2Cfg {
   static constexpr int B_STAGE = 2 * B_PLANE;
   // the wide (short-reduction) variant trades pipeline depth for 16 per-warp transposition buffers
   static constexpr int A_STAGES = WIDE ? 2 : (CG == 2 ? 3 : 2);
-  static constexpr int B_STAGES = WIDE ? (CG == 2 ? 4 : 2) : (CG == 2 ? 6 : 4);
+  static constexpr int B_STAGES = WIDE ? (CG == 2 ? 4 : 2) : (CG == 2 ? 5 : 3);
+  static constexpr int EPI_WARPS = WIDE ? 16 : 8;
   static constexpr int SMEM_TILES = A_STAGES * G2_A_STAGE + B_STAGES * B_STAGE;
-  static constexpr int SMEM_BYTES = SMEM_TILES + 1024 + 512 + 4 * G2_BIAS_MAX + (WIDE ? 16 * G2_STAGE_WARP_BYTES : 0);
+  static constexpr int SMEM_BYTES = SMEM_TILES + 1024 + 512 + 4 * G2_BIAS_MAX + EPI_WARPS * G2_STAGE_WARP_BYTES;
   static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB");
 };
 
@@ -85,6 +86,58 @@ __global__ void build_tile_list_kernel(const int* __restrict__ lens, int B, int 
     __syncthreads();
   }
   if (threadIdx.x == 0) *count = carry_s;
+}
+
+// Transposed store of one warp's 32 rows x 32 columns block staged in shared memory (row stride 144 B):
+// lane (sub_row, sub_col) owns four consecutive columns of row 4 * itr + sub_row, so eight lanes cover one row's
+// 128 contiguous bytes and every global access is made of whole lines -- scattered one-row-per-thread 16-byte
+// accesses cost the LSU two cycles per row and instruction and an L2 request per half sector.  Adds the fp32
+// residual (all eight row loads are issued before the first store), zeroes rows past the utterance, writes the
+// fp32 result and its fp16 hi/lo operand planes, and range-checks what becomes an operand.
+__device__ __forceinline__ void g2_store_block32(const GemmParams& p, uint32_t stg, int b, int t_base, int n,
+                                                 int lens_b, int check_b, int lane) {
+  const int sub_row = lane >> 3, sub_col = (lane & 7) * 4;
+  const int nn = n + sub_col;
+  const bool col_ok = nn < p.N;
+  float4 res[8];
+  if (p.resid != nullptr) {
+#pragma unroll
+    for (int itr = 0; itr < 8; ++itr) {
+      const int tr = t_base + itr * 4 + sub_row;
+      res[itr] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      if (tr < p.T && col_ok)
+        res[itr] = *reinterpret_cast<const float4*>(p.resid + (static_cast<size_t>(b) * p.T + tr) * p.ld_out + nn);
+    }
+  }
+#pragma unroll
+  for (int itr = 0; itr < 8; ++itr) {
+    const int rr = itr * 4 + sub_row;
+    const int tr = t_base + rr;
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "r"(stg + rr * G2_STAGE_ROW_BYTES + sub_col * 4) : "memory");
+    if (tr < p.T && col_ok) {
+      const size_t mr = static_cast<size_t>(b) * p.T + tr;
+      if (p.resid != nullptr) {
+        v.x = res[itr].x + v.x; v.y = res[itr].y + v.y; v.z = res[itr].z + v.z; v.w = res[itr].w + v.w;
+      }
+      if (tr >= lens_b) v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      if (p.out != nullptr && !(p.debug_mask & 1)) *reinterpret_cast<float4*>(p.out + mr * p.ld_out + nn) = v;
+      if (p.out_hi != nullptr && !(p.debug_mask & 2)) {
+        const float amax = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+        if (tr < check_b && amax > 65504.0f && p.err_flag != nullptr) atomicOr(p.err_flag, 8 | p.err_code);
+        const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
+        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+        const __half2 l01 = __floats2half2_rn((v.x - f01.x) * SPLIT_SCALE, (v.y - f01.y) * SPLIT_SCALE);
+        const __half2 l23 = __floats2half2_rn((v.z - f23.x) * SPLIT_SCALE, (v.w - f23.y) * SPLIT_SCALE);
+        uint2 ph, pl;
+        ph.x = *reinterpret_cast<const uint32_t*>(&h01); ph.y = *reinterpret_cast<const uint32_t*>(&h23);
+        pl.x = *reinterpret_cast<const uint32_t*>(&l01); pl.y = *reinterpret_cast<const uint32_t*>(&l23);
+        *reinterpret_cast<uint2*>(p.out_hi + mr * p.ld_pl + nn) = ph;
+        *reinterpret_cast<uint2*>(p.out_lo + mr * p.ld_pl + nn) = pl;
+      }
+    }
+  }
 }
 
 // EPI selects how much epilogue is compiled in (the fully unrolled column loop makes every option cost
@@ -300,7 +353,6 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
     const int row = q * 32 + lane;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const uint32_t stg = sStage + ew * G2_STAGE_WARP_BYTES;
-    const int sub_row = lane >> 3, sub_col = (lane & 7) * 4;
     auto release = [&](uint32_t bar) {
       ptx::tc_fence_before();
       __syncwarp();
@@ -376,37 +428,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
         }
         __syncwarp();
         if (!tile_live) continue;                   // warp-uniform
-#pragma unroll
-        for (int itr = 0; itr < 8; ++itr) {
-          const int rr = itr * 4 + sub_row;
-          const int tr = t0 + q * 32 + rr;
-          const int nn = n + sub_col;
-          float4 v;
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                       : "r"(stg + rr * G2_STAGE_ROW_BYTES + sub_col * 4) : "memory");
-          if (tr < p.T && nn < p.N) {
-            const size_t mr = static_cast<size_t>(b) * p.T + tr;
-            if (p.resid != nullptr) {
-              const float4 x = *reinterpret_cast<const float4*>(p.resid + mr * p.ld_out + nn);
-              v.x = x.x + v.x; v.y = x.y + v.y; v.z = x.z + v.z; v.w = x.w + v.w;
-            }
-            if (tr >= lens_b) v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            if (p.out != nullptr && !(p.debug_mask & 1)) *reinterpret_cast<float4*>(p.out + mr * p.ld_out + nn) = v;
-            if (p.out_hi != nullptr && !(p.debug_mask & 2)) {
-              const float amax = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
-              if (tr < check_b && amax > 65504.0f && p.err_flag != nullptr) atomicOr(p.err_flag, 8 | p.err_code);
-              const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
-              const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-              const __half2 l01 = __floats2half2_rn((v.x - f01.x) * SPLIT_SCALE, (v.y - f01.y) * SPLIT_SCALE);
-              const __half2 l23 = __floats2half2_rn((v.z - f23.x) * SPLIT_SCALE, (v.w - f23.y) * SPLIT_SCALE);
-              uint2 ph, pl;
-              ph.x = *reinterpret_cast<const uint32_t*>(&h01); ph.y = *reinterpret_cast<const uint32_t*>(&h23);
-              pl.x = *reinterpret_cast<const uint32_t*>(&l01); pl.y = *reinterpret_cast<const uint32_t*>(&l23);
-              *reinterpret_cast<uint2*>(p.out_hi + mr * p.ld_pl + nn) = ph;
-              *reinterpret_cast<uint2*>(p.out_lo + mr * p.ld_pl + nn) = pl;
-            }
-          }
-        }
+        g2_store_block32(p, stg, b, t0 + q * 32, n, lens_b, check_b, lane);
       }
     }
   } else {
@@ -482,8 +504,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
         }
       }
       release(acc1_empty(tb));
-      if (!row_ok) continue;
+      if (!tile_live) continue;                     // warp-uniform: the stores below are warp-cooperative
       if (EPI == EPI_SOFTMAX) {
+        if (!row_ok) continue;
         // scaled-dot-product softmax over tokens, one partial per column tile (models/efficient_tts.py:390-398):
         // the scores never leave the SM; imv_scan_kernel merges the partials into the position expectation.
         const int L = p.col_lens[b];
@@ -508,83 +531,52 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
         continue;
       }
       if (EPI == EPI_SOFTMAX) continue;
-      // residual rows are prefetched two 8-column groups ahead: the stores in between may alias for all
-      // the compiler knows, so without this every group would wait a full memory round trip
-      // residual rows are prefetched two 8-column groups ahead: the stores in between may alias for all
-      // the compiler knows, so without this every group would wait a full memory round trip
-      const bool has_resid = p.resid != nullptr;
-      const float* rp = has_resid ? p.resid + m * p.ld_out + n0 : nullptr;
-      float4 rx[2][2];
+      // stores: 32 columns at a time through this warp's transposition buffer (see g2_store_block32)
+      const uint32_t stg = sStage + static_cast<uint32_t>(warp - 4) * G2_STAGE_WARP_BYTES;
+      const int lens_b = p.lens != nullptr ? p.lens[b] : p.T;
+      const int check_b = p.skip_lens != nullptr ? p.skip_lens[b] + p.skip_halo : p.T;
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        rx[k][0] = rx[k][1] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        if (has_resid && n0 + k * 8 < p.N) {
-          rx[k][0] = *reinterpret_cast<const float4*>(rp + k * 8);
-          rx[k][1] = *reinterpret_cast<const float4*>(rp + k * 8 + 4);
-        }
-      }
+      for (int c32 = 0; c32 < G2_BN / 32; ++c32) {
+        const int n = n0 + c32 * 32;
+        if (n >= p.N) break;                        // warp-uniform
+        __syncwarp();                               // the previous block's transposed reads are done
 #pragma unroll
-      for (int c8 = 0; c8 < G2_BN / 8; ++c8) {
-        const int n = n0 + c8 * 8;
-        if (n >= p.N) break;
-        float vv[8];
+        for (int k4 = 0; k4 < 8; ++k4) {
+          const int nn = n + k4 * 4;
+          float vv[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          vv[j] = sum[c8 * 8 + j];
-          if (EPI == EPI_FULL && p.divisor != 1.0f) vv[j] = __fdiv_rn(vv[j], p.divisor);
-        }
-        if (p.bias != nullptr) {
-          float4 b0, b1;
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b0.x), "=f"(b0.y), "=f"(b0.z), "=f"(b0.w)
-                       : "r"(sBias + 4u * n));
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b1.x), "=f"(b1.y), "=f"(b1.z), "=f"(b1.w)
-                       : "r"(sBias + 4u * n + 16u));
-          vv[0] += b0.x; vv[1] += b0.y; vv[2] += b0.z; vv[3] += b0.w;
-          vv[4] += b1.x; vv[5] += b1.y; vv[6] += b1.z; vv[7] += b1.w;
-        }
-        if (p.act == ACT_LRELU) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) vv[j] = vv[j] > 0.0f ? vv[j] : vv[j] * 0.1f;
-        } else if (p.act == ACT_RELU) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) vv[j] = fmaxf(vv[j], 0.0f);
-        }
-        if (has_resid) {
-          const float4 x0 = rx[c8 & 1][0];
-          const float4 x1 = rx[c8 & 1][1];
-          if (n + 16 < p.N) {
-            rx[c8 & 1][0] = *reinterpret_cast<const float4*>(rp + c8 * 8 + 16);
-            rx[c8 & 1][1] = *reinterpret_cast<const float4*>(rp + c8 * 8 + 20);
+          for (int j = 0; j < 4; ++j) {
+            vv[j] = sum[c32 * 32 + k4 * 4 + j];
+            if (EPI == EPI_FULL && p.divisor != 1.0f) vv[j] = __fdiv_rn(vv[j], p.divisor);
           }
-          vv[0] = x0.x + vv[0]; vv[1] = x0.y + vv[1]; vv[2] = x0.z + vv[2]; vv[3] = x0.w + vv[3];
-          vv[4] = x1.x + vv[4]; vv[5] = x1.y + vv[5]; vv[6] = x1.z + vv[6]; vv[7] = x1.w + vv[7];
-        }
-        if (!row_live) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) vv[j] = 0.0f;
-        }
-        if (p.out != nullptr && !(p.debug_mask & 1)) {
-          float* op = p.out + m * p.ld_out + n;
-          *reinterpret_cast<float4*>(op) = make_float4(vv[0], vv[1], vv[2], vv[3]);
-          *reinterpret_cast<float4*>(op + 4) = make_float4(vv[4], vv[5], vv[6], vv[7]);
-        }
-        if (p.out_hi != nullptr && !(p.debug_mask & 2)) {
-          const float amax = fmaxf(fmaxf(fmaxf(fabsf(vv[0]), fabsf(vv[1])), fmaxf(fabsf(vv[2]), fabsf(vv[3]))),
-                                   fmaxf(fmaxf(fabsf(vv[4]), fabsf(vv[5])), fmaxf(fabsf(vv[6]), fabsf(vv[7]))));
-          // (a NaN can only follow an overflow, which is flagged where it first exceeds the range)
-          if (row_checked && amax > 65504.0f && p.err_flag != nullptr)
-            atomicOr(p.err_flag, 8 | p.err_code);   // outside the fp16 operand range (or already non-finite)
-          split_store8(p.out_hi + m * p.ld_pl + n, p.out_lo + m * p.ld_pl + n, vv);
-        }
-        if (EPI == EPI_FULL && p.outT_hi != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const size_t o = (static_cast<size_t>(b) * p.N + (n + j)) * p.ld_t + t;
-            const __half h = __float2half_rn(vv[j]);
-            p.outT_hi[o] = h;
-            p.outT_lo[o] = __float2half_rn((vv[j] - __half2float(h)) * SPLIT_SCALE);
+          if (p.bias != nullptr && nn < p.N) {
+            float4 bb;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(bb.x), "=f"(bb.y), "=f"(bb.z), "=f"(bb.w)
+                         : "r"(sBias + 4u * nn));
+            vv[0] += bb.x; vv[1] += bb.y; vv[2] += bb.z; vv[3] += bb.w;
           }
+          if (p.act == ACT_LRELU) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) vv[j] = vv[j] > 0.0f ? vv[j] : vv[j] * 0.1f;
+          } else if (p.act == ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) vv[j] = fmaxf(vv[j], 0.0f);
+          }
+          if (EPI == EPI_FULL && p.outT_hi != nullptr && row_ok && nn < p.N) {   // t-contiguous planes: thread = row
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float x = row_live ? vv[j] : 0.0f;
+              const size_t o = (static_cast<size_t>(b) * p.N + (nn + j)) * p.ld_t + t;
+              const __half hh = __float2half_rn(x);
+              p.outT_hi[o] = hh;
+              p.outT_lo[o] = __float2half_rn((x - __half2float(hh)) * SPLIT_SCALE);
+            }
+          }
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * G2_STAGE_ROW_BYTES + k4 * 16),
+                       "f"(vv[0]), "f"(vv[1]), "f"(vv[2]), "f"(vv[3]) : "memory");
         }
+        __syncwarp();
+        g2_store_block32(p, stg, b, t0 + q * 32, n, lens_b, check_b, lane);
       }
     }
   }
