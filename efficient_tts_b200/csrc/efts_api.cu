@@ -225,10 +225,11 @@ int launch_gemm(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, GemmPa
     // short reductions (<= 40 MMA steps: one accumulation chain is as accurate as a flushed one) are bound by
     // their epilogue: they take the wide variant, which reads the single chunk straight from tensor memory
     const int steps = p.ntaps * ((p.K + G2_BK - 1) / G2_BK) * (G2_BK / 16);
-    const bool wide = c->wide && epi != EPI_SOFTMAX && steps <= 40;
+    const bool wide = c->wide && steps <= 40;
     if (wide) {
       p.chunk_kb = 0;
       if (epi == EPI_STD) return pair ? launch_gemm2_t<2, EPI_STD, 1>(c, st, a, b, p) : launch_gemm2_t<1, EPI_STD, 1>(c, st, a, b, p);
+      if (epi == EPI_SOFTMAX) return pair ? launch_gemm2_t<2, EPI_SOFTMAX, 1>(c, st, a, b, p) : launch_gemm2_t<1, EPI_SOFTMAX, 1>(c, st, a, b, p);
       return pair ? launch_gemm2_t<2, EPI_FULL, 1>(c, st, a, b, p) : launch_gemm2_t<1, EPI_FULL, 1>(c, st, a, b, p);
     }
     if (epi == EPI_STD) return pair ? launch_gemm2_t<2, EPI_STD, 0>(c, st, a, b, p) : launch_gemm2_t<1, EPI_STD, 0>(c, st, a, b, p);
@@ -271,8 +272,8 @@ int set_kernel_attributes() {
   CUDA_TRY(cudaFuncSetAttribute(gemm2_kernel<CG_, EPI_, W_>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2Cfg<CG_, W_>::SMEM_BYTES))
   EFTS_OPT_IN_V2(1, EPI_STD, 0); EFTS_OPT_IN_V2(1, EPI_FULL, 0); EFTS_OPT_IN_V2(1, EPI_SOFTMAX, 0);
   EFTS_OPT_IN_V2(2, EPI_STD, 0); EFTS_OPT_IN_V2(2, EPI_FULL, 0); EFTS_OPT_IN_V2(2, EPI_SOFTMAX, 0);
-  EFTS_OPT_IN_V2(1, EPI_STD, 1); EFTS_OPT_IN_V2(1, EPI_FULL, 1);
-  EFTS_OPT_IN_V2(2, EPI_STD, 1); EFTS_OPT_IN_V2(2, EPI_FULL, 1);
+  EFTS_OPT_IN_V2(1, EPI_STD, 1); EFTS_OPT_IN_V2(1, EPI_FULL, 1); EFTS_OPT_IN_V2(1, EPI_SOFTMAX, 1);
+  EFTS_OPT_IN_V2(2, EPI_STD, 1); EFTS_OPT_IN_V2(2, EPI_FULL, 1); EFTS_OPT_IN_V2(2, EPI_SOFTMAX, 1);
 #undef EFTS_OPT_IN_V2
   CUDA_TRY(cudaFuncSetAttribute(reconstruct_alignment_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(kReconstructSmemMax)));
@@ -548,7 +549,9 @@ int run_imv(efts_ctx* c, cudaStream_t st, const __half* q_hi, const __half* q_lo
   // v2 kernel: the token softmax runs in the GEMM epilogue and only (max, sum, weighted sum) per column
   // tile reaches memory (the buffer S is reused for them); v1 writes the scores and a separate kernel reads them.
   const bool fused = c->gemm_version == 2;
-  const int n_part = (T1p + G2_BN - 1) / G2_BN;
+  // the wide (16-warp) variant emits one partial per 64-column half tile, the narrow one per 128-column tile
+  const bool wide_softmax = c->wide && ((C + G2_BK - 1) / G2_BK) * (G2_BK / 16) <= 40;
+  const int n_part = ((T1p + G2_BN - 1) / G2_BN) * (wide_softmax ? 2 : 1);
   if (fused) {
     p.softmax_part = reinterpret_cast<float4*>(S);
     p.col_lens = tl;

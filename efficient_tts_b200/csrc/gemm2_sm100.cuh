@@ -376,6 +376,50 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       if (buf) ++uses1; else ++uses0;
       ptx::mbar_wait(acc1_full(tb), (it >> 1) & 1u);
       ptx::tc_fence_after();
+      if (EPI == EPI_SOFTMAX) {
+        // token softmax of this warp's 64 columns, 16 at a time with a running maximum (online softmax); the two
+        // sums are kept in double.  One partial per (row, column half): softmax_part[row][2 * tile + half].
+        const int L = valid ? p.col_lens[b] : 0;
+        float mx = -CUDART_INF_F;
+        double den = 0.0, num = 0.0;
+#pragma unroll
+        for (int c16 = 0; c16 < G2_BN / 32; ++c16) {
+          uint32_t r0[16], r1[16];
+          __syncwarp();
+          ptx::tmem_ld_32x16(lane_addr + buf * G2_BN + cbase + c16 * 16, r0);
+          ptx::tmem_ld_32x16(lane_addr + 256u + tb * G2_BN + cbase + c16 * 16, r1);
+          ptx::tmem_ld_wait();
+          if (c16 == G2_BN / 32 - 1) {
+            release(acc0_empty(buf));
+            release(acc1_empty(tb));
+          }
+          const int nb = n0 + cbase + c16 * 16;
+          float sv[16];
+          float cm = -CUDART_INF_F;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            sv[j] = __fdiv_rn(__fadd_rn(__uint_as_float(r0[j]), __uint_as_float(r1[j]) * SPLIT_INV_SCALE), p.divisor);
+            if (nb + j < L) cm = fmaxf(cm, sv[j]);
+          }
+          if (cm > mx) {
+            const double sc = static_cast<double>(expf(mx - cm));      // exp(-inf) = 0 on the first block
+            den *= sc; num *= sc;
+            mx = cm;
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (nb + j < L) {
+              const double ev = static_cast<double>(expf(sv[j] - mx));
+              den += ev;
+              num = fma(ev, static_cast<double>(nb + j), num);
+            }
+          }
+        }
+        if (row_ok)
+          p.softmax_part[(static_cast<size_t>(b) * p.T + t) * (2 * n_nt) + 2 * (n0 / G2_BN) + (cbase ? 1 : 0)] =
+              make_float4(mx, static_cast<float>(den), static_cast<float>(num), 0.0f);
+        continue;
+      }
 #pragma unroll
       for (int c32 = 0; c32 < G2_BN / 64; ++c32) {
         const int n = n0 + cbase + c32 * 32;
