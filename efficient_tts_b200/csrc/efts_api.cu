@@ -95,6 +95,8 @@ struct efts_ctx {
   int wide = 1;              // v2: short-reduction launches use the 16-epilogue-warp variant
   int debug_mask = 0;        // timing experiments only
   int chunk_kb = 2;          // v2: k-blocks per main-accumulator flush (1 = most accurate, 0 = never)
+  int imv_version = 2;           // 2: block-per-utterance scan / aligned positions, 1: warp-per-utterance / token
+  int reconstruct_version = 3;   // 3: frame-per-lane Gaussian reconstruction, 2: warp-per-frame tiled kernel
   int64_t launches = 0;
   bool finalized = false;
   EncodeTiledFn encode = nullptr;
@@ -277,6 +279,58 @@ int set_kernel_attributes() {
 #undef EFTS_OPT_IN_V2
   CUDA_TRY(cudaFuncSetAttribute(reconstruct_alignment_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(kReconstructSmemMax)));
+  CUDA_TRY(cudaFuncSetAttribute(reconstruct_alignment_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(kReconstructSmemMax)));
+  CUDA_TRY(cudaFuncSetAttribute(imv_scan_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(kReconstructSmemMax)));
+  CUDA_TRY(cudaFuncSetAttribute(aligned_positions_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(kReconstructSmemMax)));
+  return EFTS_OK;
+}
+
+// IMV scan / aligned positions: version 2 = one block per utterance out of shared memory, 1 = one warp per
+// utterance / token from global memory (A/B baseline, and the fallback when a row does not fit shared memory).
+int launch_imv_scan(int version, cudaStream_t st, const float* imv_raw, const float4* part, int n_part, const int* tl,
+                    const int* sl, int B, int T2, float* imv) {
+  const size_t smem = static_cast<size_t>(T2) * sizeof(float);
+  if (version >= 2 && smem <= kReconstructSmemMax)
+    imv_scan_block_kernel<<<B, IMV_BLOCK_THREADS, smem, st>>>(imv_raw, part, n_part, tl, sl, T2, imv);
+  else
+    imv_scan_kernel<<<(B + 3) / 4, 128, 0, st>>>(imv_raw, part, n_part, tl, sl, B, T2, imv);
+  CUDA_TRY(cudaGetLastError());
+  return EFTS_OK;
+}
+int launch_aligned_positions(int version, cudaStream_t st, const float* imv, const int* tl, const int* sl, int B,
+                             int T1, int T2, float sigma_e, float* e, const float* pvec) {
+  const size_t smem = static_cast<size_t>(T2) * sizeof(float);
+  if (version >= 2 && smem <= kReconstructSmemMax)
+    aligned_positions_block_kernel<<<dim3((T1 + AP_TOKENS - 1) / AP_TOKENS, B), IMV_BLOCK_THREADS, smem, st>>>(
+        imv, tl, sl, T1, T2, sigma_e, e, pvec);
+  else
+    aligned_positions_kernel<<<dim3((T1 + 7) / 8, B), 256, 0, st>>>(imv, tl, sl, T1, T2, sigma_e, e, pvec);
+  CUDA_TRY(cudaGetLastError());
+  return EFTS_OK;
+}
+
+// Gaussian reconstruction launch: version 3 = frame-per-lane kernel, 2 = warp-per-frame tiled kernel (A/B
+// baseline); both fall back to the one-thread-per-frame kernel when the token count does not fit shared memory.
+int launch_reconstruct(int version, cudaStream_t st, const float* e, const int* tl, const int* sl, int B, int T1,
+                       int T2, int T1p, float neg_sigma, float* reconst_alpha, __half* R_hi, __half* R_lo) {
+  const size_t smem2 = (static_cast<size_t>(T1p) * (RT_FRAMES + 1) + T1) * sizeof(float);
+  if (version >= 3 && r3_smem_bytes(T1p) <= kReconstructSmemMax) {
+    dim3 grid((T2 + R3_FRAMES - 1) / R3_FRAMES, B);
+    reconstruct_alignment_rows_kernel<<<grid, 32 * R3_WARPS, r3_smem_bytes(T1p), st>>>(
+        e, tl, sl, T1, T2, T1p, neg_sigma, reconst_alpha, R_hi, R_lo);
+  } else if (T1 <= 32 * RT_KMAX && smem2 <= kReconstructSmemMax) {
+    dim3 grid((T2 + RT_FRAMES - 1) / RT_FRAMES, B);
+    reconstruct_alignment_tiled_kernel<<<grid, 256, smem2, st>>>(e, tl, sl, T1, T2, T1p, neg_sigma, reconst_alpha,
+                                                                 R_hi, R_lo);
+  } else {
+    dim3 grid((T2 + 127) / 128, B);
+    reconstruct_alignment_kernel<<<grid, 128, T1 * sizeof(float), st>>>(e, tl, sl, T1, T2, T1p, neg_sigma,
+                                                                        reconst_alpha, R_hi, R_lo);
+  }
+  CUDA_TRY(cudaGetLastError());
   return EFTS_OK;
 }
 
@@ -509,17 +563,7 @@ int run_reconstruct_expand(efts_ctx* c, cudaStream_t st, const float* e, const i
   {
     ProfScope ps(c, st, TAG_RECONSTRUCT);
     const float neg_sigma = -1.0f * c->cfg.sigma;
-    const size_t smem = (static_cast<size_t>(T1p) * (RT_FRAMES + 1) + T1) * sizeof(float);
-    if (T1 <= 32 * RT_KMAX && smem <= kReconstructSmemMax) {
-      dim3 grid((T2 + RT_FRAMES - 1) / RT_FRAMES, B);
-      reconstruct_alignment_tiled_kernel<<<grid, 256, smem, st>>>(e, tl, sl, T1, T2, T1p, neg_sigma, reconst_alpha,
-                                                                 R_hi, R_lo);
-    } else {
-      dim3 grid((T2 + 127) / 128, B);
-      reconstruct_alignment_kernel<<<grid, 128, T1 * sizeof(float), st>>>(e, tl, sl, T1, T2, T1p, neg_sigma,
-                                                                          reconst_alpha, R_hi, R_lo);
-    }
-    CUDA_TRY(cudaGetLastError());
+    TRY(launch_reconstruct(c->reconstruct_version, st, e, tl, sl, B, T1, T2, T1p, neg_sigma, reconst_alpha, R_hi, R_lo));
     c->launches++;
   }
   GemmParams p = gemm_defaults();
@@ -572,14 +616,12 @@ int run_imv(efts_ctx* c, cudaStream_t st, const __half* q_hi, const __half* q_lo
   }
   {
     ProfScope ps(c, st, TAG_SCAN);
-    imv_scan_kernel<<<(B + 3) / 4, 128, 0, st>>>(imv_raw, fused ? reinterpret_cast<const float4*>(S) : nullptr, n_part,
-                                                 tl, sl, B, T2, imv);
-    CUDA_TRY(cudaGetLastError());
+    TRY(launch_imv_scan(c->imv_version, st, imv_raw, fused ? reinterpret_cast<const float4*>(S) : nullptr, n_part, tl, sl,
+                        B, T2, imv));
   }
   {
     ProfScope ps(c, st, TAG_ALIGNED);
-    aligned_positions_kernel<<<dim3((T1 + 7) / 8, B), 256, 0, st>>>(imv, tl, sl, T1, T2, c->cfg.sigma_e, e);
-    CUDA_TRY(cudaGetLastError());
+    TRY(launch_aligned_positions(c->imv_version, st, imv, tl, sl, B, T1, T2, c->cfg.sigma_e, e, nullptr));
   }
   c->launches += 3;
   return EFTS_OK;
@@ -735,6 +777,16 @@ int efts_set_option(efts_ctx* c, const char* name, int32_t value) {
   if (strcmp(name, "pair") == 0) { c->pair = value != 0; return EFTS_OK; }
   if (strcmp(name, "debug_mask") == 0) { c->debug_mask = value; return EFTS_OK; }
   if (strcmp(name, "wide") == 0) { c->wide = value != 0; return EFTS_OK; }
+  if (strcmp(name, "imv_version") == 0) {
+    if (value != 1 && value != 2) return fail(EFTS_ERR_ARG, "imv_version must be 1 or 2");
+    c->imv_version = value;
+    return EFTS_OK;
+  }
+  if (strcmp(name, "reconstruct_version") == 0) {
+    if (value != 2 && value != 3) return fail(EFTS_ERR_ARG, "reconstruct_version must be 2 or 3");
+    c->reconstruct_version = value;
+    return EFTS_OK;
+  }
   if (strcmp(name, "chunk_kb") == 0) {
     if (value < 0 || value > 64) return fail(EFTS_ERR_ARG, "chunk_kb out of range");
     c->chunk_kb = value;
@@ -1191,19 +1243,19 @@ int efts_imv_generator(const float* alpha, const float* p, const int32_t* text_l
   if (!a.ok) return fail(EFTS_ERR_WORKSPACE, "workspace too small: need %zu, have %zu", a.off, workspace_bytes);
   alpha_expectation_kernel<<<dim3((T2 + 127) / 128, B), 128, 0, st>>>(alpha, p, T1, T2, raw);
   CUDA_TRY(cudaGetLastError());
-  imv_scan_kernel<<<(B + 3) / 4, 128, 0, st>>>(raw, nullptr, 0, text_lengths, speech_lengths, B, T2, imv);
-  CUDA_TRY(cudaGetLastError());
-  return EFTS_OK;
+  CUDA_TRY(cudaFuncSetAttribute(imv_scan_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(kReconstructSmemMax)));
+  return launch_imv_scan(2, st, raw, nullptr, 0, text_lengths, speech_lengths, B, T2, imv);
 }
 
 int efts_aligned_positions(const float* imv, const float* p, const int32_t* text_lengths, const int32_t* speech_lengths,
                            int32_t B, int32_t T1, int32_t T2, float sigma_e, float* e, void* stream) {
   if (!imv || !text_lengths || !speech_lengths || !e || B < 1 || T1 < 1 || T2 < 1 || B > 65535)
     return fail(EFTS_ERR_ARG, "efts_aligned_positions: bad argument");
-  aligned_positions_kernel<<<dim3((T1 + 7) / 8, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      imv, text_lengths, speech_lengths, T1, T2, sigma_e, e, p);
-  CUDA_TRY(cudaGetLastError());
-  return EFTS_OK;
+  CUDA_TRY(cudaFuncSetAttribute(aligned_positions_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(kReconstructSmemMax)));
+  return launch_aligned_positions(2, static_cast<cudaStream_t>(stream), imv, text_lengths, speech_lengths, B, T1, T2,
+                                  sigma_e, e, p);
 }
 
 int efts_reconstruct_alignment(const float* e, const int32_t* text_lengths, const int32_t* speech_lengths, int32_t B,
@@ -1213,18 +1265,10 @@ int efts_reconstruct_alignment(const float* e, const int32_t* text_lengths, cons
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int T1p = round8(T1);
   const float neg_sigma = -1.0f * delta;
-  const size_t smem = (static_cast<size_t>(T1p) * (RT_FRAMES + 1) + T1) * sizeof(float);
-  if (T1 <= 32 * RT_KMAX && smem <= kReconstructSmemMax) {
-    CUDA_TRY(cudaFuncSetAttribute(reconstruct_alignment_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(kReconstructSmemMax)));
-    reconstruct_alignment_tiled_kernel<<<dim3((T2 + RT_FRAMES - 1) / RT_FRAMES, B), 256, smem, st>>>(
-        e, text_lengths, speech_lengths, T1, T2, T1p, neg_sigma, reconst_alpha, nullptr, nullptr);
-  } else {
-    reconstruct_alignment_kernel<<<dim3((T2 + 127) / 128, B), 128, T1 * sizeof(float), st>>>(
-        e, text_lengths, speech_lengths, T1, T2, T1p, neg_sigma, reconst_alpha, nullptr, nullptr);
-  }
-  CUDA_TRY(cudaGetLastError());
-  return EFTS_OK;
+  CUDA_TRY(cudaFuncSetAttribute(reconstruct_alignment_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(kReconstructSmemMax)));
+  return launch_reconstruct(3, st, e, text_lengths, speech_lengths, B, T1, T2, T1p, neg_sigma, reconst_alpha, nullptr,
+                            nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------

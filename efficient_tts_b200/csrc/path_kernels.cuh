@@ -279,6 +279,143 @@ __global__ void aligned_positions_kernel(const float* __restrict__ imv, const in
   if (lane == 0) e[static_cast<size_t>(b) * T1 + i] = __fdiv_rn(num, den);
 }
 
+// B2 / B3, one block per utterance (the launches forward() uses).  Same arithmetic, element for element and in
+// the same order, as imv_scan_kernel / aligned_positions_kernel above -- those run one warp per utterance /
+// per token straight from global memory and spend their time waiting on dependent loads (59 + 49 us at C3 for
+// a few MB).  Here the whole block merges the softmax partials into shared memory, one warp runs the prefix
+// scan out of shared memory, and the block normalises and stores; the aligned-position kernel stages imv[b,:]
+// in shared memory once per 32 tokens and takes max_t G from min_t |imv[t] - p| (G is monotone in |d|).
+constexpr int IMV_BLOCK_THREADS = 256;
+__global__ void __launch_bounds__(IMV_BLOCK_THREADS)
+imv_scan_block_kernel(const float* __restrict__ imv_raw, const float4* __restrict__ part, int n_part,
+                      const int* __restrict__ tl, const int* __restrict__ sl, int T2, float* __restrict__ imv) {
+  extern __shared__ float scan_smem[];                       // [T2]
+  __shared__ float s_last;
+  const int b = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int L2 = sl[b];
+  float* y = imv + static_cast<size_t>(b) * T2;
+  for (int t = threadIdx.x; t < T2; t += IMV_BLOCK_THREADS) {
+    float r = 0.0f;
+    if (part == nullptr) {
+      r = imv_raw[static_cast<size_t>(b) * T2 + t];
+    } else if (t < L2) {                                     // pad frames: alpha is zeroed (:168) -> expectation 0
+      const float4* pp = part + (static_cast<size_t>(b) * T2 + t) * n_part;
+      float mx = -CUDART_INF_F;
+      for (int k = 0; k < n_part; ++k) mx = fmaxf(mx, pp[k].x);
+      double den = 0.0, num = 0.0;
+      for (int k = 0; k < n_part; ++k) {
+        const float4 v = pp[k];
+        const double sc = static_cast<double>(expf(v.x - mx));
+        den = fma(static_cast<double>(v.y), sc, den);
+        num = fma(static_cast<double>(v.z), sc, num);
+      }
+      r = static_cast<float>(num / den);
+    }
+    scan_smem[t] = r;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    double carry = 0.0;
+    float vmax = -CUDART_INF_F;
+    float prev_last = 0.0f;
+    for (int base = 0; base < T2; base += 32) {
+      const int t = base + lane;
+      const float r = t < T2 ? scan_smem[t] : 0.0f;
+      float prev = __shfl_up_sync(0xffffffffu, r, 1);
+      if (lane == 0) prev = prev_last;
+      prev_last = __shfl_sync(0xffffffffu, r, 31);
+      float d = 0.0f;
+      if (t > 0 && t < T2) d = fmaxf(__fsub_rn(r, prev), 0.0f);
+      double s = static_cast<double>(d);
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double n = __shfl_up_sync(0xffffffffu, s, o);
+        if (lane >= o) s += n;
+      }
+      s += carry;
+      carry = __shfl_sync(0xffffffffu, s, 31);
+      if (t < T2) {
+        const float c = __fmul_rn(static_cast<float>(s), t < L2 ? 1.0f : 0.0f);
+        scan_smem[t] = c;
+        vmax = fmaxf(vmax, c);
+      }
+    }
+    vmax = warp_max(vmax);
+    if (lane == 0) s_last = fmaxf(vmax, 1e-8f);
+  }
+  __syncthreads();
+  const float last = s_last;
+  const float scale = static_cast<float>(tl[b]) - 1.0f;
+  for (int t = threadIdx.x; t < T2; t += IMV_BLOCK_THREADS) y[t] = __fmul_rn(__fdiv_rn(scan_smem[t], last), scale);
+}
+
+constexpr int AP_TOKENS = 32;                                // tokens per block: 8 warps x 4
+__global__ void __launch_bounds__(IMV_BLOCK_THREADS)
+aligned_positions_block_kernel(const float* __restrict__ imv, const int* __restrict__ tl,
+                               const int* __restrict__ sl, int T1, int T2, float sigma_e,
+                               float* __restrict__ e, const float* __restrict__ pvec) {
+  extern __shared__ float ap_smem[];                         // [L2]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.y;
+  const int i0 = blockIdx.x * AP_TOKENS;
+  const int L1 = tl[b], L2 = sl[b];
+  if (i0 < L1) {
+    const float* x = imv + static_cast<size_t>(b) * T2;
+    for (int t = threadIdx.x; t < L2; t += IMV_BLOCK_THREADS) ap_smem[t] = x[t];
+  }
+  __syncthreads();
+  // each warp owns four consecutive tokens and walks the frames once for all of them (one shared-memory load
+  // and one int->float conversion per frame serve four softmax rows); per token the sums run over the frames in
+  // the same order as in aligned_positions_kernel
+  const int ib = i0 + warp * 4;
+  if (ib >= T1) return;
+  if (ib >= L1) {
+    if (lane < 4 && ib + lane < T1) e[static_cast<size_t>(b) * T1 + ib + lane] = 0.0f;
+    return;
+  }
+  float p[4], dmin[4], m[4], den[4], num[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int i = min(ib + k, T1 - 1);
+    p[k] = pvec != nullptr ? pvec[static_cast<size_t>(b) * T1 + i] : static_cast<float>(ib + k);
+    dmin[k] = CUDART_INF_F;
+    den[k] = 0.0f; num[k] = 0.0f;
+  }
+  for (int t = lane; t < L2; t += 32) {
+    const float x = ap_smem[t];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) dmin[k] = fminf(dmin[k], fabsf(__fsub_rn(x, p[k])));
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dmin[k] = fminf(dmin[k], __shfl_xor_sync(0xffffffffu, dmin[k], o));
+    // max_t G: for L2 == 0 the reference's softmax over an empty row gives NaN; dmin = inf reproduces it
+    m[k] = __fmul_rn(__fmul_rn(-1.0f, __fmul_rn(dmin[k], dmin[k])), sigma_e);
+  }
+#pragma unroll 2
+  for (int t = lane; t < L2; t += 32) {
+    const float x = ap_smem[t];
+    const float tf = static_cast<float>(t);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float d = __fsub_rn(x, p[k]);
+      const float g = __fmul_rn(__fmul_rn(-1.0f, __fmul_rn(d, d)), sigma_e);
+      const float ev = expf(g - m[k]);
+      den[k] += ev;
+      num[k] = fmaf(ev, tf, num[k]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    den[k] = warp_sum(den[k]);
+    num[k] = warp_sum(num[k]);
+    const int i = ib + k;
+    if (lane == 0 && i < T1) e[static_cast<size_t>(b) * T1 + i] = i < L1 ? __fdiv_rn(num[k], den[k]) : 0.0f;
+  }
+}
+
 // B4: reconstruct_align_from_aligned_position (models/efficient_tts.py:366-375, :186):
 // R[b,i,t] = softmax_i( fl32(-sigma) * (q_t - e_i)^2 over valid tokens ), zero at pad tokens/frames;
 // q_t = t on valid frames.  One thread per frame t, e[b,:] staged in shared memory.  Writes the
@@ -414,6 +551,206 @@ reconstruct_alignment_tiled_kernel(const float* __restrict__ e, const int* __res
       const __half cl = __float2half_rn((c - __half2float(ch)) * kSplitScale);
       *reinterpret_cast<__half2*>(p_hi + o + 2 * i2) = __halves2half2(ah, ch);
       *reinterpret_cast<__half2*>(p_lo + o + 2 * i2) = __halves2half2(al, cl);
+    }
+  }
+}
+
+// B4, frame-per-lane: the tiled kernel above issues ~150 M warp instructions for 404 MB at C3 and is bound by
+// instruction issue (ncu: 80 % issue-active, 25 % of DRAM peak), not by HBM.  Here every lane owns two frames
+// of a 64-frame tile and walks the tokens eight at a time (the warps of a block interleave over the 8-token
+// chunks), so that
+//   * the softmax over tokens needs no shuffles: per-frame partial minima of |q - e_i| / partial sums go through
+//     4 KB of shared memory once per pass.  max_i h_i is h at min_i |q - e_i| exactly (fl(d^2) and
+//     fl(neg_sigma * x) are monotone), so the first pass costs two instructions per element;
+//   * the exponentials are computed once: the second pass parks them in shared memory ([frame][token] fp32, 32
+//     bytes per lane and chunk), the third pass multiplies by the frame's reciprocal sum;
+//   * rows of the returned fp32 matrix [B,T1,T2] are stored straight from registers (lanes = consecutive
+//     frames, 128 B per warp store);
+//   * the K-major fp16 hi/lo operand rows [B,T2,ldp] overwrite the parked exponentials in place (the 32 bytes
+//     of a chunk become 16 B of hi + 16 B of lo) and are copied out with 16-byte vectors, each frame's row
+//     being one contiguous run in global memory.
+// Pad tokens of the last live chunk carry e = 3e38: d^2 = inf, h = -inf, exp = 0 -- no per-element predicate.
+// Same arithmetic per element as the kernels above (expf(h - m) * rcp(sum)); only the order of the partial sums
+// of the denominator differs.
+constexpr int R3_FRAMES = 64;
+constexpr int R3_WARPS = 8;
+// shared-memory row of one frame in bytes: 4 * ldp, padded so that (bytes / 16) is odd (conflict-free 16-byte
+// accesses with lanes = frames)
+__host__ __device__ __forceinline__ int r3_row_bytes(int ldp) { return (((ldp >> 2) | 1) << 4); }
+__host__ __device__ __forceinline__ size_t r3_smem_bytes(int ldp) {
+  return static_cast<size_t>(ldp) * 4 + 2 * R3_WARPS * R3_FRAMES * 4 + static_cast<size_t>(R3_FRAMES) * r3_row_bytes(ldp);
+}
+
+// eight fp32 values -> 16 B of fp16 hi + 16 B of fp16 lo (lo = fp16((x - hi) * 2^11))
+__device__ __forceinline__ void r3_split8(const float (&r)[8], uint4& h, uint4& l) {
+  uint32_t hh[4], ll[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const __half2 h2 = __floats2half2_rn(r[2 * k], r[2 * k + 1]);
+    const float2 f = __half22float2(h2);
+    const __half2 l2 = __floats2half2_rn((r[2 * k] - f.x) * kSplitScale, (r[2 * k + 1] - f.y) * kSplitScale);
+    hh[k] = *reinterpret_cast<const uint32_t*>(&h2);
+    ll[k] = *reinterpret_cast<const uint32_t*>(&l2);
+  }
+  h = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+  l = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+}
+
+__global__ void __launch_bounds__(32 * R3_WARPS)
+reconstruct_alignment_rows_kernel(const float* __restrict__ e, const int* __restrict__ tl,
+                                  const int* __restrict__ sl, int T1, int T2, int ldp, float neg_sigma,
+                                  float* __restrict__ R, __half* __restrict__ p_hi, __half* __restrict__ p_lo) {
+  extern __shared__ __align__(16) uint8_t r3_smem[];
+  float* se = reinterpret_cast<float*>(r3_smem);                      // [ldp]
+  float* red_m = se + ldp;                                            // [warps][64] partial min |q - e|
+  float* red_d = red_m + R3_WARPS * R3_FRAMES;                        // [warps][64] partial denominators
+  uint8_t* tile = reinterpret_cast<uint8_t*>(red_d + R3_WARPS * R3_FRAMES);   // [64][row_bytes]
+  const int rowb = r3_row_bytes(ldp);
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * R3_FRAMES;
+  const int L1 = tl != nullptr ? tl[b] : T1;
+  const int L2 = sl != nullptr ? sl[b] : T2;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* Rb = R + static_cast<size_t>(b) * T1 * T2;
+  const int ta = t0 + lane, tb = ta + 32;                              // this lane's two frames
+  const bool in_a = ta < T2, in_b = tb < T2;
+  if (t0 >= L2) {                                                      // whole tile is padding
+    float* pa = Rb + static_cast<size_t>(warp) * T2 + ta;
+    for (int i = warp; i < T1; i += R3_WARPS) {
+      if (in_a) pa[0] = 0.0f;
+      if (in_b) pa[32] = 0.0f;
+      pa += static_cast<size_t>(R3_WARPS) * T2;
+    }
+    return;
+  }
+  for (int i = threadIdx.x; i < ldp; i += 32 * R3_WARPS) se[i] = i < L1 ? e[static_cast<size_t>(b) * T1 + i] : 3.0e38f;
+  __syncthreads();
+  const int nch = (L1 + 7) >> 3;                                       // 8-token chunks that hold valid tokens
+  const bool live_a = ta < L2, live_b = tb < L2;
+  const float qa = live_a ? static_cast<float>(ta) : 0.0f;            // q = t * mel_mask (:368)
+  const float qb = live_b ? static_cast<float>(tb) : 0.0f;
+  // pass 1: min_i |q - e_i|
+  float da = CUDART_INF_F, db = CUDART_INF_F;
+  for (int c = warp; c < nch; c += R3_WARPS) {
+    const float4 e0 = *reinterpret_cast<const float4*>(se + 8 * c);
+    const float4 e1 = *reinterpret_cast<const float4*>(se + 8 * c + 4);
+    const float ev[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      da = fminf(da, fabsf(__fsub_rn(qa, ev[j])));
+      db = fminf(db, fabsf(__fsub_rn(qb, ev[j])));
+    }
+  }
+  red_m[warp * R3_FRAMES + lane] = da;
+  red_m[warp * R3_FRAMES + lane + 32] = db;
+  __syncthreads();
+#pragma unroll
+  for (int w = 0; w < R3_WARPS; ++w) {
+    da = fminf(da, red_m[w * R3_FRAMES + lane]);
+    db = fminf(db, red_m[w * R3_FRAMES + lane + 32]);
+  }
+  const float ma = __fmul_rn(neg_sigma, __fmul_rn(da, da));            // = max_i h_i
+  const float mb = __fmul_rn(neg_sigma, __fmul_rn(db, db));
+  // pass 2: exponentials (parked in shared memory) and denominators
+  uint8_t* rowa = tile + lane * rowb;
+  uint8_t* rowbp = rowa + 32 * rowb;
+  float sa = 0.0f, sb = 0.0f;
+  for (int c = warp; c < nch; c += R3_WARPS) {
+    const float4 e0 = *reinterpret_cast<const float4*>(se + 8 * c);
+    const float4 e1 = *reinterpret_cast<const float4*>(se + 8 * c + 4);
+    const float ev[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+    float xa[8], xb[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float ua = __fsub_rn(qa, ev[j]), ub = __fsub_rn(qb, ev[j]);
+      xa[j] = expf(__fmul_rn(neg_sigma, __fmul_rn(ua, ua)) - ma);
+      xb[j] = expf(__fmul_rn(neg_sigma, __fmul_rn(ub, ub)) - mb);
+      sa += xa[j];
+      sb += xb[j];
+    }
+    *reinterpret_cast<float4*>(rowa + 32 * c) = make_float4(xa[0], xa[1], xa[2], xa[3]);
+    *reinterpret_cast<float4*>(rowa + 32 * c + 16) = make_float4(xa[4], xa[5], xa[6], xa[7]);
+    *reinterpret_cast<float4*>(rowbp + 32 * c) = make_float4(xb[0], xb[1], xb[2], xb[3]);
+    *reinterpret_cast<float4*>(rowbp + 32 * c + 16) = make_float4(xb[4], xb[5], xb[6], xb[7]);
+  }
+  red_d[warp * R3_FRAMES + lane] = sa;
+  red_d[warp * R3_FRAMES + lane + 32] = sb;
+  __syncthreads();
+  sa = 0.0f; sb = 0.0f;
+#pragma unroll
+  for (int w = 0; w < R3_WARPS; ++w) {                                 // same order in every warp: one sum per frame
+    sa += red_d[w * R3_FRAMES + lane];
+    sb += red_d[w * R3_FRAMES + lane + 32];
+  }
+  // one correctly rounded reciprocal per frame instead of a division per element
+  const float inv_a = live_a ? __frcp_rn(sa) : 0.0f;
+  const float inv_b = live_b ? __frcp_rn(sb) : 0.0f;
+  // pass 3 (each thread revisits exactly what it parked): values -> fp32 rows from registers, hi/lo groups in place
+  const bool planes = p_hi != nullptr;
+  for (int c = warp; c < nch; c += R3_WARPS) {
+    const float4 a0 = *reinterpret_cast<const float4*>(rowa + 32 * c);
+    const float4 a1 = *reinterpret_cast<const float4*>(rowa + 32 * c + 16);
+    const float4 b0 = *reinterpret_cast<const float4*>(rowbp + 32 * c);
+    const float4 b1 = *reinterpret_cast<const float4*>(rowbp + 32 * c + 16);
+    float ra[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    float rb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      ra[j] = __fmul_rn(ra[j], inv_a);
+      rb[j] = __fmul_rn(rb[j], inv_b);
+    }
+    float* pa = Rb + static_cast<size_t>(8 * c) * T2 + ta;              // frame b sits 32 floats further
+    if (8 * c + 8 <= T1) {                                             // warp-uniform
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (in_a) pa[0] = ra[j];
+        if (in_b) pa[32] = rb[j];
+        pa += T2;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (8 * c + j < T1) {
+          if (in_a) pa[0] = ra[j];
+          if (in_b) pa[32] = rb[j];
+        }
+        pa += T2;
+      }
+    }
+    if (planes) {
+      uint4 h, l;
+      r3_split8(ra, h, l);
+      *reinterpret_cast<uint4*>(rowa + 32 * c) = h;
+      *reinterpret_cast<uint4*>(rowa + 32 * c + 16) = l;
+      r3_split8(rb, h, l);
+      *reinterpret_cast<uint4*>(rowbp + 32 * c) = h;
+      *reinterpret_cast<uint4*>(rowbp + 32 * c + 16) = l;
+    }
+  }
+  {                                                                    // pad tokens past the last live chunk
+    float* pa = Rb + static_cast<size_t>(8 * nch + warp) * T2 + ta;
+    for (int i = 8 * nch + warp; i < T1; i += R3_WARPS) {
+      if (in_a) pa[0] = 0.0f;
+      if (in_b) pa[32] = 0.0f;
+      pa += static_cast<size_t>(R3_WARPS) * T2;
+    }
+  }
+  if (!planes) return;
+  __syncthreads();
+  // operand rows of the live frames: ldp / 8 sixteen-byte groups per frame and plane, zeros past the live chunks
+  const int nlive = min(min(R3_FRAMES, T2 - t0), L2 - t0);
+  const int upr = ldp >> 3;
+  for (int r = warp; r < nlive; r += R3_WARPS) {
+    const size_t o = (static_cast<size_t>(b) * T2 + t0 + r) * ldp;
+    const uint8_t* src = tile + r * rowb;
+    for (int u = lane; u < upr; u += 32) {
+      uint4 vh = make_uint4(0u, 0u, 0u, 0u), vl = vh;
+      if (u < nch) {
+        vh = *reinterpret_cast<const uint4*>(src + 32 * u);
+        vl = *reinterpret_cast<const uint4*>(src + 32 * u + 16);
+      }
+      *reinterpret_cast<uint4*>(p_hi + o + 8 * u) = vh;
+      *reinterpret_cast<uint4*>(p_lo + o + 8 * u) = vl;
     }
   }
 }

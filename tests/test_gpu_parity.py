@@ -234,6 +234,35 @@ def test_skip_pad_tiles_does_not_change_results(model, dev):
     assert abs(a[1]["loss"] - b[1]["loss"]) <= 1e-6 * max(1.0, abs(a[1]["loss"]))
 
 
+def test_block_imv_kernels_equal_the_per_warp_kernels(model, dev):
+    """The block-per-utterance scan / aligned-position kernels do the same arithmetic in the same order as the
+    warp-per-row ones: imv bitwise equal.  The frame-per-lane reconstruction only reorders the partial sums of
+    the softmax denominator: reconst_alpha within 1e-6, mel within 1e-5."""
+    text, tl, speech, sl = make_forward_inputs(23, [77, 200, 9, 130], [460, 1200, 50, 777])
+    args = dict(text=text.to(dev), text_lengths=tl.to(dev), speech=speech.to(dev), speech_lengths=sl.to(dev))
+    eng = model._get_engine()
+    a = model(**args)
+    eng.set_option("imv_version", 1)
+    try:
+        b = model(**args)
+    finally:
+        eng.set_option("imv_version", 2)
+    for k in (2, 3, 4):
+        assert torch.equal(a[k], b[k])
+    eng.set_option("reconstruct_version", 2)
+    try:
+        c = model(**args)
+    finally:
+        eng.set_option("reconstruct_version", 3)
+    assert torch.equal(a[2], c[2])
+    assert (a[3] - c[3]).abs().max().item() <= 1e-6
+    assert (a[4] - c[4]).abs().max().item() <= 1e-5
+    # pad tokens / pad frames of the returned matrix are exact zeros in both
+    for bi in range(4):
+        assert a[3][bi, int(tl[bi]):, :].abs().max().item() == 0.0 if int(tl[bi]) < a[3].shape[1] else True
+        assert a[3][bi, :, int(sl[bi]):].abs().max().item() == 0.0 if int(sl[bi]) < a[3].shape[2] else True
+
+
 def test_forward_rejects_what_the_reference_rejects(model, dev):
     text, tl, speech, sl = make_forward_inputs(23, [12, 9], [60, 40])
     with pytest.raises(RuntimeError):       # padded dim != max(lengths): nets_utils.py:148 broadcast error
