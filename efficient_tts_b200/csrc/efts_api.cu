@@ -95,6 +95,7 @@ struct efts_ctx {
   int wide = 1;              // v2: short-reduction launches use the 16-epilogue-warp variant
   int debug_mask = 0;        // timing experiments only
   int chunk_kb = 2;          // v2: k-blocks per main-accumulator flush (1 = most accurate, 0 = never)
+  int fuse_b = 1;                // v2 conv layers: Ahi*[Bhi|Blo] as one N = 256 MMA (two MMAs per k-step instead of three)
   int imv_version = 2;           // 2: block-per-utterance scan / aligned positions, 1: warp-per-utterance / token
   int reconstruct_version = 3;   // 3: frame-per-lane Gaussian reconstruction, 2: warp-per-frame tiled kernel
   int64_t launches = 0;
@@ -178,10 +179,10 @@ int launch_gemm_t(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, cons
   return EFTS_OK;
 }
 
-template <int CG, int EPI, int WIDE>
+template <int CG, int EPI, int WIDE, int FUSE = 0>
 int launch_gemm2_t(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, const GemmParams& p) {
-  using Cfg = G2Cfg<CG, WIDE>;
-  auto kern = gemm2_kernel<CG, EPI, WIDE>;
+  using Cfg = G2Cfg<CG, WIDE, FUSE>;
+  auto kern = gemm2_kernel<CG, EPI, WIDE, FUSE>;
   alignas(64) CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   TRY(make_map(c, &ma_hi, a.hi, a.K, a.T, a.B, a.ld, G2_A_ROWS));
   TRY(make_map(c, &ma_lo, a.lo, a.K, a.T, a.B, a.ld, G2_A_ROWS));
@@ -234,6 +235,7 @@ int launch_gemm(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, GemmPa
       if (epi == EPI_SOFTMAX) return pair ? launch_gemm2_t<2, EPI_SOFTMAX, 1>(c, st, a, b, p) : launch_gemm2_t<1, EPI_SOFTMAX, 1>(c, st, a, b, p);
       return pair ? launch_gemm2_t<2, EPI_FULL, 1>(c, st, a, b, p) : launch_gemm2_t<1, EPI_FULL, 1>(c, st, a, b, p);
     }
+    if (epi == EPI_STD && pair && c->fuse_b && p.chunk_kb > 0) return launch_gemm2_t<2, EPI_STD, 0, 1>(c, st, a, b, p);
     if (epi == EPI_STD) return pair ? launch_gemm2_t<2, EPI_STD, 0>(c, st, a, b, p) : launch_gemm2_t<1, EPI_STD, 0>(c, st, a, b, p);
     if (epi == EPI_FULL) return pair ? launch_gemm2_t<2, EPI_FULL, 0>(c, st, a, b, p) : launch_gemm2_t<1, EPI_FULL, 0>(c, st, a, b, p);
     return pair ? launch_gemm2_t<2, EPI_SOFTMAX, 0>(c, st, a, b, p) : launch_gemm2_t<1, EPI_SOFTMAX, 0>(c, st, a, b, p);
@@ -277,6 +279,8 @@ int set_kernel_attributes() {
   EFTS_OPT_IN_V2(1, EPI_STD, 1); EFTS_OPT_IN_V2(1, EPI_FULL, 1); EFTS_OPT_IN_V2(1, EPI_SOFTMAX, 1);
   EFTS_OPT_IN_V2(2, EPI_STD, 1); EFTS_OPT_IN_V2(2, EPI_FULL, 1); EFTS_OPT_IN_V2(2, EPI_SOFTMAX, 1);
 #undef EFTS_OPT_IN_V2
+  CUDA_TRY(cudaFuncSetAttribute(gemm2_kernel<2, EPI_STD, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                G2Cfg<2, 0, 1>::SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(reconstruct_alignment_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(kReconstructSmemMax)));
   CUDA_TRY(cudaFuncSetAttribute(reconstruct_alignment_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -777,6 +781,7 @@ int efts_set_option(efts_ctx* c, const char* name, int32_t value) {
   if (strcmp(name, "pair") == 0) { c->pair = value != 0; return EFTS_OK; }
   if (strcmp(name, "debug_mask") == 0) { c->debug_mask = value; return EFTS_OK; }
   if (strcmp(name, "wide") == 0) { c->wide = value != 0; return EFTS_OK; }
+  if (strcmp(name, "fuse_b") == 0) { c->fuse_b = value != 0; return EFTS_OK; }
   if (strcmp(name, "imv_version") == 0) {
     if (value != 1 && value != 2) return fail(EFTS_ERR_ARG, "imv_version must be 1 or 2");
     c->imv_version = value;

@@ -36,14 +36,21 @@ constexpr int G2_REGS_EPI = 216;                     // 32 * (72 + 2 * 216) = 16
 constexpr int G2_STAGE_ROW_BYTES = 144;               // wide epilogue staging: 32 fp32 + pad per row (conflict-free v4 stores)
 constexpr int G2_STAGE_WARP_BYTES = 32 * G2_STAGE_ROW_BYTES;
 
-template <int CG, int WIDE = 0>
+// FUSE = 1 (CTA pairs, long reductions): the products that share the A operand, Ahi*Bhi and Ahi*Blo, are issued as
+// ONE N = 256 MMA whose B operand is [Bhi (leader CTA's 128 rows) ; Blo (peer CTA's 128 rows)], the third product
+// Alo*Bhi follows as an N = 128 MMA into the upper 128 accumulator columns (same 2^-11 scale as Ahi*Blo).  Two MMAs
+// per k-step instead of three, A fetched from shared memory twice instead of three times.  The N = 128 MMA needs
+// Bhi split 64 + 64 over the two CTAs at one common offset, so a third 64-row block per stage holds Bhi[0:64]
+// (leader, a duplicate) / Bhi[64:128] (peer).  Both accumulator halves restart with every chunk.
+template <int CG, int WIDE = 0, int FUSE = 0>
 struct G2Cfg {
+  static_assert(!FUSE || (CG == 2 && !WIDE), "the fused-B variant is the CTA-pair, long-reduction kernel");
   static constexpr int B_ROWS = G2_BN / CG;
   static constexpr int B_PLANE = B_ROWS * 128;
-  static constexpr int B_STAGE = 2 * B_PLANE;
+  static constexpr int B_STAGE = (FUSE ? 3 : 2) * B_PLANE;
   // the wide (short-reduction) variant trades pipeline depth for 16 per-warp transposition buffers
-  static constexpr int A_STAGES = WIDE ? 2 : (CG == 2 ? 3 : 2);
-  static constexpr int B_STAGES = WIDE ? (CG == 2 ? 4 : 2) : (CG == 2 ? 5 : 3);
+  static constexpr int A_STAGES = WIDE ? 2 : (CG == 2 ? (FUSE ? 2 : 3) : 2);
+  static constexpr int B_STAGES = WIDE ? (CG == 2 ? 4 : 2) : (CG == 2 ? (FUSE ? 4 : 5) : 3);
   static constexpr int EPI_WARPS = WIDE ? 16 : 8;
   static constexpr int SMEM_TILES = A_STAGES * G2_A_STAGE + B_STAGES * B_STAGE;
   static constexpr int SMEM_BYTES = SMEM_TILES + 1024 + 512 + 4 * G2_BIAS_MAX + EPI_WARPS * G2_STAGE_WARP_BYTES;
@@ -151,12 +158,12 @@ enum Gemm2Epi { EPI_STD = 0, EPI_FULL = 1, EPI_SOFTMAX = 2 };
 // columns at a time -- no running sums, 96 registers per thread, twice the warps to hide the store latency.
 constexpr int G2_THREADS_WIDE = 128 + 32 * 16;
 
-template <int CG, int EPI, int WIDE>
+template <int CG, int EPI, int WIDE, int FUSE = 0>
 __global__ void __launch_bounds__(WIDE ? G2_THREADS_WIDE : G2_THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
              const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
              const GemmParams p) {
-  using Cfg = G2Cfg<CG, WIDE>;
+  using Cfg = G2Cfg<CG, WIDE, FUSE>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = smem_base;
@@ -245,7 +252,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
             const int s = ia % Cfg::A_STAGES; const uint32_t ph = (ia / Cfg::A_STAGES) & 1;
             ptx::mbar_wait(emptyA(s), ph ^ 1u);
             const uint32_t dst = sA + s * G2_A_STAGE;
-            if (CG == 2) {
+            if ((p.debug_mask & 8) && ia >= static_cast<uint32_t>(Cfg::A_STAGES)) {   // timing experiment: no A traffic
+              if (leader || CG == 1) ptx::mbar_arrive(fullA(s));
+            } else if (CG == 2) {
               const uint32_t bar = ptx::map_to_cta(fullA(s), 0);
               if (leader) ptx::mbar_expect_tx(fullA(s), 2 * G2_A_STAGE);
               ptx::tma_load_3d_pair(&tmA_hi, bar, dst, kb * G2_BK, t0 - p.pad, b);
@@ -263,7 +272,17 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
             const uint32_t dst = sB + s * Cfg::B_STAGE;
             const int z = p.b_batched ? b : tap;
             const int nrow = n0 + static_cast<int>(rank) * Cfg::B_ROWS;
-            if (CG == 2) {
+            if ((p.debug_mask & 4) && ib >= static_cast<uint32_t>(Cfg::B_STAGES)) {   // timing experiment: no W traffic
+              if (leader || CG == 1) ptx::mbar_arrive(fullB(s));
+            } else if (FUSE) {
+              // leader: Bhi[0:64], Bhi[64:128], Bhi[0:64] again; peer: Blo[0:64], Blo[64:128], Bhi[64:128]
+              const uint32_t bar = ptx::map_to_cta(fullB(s), 0);
+              if (leader) ptx::mbar_expect_tx(fullB(s), 2 * Cfg::B_STAGE);
+              const CUtensorMap* own = leader ? &tmB_hi : &tmB_lo;
+              ptx::tma_load_3d_pair(own, bar, dst, kb * G2_BK, n0, z);
+              ptx::tma_load_3d_pair(own, bar, dst + Cfg::B_PLANE, kb * G2_BK, n0 + Cfg::B_ROWS, z);
+              ptx::tma_load_3d_pair(&tmB_hi, bar, dst + 2 * Cfg::B_PLANE, kb * G2_BK, nrow, z);
+            } else if (CG == 2) {
               const uint32_t bar = ptx::map_to_cta(fullB(s), 0);
               if (leader) ptx::mbar_expect_tx(fullB(s), 2 * Cfg::B_STAGE);
               ptx::tma_load_3d_pair(&tmB_hi, bar, dst, kb * G2_BK, nrow, z);
@@ -283,20 +302,21 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
     if (!WIDE) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(G2_REGS_CTRL));
     if (lane == 0 && leader) {
       constexpr uint32_t idesc = ptx::make_idesc_f16(G2_BM * CG, G2_BN);
+      constexpr uint32_t idesc_wide = ptx::make_idesc_f16(G2_BM * CG, 2 * G2_BN);
       auto commit = [&](uint32_t bar) {
         if (CG == 2) ptx::tc_commit_pair(bar, 3); else ptx::tc_commit(bar);
       };
       uint32_t ia = 0, ib = 0, g = 0, it = 0;
       for (long long w = cid; w < total; w += ncl) {
         const uint32_t tb = it & 1u;
-        ptx::mbar_wait(acc1_empty(tb), ((it >> 1) & 1u) ^ 1u);
+        if (!FUSE) ptx::mbar_wait(acc1_empty(tb), ((it >> 1) & 1u) ^ 1u);
         const uint32_t acc1 = tmem_base + 256u + tb * G2_BN;
         uint32_t first1 = 1;
         for (int kb0 = 0; kb0 < num_kb; kb0 += chunk_kb) {
           const uint32_t buf = g & 1u;
           ptx::mbar_wait(acc0_empty(buf), ((g >> 1) & 1u) ^ 1u);
           ptx::tc_fence_after();
-          const uint32_t acc0 = tmem_base + buf * G2_BN;
+          const uint32_t acc0 = tmem_base + buf * (FUSE ? 2 * G2_BN : G2_BN);
           uint32_t first0 = 1;
           const int kb1 = min(kb0 + chunk_kb, num_kb);
           for (int kb = kb0; kb < kb1; ++kb) {
@@ -317,7 +337,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
 #pragma unroll
               for (int k = 0; k < G2_BK / 16; ++k) {
                 const uint64_t ko = static_cast<uint64_t>(k * 2);
-                if (CG == 2) {
+                if (FUSE) {
+                  // columns [0,128): Ahi*Bhi, [128,256): Ahi*Blo + Alo*Bhi (dBl + one plane = the third block)
+                  const uint64_t dB3 = ptx::make_desc_sw128(b_addr + 2 * Cfg::B_PLANE, 0);
+                  ptx::mma_f16_ss_pair(acc0, dAh + ko, dBh + ko, idesc_wide, first0 ? 0u : 1u);
+                  ptx::mma_f16_ss_pair(acc0 + G2_BN, dAl + ko, dB3 + ko, idesc, 1u);
+                } else if (CG == 2) {
                   ptx::mma_f16_ss_pair(acc0, dAh + ko, dBh + ko, idesc, first0 ? 0u : 1u);
                   ptx::mma_f16_ss_pair(acc1, dAh + ko, dBl + ko, idesc, first1 ? 0u : 1u);
                   ptx::mma_f16_ss_pair(acc1, dAl + ko, dBh + ko, idesc, 1u);
@@ -335,7 +360,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
           commit(acc0_full(static_cast<int>(it & 1u), static_cast<int>(buf)));
           ++g;
         }
-        commit(acc1_full(tb));
+        if (!FUSE) commit(acc1_full(tb));
         ++it;
       }
     }
@@ -516,38 +541,55 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
         if (buf) ++uses1; else ++uses0;
         ptx::tc_fence_after();
         __syncwarp();
+        if (FUSE) {
+          // both halves of the chunk: main product and the 2^-11 correction, folded with one rounding
 #pragma unroll
-        for (int c = 0; c < G2_BN / 32; ++c) {     // two TMEM loads in flight per wait
-          uint32_t r0[16], r1[16];
-          ptx::tmem_ld_32x16(lane_addr + buf * G2_BN + c * 32, r0);
-          ptx::tmem_ld_32x16(lane_addr + buf * G2_BN + c * 32 + 16, r1);
-          ptx::tmem_ld_wait();
+          for (int c = 0; c < G2_BN / 16; ++c) {
+            uint32_t r0[16], r1[16];
+            ptx::tmem_ld_32x16(lane_addr + buf * (2 * G2_BN) + c * 16, r0);
+            ptx::tmem_ld_32x16(lane_addr + buf * (2 * G2_BN) + G2_BN + c * 16, r1);
+            ptx::tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            sum[c * 32 + j] = __fadd_rn(sum[c * 32 + j], __uint_as_float(r0[j]));
-            sum[c * 32 + 16 + j] = __fadd_rn(sum[c * 32 + 16 + j], __uint_as_float(r1[j]));
+            for (int j = 0; j < 16; ++j)
+              sum[c * 16 + j] = __fadd_rn(sum[c * 16 + j],
+                                          __fmaf_rn(__uint_as_float(r1[j]), SPLIT_INV_SCALE, __uint_as_float(r0[j])));
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < G2_BN / 32; ++c) {     // two TMEM loads in flight per wait
+            uint32_t r0[16], r1[16];
+            ptx::tmem_ld_32x16(lane_addr + buf * G2_BN + c * 32, r0);
+            ptx::tmem_ld_32x16(lane_addr + buf * G2_BN + c * 32 + 16, r1);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              sum[c * 32 + j] = __fadd_rn(sum[c * 32 + j], __uint_as_float(r0[j]));
+              sum[c * 32 + 16 + j] = __fadd_rn(sum[c * 32 + 16 + j], __uint_as_float(r1[j]));
+            }
           }
         }
         release(acc0_empty(buf));
       }
-      // fold the correction accumulator in and hand its TMEM back before the stores start
-      const uint32_t tb = it & 1u;
-      ptx::mbar_wait(acc1_full(tb), (it >> 1) & 1u);
-      ptx::tc_fence_after();
-      __syncwarp();
+      if (!FUSE) {
+        // fold the correction accumulator in and hand its TMEM back before the stores start
+        const uint32_t tb = it & 1u;
+        ptx::mbar_wait(acc1_full(tb), (it >> 1) & 1u);
+        ptx::tc_fence_after();
+        __syncwarp();
 #pragma unroll
-      for (int c = 0; c < G2_BN / 32; ++c) {
-        uint32_t r0[16], r1[16];
-        ptx::tmem_ld_32x16(lane_addr + 256u + tb * G2_BN + c * 32, r0);
-        ptx::tmem_ld_32x16(lane_addr + 256u + tb * G2_BN + c * 32 + 16, r1);
-        ptx::tmem_ld_wait();
+        for (int c = 0; c < G2_BN / 32; ++c) {
+          uint32_t r0[16], r1[16];
+          ptx::tmem_ld_32x16(lane_addr + 256u + tb * G2_BN + c * 32, r0);
+          ptx::tmem_ld_32x16(lane_addr + 256u + tb * G2_BN + c * 32 + 16, r1);
+          ptx::tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          sum[c * 32 + j] = __fadd_rn(sum[c * 32 + j], __uint_as_float(r0[j]) * SPLIT_INV_SCALE);
-          sum[c * 32 + 16 + j] = __fadd_rn(sum[c * 32 + 16 + j], __uint_as_float(r1[j]) * SPLIT_INV_SCALE);
+          for (int j = 0; j < 16; ++j) {
+            sum[c * 32 + j] = __fadd_rn(sum[c * 32 + j], __uint_as_float(r0[j]) * SPLIT_INV_SCALE);
+            sum[c * 32 + 16 + j] = __fadd_rn(sum[c * 32 + 16 + j], __uint_as_float(r1[j]) * SPLIT_INV_SCALE);
+          }
         }
+        release(acc1_empty(tb));
       }
-      release(acc1_empty(tb));
       if (!tile_live) continue;                     // warp-uniform: the stores below are warp-cooperative
       if (EPI == EPI_SOFTMAX) {
         if (!row_ok) continue;
