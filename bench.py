@@ -180,6 +180,16 @@ def run_ours(args, rank, local_rank, world):
     for _ in range(max(args.warmup, 3)):
         eng.forward(text, tl, speech, sl)
     barrier()
+    # one untimed profiled pass creates every CUDA event the per-kernel breakdown needs; the timed pass reuses them
+    eng.profile_enable(0x1FFF)
+    for _ in range(args.steps):
+        eng.forward(text, tl, speech, sl)
+    barrier()
+    t_host0 = time.perf_counter()                # host cost of enqueueing one step (launch queue empty: 2 steps fit)
+    for _ in range(2):
+        eng.forward(text, tl, speech, sl)
+    host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / 2
+    barrier()
     sampler = ClockSampler(physical_gpu_index(local_rank))
     sampler.start()
     eng.profile_enable(0x1FFF)
@@ -254,22 +264,25 @@ def run_ours(args, rank, local_rank, world):
         rows = np.mean([computed_rows(t2, T2p, 2 * (n_dec - 1 - l)) for l in range(n_dec)])
         flops_per_launch = 2.0 * rows * 512 * 512 * 5
         ach = flops_per_launch / (dec_ms / max(dec_n, 1) * 1e-3) / 1e12 if dec_n else None
-        traffic = None
+        traffic, pipe_ncu, rec_traffic = None, None, None
         tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("decoder_conv_dram_bytes_per_launch")
+                tj = json.load(open(tp))
+                traffic = tj.get("decoder_conv_dram_bytes_per_launch")
+                pipe_ncu = tj.get("decoder_conv_tensor_pipe_active_pct")
+                rec_traffic = tj.get("reconstruct_dram_bytes_per_launch")
             except Exception:
                 traffic = None
-        roof = {"bound": "tensor", "kernel": "gemm2_kernel<2> (CTA-pair tcgen05 tap-GEMM) on the decoder Conv1d layers (k=5, 512->512)",
+        roof = {"bound": "tensor", "kernel": "gemm2_kernel<2,0,0,1> (CTA-pair tcgen05 tap-GEMM, fused-B) on the decoder Conv1d layers (k=5, 512->512)",
                 "achieved": ach, "peak": peaks["tf"], "unit": "TFLOP/s", "frac": (ach / peaks["tf"]) if ach else None,
-                "traffic": traffic, "peak_source": peaks["src"], "passes": 3,
+                "traffic": traffic, "tensor_pipe_active_pct_ncu": pipe_ncu, "peak_source": peaks["src"], "passes": 3,
                 "executed_frac": (3 * ach / peaks["tf"]) if ach else None,
                 "flops_per_launch": flops_per_launch, "launches_timed": dec_n,
                 "avg_launch_ms": dec_ms / max(dec_n, 1),
                 "share_of_step": dec_ms / ms if ms else None,
                 "note": "achieved = single-pass algorithmic FLOPs; the split-fp16 scheme executes 3 tensor passes "
-                        "(executed_frac = 3 x frac is the tensor-pipe occupancy estimate)"}
+                        "(executed_frac = 3 x frac, against the power-capped cuBLAS bf16 rate)"}
         names = ["text_conv", "mel_conv", "dec_conv", "linear", "energy_gemm", "softmax_expect", "imv_scan",
                  "aligned_pos", "reconstruct", "expand_gemm", "duration", "loss", "embed_split"]
         breakdown = {names[k]: round(v[0] / args.steps, 4) for k, v in prof.items()}
@@ -284,10 +297,12 @@ def run_ours(args, rank, local_rank, world):
         imv_bytes = scan_bytes + aligned_bytes + recon_bytes
         imv_ms = sum(prof[k][0] for k in (5, 6, 7, 8)) / args.steps
         rec_ms = prof[8][0] / args.steps
-        hbm = {"kernels": "imv_scan + aligned_positions + reconstruct_alignment_tiled", "bytes_per_step": imv_bytes,
+        hbm = {"kernels": "imv_scan_block + aligned_positions_block + reconstruct_alignment_rows", "bytes_per_step": imv_bytes,
                "ms_per_step": imv_ms, "achieved_gbs": imv_bytes / (imv_ms * 1e-3) / 1e9 if imv_ms else None,
                "peak_gbs": peaks["hbm"], "frac": (imv_bytes / (imv_ms * 1e-3) / 1e9 / peaks["hbm"]) if imv_ms else None,
-               "reconstruct": {"bytes": recon_bytes, "ms": rec_ms,
+               "note": "scan and aligned positions move ~11 MB and are latency / exp-throughput bound; the HBM-bound "
+                       "kernel of the chain is the Gaussian reconstruction (97 % of the bytes)",
+               "reconstruct": {"bytes": recon_bytes, "ms": rec_ms, "traffic": rec_traffic,
                                "achieved_gbs": recon_bytes / (rec_ms * 1e-3) / 1e9 if rec_ms else None,
                                "frac": (recon_bytes / (rec_ms * 1e-3) / 1e9 / peaks["hbm"]) if rec_ms else None}}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -297,7 +312,7 @@ def run_ours(args, rank, local_rank, world):
                 "config": {"workload": WORKLOAD, "utterances_per_gpu": B, "valid_frames_per_gpu": frames,
                            "padded": [T1p, T2p], "l2": "working set per step ~3.3 GB >> 126 MB L2 (no flush needed)",
                            "parallelism": "dp%d (utterance shards, no data-path collective)" % world},
-                "clocks": clocks, "gpu_launches": launches,
+                "clocks": clocks, "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps, "stats": stats,
                         "pipeline": "H2D of step i+1 on a copy stream overlaps step i; loss read back every step"},
