@@ -95,6 +95,7 @@ struct efts_ctx {
   int wide = 1;              // v2: short-reduction launches use the 16-epilogue-warp variant
   int debug_mask = 0;        // timing experiments only
   int chunk_kb = 2;          // v2: k-blocks per main-accumulator flush (1 = most accurate, 0 = never)
+  int split_k = 1;               // fused-B kernel: split the reduction of small launches over more SMs
   int fuse_b = 1;                // v2 conv layers: Ahi*[Bhi|Blo] as one N = 256 MMA (two MMAs per k-step instead of three)
   int imv_version = 2;           // 2: block-per-utterance scan / aligned positions, 1: warp-per-utterance / token
   int reconstruct_version = 3;   // 3: frame-per-lane Gaussian reconstruction, 2: warp-per-frame tiled kernel
@@ -179,6 +180,9 @@ int launch_gemm_t(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, cons
   return EFTS_OK;
 }
 
+constexpr size_t kReconstructSmemMax = 200 * 1024;
+constexpr size_t kSplitScratchBytes = 16u << 20;       // partial planes of a split reduction (workspace, text side)
+
 template <int CG, int EPI, int WIDE, int FUSE = 0>
 int launch_gemm2_t(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, const GemmParams& p) {
   using Cfg = G2Cfg<CG, WIDE, FUSE>;
@@ -190,7 +194,7 @@ int launch_gemm2_t(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, con
   TRY(make_map(c, &mb_lo, b.lo, b.K, b.N, b.Z, b.ld, Cfg::B_ROWS));
   // persistent: one CTA per SM (CTA pairs when CG == 2), never more than there are tiles
   const long long n_rt = static_cast<long long>(p.B) * ((p.T + G2_BM - 1) / G2_BM);
-  const long long work = ((n_rt + CG - 1) / CG) * ((p.N + G2_BN - 1) / G2_BN);
+  const long long work = ((n_rt + CG - 1) / CG) * ((p.N + G2_BN - 1) / G2_BN) * (FUSE && p.splits > 1 ? p.splits : 1);
   long long ctas = std::min<long long>(c->sm_count / CG, work) * CG;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -235,7 +239,30 @@ int launch_gemm(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, GemmPa
       if (epi == EPI_SOFTMAX) return pair ? launch_gemm2_t<2, EPI_SOFTMAX, 1>(c, st, a, b, p) : launch_gemm2_t<1, EPI_SOFTMAX, 1>(c, st, a, b, p);
       return pair ? launch_gemm2_t<2, EPI_FULL, 1>(c, st, a, b, p) : launch_gemm2_t<1, EPI_FULL, 1>(c, st, a, b, p);
     }
-    if (epi == EPI_STD && pair && c->fuse_b && p.chunk_kb > 0) return launch_gemm2_t<2, EPI_STD, 0, 1>(c, st, a, b, p);
+    if (epi == EPI_STD && pair && c->fuse_b && p.chunk_kb > 0) {
+      // small problems (B = 1 synthesis: a handful of 27-us tiles on 148 SMs): one work item per accumulation
+      // chunk, partial planes summed in chunk order by splitk_reduce_kernel -- bitwise the unsplit result
+      const int num_kb = (p.K + G2_BK - 1) / G2_BK;
+      const int nchunks = (num_kb + p.chunk_kb - 1) / p.chunk_kb;
+      const long long n_rt = static_cast<long long>(p.B) * ((p.T + G2_BM - 1) / G2_BM);
+      const long long items = ((n_rt + 1) / 2) * ((p.N + G2_BN - 1) / G2_BN);
+      const size_t plane = static_cast<size_t>(p.B) * p.T * p.N;
+      if (c->split_k && p.split_scratch != nullptr && p.tile_list == nullptr && p.skip_lens == nullptr &&
+          nchunks > 1 && nchunks <= 8 && items * 4 <= c->sm_count && p.N % 4 == 0 && p.ld_out % 4 == 0 &&
+          p.ld_pl % 4 == 0 && plane * nchunks * sizeof(float) <= kSplitScratchBytes) {
+        GemmParams q = p;
+        q.bias = nullptr; q.act = ACT_NONE; q.resid = nullptr; q.lens = nullptr;
+        q.out = p.split_scratch; q.ld_out = p.N; q.out_hi = nullptr; q.out_lo = nullptr;
+        q.splits = nchunks; q.split_stride = plane;
+        TRY((launch_gemm2_t<2, EPI_STD, 0, 1>(c, st, a, b, q)));
+        const size_t n = plane / 4;
+        splitk_reduce_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(p, p.split_scratch, nchunks, plane);
+        CUDA_TRY(cudaGetLastError());
+        c->launches++;
+        return EFTS_OK;
+      }
+      return launch_gemm2_t<2, EPI_STD, 0, 1>(c, st, a, b, p);
+    }
     if (epi == EPI_STD) return pair ? launch_gemm2_t<2, EPI_STD, 0>(c, st, a, b, p) : launch_gemm2_t<1, EPI_STD, 0>(c, st, a, b, p);
     if (epi == EPI_FULL) return pair ? launch_gemm2_t<2, EPI_FULL, 0>(c, st, a, b, p) : launch_gemm2_t<1, EPI_FULL, 0>(c, st, a, b, p);
     return pair ? launch_gemm2_t<2, EPI_SOFTMAX, 0>(c, st, a, b, p) : launch_gemm2_t<1, EPI_SOFTMAX, 0>(c, st, a, b, p);
@@ -259,7 +286,7 @@ int launch_gemm(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, GemmPa
 #undef EFTS_DISPATCH
 }
 
-constexpr size_t kReconstructSmemMax = 200 * 1024;
+
 
 // Opt every kernel that needs more than 48 KB of dynamic shared memory in, once per context (the attribute
 // is per device, so it is not cached in a process-wide static).
@@ -423,6 +450,7 @@ struct FwdWs {
   float* xm_f[2]; __half *xm_hi[2], *xm_lo[2];
   float *S, *imv_raw;
   __half *R_hi, *R_lo;
+  float* splitk;              // partial planes of split reductions (kSplitScratchBytes)
   int2 *list_t, *list_m;      // compacted live row tiles (text side / mel side)
   int *cnt_t, *cnt_m;
   int T1p;
@@ -453,6 +481,7 @@ void carve_text(Arena& a, FwdWs& w, int B, int T1, int C) {
   w.e = a.get<float>(m1);
   w.list_t = a.get<int2>(static_cast<size_t>(B) * ((T1 + G2_BM - 1) / G2_BM));
   w.cnt_t = a.get<int>(4);
+  w.splitk = a.get<float>(kSplitScratchBytes / sizeof(float));
 }
 
 void carve_mel(Arena& a, FwdWs& w, int B, int T2, int C, int odim, bool teacher_forced) {
@@ -482,7 +511,7 @@ void carve_mel(Arena& a, FwdWs& w, int B, int T2, int C, int odim, bool teacher_
 // is non-null the last layer writes its fp32 result there instead (planes still go to the set).
 int run_conv_stack(efts_ctx* c, cudaStream_t st, const PackedW* layers, int n, int B, int T, float* f[2],
                    __half* hi[2], __half* lo[2], const float* first_resid, float* final_f,
-                   const Skip* skip, int* cur_io, int tag, bool ragged = false) {
+                   const Skip* skip, int* cur_io, int tag, bool ragged = false, float* splitk = nullptr) {
   const int C = c->cfg.n_channels;
   int cur = *cur_io;
   for (int l = 0; l < n; ++l) {
@@ -504,6 +533,7 @@ int run_conv_stack(efts_ctx* c, cudaStream_t st, const PackedW* layers, int n, i
     // ragged synthesis: every layer's rows t >= L_b are written as zeros, so utterance b convolves against
     // the zero padding it would see alone (tiles within `pad` rows of L_b are computed to produce those zeros)
     if (ragged) p.lens = skip->lens;
+    p.split_scratch = splitk;
     {
       ProfScope ps(c, st, tag);
       TRY(launch_gemm(c, st, OpA{hi[cur], lo[cur], B, T, C, C}, weight_op(layers[l]), p));
@@ -518,7 +548,7 @@ int run_conv_stack(efts_ctx* c, cudaStream_t st, const PackedW* layers, int n, i
 // Input operand planes in_hi/in_lo [B,T,C]; scratch dp_f, dp_hi/lo.
 int run_duration_predictor(efts_ctx* c, cudaStream_t st, const __half* in_hi, const __half* in_lo, int B,
                            int T, float* dp_f, __half* dp_hi, __half* dp_lo, const int* lens, int mode,
-                           void* out, bool mask_hidden = false, const Skip* skip = nullptr) {
+                           void* out, bool mask_hidden = false, const Skip* skip = nullptr, float* splitk = nullptr) {
   const int C = c->cfg.n_channels;
   const size_t rows = static_cast<size_t>(B) * T;
   const int nl = c->cfg.n_duration_layer;
@@ -537,6 +567,7 @@ int run_duration_predictor(efts_ctx* c, cudaStream_t st, const __half* in_hi, co
       p.skip_lens = skip->lens; p.tile_list = skip->list; p.tile_count = skip->count;
       p.skip_halo = p.pad * (nl - 1 - l);
     }
+    p.split_scratch = splitk;
     TRY(launch_gemm(c, st, OpA{ahi, alo, B, T, C, C}, weight_op(c->dp[l]), p));
     const int wpb = 8;
     const unsigned grid = static_cast<unsigned>((rows + wpb - 1) / wpb);
@@ -782,6 +813,7 @@ int efts_set_option(efts_ctx* c, const char* name, int32_t value) {
   if (strcmp(name, "debug_mask") == 0) { c->debug_mask = value; return EFTS_OK; }
   if (strcmp(name, "wide") == 0) { c->wide = value != 0; return EFTS_OK; }
   if (strcmp(name, "fuse_b") == 0) { c->fuse_b = value != 0; return EFTS_OK; }
+  if (strcmp(name, "split_k") == 0) { c->split_k = value != 0; return EFTS_OK; }
   if (strcmp(name, "imv_version") == 0) {
     if (value != 1 && value != 2) return fail(EFTS_ERR_ARG, "imv_version must be 1 or 2");
     c->imv_version = value;
@@ -963,7 +995,7 @@ int efts_inference_phase1(efts_ctx* c, const int64_t* text, int32_t T1, int32_t*
   c->launches++;
   int cur = 0;
   TRY(run_conv_stack(c, st, c->text, g.n_text_encoder_layer, 1, T1, w.xt_f, w.xt_hi, w.xt_lo, nullptr, nullptr,
-                     nullptr, &cur, TAG_TEXT_CONV));
+                     nullptr, &cur, TAG_TEXT_CONV, false, w.splitk));
   {   // value only: the key projection at :251 is computed by the reference but never used
     GemmParams p = gemm_defaults();
     p.N = C; p.bias = c->value.bias;
@@ -976,7 +1008,8 @@ int efts_inference_phase1(efts_ctx* c, const int64_t* text, int32_t T1, int32_t*
     TRY(launch_gemm(c, st, OpA{w.xt_hi[cur], w.xt_lo[cur], 1, T1, C, C}, weight_op(c->value), p));
   }
   // durations clamp(exp(x) - offset, 0) (:258) and their cumsum (:260); T2 = round(e[-1]) (:361)
-  TRY(run_duration_predictor(c, st, w.val_hi, w.val_lo, 1, T1, w.dp_f, w.dp_hi, w.dp_lo, nullptr, 1, w.dur));
+  TRY(run_duration_predictor(c, st, w.val_hi, w.val_lo, 1, T1, w.dp_f, w.dp_hi, w.dp_lo, nullptr, 1, w.dur, false,
+                             nullptr, w.splitk));
   duration_cumsum_kernel<<<1, 32, 0, st>>>(w.dur, T1, w.e, t2_dev);
   CUDA_TRY(cudaGetLastError());
   c->launches++;
@@ -1001,7 +1034,7 @@ int efts_inference_phase2(efts_ctx* c, int32_t T1, int32_t T2, float* mel_pred, 
                              reconst_alpha, w.xm_f[0], w.xm_hi[0], w.xm_lo[0]));
   int curm = 0;
   TRY(run_conv_stack(c, st, c->dec, g.n_decoder_layer, 1, T2, w.xm_f, w.xm_hi, w.xm_lo, nullptr, nullptr, nullptr,
-                     &curm, TAG_DEC_CONV));
+                     &curm, TAG_DEC_CONV, false, w.splitk));
   GemmParams p = gemm_defaults();
   p.N = g.odim; p.bias = c->melout.bias;
   p.out = mel_pred; p.ld_out = g.odim;

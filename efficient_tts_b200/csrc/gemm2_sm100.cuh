@@ -102,7 +102,7 @@ __global__ void build_tile_list_kernel(const int* __restrict__ lens, int B, int 
 // residual (all eight row loads are issued before the first store), zeroes rows past the utterance, writes the
 // fp32 result and its fp16 hi/lo operand planes, and range-checks what becomes an operand.
 __device__ __forceinline__ void g2_store_block32(const GemmParams& p, uint32_t stg, int b, int t_base, int n,
-                                                 int lens_b, int check_b, int lane) {
+                                                 int lens_b, int check_b, int lane, size_t out_off = 0) {
   const int sub_row = lane >> 3, sub_col = (lane & 7) * 4;
   const int nn = n + sub_col;
   const bool col_ok = nn < p.N;
@@ -129,7 +129,7 @@ __device__ __forceinline__ void g2_store_block32(const GemmParams& p, uint32_t s
         v.x = res[itr].x + v.x; v.y = res[itr].y + v.y; v.z = res[itr].z + v.z; v.w = res[itr].w + v.w;
       }
       if (tr >= lens_b) v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-      if (p.out != nullptr && !(p.debug_mask & 1)) *reinterpret_cast<float4*>(p.out + mr * p.ld_out + nn) = v;
+      if (p.out != nullptr && !(p.debug_mask & 1)) *reinterpret_cast<float4*>(p.out + out_off + mr * p.ld_out + nn) = v;
       if (p.out_hi != nullptr && !(p.debug_mask & 2)) {
         const float amax = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
         if (tr < check_b && amax > 65504.0f && p.err_flag != nullptr) atomicOr(p.err_flag, 8 | p.err_code);
@@ -218,12 +218,17 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
   const int tiles_per_b = (p.T + G2_BM - 1) / G2_BM;
   const int n_rt = p.tile_list != nullptr ? *p.tile_count : p.B * tiles_per_b;
   const int n_prt = (n_rt + CG - 1) / CG;
-  const long long total = static_cast<long long>(n_prt) * n_nt;
-  const int cid = blockIdx.x / CG, ncl = gridDim.x / CG;
   const int num_kb = (p.K + G2_BK - 1) / G2_BK;
   const int chunk_kb = p.chunk_kb < 1 ? num_kb : p.chunk_kb;
+  // split reduction: item w is chunk (w % splits) of tile (w / splits); every item is one accumulation chunk
+  const int splits = (FUSE && p.splits > 1) ? p.splits : 1;
+  const long long total = static_cast<long long>(n_prt) * n_nt * splits;
+  const int cid = blockIdx.x / CG, ncl = gridDim.x / CG;
+  const int item_kb = splits > 1 ? chunk_kb : num_kb;              // k-blocks per work item
+  auto kb_first = [&](long long w) { return splits > 1 ? static_cast<int>(w % splits) * chunk_kb : 0; };
 
-  auto locate = [&](long long w, int& b, int& t0, int& n0, bool& valid) {
+  auto locate = [&](long long w_in, int& b, int& t0, int& n0, bool& valid) {
+    const long long w = w_in / splits;
     const int nt = static_cast<int>(w % n_nt);
     const int rt = static_cast<int>(w / n_nt) * CG + static_cast<int>(rank);
     n0 = nt * G2_BN;
@@ -247,7 +252,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       for (long long w = cid; w < total; w += ncl) {
         int b, t0, n0; bool valid;
         locate(w, b, t0, n0, valid);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int kbf = kb_first(w);
+        for (int kb = kbf; kb < min(kbf + item_kb, num_kb); ++kb) {
           {
             const int s = ia % Cfg::A_STAGES; const uint32_t ph = (ia / Cfg::A_STAGES) & 1;
             ptx::mbar_wait(emptyA(s), ph ^ 1u);
@@ -312,13 +318,14 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
         if (!FUSE) ptx::mbar_wait(acc1_empty(tb), ((it >> 1) & 1u) ^ 1u);
         const uint32_t acc1 = tmem_base + 256u + tb * G2_BN;
         uint32_t first1 = 1;
-        for (int kb0 = 0; kb0 < num_kb; kb0 += chunk_kb) {
+        const int kbf = kb_first(w), kbl = min(kbf + item_kb, num_kb);
+        for (int kb0 = kbf; kb0 < kbl; kb0 += chunk_kb) {
           const uint32_t buf = g & 1u;
           ptx::mbar_wait(acc0_empty(buf), ((g >> 1) & 1u) ^ 1u);
           ptx::tc_fence_after();
           const uint32_t acc0 = tmem_base + buf * (FUSE ? 2 * G2_BN : G2_BN);
           uint32_t first0 = 1;
-          const int kb1 = min(kb0 + chunk_kb, num_kb);
+          const int kb1 = min(kb0 + chunk_kb, kbl);
           for (int kb = kb0; kb < kb1; ++kb) {
             const int sa = ia % Cfg::A_STAGES;
             ptx::mbar_wait(fullA(sa), (ia / Cfg::A_STAGES) & 1);
@@ -510,7 +517,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
     const uint32_t grp = static_cast<uint32_t>(warp - 4) >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    const uint32_t nchunks = static_cast<uint32_t>((num_kb + chunk_kb - 1) / chunk_kb);
+    const uint32_t nchunks = static_cast<uint32_t>((item_kb + chunk_kb - 1) / chunk_kb);
     auto release = [&](uint32_t bar) {            // one arrival per warp, on the leader's barrier
       ptx::tc_fence_before();
       __syncwarp();
@@ -662,7 +669,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
                        "f"(vv[0]), "f"(vv[1]), "f"(vv[2]), "f"(vv[3]) : "memory");
         }
         __syncwarp();
-        g2_store_block32(p, stg, b, t0 + q * 32, n, lens_b, check_b, lane);
+        g2_store_block32(p, stg, b, t0 + q * 32, n, lens_b, check_b, lane,
+                         splits > 1 ? static_cast<size_t>(w % splits) * p.split_stride : 0);
       }
     }
   }
@@ -673,6 +681,55 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
   if (CG == 2) ptx::cluster_sync(); else __syncthreads();
   if (warp == 1) {
     if (CG == 2) ptx::tmem_dealloc_pair(tmem_base, 512); else ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// Second half of a split reduction: sums the `splits` partial planes in chunk order (the same fp32 additions, in
+// the same order, as the running sums of the unsplit kernel: results are bitwise equal to it) and applies the
+// epilogue -- bias, activation, residual, row mask, fp32 store, fp16 hi/lo operand planes, operand range check.
+// One thread per (row, 4 columns).  Launches without tile lists only (every row of [B*T, N] is computed).
+__global__ void splitk_reduce_kernel(const GemmParams p, const float* __restrict__ part, int splits, size_t split_stride) {
+  const size_t n4 = static_cast<size_t>(p.N) >> 2;
+  const size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  const size_t rows = static_cast<size_t>(p.B) * p.T;
+  if (idx >= rows * n4) return;
+  const size_t mr = idx / n4;
+  const int nn = static_cast<int>(idx % n4) * 4;
+  float4 v = *reinterpret_cast<const float4*>(part + mr * p.N + nn);
+  v.x = __fadd_rn(0.0f, v.x); v.y = __fadd_rn(0.0f, v.y); v.z = __fadd_rn(0.0f, v.z); v.w = __fadd_rn(0.0f, v.w);
+  for (int s = 1; s < splits; ++s) {
+    const float4 u = *reinterpret_cast<const float4*>(part + s * split_stride + mr * p.N + nn);
+    v.x = __fadd_rn(v.x, u.x); v.y = __fadd_rn(v.y, u.y); v.z = __fadd_rn(v.z, u.z); v.w = __fadd_rn(v.w, u.w);
+  }
+  if (p.bias != nullptr) {
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + nn));
+    v.x = __fadd_rn(v.x, bb.x); v.y = __fadd_rn(v.y, bb.y); v.z = __fadd_rn(v.z, bb.z); v.w = __fadd_rn(v.w, bb.w);
+  }
+  if (p.act == ACT_LRELU) {
+    v.x = v.x > 0.0f ? v.x : __fmul_rn(v.x, 0.1f); v.y = v.y > 0.0f ? v.y : __fmul_rn(v.y, 0.1f);
+    v.z = v.z > 0.0f ? v.z : __fmul_rn(v.z, 0.1f); v.w = v.w > 0.0f ? v.w : __fmul_rn(v.w, 0.1f);
+  } else if (p.act == ACT_RELU) {
+    v.x = fmaxf(v.x, 0.0f); v.y = fmaxf(v.y, 0.0f); v.z = fmaxf(v.z, 0.0f); v.w = fmaxf(v.w, 0.0f);
+  }
+  if (p.resid != nullptr) {
+    const float4 r = *reinterpret_cast<const float4*>(p.resid + mr * p.ld_out + nn);
+    v.x = __fadd_rn(r.x, v.x); v.y = __fadd_rn(r.y, v.y); v.z = __fadd_rn(r.z, v.z); v.w = __fadd_rn(r.w, v.w);
+  }
+  const int b = static_cast<int>(mr / p.T), tr = static_cast<int>(mr % p.T);
+  if (p.lens != nullptr && tr >= p.lens[b]) v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  if (p.out != nullptr) *reinterpret_cast<float4*>(p.out + mr * p.ld_out + nn) = v;
+  if (p.out_hi != nullptr) {
+    const float amax = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+    if (amax > 65504.0f && p.err_flag != nullptr) atomicOr(p.err_flag, 8 | p.err_code);
+    const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
+    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+    const __half2 l01 = __floats2half2_rn((v.x - f01.x) * SPLIT_SCALE, (v.y - f01.y) * SPLIT_SCALE);
+    const __half2 l23 = __floats2half2_rn((v.z - f23.x) * SPLIT_SCALE, (v.w - f23.y) * SPLIT_SCALE);
+    uint2 ph, pl;
+    ph.x = *reinterpret_cast<const uint32_t*>(&h01); ph.y = *reinterpret_cast<const uint32_t*>(&h23);
+    pl.x = *reinterpret_cast<const uint32_t*>(&l01); pl.y = *reinterpret_cast<const uint32_t*>(&l23);
+    *reinterpret_cast<uint2*>(p.out_hi + mr * p.ld_pl + nn) = ph;
+    *reinterpret_cast<uint2*>(p.out_lo + mr * p.ld_pl + nn) = pl;
   }
 }
 

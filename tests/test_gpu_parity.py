@@ -407,6 +407,28 @@ def test_inference_c1_shape_matches_oracle(dev):
         m.inference(torch.zeros(2, 5, dtype=torch.long, device=dev))
 
 
+def test_split_reduction_is_bitwise_the_unsplit_result(dev):
+    """B = 1 synthesis splits every conv layer's reduction into one work item per accumulation chunk
+    (splitk_reduce_kernel adds the partial planes in chunk order): same bits as the unsplit kernel."""
+    w1 = orc.make_weights(seed=1234, dur_bias=1.7917594692, dur_weight_scale=0.05)
+    m = build_model(w1, dev)
+    eng = m._get_engine()
+    for n_tok in (7, 40):
+        t = make_inference_inputs(11 + n_tok, n_tok).to(dev)
+        n0 = eng.launch_count()
+        mel_a, ra_a = m.inference(t)
+        n_split = eng.launch_count() - n0
+        eng.set_option("split_k", 0)
+        try:
+            n0 = eng.launch_count()
+            mel_b, ra_b = m.inference(t)
+            n_plain = eng.launch_count() - n0
+        finally:
+            eng.set_option("split_k", 1)
+        assert n_split > n_plain            # the reduce launches are there: the split path really ran
+        assert torch.equal(mel_a, mel_b) and torch.equal(ra_a, ra_b)
+
+
 def test_helper_methods_match_oracle(model, dev):
     """The reference's public stage methods (models/efficient_tts.py:287-398) called one by one."""
     w = orc.make_weights(seed=1234)
