@@ -1123,15 +1123,27 @@ __global__ void length_regulator_fwd_kernel(const float* __restrict__ xs, const 
   if ((D & 3) == 0) {
     const int d4 = D >> 2;
     const float4 padv = make_float4(pad_value, pad_value, pad_value, pad_value);
-    for (int k = threadIdx.x; k < LR_FRAMES * d4; k += blockDim.x) {
-      const int f = k / d4, c = k % d4;
+    // one warp per output frame: the row is one contiguous run on both sides (512 B per warp access), no
+    // index arithmetic per element; four independent 16-byte loads are in flight per lane before the stores
+    for (int f = w; f < LR_FRAMES; f += nw) {
       const long long j = j0 + f;
       if (j >= Tout) break;
       const int s = src[f];
-      const float4 v =
-          s >= 0 ? __ldg(reinterpret_cast<const float4*>(xs + (static_cast<size_t>(b) * T1 + s) * D) + c)
-                 : padv;
-      reinterpret_cast<float4*>(out + (static_cast<size_t>(b) * Tout + j) * D)[c] = v;
+      const float4* sp = reinterpret_cast<const float4*>(xs + (static_cast<size_t>(b) * T1 + max(s, 0)) * D);
+      float4* dp = reinterpret_cast<float4*>(out + (static_cast<size_t>(b) * Tout + j) * D);
+      for (int c0 = 0; c0 < d4; c0 += 128) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int c = c0 + u * 32 + lane;
+          v[u] = (s >= 0 && c < d4) ? __ldg(sp + c) : padv;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int c = c0 + u * 32 + lane;
+          if (c < d4) dp[c] = v[u];
+        }
+      }
     }
   } else {   // D not a multiple of 4: scalar copies (never on the EFTS path, D = 512)
     for (int k = threadIdx.x; k < LR_FRAMES * D; k += blockDim.x) {

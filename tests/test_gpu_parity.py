@@ -413,20 +413,19 @@ def test_split_reduction_is_bitwise_the_unsplit_result(dev):
     w1 = orc.make_weights(seed=1234, dur_bias=1.7917594692, dur_weight_scale=0.05)
     m = build_model(w1, dev)
     eng = m._get_engine()
-    for n_tok in (7, 40):
+    for n_tok in (7, 40, 64):
         t = make_inference_inputs(11 + n_tok, n_tok).to(dev)
-        n0 = eng.launch_count()
-        mel_a, ra_a = m.inference(t)
-        n_split = eng.launch_count() - n0
-        eng.set_option("split_k", 0)
+        res, launches = {}, {}
         try:
-            n0 = eng.launch_count()
-            mel_b, ra_b = m.inference(t)
-            n_plain = eng.launch_count() - n0
+            for mode in (1, 0):
+                eng.set_option("split_k", mode)
+                n0 = eng.launch_count()
+                res[mode] = m.inference(t)
+                launches[mode] = eng.launch_count() - n0
         finally:
             eng.set_option("split_k", 1)
-        assert n_split > n_plain            # the reduce launches are there: the split path really ran
-        assert torch.equal(mel_a, mel_b) and torch.equal(ra_a, ra_b)
+        assert launches[1] > launches[0]    # the reduce launches are there: the split path really ran
+        assert torch.equal(res[1][0], res[0][0]) and torch.equal(res[1][1], res[0][1])
 
 
 def test_helper_methods_match_oracle(model, dev):
