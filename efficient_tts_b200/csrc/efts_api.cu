@@ -96,6 +96,7 @@ struct efts_ctx {
   int debug_mask = 0;        // timing experiments only
   int chunk_kb = 2;          // v2: k-blocks per main-accumulator flush (1 = most accurate, 0 = never)
   int split_k = 1;               // fused-B kernel: split the reduction of small launches over more SMs
+  int pdl = 1;                   // programmatic dependent launch for the v2 GEMM and split-reduce kernels
   int fuse_b = 1;                // v2 conv layers: Ahi*[Bhi|Blo] as one N = 256 MMA (two MMAs per k-step instead of three)
   int imv_version = 2;           // 2: block-per-utterance scan / aligned positions, 1: warp-per-utterance / token
   int reconstruct_version = 3;   // 3: frame-per-lane Gaussian reconstruction, 2: warp-per-frame tiled kernel
@@ -202,13 +203,15 @@ int launch_gemm2_t(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, con
   cfg.blockDim = dim3(WIDE ? G2_THREADS_WIDE : G2_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // prologue overlaps the predecessor's tail
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = c->pdl ? 2 : 1;
   CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ma_hi, ma_lo, mb_hi, mb_lo, p));
   c->launches++;
   return EFTS_OK;
@@ -256,8 +259,18 @@ int launch_gemm(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, GemmPa
         q.splits = nchunks; q.split_stride = plane;
         TRY((launch_gemm2_t<2, EPI_STD, 0, 1>(c, st, a, b, q)));
         const size_t n = plane / 4;
-        splitk_reduce_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(p, p.split_scratch, nchunks, plane);
-        CUDA_TRY(cudaGetLastError());
+        cudaLaunchConfig_t rc;
+        memset(&rc, 0, sizeof(rc));
+        rc.gridDim = dim3(static_cast<unsigned>((n + 255) / 256));
+        rc.blockDim = dim3(256);
+        rc.stream = st;
+        cudaLaunchAttribute ra[1];
+        ra[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        ra[0].val.programmaticStreamSerializationAllowed = 1;
+        rc.attrs = ra;
+        rc.numAttrs = c->pdl ? 1 : 0;
+        const float* part = p.split_scratch;
+        CUDA_TRY(cudaLaunchKernelEx(&rc, splitk_reduce_kernel, p, part, nchunks, plane));
         c->launches++;
         return EFTS_OK;
       }
@@ -814,6 +827,7 @@ int efts_set_option(efts_ctx* c, const char* name, int32_t value) {
   if (strcmp(name, "wide") == 0) { c->wide = value != 0; return EFTS_OK; }
   if (strcmp(name, "fuse_b") == 0) { c->fuse_b = value != 0; return EFTS_OK; }
   if (strcmp(name, "split_k") == 0) { c->split_k = value != 0; return EFTS_OK; }
+  if (strcmp(name, "pdl") == 0) { c->pdl = value != 0; return EFTS_OK; }
   if (strcmp(name, "imv_version") == 0) {
     if (value != 1 && value != 2) return fail(EFTS_ERR_ARG, "imv_version must be 1 or 2");
     c->imv_version = value;

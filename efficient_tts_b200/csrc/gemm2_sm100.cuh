@@ -212,6 +212,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
   ptx::tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  // Everything above (barriers, tensor memory, bias = weights) is independent of the previous launch: with
+  // programmatic dependent launch it overlaps the predecessor's tail.  From here on activations are touched.
+  ptx::pdl_wait();
+  ptx::pdl_launch_dependents();
 
   // ---- work list (identical in every role) ----
   const int n_nt = (p.N + G2_BN - 1) / G2_BN;
@@ -689,6 +693,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
 // epilogue -- bias, activation, residual, row mask, fp32 store, fp16 hi/lo operand planes, operand range check.
 // One thread per (row, 4 columns).  Launches without tile lists only (every row of [B*T, N] is computed).
 __global__ void splitk_reduce_kernel(const GemmParams p, const float* __restrict__ part, int splits, size_t split_stride) {
+  ptx::pdl_wait();
+  ptx::pdl_launch_dependents();
   const size_t n4 = static_cast<size_t>(p.N) >> 2;
   const size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   const size_t rows = static_cast<size_t>(p.B) * p.T;

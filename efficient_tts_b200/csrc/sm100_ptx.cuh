@@ -153,6 +153,14 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n) {
          | (static_cast<uint32_t>(m >> 4) << 24);    // M / 16
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in
+// the stream still runs; nothing the predecessor wrote may be read (and nothing it reads overwritten) before
+// pdl_wait(), which returns once the predecessor grids have completed and flushed.  Without the launch attribute
+// both instructions are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- clusters / CTA pairs (cta_group::2)
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;

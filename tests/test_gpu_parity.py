@@ -428,6 +428,36 @@ def test_split_reduction_is_bitwise_the_unsplit_result(dev):
         assert torch.equal(res[1][0], res[0][0]) and torch.equal(res[1][1], res[0][1])
 
 
+def test_programmatic_dependent_launch_does_not_change_results(model, dev):
+    """GEMM launches carry the programmatic-stream-serialization attribute (their prologue overlaps the previous
+    kernel's tail, `griddepcontrol.wait` guards the first touch of activations): bitwise the serialized result,
+    over repeated runs (a missing wait would show up as a race)."""
+    text, tl, speech, sl = make_forward_inputs(31, [33, 90, 12], [200, 540, 70])
+    args = dict(text=text.to(dev), text_lengths=tl.to(dev), speech=speech.to(dev), speech_lengths=sl.to(dev))
+    eng = model._get_engine()
+    eng.set_option("pdl", 0)
+    try:
+        ref = model(**args)
+    finally:
+        eng.set_option("pdl", 1)
+    for _ in range(5):
+        out = model(**args)
+        for k in (2, 3, 4):
+            assert torch.equal(out[k], ref[k])
+    w1 = orc.make_weights(seed=1234, dur_bias=1.7917594692, dur_weight_scale=0.05)
+    m1 = build_model(w1, dev)
+    e1 = m1._get_engine()
+    t = make_inference_inputs(3, 48).to(dev)
+    e1.set_option("pdl", 0)
+    try:
+        mel0, ra0 = m1.inference(t)
+    finally:
+        e1.set_option("pdl", 1)
+    for _ in range(5):
+        mel1, ra1 = m1.inference(t)
+        assert torch.equal(mel0, mel1) and torch.equal(ra0, ra1)
+
+
 def test_helper_methods_match_oracle(model, dev):
     """The reference's public stage methods (models/efficient_tts.py:287-398) called one by one."""
     w = orc.make_weights(seed=1234)
