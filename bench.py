@@ -30,6 +30,24 @@ UNIT = "mel_frames/s"
 METRIC = "mel_frames_per_sec_forward_b256"
 
 
+# The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on the first
+# communicator), so file descriptor 1 is pointed at stderr for the whole run and the line goes to the saved stdout.
+_REAL_STDOUT = None
+
+
+def capture_stdout():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def load_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -142,7 +160,7 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -364,7 +382,7 @@ def run_ours(args, rank, local_rank, world):
     elif rank == 0:
         line["cpu_baseline"] = None
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -384,6 +402,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=32, help="utterances in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    capture_stdout()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
