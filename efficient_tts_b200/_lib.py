@@ -22,6 +22,12 @@ class EftsConfig(ctypes.Structure):
                 ("device", c_i32)]
 
 
+class EftsVocoderConfig(ctypes.Structure):
+    _fields_ = [("num_mels", c_i32), ("upsample_initial_channel", c_i32), ("num_upsamples", c_i32),
+                ("upsample_rates", c_i32 * 8), ("upsample_kernel_sizes", c_i32 * 8), ("num_kernels", c_i32),
+                ("resblock_kernel_sizes", c_i32 * 4), ("resblock_dilations", (c_i32 * 3) * 4), ("device", c_i32)]
+
+
 # name -> (restype, argtypes); also the export list checked by tests/test_abi.py
 SIGNATURES = {
     "efts_create": (c_i32, [ctypes.POINTER(EftsConfig), ctypes.POINTER(c_void_p)]),
@@ -61,6 +67,10 @@ SIGNATURES = {
                                        c_void_p]),
     "efts_reconstruct_alignment": (c_i32, [c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_f32, c_void_p,
                                            c_void_p]),
+    "efts_vocoder_create": (c_i32, [ctypes.POINTER(EftsVocoderConfig), ctypes.POINTER(c_void_p)]),
+    "efts_vocoder_finalize": (c_i32, [c_void_p]),
+    "efts_vocoder_workspace_bytes": (c_size_t, [c_void_p, c_i32, c_i32]),
+    "efts_vocoder_forward": (c_i32, [c_void_p, c_void_p, c_i32, c_i32, c_void_p, c_void_p, c_size_t, c_void_p]),
     "efts_set_option": (c_i32, [c_void_p, c_char_p, c_i32]),
     "efts_launch_count": (c_i64, [c_void_p]),
     "efts_error_flags": (c_i32, [c_void_p, c_void_p, ctypes.POINTER(c_i32)]),

@@ -18,6 +18,7 @@
 #include "gemm_sm100.cuh"
 #include "gemm2_sm100.cuh"
 #include "path_kernels.cuh"
+#include "vocoder_kernels.cuh"
 
 namespace {
 
@@ -114,6 +115,16 @@ struct efts_ctx {
   float* head_w = nullptr;
   float* head_b = nullptr;
   int* err_flag = nullptr;   // device word: bit 3 = activation outside the fp16 operand range
+  // HiFi-GAN generator contexts (efts_vocoder_create) carry their layers here; cfg above is unused for them
+  struct Vocoder {
+    efts_vocoder_config cfg;
+    PackedW conv_pre;
+    PackedW ups[8];                    // transposed conv as a 3-tap GEMM with N = rate * C (polyphase columns)
+    PackedW c1[32][3], c2[32][3];      // resblocks[n].convs1[m] / convs2[m]
+    float* post_w = nullptr;           // [7][C_last]
+    float post_b = 0.0f;
+  };
+  Vocoder* voc = nullptr;
   // measurement hooks (efts_profile_*): CUDA-event pairs around tagged launches
   struct ProfRec { cudaEvent_t a, b; int tag; };
   std::vector<ProfRec> prof;
@@ -184,13 +195,18 @@ int launch_gemm_t(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, cons
 constexpr size_t kReconstructSmemMax = 200 * 1024;
 constexpr size_t kSplitScratchBytes = 16u << 20;       // partial planes of a split reduction (workspace, text side)
 
-template <int CG, int EPI, int WIDE, int FUSE = 0>
+template <int CG, int EPI, int WIDE, int FUSE = 0, int AR = G2_A_ROWS>
 int launch_gemm2_t(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, const GemmParams& p) {
-  using Cfg = G2Cfg<CG, WIDE, FUSE>;
-  auto kern = gemm2_kernel<CG, EPI, WIDE, FUSE>;
+  using Cfg = G2Cfg<CG, WIDE, FUSE, AR>;
+  auto kern = gemm2_kernel<CG, EPI, WIDE, FUSE, AR>;
+  const int dil = p.dil > 1 ? p.dil : 1;
+  if (G2_BM + (p.ntaps - 1) * dil > AR)
+    return fail(EFTS_ERR_ARG, "%d taps with dilation %d need a %d-row A box (this variant holds %d)", p.ntaps, dil,
+                G2_BM + (p.ntaps - 1) * dil, AR);
+  if (p.bias != nullptr && p.N > Cfg::BIAS_MAX) return fail(EFTS_ERR_ARG, "bias supports at most %d columns", Cfg::BIAS_MAX);
   alignas(64) CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
-  TRY(make_map(c, &ma_hi, a.hi, a.K, a.T, a.B, a.ld, G2_A_ROWS));
-  TRY(make_map(c, &ma_lo, a.lo, a.K, a.T, a.B, a.ld, G2_A_ROWS));
+  TRY(make_map(c, &ma_hi, a.hi, a.K, a.T, a.B, a.ld, AR));
+  TRY(make_map(c, &ma_lo, a.lo, a.K, a.T, a.B, a.ld, AR));
   TRY(make_map(c, &mb_hi, b.hi, b.K, b.N, b.Z, b.ld, Cfg::B_ROWS));
   TRY(make_map(c, &mb_lo, b.lo, b.K, b.N, b.Z, b.ld, Cfg::B_ROWS));
   // persistent: one CTA per SM (CTA pairs when CG == 2), never more than there are tiles
@@ -222,8 +238,7 @@ int launch_gemm(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, GemmPa
   if (a.K != b.K) return fail(EFTS_ERR_ARG, "gemm K mismatch %d vs %d", a.K, b.K);
   if (p.N % 8 != 0) return fail(EFTS_ERR_ARG, "gemm N=%d must be a multiple of 8", p.N);
   if (c->gemm_version == 2) {
-    if (p.ntaps > 9) return fail(EFTS_ERR_ARG, "at most 9 taps");
-    if (p.bias != nullptr && p.N > G2_BIAS_MAX) return fail(EFTS_ERR_ARG, "bias supports at most %d columns", G2_BIAS_MAX);
+    if (p.ntaps > 11) return fail(EFTS_ERR_ARG, "at most 11 taps");
     p.chunk_kb = c->chunk_kb;
     p.debug_mask = c->debug_mask;
     p.err_flag = c->err_flag;
@@ -235,6 +250,12 @@ int launch_gemm(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, GemmPa
     // short reductions (<= 40 MMA steps: one accumulation chain is as accurate as a flushed one) are bound by
     // their epilogue: they take the wide variant, which reads the single chunk straight from tensor memory
     const int steps = p.ntaps * ((p.K + G2_BK - 1) / G2_BK) * (G2_BK / 16);
+    if (p.long_taps) {        // vocoder layers: up to 11 taps / dilation 5, always the fused-B pair kernel
+      if (epi != EPI_STD || p.b_batched || p.chunk_kb < 1)
+        return fail(EFTS_ERR_ARG, "long-tap launches are plain weight GEMMs");
+      p.splits = 0;
+      return launch_gemm2_t<2, EPI_STD, 0, 1, G2_A_ROWS_LONG>(c, st, a, b, p);
+    }
     const bool wide = c->wide && steps <= 40;
     if (wide) {
       p.chunk_kb = 0;
@@ -321,6 +342,8 @@ int set_kernel_attributes() {
 #undef EFTS_OPT_IN_V2
   CUDA_TRY(cudaFuncSetAttribute(gemm2_kernel<2, EPI_STD, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 G2Cfg<2, 0, 1>::SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(gemm2_kernel<2, EPI_STD, 0, 1, G2_A_ROWS_LONG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                G2Cfg<2, 0, 1, G2_A_ROWS_LONG>::SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(reconstruct_alignment_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(kReconstructSmemMax)));
   CUDA_TRY(cudaFuncSetAttribute(reconstruct_alignment_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -694,6 +717,8 @@ int split_planes(efts_ctx* c, cudaStream_t st, const float* x, size_t n, __half*
 }  // namespace
 
 // ================================================================================================
+namespace { int create_base(int device, efts_ctx** out); }
+
 extern "C" {
 
 const char* efts_last_error(void) { return g_err; }
@@ -712,20 +737,31 @@ int efts_create(const efts_config* cfg, efts_ctx** out) {
       cfg->n_duration_layer < 1 || cfg->n_duration_layer > 4)
     return fail(EFTS_ERR_UNSUPPORTED, "layer counts out of range");
   if (cfg->leaky_relu_slope != 0.1f) return fail(EFTS_ERR_UNSUPPORTED, "leaky_relu_slope must be 0.1");
+  efts_ctx* c = nullptr;
+  TRY(create_base(cfg->device, &c));
+  c->cfg = *cfg;
+  *out = c;
+  return EFTS_OK;
+}
+
+}  // extern "C"
+
+namespace {
+// Device checks, kernel attributes, the tensor-map encoder and the error word shared by both context kinds.
+int create_base(int device, efts_ctx** out) {
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
     return fail(EFTS_ERR_CUDA, "no CUDA device: %s (this library has no CPU path)", cudaGetErrorString(e));
-  if (cfg->device < 0 || cfg->device >= ndev) return fail(EFTS_ERR_ARG, "device %d out of range", cfg->device);
+  if (device < 0 || device >= ndev) return fail(EFTS_ERR_ARG, "device %d out of range", device);
   cudaDeviceProp prop;
-  CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10)
-    return fail(EFTS_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", cfg->device,
+    return fail(EFTS_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device,
                 prop.major, prop.minor);
-  CUDA_TRY(cudaSetDevice(cfg->device));
+  CUDA_TRY(cudaSetDevice(device));
   TRY(set_kernel_attributes());
   efts_ctx* c = new efts_ctx();
-  c->cfg = *cfg;
   c->sm_count = prop.multiProcessorCount;
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
@@ -744,11 +780,15 @@ int efts_create(const efts_config* cfg, efts_ctx** out) {
   *out = c;
   return EFTS_OK;
 }
+}  // namespace
+
+extern "C" {
 
 void efts_destroy(efts_ctx* c) {
   if (c == nullptr) return;
   for (void* p : c->device_allocs) cudaFree(p);
   for (auto& r : c->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  delete c->voc;
   delete c;
 }
 
@@ -1357,6 +1397,254 @@ int efts_length_regulator_fwd(const float* xs, const int64_t* ds_eff, const int6
       xs, reinterpret_cast<const long long*>(ds_eff), reinterpret_cast<const long long*>(ilens),
       reinterpret_cast<const long long*>(out_lens), T1, D, Tout, pad_value, out, reinterpret_cast<long long*>(idx));
   CUDA_TRY(cudaGetLastError());
+  return EFTS_OK;
+}
+
+}  // extern "C"
+
+// ================================================================================================
+// HiFi-GAN V1 generator (vocoders/hifigan_model.py:95-136).  Every convolution is a launch of
+// the fused-B tap-GEMM with the long A box (up to 11 taps, dilation up to 5):
+//   * Conv1d(k, dilation d): taps shifted by (j - pad) * d rows;
+//   * ConvTranspose1d(k = 2u, stride u, padding u/2): a 3-tap GEMM over input rows (q-1, q, q+1) whose N = u * C
+//     output columns are the u output phases of row q -- the fp32 result [B, L, u*C] IS [B, L*u, C] in memory.
+//     Phase r takes tap j = u * (1 - tau) + r + u/2 of input row q + tau - 1 (two of the three are in range);
+//   * the activation in front of a conv (F.leaky_relu(x) then conv, :58,60,123) is applied when its operand planes
+//     are written: act = LeakyReLU in the producer's epilogue when only the planes are needed, plane_act when the
+//     pre-activation fp32 value is needed too (the residual x of ResBlock1, :62).
+namespace {
+
+struct VocWs {
+  __half *m_hi, *m_lo;                 // mel planes [B, T, num_mels]
+  float *x_f, *ra_f, *rb_f, *fin[4];   // fp32 [B, L, C] (stage-sized)
+  __half *x_hi, *x_lo, *t_hi, *t_lo, *ra_hi, *ra_lo, *rb_hi, *rb_lo;
+};
+
+size_t voc_max_elems(const efts_vocoder_config& g, int B, int T) {
+  size_t L = T, best = static_cast<size_t>(T) * g.upsample_initial_channel;
+  int C = g.upsample_initial_channel;
+  for (int i = 0; i < g.num_upsamples; ++i) {
+    L *= g.upsample_rates[i];
+    C /= 2;
+    best = std::max(best, L * C);
+  }
+  return best * B;
+}
+
+void carve_voc(Arena& a, VocWs& w, const efts_vocoder_config& g, int B, int T) {
+  const size_t n = voc_max_elems(g, B, T);
+  w.m_hi = a.get<__half>(static_cast<size_t>(B) * T * g.num_mels);
+  w.m_lo = a.get<__half>(static_cast<size_t>(B) * T * g.num_mels);
+  w.x_f = a.get<float>(n); w.ra_f = a.get<float>(n); w.rb_f = a.get<float>(n);
+  for (int k = 0; k < g.num_kernels; ++k) w.fin[k] = a.get<float>(n);
+  w.x_hi = a.get<__half>(n); w.x_lo = a.get<__half>(n);
+  w.t_hi = a.get<__half>(n); w.t_lo = a.get<__half>(n);
+  w.ra_hi = a.get<__half>(n); w.ra_lo = a.get<__half>(n);
+  w.rb_hi = a.get<__half>(n); w.rb_lo = a.get<__half>(n);
+}
+
+// One convolution of the generator: planes in -> bias, optional activation / residual -> fp32 and / or planes out.
+int voc_conv(efts_ctx* c, cudaStream_t st, const PackedW& w, int dil, const __half* ahi, const __half* alo, int B,
+             int L, int act, const float* resid, float* out_f, __half* ohi, __half* olo, int plane_act) {
+  GemmParams p = gemm_defaults();
+  p.N = w.N;
+  p.ntaps = w.Z;
+  p.pad = (w.Z - 1) / 2;
+  p.dil = dil;
+  p.act = act;
+  p.bias = w.bias;
+  p.resid = resid;
+  p.out = out_f; p.ld_out = w.N;
+  p.out_hi = ohi; p.out_lo = olo; p.ld_pl = w.N;
+  p.plane_act = plane_act;
+  p.long_taps = 1;
+  return launch_gemm(c, st, OpA{ahi, alo, B, L, w.K, w.K}, weight_op(w), p);
+}
+
+// ConvTranspose1d weight [Cin, Cout, k] (k = 2u, padding u/2) -> 3-tap GEMM planes [3][u*Cout][Cin], bias tiled.
+int pack_ups(efts_ctx* c, const std::string& wname, const std::string& bname, int Cin, int Cout, int k, int u,
+             PackedW* out) {
+  const std::vector<float>* w;
+  const std::vector<float>* b;
+  TRY(need(c, wname, {Cin, Cout, k}, &w));
+  TRY(need(c, bname, {Cout}, &b));
+  const int N = u * Cout;
+  const size_t n = static_cast<size_t>(3) * N * Cin;
+  std::vector<__half> hi(n), lo(n);
+  std::vector<float> bias(N);
+  for (int tau = 0; tau < 3; ++tau)
+    for (int r = 0; r < u; ++r) {
+      const int j = u * (1 - tau) + r + u / 2;
+      for (int co = 0; co < Cout; ++co)
+        for (int ci = 0; ci < Cin; ++ci) {
+          const float x = (j >= 0 && j < k) ? (*w)[(static_cast<size_t>(ci) * Cout + co) * k + j] : 0.0f;
+          if (!(fabsf(x) <= 65504.0f))
+            return fail(EFTS_ERR_UNSUPPORTED, "weight '%s' has a value outside the fp16 operand range", wname.c_str());
+          const __half h = __float2half_rn(x);
+          const size_t d = (static_cast<size_t>(tau) * N + r * Cout + co) * Cin + ci;
+          hi[d] = h;
+          lo[d] = __float2half_rn((x - __half2float(h)) * SPLIT_SCALE);
+        }
+    }
+  for (int r = 0; r < u; ++r)
+    for (int co = 0; co < Cout; ++co) bias[r * Cout + co] = (*b)[co];
+  out->Z = 3; out->N = N; out->K = Cin;
+  TRY(upload(c, hi.data(), n * sizeof(__half), reinterpret_cast<void**>(&out->hi)));
+  TRY(upload(c, lo.data(), n * sizeof(__half), reinterpret_cast<void**>(&out->lo)));
+  TRY(upload(c, bias.data(), N * sizeof(float), reinterpret_cast<void**>(&out->bias)));
+  return EFTS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int efts_vocoder_create(const efts_vocoder_config* g, efts_ctx** out) {
+  if (g == nullptr || out == nullptr) return fail(EFTS_ERR_ARG, "null argument");
+  if (g->num_upsamples < 1 || g->num_upsamples > 8 || g->num_kernels < 1 || g->num_kernels > 4)
+    return fail(EFTS_ERR_UNSUPPORTED, "num_upsamples / num_kernels out of range");
+  if (g->num_mels % 8 != 0 || g->num_mels < 8) return fail(EFTS_ERR_UNSUPPORTED, "num_mels=%d must be a multiple of 8", g->num_mels);
+  int C = g->upsample_initial_channel;
+  if (C % 8 != 0 || C > G2_BIAS_MAX_LONG) return fail(EFTS_ERR_UNSUPPORTED, "upsample_initial_channel=%d", C);
+  for (int i = 0; i < g->num_upsamples; ++i) {
+    const int u = g->upsample_rates[i], k = g->upsample_kernel_sizes[i];
+    if (u < 2 || (u & 1) || k != 2 * u)
+      return fail(EFTS_ERR_UNSUPPORTED, "upsample %d: rate %d, kernel %d (supported: even rate, kernel = 2 * rate)", i, u, k);
+    if (C % 2) return fail(EFTS_ERR_UNSUPPORTED, "odd channel count");
+    C /= 2;
+    if (C % 8 != 0) return fail(EFTS_ERR_UNSUPPORTED, "stage %d has %d channels (must be a multiple of 8)", i, C);
+    if (u * C > G2_BIAS_MAX_LONG) return fail(EFTS_ERR_UNSUPPORTED, "rate * channels = %d exceeds %d", u * C, G2_BIAS_MAX_LONG);
+  }
+  if (C * 7 > 1024) return fail(EFTS_ERR_UNSUPPORTED, "conv_post with %d channels", C);
+  if (g->num_upsamples * g->num_kernels > 32) return fail(EFTS_ERR_UNSUPPORTED, "too many resblocks");
+  for (int j = 0; j < g->num_kernels; ++j) {
+    const int k = g->resblock_kernel_sizes[j];
+    if (k < 1 || k > 11 || !(k & 1)) return fail(EFTS_ERR_UNSUPPORTED, "resblock kernel size %d (odd, <= 11)", k);
+    for (int m = 0; m < 3; ++m) {
+      const int d = g->resblock_dilations[j][m];
+      if (d < 1 || G2_BM + (k - 1) * d > G2_A_ROWS_LONG)
+        return fail(EFTS_ERR_UNSUPPORTED, "resblock kernel %d with dilation %d exceeds the %d-row operand box", k, d,
+                    G2_A_ROWS_LONG);
+    }
+  }
+  efts_ctx* c = nullptr;
+  TRY(create_base(g->device, &c));
+  c->voc = new efts_ctx::Vocoder();
+  c->voc->cfg = *g;
+  *out = c;
+  return EFTS_OK;
+}
+
+int efts_vocoder_finalize(efts_ctx* c) {
+  if (c == nullptr || c->voc == nullptr) return fail(EFTS_ERR_ARG, "not a vocoder context");
+  if (c->finalized) return EFTS_OK;
+  efts_ctx::Vocoder& v = *c->voc;
+  const efts_vocoder_config& g = v.cfg;
+  int C = g.upsample_initial_channel;
+  TRY(pack_weight(c, "conv_pre.weight", "conv_pre.bias", C, g.num_mels, 7, &v.conv_pre));
+  for (int i = 0; i < g.num_upsamples; ++i) {
+    const std::string p = "ups." + std::to_string(i);
+    TRY(pack_ups(c, p + ".weight", p + ".bias", C, C / 2, g.upsample_kernel_sizes[i], g.upsample_rates[i], &v.ups[i]));
+    C /= 2;
+    for (int j = 0; j < g.num_kernels; ++j) {
+      const int n = i * g.num_kernels + j;
+      for (int m = 0; m < 3; ++m) {
+        const std::string q = "resblocks." + std::to_string(n);
+        TRY(pack_weight(c, q + ".convs1." + std::to_string(m) + ".weight", q + ".convs1." + std::to_string(m) + ".bias",
+                        C, C, g.resblock_kernel_sizes[j], &v.c1[n][m]));
+        TRY(pack_weight(c, q + ".convs2." + std::to_string(m) + ".weight", q + ".convs2." + std::to_string(m) + ".bias",
+                        C, C, g.resblock_kernel_sizes[j], &v.c2[n][m]));
+      }
+    }
+  }
+  {   // conv_post: weight [1, C, 7] -> [7][C] fp32 for the direct kernel
+    const std::vector<float>* w;
+    const std::vector<float>* b;
+    TRY(need(c, "conv_post.weight", {1, C, 7}, &w));
+    TRY(need(c, "conv_post.bias", {1}, &b));
+    std::vector<float> t(static_cast<size_t>(7) * C);
+    for (int j = 0; j < 7; ++j)
+      for (int ch = 0; ch < C; ++ch) t[static_cast<size_t>(j) * C + ch] = (*w)[static_cast<size_t>(ch) * 7 + j];
+    TRY(upload(c, t.data(), t.size() * sizeof(float), reinterpret_cast<void**>(&v.post_w)));
+    v.post_b = (*b)[0];
+  }
+  c->raw.clear();
+  c->raw_shape.clear();
+  c->finalized = true;
+  return EFTS_OK;
+}
+
+size_t efts_vocoder_workspace_bytes(const efts_ctx* c, int32_t B, int32_t T) {
+  if (c == nullptr || c->voc == nullptr || B < 1 || T < 1) return 0;
+  Arena a(nullptr, ~static_cast<size_t>(0));
+  VocWs w;
+  carve_voc(a, w, c->voc->cfg, B, T);
+  return a.off + 256;
+}
+
+int efts_vocoder_forward(efts_ctx* c, const float* mel, int32_t B, int32_t T, float* audio, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  TRY(check_ready(c));
+  if (c->voc == nullptr) return fail(EFTS_ERR_ARG, "not a vocoder context");
+  if (!mel || !audio || !workspace || B < 1 || T < 1 || B > 65535) return fail(EFTS_ERR_ARG, "efts_vocoder_forward: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  efts_ctx::Vocoder& v = *c->voc;
+  const efts_vocoder_config& g = v.cfg;
+  Arena a(workspace, workspace_bytes);
+  VocWs w;
+  carve_voc(a, w, g, B, T);
+  if (!a.ok) return fail(EFTS_ERR_WORKSPACE, "workspace too small: need %zu, have %zu", a.off, workspace_bytes);
+  CUDA_TRY(cudaMemsetAsync(c->err_flag, 0, sizeof(int), st));
+  voc_mel_planes_kernel<<<dim3((T + 31) / 32, (g.num_mels + 31) / 32, B), dim3(32, 8), 0, st>>>(mel, g.num_mels, T, w.m_hi,
+                                                                                              w.m_lo, c->err_flag);
+  CUDA_TRY(cudaGetLastError());
+  c->launches++;
+  // conv_pre (:121); its only consumer is leaky_relu -> ups[0] (:123-124): planes of the activated value
+  TRY(voc_conv(c, st, v.conv_pre, 1, w.m_hi, w.m_lo, B, T, ACT_LRELU, nullptr, nullptr, w.t_hi, w.t_lo, 0));
+  size_t L = T;
+  int C = g.upsample_initial_channel;
+  for (int i = 0; i < g.num_upsamples; ++i) {
+    const int u = g.upsample_rates[i];
+    // ups[i] (:124): x fp32 [B, L*u, C/2] (the residual input of every resblock) + planes of leaky_relu(x) (:58)
+    TRY(voc_conv(c, st, v.ups[i], 1, w.t_hi, w.t_lo, B, static_cast<int>(L), ACT_NONE, nullptr, w.x_f, w.x_hi, w.x_lo, 1));
+    L *= u;
+    C /= 2;
+    if (L > 0x7fffffff / 2) return fail(EFTS_ERR_ARG, "sequence too long");
+    const int Li = static_cast<int>(L);
+    for (int j = 0; j < g.num_kernels; ++j) {           // ResBlock1.forward (:56-63)
+      const int n = i * g.num_kernels + j;
+      const float* cur_f = w.x_f;
+      const __half *cur_hi = w.x_hi, *cur_lo = w.x_lo;
+      for (int m = 0; m < 3; ++m) {
+        // xt = c1(leaky_relu(x)); only leaky_relu(xt) is consumed (:59-60)
+        TRY(voc_conv(c, st, v.c1[n][m], g.resblock_dilations[j][m], cur_hi, cur_lo, B, Li, ACT_LRELU, nullptr, nullptr,
+                     w.t_hi, w.t_lo, 0));
+        // x = c2(...) + x (:61-62): fp32 x for the next residual, planes of leaky_relu(x) for the next c1
+        const bool last = m == 2;
+        float* of = last ? w.fin[j] : (m == 0 ? w.ra_f : w.rb_f);
+        __half* oh = last ? nullptr : (m == 0 ? w.ra_hi : w.rb_hi);
+        __half* ol = last ? nullptr : (m == 0 ? w.ra_lo : w.rb_lo);
+        TRY(voc_conv(c, st, v.c2[n][m], 1, w.t_hi, w.t_lo, B, Li, ACT_NONE, cur_f, of, oh, ol, 1));
+        cur_f = of; cur_hi = oh; cur_lo = ol;
+      }
+    }
+    // x = (r0 + r1 + r2) / num_kernels (:126-131), then leaky_relu for the next ups (:123) or conv_post (:132)
+    VocAvgArgs av;
+    av.n = g.num_kernels;
+    for (int k = 0; k < 4; ++k) av.r[k] = k < g.num_kernels ? w.fin[k] : nullptr;
+    const size_t n4 = static_cast<size_t>(B) * L * C / 4;
+    const unsigned grid = static_cast<unsigned>(std::min<size_t>((n4 + 255) / 256, static_cast<size_t>(c->sm_count) * 16));
+    const bool final_stage = i == g.num_upsamples - 1;
+    voc_average_kernel<<<grid, 256, 0, st>>>(av, n4, final_stage ? 0.01f : 0.1f, final_stage ? nullptr : w.t_hi,
+                                             final_stage ? nullptr : w.t_lo, final_stage ? w.x_f : nullptr, c->err_flag);
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+  }
+  // conv_post + tanh (:133-134)
+  voc_post_kernel<<<dim3(static_cast<unsigned>((L + 255) / 256), B), 256, 0, st>>>(w.x_f, v.post_w, v.post_b,
+                                                                                 static_cast<int>(L), C, 7, audio);
+  CUDA_TRY(cudaGetLastError());
+  c->launches++;
   return EFTS_OK;
 }
 

@@ -24,12 +24,12 @@ namespace efts {
 constexpr int G2_BM = 128;
 constexpr int G2_BN = 128;
 constexpr int G2_BK = 64;
-constexpr int G2_A_ROWS = 136;
-constexpr int G2_A_PLANE = G2_A_ROWS * 128;
-constexpr int G2_A_STAGE = 2 * G2_A_PLANE;
+constexpr int G2_A_ROWS = 136;                      // A box: 128 rows + the halo of 9 undilated taps
+constexpr int G2_A_ROWS_LONG = 184;                 // vocoder layers: up to 11 taps, dilation up to 5 (halo 50 rows)
 constexpr int G2_EPI_WARPS = 8;                    // two groups of four (one warp per TMEM lane quadrant)
 constexpr int G2_THREADS = 128 + 32 * G2_EPI_WARPS;   // warpgroup 0: TMA, MMA, 2 idle warps; warpgroups 1, 2: epilogue groups
 constexpr int G2_BIAS_MAX = 1024;                     // columns whose bias is staged in shared memory
+constexpr int G2_BIAS_MAX_LONG = 2048;                // long-tap variant (the transposed-conv GEMM has N = stride * C)
 constexpr int G2_REGS_CTRL = 72;                     // setmaxnreg budgets: 3 warps per SM sub-partition,
 constexpr int G2_REGS_EPI = 216;                     // 32 * (72 + 2 * 216) = 16128 <= 16384 registers
 
@@ -42,18 +42,23 @@ constexpr int G2_STAGE_WARP_BYTES = 32 * G2_STAGE_ROW_BYTES;
 // per k-step instead of three, A fetched from shared memory twice instead of three times.  The N = 128 MMA needs
 // Bhi split 64 + 64 over the two CTAs at one common offset, so a third 64-row block per stage holds Bhi[0:64]
 // (leader, a duplicate) / Bhi[64:128] (peer).  Both accumulator halves restart with every chunk.
-template <int CG, int WIDE = 0, int FUSE = 0>
+template <int CG, int WIDE = 0, int FUSE = 0, int AR = G2_A_ROWS>
 struct G2Cfg {
   static_assert(!FUSE || (CG == 2 && !WIDE), "the fused-B variant is the CTA-pair, long-reduction kernel");
+  static_assert(AR == G2_A_ROWS || FUSE, "the long A box exists for the fused-B kernel only");
+  static constexpr int A_ROWS = AR;
+  static constexpr int A_PLANE = AR * 128;
+  static constexpr int A_STAGE = 2 * A_PLANE;
+  static constexpr int BIAS_MAX = AR == G2_A_ROWS ? G2_BIAS_MAX : G2_BIAS_MAX_LONG;
   static constexpr int B_ROWS = G2_BN / CG;
   static constexpr int B_PLANE = B_ROWS * 128;
   static constexpr int B_STAGE = (FUSE ? 3 : 2) * B_PLANE;
   // the wide (short-reduction) variant trades pipeline depth for 16 per-warp transposition buffers
   static constexpr int A_STAGES = WIDE ? 2 : (CG == 2 ? (FUSE ? 2 : 3) : 2);
-  static constexpr int B_STAGES = WIDE ? (CG == 2 ? 4 : 2) : (CG == 2 ? (FUSE ? 4 : 5) : 3);
+  static constexpr int B_STAGES = WIDE ? (CG == 2 ? 4 : 2) : (CG == 2 ? (FUSE ? (AR == G2_A_ROWS ? 4 : 3) : 5) : 3);
   static constexpr int EPI_WARPS = WIDE ? 16 : 8;
-  static constexpr int SMEM_TILES = A_STAGES * G2_A_STAGE + B_STAGES * B_STAGE;
-  static constexpr int SMEM_BYTES = SMEM_TILES + 1024 + 512 + 4 * G2_BIAS_MAX + EPI_WARPS * G2_STAGE_WARP_BYTES;
+  static constexpr int SMEM_TILES = A_STAGES * A_STAGE + B_STAGES * B_STAGE;
+  static constexpr int SMEM_BYTES = SMEM_TILES + 1024 + 512 + 4 * BIAS_MAX + EPI_WARPS * G2_STAGE_WARP_BYTES;
   static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB");
 };
 
@@ -133,6 +138,10 @@ __device__ __forceinline__ void g2_store_block32(const GemmParams& p, uint32_t s
       if (p.out_hi != nullptr && !(p.debug_mask & 2)) {
         const float amax = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
         if (tr < check_b && amax > 65504.0f && p.err_flag != nullptr) atomicOr(p.err_flag, 8 | p.err_code);
+        if (p.plane_act) {                          // operand of the next layer = LeakyReLU(0.1) of the stored value
+          v.x = v.x > 0.0f ? v.x : v.x * 0.1f; v.y = v.y > 0.0f ? v.y : v.y * 0.1f;
+          v.z = v.z > 0.0f ? v.z : v.z * 0.1f; v.w = v.w > 0.0f ? v.w : v.w * 0.1f;
+        }
         const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
         const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
         const __half2 l01 = __floats2half2_rn((v.x - f01.x) * SPLIT_SCALE, (v.y - f01.y) * SPLIT_SCALE);
@@ -158,12 +167,15 @@ enum Gemm2Epi { EPI_STD = 0, EPI_FULL = 1, EPI_SOFTMAX = 2 };
 // columns at a time -- no running sums, 96 registers per thread, twice the warps to hide the store latency.
 constexpr int G2_THREADS_WIDE = 128 + 32 * 16;
 
-template <int CG, int EPI, int WIDE, int FUSE = 0>
+template <int CG, int EPI, int WIDE, int FUSE = 0, int AR = G2_A_ROWS>
 __global__ void __launch_bounds__(WIDE ? G2_THREADS_WIDE : G2_THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
              const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
              const GemmParams p) {
-  using Cfg = G2Cfg<CG, WIDE, FUSE>;
+  using Cfg = G2Cfg<CG, WIDE, FUSE, AR>;
+  constexpr int G2_A_PLANE = Cfg::A_PLANE;
+  constexpr int G2_A_STAGE = Cfg::A_STAGE;
+  const int dil = p.dil > 1 ? p.dil : 1;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = smem_base;
@@ -181,7 +193,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
   auto acc1_empty = [&](int s) { return sBar + 256u + 8u * s; };   // [2]
   const uint32_t tmem_slot = sBar + 272u;
   const uint32_t sBias = sBar + 512u;              // [G2_BIAS_MAX] fp32 copy of the bias (epilogue reads it per row)
-  const uint32_t sStage = sBias + 4u * G2_BIAS_MAX; // wide variant: [16 warps][32 rows][144 B]
+  const uint32_t sStage = sBias + 4u * Cfg::BIAS_MAX; // per-warp transposition buffers [warps][32 rows][144 B]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -267,12 +279,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
             } else if (CG == 2) {
               const uint32_t bar = ptx::map_to_cta(fullA(s), 0);
               if (leader) ptx::mbar_expect_tx(fullA(s), 2 * G2_A_STAGE);
-              ptx::tma_load_3d_pair(&tmA_hi, bar, dst, kb * G2_BK, t0 - p.pad, b);
-              ptx::tma_load_3d_pair(&tmA_lo, bar, dst + G2_A_PLANE, kb * G2_BK, t0 - p.pad, b);
+              ptx::tma_load_3d_pair(&tmA_hi, bar, dst, kb * G2_BK, t0 - p.pad * dil, b);
+              ptx::tma_load_3d_pair(&tmA_lo, bar, dst + G2_A_PLANE, kb * G2_BK, t0 - p.pad * dil, b);
             } else {
               ptx::mbar_expect_tx(fullA(s), G2_A_STAGE);
-              ptx::tma_load_3d(&tmA_hi, fullA(s), dst, kb * G2_BK, t0 - p.pad, b);
-              ptx::tma_load_3d(&tmA_lo, fullA(s), dst + G2_A_PLANE, kb * G2_BK, t0 - p.pad, b);
+              ptx::tma_load_3d(&tmA_hi, fullA(s), dst, kb * G2_BK, t0 - p.pad * dil, b);
+              ptx::tma_load_3d(&tmA_lo, fullA(s), dst + G2_A_PLANE, kb * G2_BK, t0 - p.pad * dil, b);
             }
             ++ia;
           }
@@ -339,7 +351,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
               ptx::mbar_wait(fullB(sb), (ib / Cfg::B_STAGES) & 1);
               ++ib;
               ptx::tc_fence_after();
-              const uint32_t a_addr = sA + sa * G2_A_STAGE + tap * 128;     // row shift = tap
+              const uint32_t a_addr = sA + sa * G2_A_STAGE + tap * dil * 128;     // row shift = tap * dilation
               const uint32_t b_addr = sB + sb * Cfg::B_STAGE;
               const uint64_t dAh = ptx::make_desc_sw128(a_addr, 0);
               const uint64_t dAl = ptx::make_desc_sw128(a_addr + G2_A_PLANE, 0);
@@ -727,6 +739,10 @@ __global__ void splitk_reduce_kernel(const GemmParams p, const float* __restrict
   if (p.out_hi != nullptr) {
     const float amax = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
     if (amax > 65504.0f && p.err_flag != nullptr) atomicOr(p.err_flag, 8 | p.err_code);
+    if (p.plane_act) {
+      v.x = v.x > 0.0f ? v.x : __fmul_rn(v.x, 0.1f); v.y = v.y > 0.0f ? v.y : __fmul_rn(v.y, 0.1f);
+      v.z = v.z > 0.0f ? v.z : __fmul_rn(v.z, 0.1f); v.w = v.w > 0.0f ? v.w : __fmul_rn(v.w, 0.1f);
+    }
     const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
     const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
     const __half2 l01 = __floats2half2_rn((v.x - f01.x) * SPLIT_SCALE, (v.y - f01.y) * SPLIT_SCALE);

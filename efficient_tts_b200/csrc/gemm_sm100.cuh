@@ -71,6 +71,11 @@ struct GemmParams {
   int splits;            // 0 / 1 = off
   size_t split_stride;   // elements between the partial planes
   float* split_scratch;  // host side only: room for the partial planes (kSplitScratchBytes), or nullptr = never split
+  // dilated taps / vocoder layers (second-generation kernel only)
+  int dil;               // row shift of tap j is (j - pad) * dil; 0 is read as 1
+  int plane_act;         // 1: the fp16 operand planes hold LeakyReLU(0.1) of the stored fp32 value (the next layer's
+                         // input activation, vocoders/hifigan_model.py:58,123), the fp32 store stays pre-activation
+  int long_taps;         // host side only: use the 184-row A box variant (128 + (ntaps - 1) * dil <= 184)
 };
 
 template <int BN, int AMODE>

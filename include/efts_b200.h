@@ -186,6 +186,35 @@ int efts_reconstruct_alignment(const float* e, const int32_t* text_lengths, cons
                                int32_t B, int32_t T1, int32_t T2, float delta, float* reconst_alpha,
                                void* stream);
 
+/* ---- HiFi-GAN V1 generator: the vocoder the reference runs right after inference(),
+ * `y = voc_model(mel_pred.transpose(1, 2))` (bin/inference.py:108-109, vocoders/hifigan_model.py:95-136).
+ * Same context type, same weight protocol: efts_vocoder_create, one efts_set_weight per tensor of the
+ * Generator's state_dict with the weight-norm pairs folded (names as left by remove_weight_norm():
+ * "conv_pre.weight" [C0,80,7], "ups.i.weight" [Cin,Cout,k] (ConvTranspose1d layout), "resblocks.n.convs1.m.weight"
+ * [C,C,k], "resblocks.n.convs2.m.weight", "conv_post.weight" [1,C,7] and the matching ".bias"), then
+ * efts_vocoder_finalize.  Supported: resblock type "1", upsample_kernel_size == 2 * upsample_rate (rate even),
+ * resblock kernels <= 11 with dilation * (k - 1) <= 56, channels multiples of 8; anything else is
+ * EFTS_ERR_UNSUPPORTED. */
+typedef struct {
+  int32_t num_mels;                    /* 80 (Conv1d(80, ...) at vocoders/hifigan_model.py:101)            */
+  int32_t upsample_initial_channel;    /* 512                                                             */
+  int32_t num_upsamples;               /* 4                                                               */
+  int32_t upsample_rates[8];           /* 8, 8, 2, 2                                                      */
+  int32_t upsample_kernel_sizes[8];    /* 16, 16, 4, 4                                                    */
+  int32_t num_kernels;                 /* 3 (resblocks per stage)                                         */
+  int32_t resblock_kernel_sizes[4];    /* 3, 7, 11                                                        */
+  int32_t resblock_dilations[4][3];    /* {1, 3, 5} each                                                  */
+  int32_t device;
+} efts_vocoder_config;
+int efts_vocoder_create(const efts_vocoder_config* cfg, efts_ctx** out);
+int efts_vocoder_finalize(efts_ctx* ctx);
+size_t efts_vocoder_workspace_bytes(const efts_ctx* ctx, int32_t B, int32_t T);
+/* Generator.forward (vocoders/hifigan_model.py:120-136): mel fp32 [B, num_mels, T] (channels-first, exactly what
+ * the reference passes) -> waveform fp32 [B, 1, T * prod(upsample_rates)].  Raises bit 3 of the error flags
+ * (efts_error_flags) when an activation leaves the fp16 operand range. */
+int efts_vocoder_forward(efts_ctx* ctx, const float* mel, int32_t B, int32_t T, float* audio, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
 /* ---- introspection ---- */
 /* Options: "amode" (A-operand staging of the tap-GEMM: 0 one TMA box per tap, 1 one shifted box
  * per k-block), "skip_pad_tiles" (0/1).  Returns EFTS_ERR_ARG for an unknown name. */

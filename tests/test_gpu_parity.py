@@ -577,3 +577,63 @@ def test_length_regulator_full_size_properties(dev):
     assert torch.equal(counts, ds * valid)                                # histogram of idx == durations
     gathered = torch.gather(xs, 1, idx.clamp(min=0)[..., None].expand(-1, -1, D)) * live[..., None]
     assert torch.equal(gathered, out)
+
+
+# ------------------------------------------------------------------------------------------------
+# HiFi-GAN V1 generator: waveform within 1e-4 abs of the fp32 reference (values in [-1, 1])
+AUDIO_TOL = 1e-4
+
+
+class _H(dict):
+    __getattr__ = dict.__getitem__
+
+
+@pytest.fixture(scope="module")
+def vocoder(dev):
+    from oracle import hifigan_oracle as hor
+    from efficient_tts_b200.vocoder import Generator
+    g = Generator(_H(hor.V1_CONFIG))
+    res = g.load_state_dict(hor.make_weights(seed=4321), strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    return g.eval().to(dev)
+
+
+@pytest.mark.parametrize("name", ["hifigan_small", "hifigan_batch"])
+def test_vocoder_matches_golden_and_oracle(vocoder, dev, name):
+    from oracle import hifigan_oracle as hor
+    z = np.load(os.path.join(G, name + ".npz"))
+    mel = hor.make_mel(int(z["seed"]), int(z["batch"]), int(z["frames"]))
+    y = vocoder(mel.to(dev)).cpu()
+    assert tuple(y.shape) == z["audio"].shape
+    d = (y - torch.from_numpy(z["audio"])).abs().max().item()
+    print("vocoder %s: max-abs vs reference fixture %.3e (signal max %.2f)" % (name, d, float(np.abs(z["audio"]).max())))
+    assert d <= AUDIO_TOL
+
+
+@pytest.mark.parametrize("batch,frames", [(1, 1), (1, 37), (3, 64), (1, 517)])
+def test_vocoder_matches_oracle_across_lengths(vocoder, dev, batch, frames):
+    """One frame (every layer is almost all zero padding), lengths that are not multiples of the 128-row tile,
+    a batch, and the C1 length (517 frames -> 132 352 samples)."""
+    from oracle import hifigan_oracle as hor
+    mel = hor.make_mel(100 + frames, batch, frames)
+    with torch.no_grad():
+        ref = hor.generator_forward(hor.make_weights(seed=4321), mel)
+    y = vocoder(mel.to(dev)).cpu()
+    assert y.shape == ref.shape == (batch, 1, frames * 256)
+    d = (y - ref).abs().max().item()
+    print("vocoder B=%d T=%d: max-abs %.3e" % (batch, frames, d))
+    assert d <= AUDIO_TOL
+
+
+def test_vocoder_after_remove_weight_norm_and_batch_independence(dev):
+    from oracle import hifigan_oracle as hor
+    from efficient_tts_b200.vocoder import Generator
+    g = Generator(_H(hor.V1_CONFIG))
+    g.load_state_dict(hor.make_weights(seed=4321))
+    g = g.eval().to(dev)
+    mel = hor.make_mel(5, 2, 21).to(dev)
+    a = g(mel)
+    g.remove_weight_norm()
+    b = g(mel)
+    assert torch.equal(a, b)                       # folded weights are bit-identical (torch._weight_norm both ways)
+    assert torch.equal(g(mel[1:2]), a[1:2])        # an utterance does not depend on its batch neighbours

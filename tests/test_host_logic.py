@@ -197,3 +197,47 @@ def test_bench_reference_arm_prints_contract_line():
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "mel_frames/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+# ---------------------------------------------------------------- HiFi-GAN generator mirror
+def test_vocoder_mirror_keeps_the_reference_parameter_contract():
+    """``efficient_tts_b200.vocoder.Generator(h)`` registers exactly the parameters of the reference Generator
+    (vocoders/hifigan_model.py:97-118): the oracle's key list (pinned to the reference through the golden
+    fixtures' strict load_state_dict) loads strictly, before and after remove_weight_norm()."""
+    from oracle import hifigan_oracle as hor
+    from efficient_tts_b200.vocoder import Generator
+
+    class H(dict):
+        __getattr__ = dict.__getitem__
+
+    w = hor.make_weights(seed=4321)
+    g = Generator(H(hor.V1_CONFIG))
+    res = g.load_state_dict(w, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert sum(p.numel() for p in g.parameters()) == sum(v.numel() for v in w.values())
+    g.remove_weight_norm()
+    keys = set(g.state_dict().keys())
+    assert "conv_pre.weight" in keys and "ups.0.weight" in keys and "resblocks.11.convs2.2.weight" in keys
+    assert not any(k.endswith("weight_g") or k.endswith("weight_v") for k in keys)
+    # no device, no result: the forward never falls back to the CPU
+    with pytest.raises(RuntimeError):
+        g.eval()(hor.make_mel(1, 1, 4))
+    with pytest.raises(NotImplementedError):
+        Generator(H(dict(hor.V1_CONFIG, resblock="2")))
+
+
+def test_vocoder_create_rejects_unsupported_topologies():
+    import ctypes
+    from efficient_tts_b200 import _lib
+    lib = _lib.load()
+    cfg = _lib.EftsVocoderConfig()
+    cfg.num_mels, cfg.upsample_initial_channel, cfg.num_upsamples, cfg.num_kernels = 80, 512, 1, 1
+    cfg.upsample_rates[0], cfg.upsample_kernel_sizes[0] = 8, 12          # kernel != 2 * rate
+    cfg.resblock_kernel_sizes[0] = 3
+    for m in range(3):
+        cfg.resblock_dilations[0][m] = 1
+    h = ctypes.c_void_p()
+    assert lib.efts_vocoder_create(ctypes.byref(cfg), ctypes.byref(h)) == -2     # EFTS_ERR_UNSUPPORTED
+    cfg.upsample_kernel_sizes[0] = 16
+    cfg.resblock_kernel_sizes[0] = 13                                            # more than 11 taps
+    assert lib.efts_vocoder_create(ctypes.byref(cfg), ctypes.byref(h)) == -2
