@@ -96,6 +96,7 @@ struct efts_ctx {
   int wide = 1;              // v2: short-reduction launches use the 16-epilogue-warp variant
   int debug_mask = 0;        // timing experiments only
   int chunk_kb = 2;          // v2: k-blocks per main-accumulator flush (1 = most accurate, 0 = never)
+  int voc_group = 1;             // vocoder: grouped (super-tap) packing of the 32 / 64-channel layers (read at finalize)
   int split_k = 1;               // fused-B kernel: split the reduction of small launches over more SMs
   int pdl = 1;                   // programmatic dependent launch for the v2 GEMM and split-reduce kernels
   int fuse_b = 1;                // v2 conv layers: Ahi*[Bhi|Blo] as one N = 256 MMA (two MMAs per k-step instead of three)
@@ -121,6 +122,8 @@ struct efts_ctx {
     PackedW conv_pre;
     PackedW ups[8];                    // transposed conv as a 3-tap GEMM with N = rate * C (polyphase columns)
     PackedW c1[32][3], c2[32][3];      // resblocks[n].convs1[m] / convs2[m]
+    int g1[32][3], g2[32][3];          // time steps per GEMM row of that layer (1 = plain [B, L, C] view, see pack_grouped)
+    int d1[32][3];                     // dilation handed to the kernel (1 when the grouped packing absorbed it)
     float* post_w = nullptr;           // [7][C_last]
     float post_b = 0.0f;
   };
@@ -868,6 +871,7 @@ int efts_set_option(efts_ctx* c, const char* name, int32_t value) {
   if (strcmp(name, "fuse_b") == 0) { c->fuse_b = value != 0; return EFTS_OK; }
   if (strcmp(name, "split_k") == 0) { c->split_k = value != 0; return EFTS_OK; }
   if (strcmp(name, "pdl") == 0) { c->pdl = value != 0; return EFTS_OK; }
+  if (strcmp(name, "voc_group") == 0) { c->voc_group = value != 0; return EFTS_OK; }
   if (strcmp(name, "imv_version") == 0) {
     if (value != 1 && value != 2) return fail(EFTS_ERR_ARG, "imv_version must be 1 or 2");
     c->imv_version = value;
@@ -1445,7 +1449,8 @@ void carve_voc(Arena& a, VocWs& w, const efts_vocoder_config& g, int B, int T) {
 
 // One convolution of the generator: planes in -> bias, optional activation / residual -> fp32 and / or planes out.
 int voc_conv(efts_ctx* c, cudaStream_t st, const PackedW& w, int dil, const __half* ahi, const __half* alo, int B,
-             int L, int act, const float* resid, float* out_f, __half* ohi, __half* olo, int plane_act) {
+             int L, int act, const float* resid, float* out_f, __half* ohi, __half* olo, int plane_act, int group = 1) {
+  L /= group;                          // grouped packing: [B, L, C] read as [B, L / G, G * C] (pack_grouped)
   GemmParams p = gemm_defaults();
   p.N = w.N;
   p.ntaps = w.Z;
@@ -1495,6 +1500,72 @@ int pack_ups(efts_ctx* c, const std::string& wname, const std::string& bname, in
   return EFTS_OK;
 }
 
+// Narrow layers (C = 32 / 64 channels) waste a 128 x 128 x 64 MMA tile: only C of 128 output columns and C of 64
+// reduction columns are real.  The same buffer [B, L, C] read as [B, L / G, G * C] (G = 128 / C consecutive time
+// steps per row) turns the conv into an undilated "super-tap" GEMM with K = N = 128:
+//   y[G q + r, co] = sum_j sum_ci W[co, ci, j] * x[G q + r + (j - pad) d, ci]
+//                  = sum_tau sum_{r', ci} W'[tau][(r, co)][(r', ci)] * X[q + tau][(r', ci)],
+//   W'[tau][(r, co)][(r', ci)] = W[co, ci, j]  where  G tau + r' - r = (j - pad) d  (zero if no such j).
+// Super-taps: 2 * floor((pad * d + G - 1) / G) + 1.  Every other part of the layer (bias, activation, residual,
+// planes) is element-wise, so only the view changes.  k = 11, d = 1 at C = 32: 5 x 128 x 128 MACs per 4 steps
+// instead of 4 x 11 x 64 x 128 (4.4 x fewer); the dilation moves into the weights.
+int grouped_taps(int k, int d, int G) { return 2 * (((k - 1) / 2 * d + G - 1) / G) + 1; }
+
+int pack_grouped(efts_ctx* c, const std::string& wname, const std::string& bname, int C, int k, int d, int G,
+                 PackedW* out) {
+  const std::vector<float>* w;
+  const std::vector<float>* b;
+  TRY(need(c, wname, {C, C, k}, &w));
+  TRY(need(c, bname, {C}, &b));
+  const int S = grouped_taps(k, d, G), tmax = (S - 1) / 2, pad = (k - 1) / 2, N = G * C;
+  const size_t n = static_cast<size_t>(S) * N * N;
+  std::vector<__half> hi(n, __float2half_rn(0.0f)), lo(n, __float2half_rn(0.0f));
+  std::vector<float> bias(N);
+  for (int tau = -tmax; tau <= tmax; ++tau)
+    for (int r = 0; r < G; ++r)
+      for (int rp = 0; rp < G; ++rp) {
+        const int off = G * tau + rp - r;                   // = (j - pad) * d
+        if (off % d != 0) continue;
+        const int j = off / d + pad;
+        if (j < 0 || j >= k) continue;
+        for (int co = 0; co < C; ++co)
+          for (int ci = 0; ci < C; ++ci) {
+            const float x = (*w)[(static_cast<size_t>(co) * C + ci) * k + j];
+            if (!(fabsf(x) <= 65504.0f))
+              return fail(EFTS_ERR_UNSUPPORTED, "weight '%s' has a value outside the fp16 operand range", wname.c_str());
+            const __half h = __float2half_rn(x);
+            const size_t dst = (static_cast<size_t>(tau + tmax) * N + r * C + co) * N + rp * C + ci;
+            hi[dst] = h;
+            lo[dst] = __float2half_rn((x - __half2float(h)) * SPLIT_SCALE);
+          }
+      }
+  for (int r = 0; r < G; ++r)
+    for (int co = 0; co < C; ++co) bias[r * C + co] = (*b)[co];
+  out->Z = S; out->N = N; out->K = N;
+  TRY(upload(c, hi.data(), n * sizeof(__half), reinterpret_cast<void**>(&out->hi)));
+  TRY(upload(c, lo.data(), n * sizeof(__half), reinterpret_cast<void**>(&out->lo)));
+  TRY(upload(c, bias.data(), N * sizeof(float), reinterpret_cast<void**>(&out->bias)));
+  return EFTS_OK;
+}
+
+// Plain or grouped packing of one resblock conv, whichever issues fewer MMA columns (grouping needs <= 11 super-taps
+// and a sequence length that is a multiple of G: L = T * prod(rates) always is when the last rates cover G).
+int pack_voc_conv(efts_ctx* c, const std::string& prefix, int C, int k, int d, int Lmult, PackedW* out, int* group,
+                  int* dil) {
+  int G = 1;
+  if (c->voc_group && C < 128 && 128 % C == 0 && Lmult % (128 / C) == 0) {
+    G = 128 / C;
+    const int S = grouped_taps(k, d, G);
+    const long plain = static_cast<long>(G) * k * 64 * 128;       // per G steps: K padded to 64, N tile 128
+    const long grouped = static_cast<long>(S) * 128 * 128;
+    if (S > 11 || grouped >= plain) G = 1;
+  }
+  *group = G;
+  *dil = G == 1 ? d : 1;
+  if (G == 1) return pack_weight(c, prefix + ".weight", prefix + ".bias", C, C, k, out);
+  return pack_grouped(c, prefix + ".weight", prefix + ".bias", C, k, d, G, out);
+}
+
 }  // namespace
 
 extern "C" {
@@ -1541,19 +1612,22 @@ int efts_vocoder_finalize(efts_ctx* c) {
   efts_ctx::Vocoder& v = *c->voc;
   const efts_vocoder_config& g = v.cfg;
   int C = g.upsample_initial_channel;
+  int lmult = 1;                       // L is a multiple of this at the current stage
   TRY(pack_weight(c, "conv_pre.weight", "conv_pre.bias", C, g.num_mels, 7, &v.conv_pre));
   for (int i = 0; i < g.num_upsamples; ++i) {
     const std::string p = "ups." + std::to_string(i);
     TRY(pack_ups(c, p + ".weight", p + ".bias", C, C / 2, g.upsample_kernel_sizes[i], g.upsample_rates[i], &v.ups[i]));
     C /= 2;
+    lmult *= g.upsample_rates[i];
     for (int j = 0; j < g.num_kernels; ++j) {
       const int n = i * g.num_kernels + j;
       for (int m = 0; m < 3; ++m) {
         const std::string q = "resblocks." + std::to_string(n);
-        TRY(pack_weight(c, q + ".convs1." + std::to_string(m) + ".weight", q + ".convs1." + std::to_string(m) + ".bias",
-                        C, C, g.resblock_kernel_sizes[j], &v.c1[n][m]));
-        TRY(pack_weight(c, q + ".convs2." + std::to_string(m) + ".weight", q + ".convs2." + std::to_string(m) + ".bias",
-                        C, C, g.resblock_kernel_sizes[j], &v.c2[n][m]));
+        int unused = 1;
+        TRY(pack_voc_conv(c, q + ".convs1." + std::to_string(m), C, g.resblock_kernel_sizes[j], g.resblock_dilations[j][m],
+                          lmult, &v.c1[n][m], &v.g1[n][m], &v.d1[n][m]));
+        TRY(pack_voc_conv(c, q + ".convs2." + std::to_string(m), C, g.resblock_kernel_sizes[j], 1, lmult, &v.c2[n][m],
+                          &v.g2[n][m], &unused));
       }
     }
   }
@@ -1617,14 +1691,14 @@ int efts_vocoder_forward(efts_ctx* c, const float* mel, int32_t B, int32_t T, fl
       const __half *cur_hi = w.x_hi, *cur_lo = w.x_lo;
       for (int m = 0; m < 3; ++m) {
         // xt = c1(leaky_relu(x)); only leaky_relu(xt) is consumed (:59-60)
-        TRY(voc_conv(c, st, v.c1[n][m], g.resblock_dilations[j][m], cur_hi, cur_lo, B, Li, ACT_LRELU, nullptr, nullptr,
-                     w.t_hi, w.t_lo, 0));
+        TRY(voc_conv(c, st, v.c1[n][m], v.d1[n][m], cur_hi, cur_lo, B, Li, ACT_LRELU, nullptr, nullptr, w.t_hi, w.t_lo, 0,
+                     v.g1[n][m]));
         // x = c2(...) + x (:61-62): fp32 x for the next residual, planes of leaky_relu(x) for the next c1
         const bool last = m == 2;
         float* of = last ? w.fin[j] : (m == 0 ? w.ra_f : w.rb_f);
         __half* oh = last ? nullptr : (m == 0 ? w.ra_hi : w.rb_hi);
         __half* ol = last ? nullptr : (m == 0 ? w.ra_lo : w.rb_lo);
-        TRY(voc_conv(c, st, v.c2[n][m], 1, w.t_hi, w.t_lo, B, Li, ACT_NONE, cur_f, of, oh, ol, 1));
+        TRY(voc_conv(c, st, v.c2[n][m], 1, w.t_hi, w.t_lo, B, Li, ACT_NONE, cur_f, of, oh, ol, 1, v.g2[n][m]));
         cur_f = of; cur_hi = oh; cur_lo = ol;
       }
     }

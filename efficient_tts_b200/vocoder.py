@@ -51,7 +51,7 @@ class ResBlock1(torch.nn.Module):
 class VocoderEngine:
     """One prepacked generator on one CUDA device."""
 
-    def __init__(self, device, state_dict, h):
+    def __init__(self, device, state_dict, h, options=None):
         self.lib = _lib.load()
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -84,6 +84,8 @@ class VocoderEngine:
         with torch.cuda.device(self.device):
             _lib.check(self.lib.efts_vocoder_create(ctypes.byref(cfg), ctypes.byref(h_ctx)))
             self._h = h_ctx
+            for name, value in (options or {}).items():          # packing options are read by finalize
+                _lib.check(self.lib.efts_set_option(self._h, name.encode(), int(value)))
             for name, t in fold_state_dict(state_dict).items():
                 shape = (ctypes.c_int64 * t.dim())(*t.shape)
                 _lib.check(self.lib.efts_set_weight(self._h, name.encode(), _ptr(t), shape, t.dim()))
@@ -172,10 +174,17 @@ class Generator(torch.nn.Module):
             if dev.type != "cuda":
                 raise RuntimeError("efficient_tts_b200 modules compute on a CUDA sm_100a device only (parameters are "
                                    "on %s); there is no CPU path -- call .to('cuda')" % dev)
-            eng = VocoderEngine(dev, self.state_dict(), self.h)
+            eng = VocoderEngine(dev, self.state_dict(), self.h, self.__dict__.get("_efts_options"))
             self.__dict__["_efts_engine"] = eng
             self.__dict__["_efts_fp"] = fp
         return eng
+
+    def set_engine_options(self, **options):
+        """Packing / launch options of the C library (``efts_set_option``), applied when the engine is (re)built."""
+        self.__dict__["_efts_options"] = dict(options)
+        eng = self.__dict__.pop("_efts_engine", None)
+        if eng is not None:
+            eng.close()
 
     # ------------------------------------------------------------------ reference surface
     def forward(self, x):
