@@ -64,6 +64,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self.query_ms = []
         self._stop_evt = threading.Event()
         self.ok = False
         try:
@@ -86,8 +87,10 @@ class ClockSampler(threading.Thread):
                  "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
         while not self._stop_evt.is_set():
             try:
+                t0 = time.perf_counter()
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.query_ms.append((time.perf_counter() - t0) * 1e3)
                 for k, bit in names.items():
                     if r & bit:
                         self.reasons.add(k)
@@ -100,7 +103,8 @@ class ClockSampler(threading.Thread):
         if self.is_alive():
             self.join(timeout=2)
         return dict(sm_mhz=float(np.median(self.samples)) if self.samples else None,
-                    sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons), samples=len(self.samples))
+                    sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons), samples=len(self.samples),
+                    nvml_ms_per_query=float(np.mean(self.query_ms)) if self.query_ms else None)
 
 
 def physical_gpu_index(local_rank):
@@ -219,11 +223,31 @@ def run_ours(args, rank, local_rank, world):
         out = eng.forward(text, tl, speech, sl)
     ev1.record()
     barrier()
-    ms = ev0.elapsed_time(ev1)
+    ms_sampled = ev0.elapsed_time(ev1)
     launches = eng.launch_count() - launches0
     prof = {tag: eng.profile_read(tag) for tag in range(13)}
     eng.profile_enable(0)
     clocks = sampler.stop()
+    # The same K steps once more, immediately, without the NVML sampler thread: on some boxes every NVML query
+    # takes ~10 ms and stalls the GPU's work submission (seen as a timed pass 30-70 % slower than the sum of its own
+    # kernel times while the SM clock reads idle-high).  Both timings are reported; `value` uses the sampled pass
+    # unless the queries were slow AND the unsampled pass is more than 3 % faster.
+    barrier()
+    ev4, ev5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev4.record()
+    for _ in range(args.steps):
+        out = eng.forward(text, tl, speech, sl)
+    ev5.record()
+    barrier()
+    ms_unsampled = ev4.elapsed_time(ev5)
+    slow_nvml = (clocks.get("nvml_ms_per_query") or 0.0) > 1.0
+    use_unsampled = slow_nvml and ms_unsampled < 0.97 * ms_sampled
+    ms = ms_unsampled if use_unsampled else ms_sampled
+    timing = {"ms_per_step_clock_sampled_pass": ms_sampled / args.steps,
+              "ms_per_step_unsampled_pass": ms_unsampled / args.steps,
+              "reported": "unsampled pass (NVML queries took %.1f ms each and stalled the sampled pass; clocks are "
+                          "from the sampled pass of the same K steps run immediately before)" % clocks["nvml_ms_per_query"]
+              if use_unsampled else "clock-sampled pass"}
 
     # ---- end to end through the public API: pinned host inputs -> H2D -> forward -> stats read-back.
     # Like a prefetching loader (the reference trains with pin_memory + non_blocking copies), the copy of
@@ -330,7 +354,7 @@ def run_ours(args, rank, local_rank, world):
                 "config": {"workload": WORKLOAD, "utterances_per_gpu": B, "valid_frames_per_gpu": frames,
                            "padded": [T1p, T2p], "l2": "working set per step ~3.3 GB >> 126 MB L2 (no flush needed)",
                            "parallelism": "dp%d (utterance shards, no data-path collective)" % world},
-                "clocks": clocks, "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms,
+                "clocks": clocks, "timing": timing, "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps, "stats": stats,
                         "pipeline": "H2D of step i+1 on a copy stream overlaps step i; loss read back every step"},
@@ -371,6 +395,54 @@ def run_ours(args, rank, local_rank, world):
             line["inference_batch64"] = {"config": "inference_batch, 64 utterances x 32-64 tokens -> %d frames" % int(blen.sum()),
                                          "ms": dt * 1e3, "frames_per_s": float(blen.sum()) / dt,
                                          "rtf_mel_only": dt / (float(blen.sum()) * 256 / 22050.0)}
+            # the step right after the path: HiFi-GAN V1 generator, and the text -> waveform RTF
+            # the reference defines (bin/inference.py:100-111 times inference + vocoder)
+            from efficient_tts_b200.vocoder import Generator
+            voc = Generator(wl.AttrDict(wl.HIFIGAN_V1))
+            voc.load_state_dict(wl.vocoder_state_dict())
+            voc = voc.eval().to(dev)
+            vmel = wl.make_mel(1, 16, 800).to(dev)
+            for _ in range(2):
+                wav = voc(vmel)
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            n = 5
+            for _ in range(n):
+                wav = voc(vmel)
+            torch.cuda.synchronize(dev)
+            dt = (time.perf_counter() - t0) / n
+            vline = {"config": "HiFi-GAN V1 generator, 16 x 800 frames -> %d samples" % wav.numel(),
+                     "ms": dt * 1e3, "samples_per_s": wav.numel() / dt, "rtf": dt / (wav.numel() / 22050.0)}
+
+            def tts():
+                m_, _ = mc1.inference(txt)
+                return voc(m_.transpose(1, 2))
+            for _ in range(3):
+                wav = tts()
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            n = 20
+            for _ in range(n):
+                wav = tts()
+            torch.cuda.synchronize(dev)
+            dt = (time.perf_counter() - t0) / n
+            vline["text_to_wave_c1"] = {"config": "inference(64 phonemes) + generator, B=1 -> %d samples" % wav.shape[-1],
+                                        "ms": dt * 1e3, "rtf": dt / (wav.shape[-1] / 22050.0)}
+            if not args.no_cpu_baseline:
+                from oracle import hifigan_oracle as hor
+                torch.set_num_threads(os.cpu_count() or 1)
+                cmel = wl.make_mel(2, 1, 64)
+                cw = wl.vocoder_state_dict()
+                with torch.no_grad():
+                    hor.generator_forward(cw, cmel)
+                    t0 = time.perf_counter()
+                    cy = hor.generator_forward(cw, cmel)
+                    cdt = time.perf_counter() - t0
+                vline["cpu_baseline"] = {"value": cy.numel() / cdt, "unit": "samples/s", "cores": os.cpu_count() or 1,
+                                         "kind": "port", "sample": "B=1 x 64 frames (16 384 samples), 1 pass",
+                                         "rtf": cdt / (cy.numel() / 22050.0)}
+            line["vocoder"] = vline
+            del voc
             del mc1
         except Exception as exc:  # the headline line must still print
             line["rtf_batch1"] = {"error": str(exc)[:200]}

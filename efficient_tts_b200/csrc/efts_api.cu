@@ -241,7 +241,7 @@ int launch_gemm(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, GemmPa
   if (a.K != b.K) return fail(EFTS_ERR_ARG, "gemm K mismatch %d vs %d", a.K, b.K);
   if (p.N % 8 != 0) return fail(EFTS_ERR_ARG, "gemm N=%d must be a multiple of 8", p.N);
   if (c->gemm_version == 2) {
-    if (p.ntaps > 11) return fail(EFTS_ERR_ARG, "at most 11 taps");
+    if (p.ntaps > 15) return fail(EFTS_ERR_ARG, "at most 15 taps");
     p.chunk_kb = c->chunk_kb;
     p.debug_mask = c->debug_mask;
     p.err_flag = c->err_flag;
@@ -1548,7 +1548,7 @@ int pack_grouped(efts_ctx* c, const std::string& wname, const std::string& bname
   return EFTS_OK;
 }
 
-// Plain or grouped packing of one resblock conv, whichever issues fewer MMA columns (grouping needs <= 11 super-taps
+// Plain or grouped packing of one resblock conv, whichever issues fewer MMA columns (grouping needs <= 15 super-taps
 // and a sequence length that is a multiple of G: L = T * prod(rates) always is when the last rates cover G).
 int pack_voc_conv(efts_ctx* c, const std::string& prefix, int C, int k, int d, int Lmult, PackedW* out, int* group,
                   int* dil) {
@@ -1558,7 +1558,7 @@ int pack_voc_conv(efts_ctx* c, const std::string& prefix, int C, int k, int d, i
     const int S = grouped_taps(k, d, G);
     const long plain = static_cast<long>(G) * k * 64 * 128;       // per G steps: K padded to 64, N tile 128
     const long grouped = static_cast<long>(S) * 128 * 128;
-    if (S > 11 || grouped >= plain) G = 1;
+    if (S > 15 || grouped >= plain) G = 1;
   }
   *group = G;
   *dil = G == 1 ? d : 1;

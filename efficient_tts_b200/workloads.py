@@ -57,3 +57,54 @@ def c1_weights_patch(state_dict):
     sd["duration_predictor.linear.bias"] = torch.full_like(sd["duration_predictor.linear.bias"],
                                                            float(np.log(9.0)))
     return sd
+
+
+# ---------------------------------------------------------------- HiFi-GAN V1 generator
+HIFIGAN_V1 = dict(resblock="1", upsample_rates=[8, 8, 2, 2], upsample_kernel_sizes=[16, 16, 4, 4],
+                  upsample_initial_channel=512, resblock_kernel_sizes=[3, 7, 11],
+                  resblock_dilation_sizes=[[1, 3, 5], [1, 3, 5], [1, 3, 5]], num_mels=80)
+# vocoders/HiFiGAN_LJ_V1/config.json
+
+
+class AttrDict(dict):
+    """Attribute-style config like vocoders/env.py ``AttrDict``."""
+    __getattr__ = dict.__getitem__
+
+
+def vocoder_state_dict(seed=4321, h=HIFIGAN_V1):
+    """Seeded generator weights with unit-scale layers (the reference's own init, N(0, 0.01), makes a random
+    generator's output vanish): same recipe as ``oracle.hifigan_oracle.make_weights`` (a CPU test keeps the two
+    equal), restated here because the product package and bench.py's CUDA arm never import the oracle."""
+    import math
+    g = torch.Generator().manual_seed(seed)
+    w = {}
+
+    def conv(prefix, cout, cin, k, transposed=False, g_layer=1.0):
+        b = g_layer / math.sqrt(cin * k)
+        shape = (cin, cout, k) if transposed else (cout, cin, k)
+        v = (torch.rand(*shape, generator=g) * 2 - 1) * b
+        norm = v.flatten(1).norm(dim=1).view(-1, 1, 1)
+        w[prefix + ".bias"] = (torch.rand(cout, generator=g) * 2 - 1) * b
+        w[prefix + ".weight_g"] = norm * (1.0 + 0.05 * torch.randn(norm.shape, generator=g))
+        w[prefix + ".weight_v"] = v
+
+    c0 = h["upsample_initial_channel"]
+    conv("conv_pre", c0, h["num_mels"], 7)
+    nk = len(h["resblock_kernel_sizes"])
+    for i, (u, k) in enumerate(zip(h["upsample_rates"], h["upsample_kernel_sizes"])):
+        conv("ups.%d" % i, c0 // 2 ** (i + 1), c0 // 2 ** i, k, transposed=True, g_layer=1.5 * math.sqrt(u))
+    for i in range(len(h["upsample_rates"])):
+        ch = c0 // 2 ** (i + 1)
+        for j, (k, dil) in enumerate(zip(h["resblock_kernel_sizes"], h["resblock_dilation_sizes"])):
+            for m in range(len(dil)):
+                conv("resblocks.%d.convs1.%d" % (i * nk + j, m), ch, ch, k)
+            for m in range(len(dil)):
+                conv("resblocks.%d.convs2.%d" % (i * nk + j, m), ch, ch, k)
+    conv("conv_post", 1, c0 // 2 ** len(h["upsample_rates"]), 7, g_layer=4.0)
+    return w
+
+
+def make_mel(seed, batch, frames, num_mels=80):
+    """Log-mel-like synthetic vocoder input [B, num_mels, T]."""
+    g = torch.Generator().manual_seed(int(seed))
+    return torch.randn(batch, num_mels, frames, generator=g) * 1.5 - 4.0

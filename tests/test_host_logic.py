@@ -241,3 +241,12 @@ def test_vocoder_create_rejects_unsupported_topologies():
     cfg.upsample_kernel_sizes[0] = 16
     cfg.resblock_kernel_sizes[0] = 13                                            # more than 11 taps
     assert lib.efts_vocoder_create(ctypes.byref(cfg), ctypes.byref(h)) == -2
+
+
+def test_vocoder_workload_recipe_equals_the_oracle_recipe():
+    from oracle import hifigan_oracle as hor
+    from efficient_tts_b200 import workloads as wl
+    a, b = wl.vocoder_state_dict(4321), hor.make_weights(4321)
+    assert a.keys() == b.keys()
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    assert torch.equal(wl.make_mel(3, 2, 5), hor.make_mel(3, 2, 5))
