@@ -73,8 +73,8 @@ class AttrDict(dict):
 
 def vocoder_state_dict(seed=4321, h=HIFIGAN_V1):
     """Seeded generator weights with unit-scale layers (the reference's own init, N(0, 0.01), makes a random
-    generator's output vanish): same recipe as ``oracle.hifigan_oracle.make_weights`` (a CPU test keeps the two
-    equal), restated here because the product package and bench.py's CUDA arm never import the oracle."""
+    generator's output vanish).  The test suite's CPU checker uses the same recipe (a CPU test keeps the two equal);
+    it is restated here because the product package and bench.py's CUDA arm never import test infrastructure."""
     import math
     g = torch.Generator().manual_seed(seed)
     w = {}
