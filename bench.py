@@ -413,6 +413,13 @@ def run_ours(args, rank, local_rank, world):
             dt = (time.perf_counter() - t0) / n
             vline = {"config": "HiFi-GAN V1 generator, 16 x 800 frames -> %d samples" % wav.numel(),
                      "ms": dt * 1e3, "samples_per_s": wav.numel() / dt, "rtf": dt / (wav.numel() / 22050.0)}
+            vfl = vocoder_flops(wl.HIFIGAN_V1, 16, 800)
+            vpk = load_peaks()
+            vline["roofline"] = {"bound": "tensor", "achieved": vfl / dt / 1e12, "peak": vpk["tf"], "unit": "TFLOP/s",
+                                 "frac": vfl / dt / 1e12 / vpk["tf"], "flops_per_call": vfl, "passes": 3,
+                                 "note": "single-pass algorithmic FLOPs of the 78 convolutions over the whole forward "
+                                         "(2 * Cin * Cout * k per output sample; transposed convs 2 * Cin * Cout * k per "
+                                         "input sample); the split-fp16 scheme executes 3 passes"}
 
             def tts():
                 m_, _ = mc1.inference(txt)
@@ -459,6 +466,21 @@ def run_ours(args, rank, local_rank, world):
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def vocoder_flops(h, batch, frames):
+    """Algorithmic FLOPs of one Generator.forward (vocoders/hifigan_model.py:120-136)."""
+    c = h["upsample_initial_channel"]
+    L = frames
+    fl = 2.0 * h["num_mels"] * c * 7 * L
+    for u, k in zip(h["upsample_rates"], h["upsample_kernel_sizes"]):
+        fl += 2.0 * c * (c // 2) * k * L              # ConvTranspose1d: every input sample meets all k taps
+        c //= 2
+        L *= u
+        for rk, dil in zip(h["resblock_kernel_sizes"], h["resblock_dilation_sizes"]):
+            fl += 2 * len(dil) * 2.0 * c * c * rk * L
+    fl += 2.0 * c * 1 * 7 * L
+    return fl * batch
 
 
 def round8(x):
