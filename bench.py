@@ -354,6 +354,7 @@ def run_ours(args, rank, local_rank, world):
                 "config": {"workload": WORKLOAD, "utterances_per_gpu": B, "valid_frames_per_gpu": frames,
                            "padded": [T1p, T2p], "l2": "working set per step ~3.3 GB >> 126 MB L2 (no flush needed)",
                            "parallelism": "dp%d (utterance shards, no data-path collective)" % world},
+                "padded_frames_per_s": float(B * T2p) * world * args.steps / (ms * 1e-3),
                 "clocks": clocks, "timing": timing, "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps, "stats": stats,
@@ -458,6 +459,25 @@ def run_ours(args, rank, local_rank, world):
             fps, dt, desc = cpu_reference_forward(state, args.cpu_sample, 0, 1, 1, threads)
             line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc,
                                     "seconds_per_sample": dt}
+            try:
+                # the reference's recipes pin OMP_NUM_THREADS=1 (egs/lj/path.sh:13, distributed/launch.py:84-85):
+                # the same CPU path on one thread, on a quarter of the sample; and its B = 1 synthesis latency (C1)
+                fps1, dt1, desc1 = cpu_reference_forward(state, max(2, args.cpu_sample // 4), 0, 1, 0, 1)
+                line["cpu_baseline"]["one_thread"] = {"value": fps1, "sample": desc1, "seconds_per_sample": dt1}
+                from oracle import efts_oracle as orc
+                torch.set_num_threads(threads)
+                w_c1 = {k: v.detach().cpu() for k, v in wl.c1_weights_patch(state).items()}
+                t_c1 = wl.make_inference_inputs(0, 64)
+                with torch.no_grad():
+                    orc.inference(w_c1, t_c1)
+                    t0 = time.perf_counter()
+                    for _ in range(3):
+                        mel_c, _ = orc.inference(w_c1, t_c1)
+                    dt_c = (time.perf_counter() - t0) / 3
+                line["cpu_baseline"]["c1_inference"] = {"ms": dt_c * 1e3, "frames": int(mel_c.shape[1]),
+                                                        "rtf_mel_only": dt_c / (mel_c.shape[1] * 256 / 22050.0)}
+            except Exception as exc:
+                line["cpu_baseline"]["extras_error"] = str(exc)[:200]
     elif rank == 0:
         line["cpu_baseline"] = None
     if rank == 0:
