@@ -25,7 +25,8 @@ class EftsConfig(ctypes.Structure):
 class EftsVocoderConfig(ctypes.Structure):
     _fields_ = [("num_mels", c_i32), ("upsample_initial_channel", c_i32), ("num_upsamples", c_i32),
                 ("upsample_rates", c_i32 * 8), ("upsample_kernel_sizes", c_i32 * 8), ("num_kernels", c_i32),
-                ("resblock_kernel_sizes", c_i32 * 4), ("resblock_dilations", (c_i32 * 3) * 4), ("device", c_i32)]
+                ("resblock_kernel_sizes", c_i32 * 4), ("resblock_dilations", (c_i32 * 3) * 4), ("resblock_type", c_i32), ("num_dilations", c_i32),
+                ("device", c_i32)]
 
 
 # name -> (restype, argtypes); also the export list checked by tests/test_abi.py

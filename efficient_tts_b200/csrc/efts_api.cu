@@ -257,6 +257,8 @@ int launch_gemm(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, GemmPa
       if (epi != EPI_STD || p.b_batched || p.chunk_kb < 1)
         return fail(EFTS_ERR_ARG, "long-tap launches are plain weight GEMMs");
       p.splits = 0;
+      if (G2_BM + (p.ntaps - 1) * (p.dil > 1 ? p.dil : 1) > G2_A_ROWS_LONG)
+        return launch_gemm2_t<2, EPI_STD, 0, 1, G2_A_ROWS_XLONG>(c, st, a, b, p);
       return launch_gemm2_t<2, EPI_STD, 0, 1, G2_A_ROWS_LONG>(c, st, a, b, p);
     }
     const bool wide = c->wide && steps <= 40;
@@ -347,6 +349,8 @@ int set_kernel_attributes() {
                                 G2Cfg<2, 0, 1>::SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(gemm2_kernel<2, EPI_STD, 0, 1, G2_A_ROWS_LONG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 G2Cfg<2, 0, 1, G2_A_ROWS_LONG>::SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(gemm2_kernel<2, EPI_STD, 0, 1, G2_A_ROWS_XLONG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                G2Cfg<2, 0, 1, G2_A_ROWS_XLONG>::SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(reconstruct_alignment_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(kReconstructSmemMax)));
   CUDA_TRY(cudaFuncSetAttribute(reconstruct_alignment_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1588,14 +1592,16 @@ int efts_vocoder_create(const efts_vocoder_config* g, efts_ctx** out) {
   }
   if (C * 7 > 1024) return fail(EFTS_ERR_UNSUPPORTED, "conv_post with %d channels", C);
   if (g->num_upsamples * g->num_kernels > 32) return fail(EFTS_ERR_UNSUPPORTED, "too many resblocks");
+  if (g->resblock_type != 1 && g->resblock_type != 2) return fail(EFTS_ERR_UNSUPPORTED, "resblock type %d", g->resblock_type);
+  if (g->num_dilations < 1 || g->num_dilations > 3) return fail(EFTS_ERR_UNSUPPORTED, "num_dilations=%d", g->num_dilations);
   for (int j = 0; j < g->num_kernels; ++j) {
     const int k = g->resblock_kernel_sizes[j];
     if (k < 1 || k > 11 || !(k & 1)) return fail(EFTS_ERR_UNSUPPORTED, "resblock kernel size %d (odd, <= 11)", k);
-    for (int m = 0; m < 3; ++m) {
+    for (int m = 0; m < g->num_dilations; ++m) {
       const int d = g->resblock_dilations[j][m];
-      if (d < 1 || G2_BM + (k - 1) * d > G2_A_ROWS_LONG)
+      if (d < 1 || G2_BM + (k - 1) * d > G2_A_ROWS_XLONG)
         return fail(EFTS_ERR_UNSUPPORTED, "resblock kernel %d with dilation %d exceeds the %d-row operand box", k, d,
-                    G2_A_ROWS_LONG);
+                    G2_A_ROWS_XLONG);
     }
   }
   efts_ctx* c = nullptr;
@@ -1621,9 +1627,14 @@ int efts_vocoder_finalize(efts_ctx* c) {
     lmult *= g.upsample_rates[i];
     for (int j = 0; j < g.num_kernels; ++j) {
       const int n = i * g.num_kernels + j;
-      for (int m = 0; m < 3; ++m) {
+      for (int m = 0; m < g.num_dilations; ++m) {
         const std::string q = "resblocks." + std::to_string(n);
         int unused = 1;
+        if (g.resblock_type == 2) {                 // ResBlock2: one conv per dilation, "convs.m"
+          TRY(pack_voc_conv(c, q + ".convs." + std::to_string(m), C, g.resblock_kernel_sizes[j], g.resblock_dilations[j][m],
+                            lmult, &v.c1[n][m], &v.g1[n][m], &v.d1[n][m]));
+          continue;
+        }
         TRY(pack_voc_conv(c, q + ".convs1." + std::to_string(m), C, g.resblock_kernel_sizes[j], g.resblock_dilations[j][m],
                           lmult, &v.c1[n][m], &v.g1[n][m], &v.d1[n][m]));
         TRY(pack_voc_conv(c, q + ".convs2." + std::to_string(m), C, g.resblock_kernel_sizes[j], 1, lmult, &v.c2[n][m],
@@ -1689,15 +1700,24 @@ int efts_vocoder_forward(efts_ctx* c, const float* mel, int32_t B, int32_t T, fl
       const int n = i * g.num_kernels + j;
       const float* cur_f = w.x_f;
       const __half *cur_hi = w.x_hi, *cur_lo = w.x_lo;
-      for (int m = 0; m < 3; ++m) {
+      const int nd = g.num_dilations;
+      for (int m = 0; m < nd && g.resblock_type == 2; ++m) {          // ResBlock2.forward (:83-88): x = c(lrelu(x)) + x
+        const bool last = m == nd - 1;
+        float* of = last ? w.fin[j] : ((m & 1) ? w.rb_f : w.ra_f);
+        __half* oh = last ? nullptr : ((m & 1) ? w.rb_hi : w.ra_hi);
+        __half* ol = last ? nullptr : ((m & 1) ? w.rb_lo : w.ra_lo);
+        TRY(voc_conv(c, st, v.c1[n][m], v.d1[n][m], cur_hi, cur_lo, B, Li, ACT_NONE, cur_f, of, oh, ol, 1, v.g1[n][m]));
+        cur_f = of; cur_hi = oh; cur_lo = ol;
+      }
+      for (int m = 0; m < nd && g.resblock_type == 1; ++m) {
         // xt = c1(leaky_relu(x)); only leaky_relu(xt) is consumed (:59-60)
         TRY(voc_conv(c, st, v.c1[n][m], v.d1[n][m], cur_hi, cur_lo, B, Li, ACT_LRELU, nullptr, nullptr, w.t_hi, w.t_lo, 0,
                      v.g1[n][m]));
         // x = c2(...) + x (:61-62): fp32 x for the next residual, planes of leaky_relu(x) for the next c1
-        const bool last = m == 2;
-        float* of = last ? w.fin[j] : (m == 0 ? w.ra_f : w.rb_f);
-        __half* oh = last ? nullptr : (m == 0 ? w.ra_hi : w.rb_hi);
-        __half* ol = last ? nullptr : (m == 0 ? w.ra_lo : w.rb_lo);
+        const bool last = m == nd - 1;
+        float* of = last ? w.fin[j] : ((m & 1) ? w.rb_f : w.ra_f);
+        __half* oh = last ? nullptr : ((m & 1) ? w.rb_hi : w.ra_hi);
+        __half* ol = last ? nullptr : ((m & 1) ? w.rb_lo : w.ra_lo);
         TRY(voc_conv(c, st, v.c2[n][m], 1, w.t_hi, w.t_lo, B, Li, ACT_NONE, cur_f, of, oh, ol, 1, v.g2[n][m]));
         cur_f = of; cur_hi = oh; cur_lo = ol;
       }

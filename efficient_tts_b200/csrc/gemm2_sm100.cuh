@@ -25,7 +25,8 @@ constexpr int G2_BM = 128;
 constexpr int G2_BN = 128;
 constexpr int G2_BK = 64;
 constexpr int G2_A_ROWS = 136;                      // A box: 128 rows + the halo of 9 undilated taps
-constexpr int G2_A_ROWS_LONG = 184;                 // vocoder layers: up to 11 taps, dilation up to 5 (halo 50 rows)
+constexpr int G2_A_ROWS_LONG = 184;                 // vocoder layers: up to 15 taps, dilation up to 5 (halo <= 56 rows)
+constexpr int G2_A_ROWS_XLONG = 200;                // ResBlock2 generators: k = 7 with dilation 12 (halo 72 rows)
 constexpr int G2_EPI_WARPS = 8;                    // two groups of four (one warp per TMEM lane quadrant)
 constexpr int G2_THREADS = 128 + 32 * G2_EPI_WARPS;   // warpgroup 0: TMA, MMA, 2 idle warps; warpgroups 1, 2: epilogue groups
 constexpr int G2_BIAS_MAX = 1024;                     // columns whose bias is staged in shared memory

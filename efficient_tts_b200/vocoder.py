@@ -48,6 +48,23 @@ class ResBlock1(torch.nn.Module):
             remove_weight_norm(m)
 
 
+class ResBlock2(torch.nn.Module):
+    """Parameter holder with the reference's layout (vocoders/hifigan_model.py:71-81)."""
+
+    def __init__(self, h, channels, kernel_size=3, dilation=(1, 3)):
+        super().__init__()
+        self.h = h
+        self.convs = torch.nn.ModuleList([
+            weight_norm(torch.nn.Conv1d(channels, channels, kernel_size, 1, dilation=d,
+                                        padding=get_padding(kernel_size, d))) for d in dilation])
+        for m in self.convs:
+            m.weight_v.data.normal_(0.0, 0.01)          # init_weights (vocoders/utils.py)
+
+    def remove_weight_norm(self):
+        for m in self.convs:
+            remove_weight_norm(m)
+
+
 class VocoderEngine:
     """One prepacked generator on one CUDA device."""
 
@@ -60,9 +77,9 @@ class VocoderEngine:
         self.device = torch.device("cuda", idx)
         rates, ksz = list(_cfg(h, "upsample_rates")), list(_cfg(h, "upsample_kernel_sizes"))
         rks, rds = list(_cfg(h, "resblock_kernel_sizes")), [list(d) for d in _cfg(h, "resblock_dilation_sizes")]
-        if str(_cfg(h, "resblock")) != "1":
-            raise NotImplementedError("only ResBlock1 generators (HiFi-GAN V1/V2 layout) are on the B200 path")
-        if len(rates) > 8 or len(rks) > 4 or any(len(d) != 3 for d in rds):
+        rtype = 1 if str(_cfg(h, "resblock")) == "1" else 2           # vocoders/hifigan_model.py:102
+        nd = len(rds[0])
+        if len(rates) > 8 or len(rks) > 4 or nd > 3 or any(len(d) != nd for d in rds):
             raise NotImplementedError("generator topology outside the B200 path")
         self.hop = 1
         for u in rates:
@@ -77,8 +94,9 @@ class VocoderEngine:
         cfg.num_kernels = len(rks)
         for j, (k, d) in enumerate(zip(rks, rds)):
             cfg.resblock_kernel_sizes[j] = int(k)
-            for m in range(3):
+            for m in range(nd):
                 cfg.resblock_dilations[j][m] = int(d[m])
+        cfg.resblock_type, cfg.num_dilations = rtype, nd
         cfg.device = idx
         h_ctx = ctypes.c_void_p()
         with torch.cuda.device(self.device):
@@ -143,8 +161,7 @@ class Generator(torch.nn.Module):
         rks, rds = _cfg(h, "resblock_kernel_sizes"), _cfg(h, "resblock_dilation_sizes")
         rates, ksz = _cfg(h, "upsample_rates"), _cfg(h, "upsample_kernel_sizes")
         c0 = _cfg(h, "upsample_initial_channel")
-        if str(_cfg(h, "resblock")) != "1":
-            raise NotImplementedError("only ResBlock1 generators are on the B200 path (the reference loads V1)")
+        resblock = ResBlock1 if str(_cfg(h, "resblock")) == "1" else ResBlock2      # :102
         self.num_kernels = len(rks)
         self.num_upsamples = len(rates)
         self.conv_pre = weight_norm(torch.nn.Conv1d(80, c0, 7, 1, padding=3))
@@ -157,7 +174,7 @@ class Generator(torch.nn.Module):
         for i in range(len(self.ups)):
             ch = c0 // (2 ** (i + 1))
             for k, d in zip(rks, rds):
-                self.resblocks.append(ResBlock1(h, ch, k, d))
+                self.resblocks.append(resblock(h, ch, k, d))
         self.conv_post = weight_norm(torch.nn.Conv1d(ch, 1, 7, 1, padding=3))
         for m in list(self.ups) + [self.conv_post]:
             m.weight_v.data.normal_(0.0, 0.01)          # init_weights

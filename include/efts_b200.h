@@ -192,8 +192,9 @@ int efts_reconstruct_alignment(const float* e, const int32_t* text_lengths, cons
  * Generator's state_dict with the weight-norm pairs folded (names as left by remove_weight_norm():
  * "conv_pre.weight" [C0,80,7], "ups.i.weight" [Cin,Cout,k] (ConvTranspose1d layout), "resblocks.n.convs1.m.weight"
  * [C,C,k], "resblocks.n.convs2.m.weight", "conv_post.weight" [1,C,7] and the matching ".bias"), then
- * efts_vocoder_finalize.  Supported: resblock type "1", upsample_kernel_size == 2 * upsample_rate (rate even),
- * resblock kernels <= 11 with dilation * (k - 1) <= 56, channels multiples of 8; anything else is
+ * efts_vocoder_finalize (ResBlock2 generators name their convs "resblocks.n.convs.m.weight").  Supported:
+ * upsample_kernel_size == 2 * upsample_rate (rate even), resblock kernels <= 11 with dilation * (k - 1) <= 72,
+ * channels multiples of 8 (the V1, V2 and V3 configurations of the HiFi-GAN release); anything else is
  * EFTS_ERR_UNSUPPORTED. */
 typedef struct {
   int32_t num_mels;                    /* 80 (Conv1d(80, ...) at vocoders/hifigan_model.py:101)            */
@@ -204,6 +205,8 @@ typedef struct {
   int32_t num_kernels;                 /* 3 (resblocks per stage)                                         */
   int32_t resblock_kernel_sizes[4];    /* 3, 7, 11                                                        */
   int32_t resblock_dilations[4][3];    /* {1, 3, 5} each                                                  */
+  int32_t resblock_type;               /* 1: ResBlock1 (:31-63, convs1/convs2 pairs); 2: ResBlock2 (:71-88) */
+  int32_t num_dilations;               /* dilations per resblock: 3 for ResBlock1, 2 for ResBlock2        */
   int32_t device;
 } efts_vocoder_config;
 int efts_vocoder_create(const efts_vocoder_config* cfg, efts_ctx** out);

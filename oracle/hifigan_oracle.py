@@ -29,6 +29,14 @@ V1_CONFIG = dict(resblock="1", upsample_rates=[8, 8, 2, 2], upsample_kernel_size
                  resblock_dilation_sizes=[[1, 3, 5], [1, 3, 5], [1, 3, 5]], num_mels=80)
 
 
+# config_v2.json / config_v3.json of the HiFi-GAN release the reference's Generator class was taken from: the same
+# class builds them (V2: ResBlock1 with 128 initial channels; V3: ResBlock2, three upsamplers, dilations up to 12)
+V2_CONFIG = dict(V1_CONFIG, upsample_initial_channel=128)
+V3_CONFIG = dict(resblock="2", upsample_rates=[8, 8, 4], upsample_kernel_sizes=[16, 16, 8],
+                 upsample_initial_channel=256, resblock_kernel_sizes=[3, 5, 7],
+                 resblock_dilation_sizes=[[1, 2], [2, 6], [3, 12]], num_mels=80)
+
+
 def get_padding(kernel_size: int, dilation: int = 1) -> int:
     """vocoders/utils.py ``get_padding``."""
     return int((kernel_size * dilation - dilation) / 2)
@@ -61,10 +69,14 @@ def make_weights(seed: int = 4321, h: dict = V1_CONFIG, gain: float = 1.0) -> We
     for i in range(len(h["upsample_rates"])):
         ch = c0 // 2 ** (i + 1)
         for j, (k, dil) in enumerate(zip(h["resblock_kernel_sizes"], h["resblock_dilation_sizes"])):
-            for m in range(len(dil)):
-                conv(f"resblocks.{i * nk + j}.convs1.{m}", ch, ch, k)
-            for m in range(len(dil)):
-                conv(f"resblocks.{i * nk + j}.convs2.{m}", ch, ch, k)
+            if h["resblock"] == "1":
+                for m in range(len(dil)):
+                    conv(f"resblocks.{i * nk + j}.convs1.{m}", ch, ch, k)
+                for m in range(len(dil)):
+                    conv(f"resblocks.{i * nk + j}.convs2.{m}", ch, ch, k)
+            else:                                   # ResBlock2 (:71-81): one conv per dilation
+                for m in range(len(dil)):
+                    conv(f"resblocks.{i * nk + j}.convs.{m}", ch, ch, k)
     conv("conv_post", 1, c0 // 2 ** len(h["upsample_rates"]), 7, g_layer=4.0)   # waveform spans tanh's range
     return w
 
@@ -90,10 +102,19 @@ def resblock1(x: torch.Tensor, w: Weights, prefix: str, k: int, dilation) -> tor
     return x
 
 
+def resblock2(x: torch.Tensor, w: Weights, prefix: str, k: int, dilation) -> torch.Tensor:
+    """vocoders/hifigan_model.py:83-88."""
+    for m, d in enumerate(dilation):
+        xt = F.leaky_relu(x, LRELU_SLOPE)
+        xt = F.conv1d(xt, conv_weight(w, f"{prefix}.convs.{m}"), w[f"{prefix}.convs.{m}.bias"], dilation=d,
+                      padding=get_padding(k, d))
+        x = xt + x
+    return x
+
+
 def generator_forward(w: Weights, mel_bct: torch.Tensor, h: dict = V1_CONFIG) -> torch.Tensor:
     """vocoders/hifigan_model.py:120-136: mel [B, 80, T] -> waveform [B, 1, T * prod(upsample_rates)]."""
-    if h["resblock"] != "1":
-        raise NotImplementedError("only ResBlock1 (the V1 generator) is restated")
+    resblock = resblock1 if h["resblock"] == "1" else resblock2          # :102
     nk = len(h["resblock_kernel_sizes"])
     x = F.conv1d(mel_bct, conv_weight(w, "conv_pre"), w["conv_pre.bias"], padding=3)            # :121
     for i, (u, k) in enumerate(zip(h["upsample_rates"], h["upsample_kernel_sizes"])):
@@ -102,8 +123,8 @@ def generator_forward(w: Weights, mel_bct: torch.Tensor, h: dict = V1_CONFIG) ->
                                padding=(k - u) // 2)                                             # :124
         xs = None
         for j in range(nk):                                                                      # :126-130
-            r = resblock1(x, w, f"resblocks.{i * nk + j}", h["resblock_kernel_sizes"][j],
-                          h["resblock_dilation_sizes"][j])
+            r = resblock(x, w, f"resblocks.{i * nk + j}", h["resblock_kernel_sizes"][j],
+                         h["resblock_dilation_sizes"][j])
             xs = r if xs is None else xs + r
         x = xs / nk                                                                              # :131
     x = F.leaky_relu(x)                                                                          # :132 (slope 0.01)

@@ -40,9 +40,9 @@ from nntts.vocoders.env import AttrDict  # noqa: E402
 from nntts.vocoders.hifigan_model import Generator  # noqa: E402
 
 
-def case(name, seed, batch, frames):
-    w = hor.make_weights(seed=4321)
-    gen = Generator(AttrDict(hor.V1_CONFIG))
+def case(name, seed, batch, frames, cfg=hor.V1_CONFIG):
+    w = hor.make_weights(seed=4321, h=cfg)
+    gen = Generator(AttrDict(cfg))
     missing = gen.load_state_dict(w, strict=True)
     assert not missing.missing_keys and not missing.unexpected_keys
     gen.eval()
@@ -60,3 +60,5 @@ def case(name, seed, batch, frames):
 if __name__ == "__main__":
     case("hifigan_small", 7, 1, 12)
     case("hifigan_batch", 8, 2, 9)
+    case("hifigan_v2", 9, 2, 10, hor.V2_CONFIG)
+    case("hifigan_v3", 10, 2, 11, hor.V3_CONFIG)

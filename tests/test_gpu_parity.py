@@ -660,3 +660,30 @@ def test_vocoder_grouped_packing_equals_plain_packing(dev):
         outs[grouped] = g(mel.to(dev)).cpu()
         assert (outs[grouped] - ref).abs().max().item() <= AUDIO_TOL
     assert (outs[1] - outs[0]).abs().max().item() <= 2e-5
+
+
+@pytest.mark.parametrize("name,cfg_name", [("hifigan_v2", "V2_CONFIG"), ("hifigan_v3", "V3_CONFIG")])
+def test_vocoder_other_release_configs(dev, name, cfg_name):
+    """The same Generator class builds the V2 (ResBlock1, 128 initial channels: stages of 64 / 32 / 16 / 8 channels,
+    all on the grouped packing) and V3 (ResBlock2, three upsamplers, k = 7 with dilation 12 -> 200-row operand box)
+    configurations of the HiFi-GAN release: reference fixtures and the oracle at a second length."""
+    from oracle import hifigan_oracle as hor
+    from efficient_tts_b200.vocoder import Generator
+    cfg = getattr(hor, cfg_name)
+    w = hor.make_weights(seed=4321, h=cfg)
+    g = Generator(_H(cfg))
+    res = g.load_state_dict(w, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    g = g.eval().to(dev)
+    z = np.load(os.path.join(G, name + ".npz"))
+    mel = hor.make_mel(int(z["seed"]), int(z["batch"]), int(z["frames"]))
+    y = g(mel.to(dev)).cpu()
+    d = (y - torch.from_numpy(z["audio"])).abs().max().item()
+    print("vocoder %s: max-abs vs reference fixture %.3e" % (name, d))
+    assert tuple(y.shape) == z["audio"].shape and d <= AUDIO_TOL
+    mel2 = hor.make_mel(77, 1, 150)
+    with torch.no_grad():
+        ref = hor.generator_forward(w, mel2, cfg)
+    d2 = (g(mel2.to(dev)).cpu() - ref).abs().max().item()
+    print("vocoder %s T=150: max-abs %.3e" % (name, d2))
+    assert d2 <= AUDIO_TOL

@@ -222,8 +222,11 @@ def test_vocoder_mirror_keeps_the_reference_parameter_contract():
     # no device, no result: the forward never falls back to the CPU
     with pytest.raises(RuntimeError):
         g.eval()(hor.make_mel(1, 1, 4))
-    with pytest.raises(NotImplementedError):
-        Generator(H(dict(hor.V1_CONFIG, resblock="2")))
+    # the other two configurations the same class builds (ResBlock1 with 128 channels; ResBlock2)
+    for cfg in (hor.V2_CONFIG, hor.V3_CONFIG):
+        g2 = Generator(H(cfg))
+        res = g2.load_state_dict(hor.make_weights(seed=4321, h=cfg), strict=True)
+        assert not res.missing_keys and not res.unexpected_keys
 
 
 def test_vocoder_create_rejects_unsupported_topologies():
@@ -236,10 +239,17 @@ def test_vocoder_create_rejects_unsupported_topologies():
     cfg.resblock_kernel_sizes[0] = 3
     for m in range(3):
         cfg.resblock_dilations[0][m] = 1
+    cfg.resblock_type, cfg.num_dilations = 1, 3
     h = ctypes.c_void_p()
     assert lib.efts_vocoder_create(ctypes.byref(cfg), ctypes.byref(h)) == -2     # EFTS_ERR_UNSUPPORTED
     cfg.upsample_kernel_sizes[0] = 16
     cfg.resblock_kernel_sizes[0] = 13                                            # more than 11 taps
+    assert lib.efts_vocoder_create(ctypes.byref(cfg), ctypes.byref(h)) == -2
+    cfg.resblock_kernel_sizes[0] = 7
+    cfg.resblock_dilations[0][1] = 13                                            # halo 78 rows > 72
+    assert lib.efts_vocoder_create(ctypes.byref(cfg), ctypes.byref(h)) == -2
+    cfg.resblock_dilations[0][1] = 1
+    cfg.resblock_type = 3
     assert lib.efts_vocoder_create(ctypes.byref(cfg), ctypes.byref(h)) == -2
 
 
