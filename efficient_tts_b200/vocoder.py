@@ -218,3 +218,22 @@ class Generator(torch.nn.Module):
             m.remove_weight_norm()
         remove_weight_norm(self.conv_pre)
         remove_weight_norm(self.conv_post)
+
+
+def load_hifigan_generator(device, config_path, ckpt_path):
+    """``nntts.vocoders.hifigan_model.load_hifigan_generator`` (vocoders/hifigan_model.py:18-28) with explicit paths
+    (the reference reads ``HiFiGAN_LJ_V1/config.json`` and ``generator_v1`` next to its own module): build the
+    generator from the JSON config, load ``state_dict["generator"]``, ``eval()``, ``remove_weight_norm()``."""
+    import json
+    with open(config_path) as f:
+        h = json.loads(f.read())
+
+    class _AttrDict(dict):
+        __getattr__ = dict.__getitem__
+
+    generator = Generator(_AttrDict(h))
+    state = torch.load(ckpt_path, map_location="cpu")
+    generator.load_state_dict(state["generator"])
+    generator.eval()
+    generator.remove_weight_norm()
+    return generator.to(device)

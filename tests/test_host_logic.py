@@ -260,3 +260,19 @@ def test_vocoder_workload_recipe_equals_the_oracle_recipe():
     assert a.keys() == b.keys()
     assert all(torch.equal(a[k], b[k]) for k in a)
     assert torch.equal(wl.make_mel(3, 2, 5), hor.make_mel(3, 2, 5))
+
+
+def test_load_hifigan_generator_mirror_reads_a_checkpoint(tmp_path):
+    """Same steps as vocoders/hifigan_model.py:18-28 on a checkpoint file written in the reference's format."""
+    import json
+    from oracle import hifigan_oracle as hor
+    from efficient_tts_b200.vocoder import load_hifigan_generator
+    cfg = dict(hor.V2_CONFIG, sampling_rate=22050)
+    (tmp_path / "config.json").write_text(json.dumps(cfg))
+    w = hor.make_weights(seed=1, h=cfg)
+    torch.save({"generator": w}, tmp_path / "g_00000001")
+    g = load_hifigan_generator("cpu", str(tmp_path / "config.json"), str(tmp_path / "g_00000001"))
+    assert not g.training
+    sd = g.state_dict()
+    assert "conv_pre.weight" in sd and "conv_pre.weight_g" not in sd           # remove_weight_norm() ran
+    assert torch.allclose(sd["conv_pre.weight"], hor.conv_weight(w, "conv_pre"), atol=1e-7)
