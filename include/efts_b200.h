@@ -16,6 +16,8 @@
  *     (except `efts_inference`, which must read T2 back exactly like the reference does, and the
  *     weight upload in `efts_finalize_weights`).
  *   - `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy default stream).
+ *   - one call in flight per context: the context owns the device error word, the launch counter and the
+ *     profile hooks next to the (immutable) prepacked weights; use one context per concurrent stream.
  *   - return value 0 = OK, negative = `efts_status`; `efts_last_error()` gives the text.
  *     There is no CPU fallback: a missing device / wrong architecture is an error.
  */
