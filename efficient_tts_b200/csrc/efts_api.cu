@@ -97,6 +97,9 @@ struct efts_ctx {
   int debug_mask = 0;        // timing experiments only
   int chunk_kb = 2;          // v2: k-blocks per main-accumulator flush (1 = most accurate, 0 = never)
   int voc_group = 1;             // vocoder: grouped (super-tap) packing of the 32 / 64-channel layers (read at finalize)
+  int voc_narrow = 0;            // vocoder: 64-column tiles for layers with N <= 64 (read at finalize and at launch).
+                                 // Off: measured 36.4 vs 34.5 ms at 16 x 800 frames -- the narrow layers are bound by
+                                 // their tile count (A-box halo, epilogue), which the grouped packing halves, not by MMA columns
   int split_k = 1;               // fused-B kernel: split the reduction of small launches over more SMs
   int pdl = 1;                   // programmatic dependent launch for the v2 GEMM and split-reduce kernels
   int fuse_b = 1;                // v2 conv layers: Ahi*[Bhi|Blo] as one N = 256 MMA (two MMAs per k-step instead of three)
@@ -198,10 +201,10 @@ int launch_gemm_t(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, cons
 constexpr size_t kReconstructSmemMax = 200 * 1024;
 constexpr size_t kSplitScratchBytes = 16u << 20;       // partial planes of a split reduction (workspace, text side)
 
-template <int CG, int EPI, int WIDE, int FUSE = 0, int AR = G2_A_ROWS>
+template <int CG, int EPI, int WIDE, int FUSE = 0, int AR = G2_A_ROWS, int BN = G2_BN>
 int launch_gemm2_t(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, const GemmParams& p) {
-  using Cfg = G2Cfg<CG, WIDE, FUSE, AR>;
-  auto kern = gemm2_kernel<CG, EPI, WIDE, FUSE, AR>;
+  using Cfg = G2Cfg<CG, WIDE, FUSE, AR, BN>;
+  auto kern = gemm2_kernel<CG, EPI, WIDE, FUSE, AR, BN>;
   const int dil = p.dil > 1 ? p.dil : 1;
   if (G2_BM + (p.ntaps - 1) * dil > AR)
     return fail(EFTS_ERR_ARG, "%d taps with dilation %d need a %d-row A box (this variant holds %d)", p.ntaps, dil,
@@ -214,7 +217,7 @@ int launch_gemm2_t(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, con
   TRY(make_map(c, &mb_lo, b.lo, b.K, b.N, b.Z, b.ld, Cfg::B_ROWS));
   // persistent: one CTA per SM (CTA pairs when CG == 2), never more than there are tiles
   const long long n_rt = static_cast<long long>(p.B) * ((p.T + G2_BM - 1) / G2_BM);
-  const long long work = ((n_rt + CG - 1) / CG) * ((p.N + G2_BN - 1) / G2_BN) * (FUSE && p.splits > 1 ? p.splits : 1);
+  const long long work = ((n_rt + CG - 1) / CG) * ((p.N + BN - 1) / BN) * (FUSE && p.splits > 1 ? p.splits : 1);
   long long ctas = std::min<long long>(c->sm_count / CG, work) * CG;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -257,8 +260,11 @@ int launch_gemm(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, GemmPa
       if (epi != EPI_STD || p.b_batched || p.chunk_kb < 1)
         return fail(EFTS_ERR_ARG, "long-tap launches are plain weight GEMMs");
       p.splits = 0;
-      if (G2_BM + (p.ntaps - 1) * (p.dil > 1 ? p.dil : 1) > G2_A_ROWS_LONG)
-        return launch_gemm2_t<2, EPI_STD, 0, 1, G2_A_ROWS_XLONG>(c, st, a, b, p);
+      const bool xlong = G2_BM + (p.ntaps - 1) * (p.dil > 1 ? p.dil : 1) > G2_A_ROWS_LONG;
+      if (p.N <= 64 && c->voc_narrow)     // 64-column tiles: half the MMA columns of a 128-column tile
+        return xlong ? launch_gemm2_t<2, EPI_STD, 0, 1, G2_A_ROWS_XLONG, 64>(c, st, a, b, p)
+                     : launch_gemm2_t<2, EPI_STD, 0, 1, G2_A_ROWS_LONG, 64>(c, st, a, b, p);
+      if (xlong) return launch_gemm2_t<2, EPI_STD, 0, 1, G2_A_ROWS_XLONG>(c, st, a, b, p);
       return launch_gemm2_t<2, EPI_STD, 0, 1, G2_A_ROWS_LONG>(c, st, a, b, p);
     }
     const bool wide = c->wide && steps <= 40;
@@ -351,6 +357,10 @@ int set_kernel_attributes() {
                                 G2Cfg<2, 0, 1, G2_A_ROWS_LONG>::SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(gemm2_kernel<2, EPI_STD, 0, 1, G2_A_ROWS_XLONG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 G2Cfg<2, 0, 1, G2_A_ROWS_XLONG>::SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(gemm2_kernel<2, EPI_STD, 0, 1, G2_A_ROWS_LONG, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                G2Cfg<2, 0, 1, G2_A_ROWS_LONG, 64>::SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(gemm2_kernel<2, EPI_STD, 0, 1, G2_A_ROWS_XLONG, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                G2Cfg<2, 0, 1, G2_A_ROWS_XLONG, 64>::SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(reconstruct_alignment_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(kReconstructSmemMax)));
   CUDA_TRY(cudaFuncSetAttribute(reconstruct_alignment_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -876,6 +886,7 @@ int efts_set_option(efts_ctx* c, const char* name, int32_t value) {
   if (strcmp(name, "split_k") == 0) { c->split_k = value != 0; return EFTS_OK; }
   if (strcmp(name, "pdl") == 0) { c->pdl = value != 0; return EFTS_OK; }
   if (strcmp(name, "voc_group") == 0) { c->voc_group = value != 0; return EFTS_OK; }
+  if (strcmp(name, "voc_narrow") == 0) { c->voc_narrow = value != 0; return EFTS_OK; }
   if (strcmp(name, "imv_version") == 0) {
     if (value != 1 && value != 2) return fail(EFTS_ERR_ARG, "imv_version must be 1 or 2");
     c->imv_version = value;
@@ -1556,14 +1567,19 @@ int pack_grouped(efts_ctx* c, const std::string& wname, const std::string& bname
 // and a sequence length that is a multiple of G: L = T * prod(rates) always is when the last rates cover G).
 int pack_voc_conv(efts_ctx* c, const std::string& prefix, int C, int k, int d, int Lmult, PackedW* out, int* group,
                   int* dil) {
+  // MMA columns issued per time step with G steps per row: taps * (K padded to 64) * (column tile: 64 when the
+  // row has <= 64 columns and narrow tiles are on, else 128) / G
+  auto cost = [&](int G) -> double {
+    const int taps = G == 1 ? k : grouped_taps(k, d, G);
+    if (taps > 15) return 1e30;
+    const int W = G * C, Kp = (W + 63) / 64 * 64;
+    const int tile = (W <= 64 && c->voc_narrow) ? 64 : 128;
+    return static_cast<double>(taps) * Kp * tile * ((W + tile - 1) / tile) / G;
+  };
   int G = 1;
-  if (c->voc_group && C < 128 && 128 % C == 0 && Lmult % (128 / C) == 0) {
-    G = 128 / C;
-    const int S = grouped_taps(k, d, G);
-    const long plain = static_cast<long>(G) * k * 64 * 128;       // per G steps: K padded to 64, N tile 128
-    const long grouped = static_cast<long>(S) * 128 * 128;
-    if (S > 15 || grouped >= plain) G = 1;
-  }
+  if (c->voc_group)
+    for (int g2 = 2; g2 * C <= 128; g2 *= 2)
+      if (Lmult % g2 == 0 && cost(g2) < cost(G)) G = g2;
   *group = G;
   *dil = G == 1 ? d : 1;
   if (G == 1) return pack_weight(c, prefix + ".weight", prefix + ".bias", C, C, k, out);

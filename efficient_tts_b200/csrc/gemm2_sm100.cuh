@@ -43,20 +43,24 @@ constexpr int G2_STAGE_WARP_BYTES = 32 * G2_STAGE_ROW_BYTES;
 // per k-step instead of three, A fetched from shared memory twice instead of three times.  The N = 128 MMA needs
 // Bhi split 64 + 64 over the two CTAs at one common offset, so a third 64-row block per stage holds Bhi[0:64]
 // (leader, a duplicate) / Bhi[64:128] (peer).  Both accumulator halves restart with every chunk.
-template <int CG, int WIDE = 0, int FUSE = 0, int AR = G2_A_ROWS>
+// BN = 64 (long-box fused-B kernel only): 64 output columns per tile for the vocoder's 64-channel layers and the
+// 32-channel layers grouped two time steps per row -- Ahi x [Bhi|Blo] is then an N = 128 MMA, Alo x Bhi an N = 64 one.
+template <int CG, int WIDE = 0, int FUSE = 0, int AR = G2_A_ROWS, int BN = G2_BN>
 struct G2Cfg {
   static_assert(!FUSE || (CG == 2 && !WIDE), "the fused-B variant is the CTA-pair, long-reduction kernel");
   static_assert(AR == G2_A_ROWS || FUSE, "the long A box exists for the fused-B kernel only");
+  static_assert(BN == G2_BN || (BN == 64 && FUSE && AR != G2_A_ROWS), "narrow tiles exist for the long-box kernel only");
   static constexpr int A_ROWS = AR;
   static constexpr int A_PLANE = AR * 128;
   static constexpr int A_STAGE = 2 * A_PLANE;
   static constexpr int BIAS_MAX = AR == G2_A_ROWS ? G2_BIAS_MAX : G2_BIAS_MAX_LONG;
-  static constexpr int B_ROWS = G2_BN / CG;
+  static constexpr int B_ROWS = BN / CG;
   static constexpr int B_PLANE = B_ROWS * 128;
   static constexpr int B_STAGE = (FUSE ? 3 : 2) * B_PLANE;
   // the wide (short-reduction) variant trades pipeline depth for 16 per-warp transposition buffers
   static constexpr int A_STAGES = WIDE ? 2 : (CG == 2 ? (FUSE ? 2 : 3) : 2);
-  static constexpr int B_STAGES = WIDE ? (CG == 2 ? 4 : 2) : (CG == 2 ? (FUSE ? (AR == G2_A_ROWS ? 4 : 3) : 5) : 3);
+  static constexpr int B_STAGES = WIDE ? (CG == 2 ? 4 : 2)
+                                       : (CG == 2 ? (FUSE ? (AR == G2_A_ROWS ? 4 : (BN == 64 ? 6 : 3)) : 5) : 3);
   static constexpr int EPI_WARPS = WIDE ? 16 : 8;
   static constexpr int SMEM_TILES = A_STAGES * A_STAGE + B_STAGES * B_STAGE;
   static constexpr int SMEM_BYTES = SMEM_TILES + 1024 + 512 + 4 * BIAS_MAX + EPI_WARPS * G2_STAGE_WARP_BYTES;
@@ -168,12 +172,13 @@ enum Gemm2Epi { EPI_STD = 0, EPI_FULL = 1, EPI_SOFTMAX = 2 };
 // columns at a time -- no running sums, 96 registers per thread, twice the warps to hide the store latency.
 constexpr int G2_THREADS_WIDE = 128 + 32 * 16;
 
-template <int CG, int EPI, int WIDE, int FUSE = 0, int AR = G2_A_ROWS>
+template <int CG, int EPI, int WIDE, int FUSE = 0, int AR = G2_A_ROWS, int BN = 128>
 __global__ void __launch_bounds__(WIDE ? G2_THREADS_WIDE : G2_THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
              const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
              const GemmParams p) {
-  using Cfg = G2Cfg<CG, WIDE, FUSE, AR>;
+  using Cfg = G2Cfg<CG, WIDE, FUSE, AR, BN>;
+  constexpr int G2_BN = BN;                          // column tile of this instantiation (shadows the default)
   constexpr int G2_A_PLANE = Cfg::A_PLANE;
   constexpr int G2_A_STAGE = Cfg::A_STAGE;
   const int dil = p.dil > 1 ? p.dil : 1;
