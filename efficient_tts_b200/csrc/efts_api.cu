@@ -97,6 +97,8 @@ struct efts_ctx {
   int debug_mask = 0;        // timing experiments only
   int chunk_kb = 2;          // v2: k-blocks per main-accumulator flush (1 = most accurate, 0 = never)
   int voc_group = 1;             // vocoder: grouped (super-tap) packing of the 32 / 64-channel layers (read at finalize)
+  int voc_short_box = 0;         // vocoder: layers whose taps reach <= 8 rows use the 136-row A box (A/B switch, off:
+                                 // -1 % at 16 x 800 frames, +12 % latency at B = 1 from alternating two kernel images)
   int voc_narrow = 0;            // vocoder: 64-column tiles for layers with N <= 64 (read at finalize and at launch).
                                  // Off: measured 36.4 vs 34.5 ms at 16 x 800 frames -- the narrow layers are bound by
                                  // their tile count (A-box halo, epilogue), which the grouped packing halves, not by MMA columns
@@ -260,7 +262,12 @@ int launch_gemm(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, GemmPa
       if (epi != EPI_STD || p.b_batched || p.chunk_kb < 1)
         return fail(EFTS_ERR_ARG, "long-tap launches are plain weight GEMMs");
       p.splits = 0;
-      const bool xlong = G2_BM + (p.ntaps - 1) * (p.dil > 1 ? p.dil : 1) > G2_A_ROWS_LONG;
+      const int box = G2_BM + (p.ntaps - 1) * (p.dil > 1 ? p.dil : 1);
+      // the halo rows of the A box are pure overhead for these tile-count-bound layers: short-reach layers (most
+      // grouped ones, k = 3, the transposed convs) take the 136-row box of the acoustic model's kernel
+      if (box <= G2_A_ROWS && c->voc_short_box && (p.bias == nullptr || p.N <= G2_BIAS_MAX))
+        return launch_gemm2_t<2, EPI_STD, 0, 1>(c, st, a, b, p);
+      const bool xlong = box > G2_A_ROWS_LONG;
       if (p.N <= 64 && c->voc_narrow)     // 64-column tiles: half the MMA columns of a 128-column tile
         return xlong ? launch_gemm2_t<2, EPI_STD, 0, 1, G2_A_ROWS_XLONG, 64>(c, st, a, b, p)
                      : launch_gemm2_t<2, EPI_STD, 0, 1, G2_A_ROWS_LONG, 64>(c, st, a, b, p);
@@ -887,6 +894,7 @@ int efts_set_option(efts_ctx* c, const char* name, int32_t value) {
   if (strcmp(name, "pdl") == 0) { c->pdl = value != 0; return EFTS_OK; }
   if (strcmp(name, "voc_group") == 0) { c->voc_group = value != 0; return EFTS_OK; }
   if (strcmp(name, "voc_narrow") == 0) { c->voc_narrow = value != 0; return EFTS_OK; }
+  if (strcmp(name, "voc_short_box") == 0) { c->voc_short_box = value != 0; return EFTS_OK; }
   if (strcmp(name, "imv_version") == 0) {
     if (value != 1 && value != 2) return fail(EFTS_ERR_ARG, "imv_version must be 1 or 2");
     c->imv_version = value;

@@ -37,6 +37,9 @@ def main():
     from oracle import hifigan_oracle as hor      # weights recipe only (unit-scale layers; the default init is N(0, 0.01))
     g = Generator(H(V1))
     g.load_state_dict(hor.make_weights(seed=4321))
+    opts = dict(kv.split("=") for kv in sys.argv[1].split(",")) if len(sys.argv) > 1 and sys.argv[1] else {}
+    if opts:
+        g.set_engine_options(**{k: int(v) for k, v in opts.items()})
     g = g.eval().to(dev)
     out = {}
     for B, T, n in ((1, 517, 20), (16, 800, 5)):
@@ -62,6 +65,7 @@ def main():
         y = tts()
     dt = timed(tts, 20)
     out["text_to_wave_c1"] = dict(ms=dt * 1e3, samples=int(y.shape[-1]), rtf=dt / (y.shape[-1] / 22050.0))
+    out["opts"] = opts
     print("VOC " + json.dumps(out))
 
 
