@@ -97,6 +97,7 @@ struct efts_ctx {
   int debug_mask = 0;        // timing experiments only
   int chunk_kb = 2;          // v2: k-blocks per main-accumulator flush (1 = most accurate, 0 = never)
   int voc_group = 1;             // vocoder: grouped (super-tap) packing of the 32 / 64-channel layers (read at finalize)
+  int voc_wide = 1;              // vocoder: short-reach, short-reduction layers use the wide-epilogue variant
   int voc_short_box = 0;         // vocoder: layers whose taps reach <= 8 rows use the 136-row A box (A/B switch, off:
                                  // -1 % at 16 x 800 frames, +12 % latency at B = 1 from alternating two kernel images)
   int voc_narrow = 0;            // vocoder: 64-column tiles for layers with N <= 64 (read at finalize and at launch).
@@ -258,6 +259,12 @@ int launch_gemm(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, GemmPa
     // short reductions (<= 40 MMA steps: one accumulation chain is as accurate as a flushed one) are bound by
     // their epilogue: they take the wide variant, which reads the single chunk straight from tensor memory
     const int steps = p.ntaps * ((p.K + G2_BK - 1) / G2_BK) * (G2_BK / 16);
+    // vocoder layers with a short reach and a short reduction (k = 3, most grouped layers: <= 40 MMA steps) are bound by
+    // their store epilogue like the Linear layers: they take the wide variant (16 epilogue warps) through the normal path
+    if (p.long_taps && c->voc_wide && c->wide && epi == EPI_STD && !p.b_batched &&
+        G2_BM + (p.ntaps - 1) * (p.dil > 1 ? p.dil : 1) <= G2_A_ROWS && (p.bias == nullptr || p.N <= G2_BIAS_MAX) &&
+        p.ntaps * ((p.K + G2_BK - 1) / G2_BK) * (G2_BK / 16) <= 40)
+      p.long_taps = 0;
     if (p.long_taps) {        // vocoder layers: up to 11 taps / dilation 5, always the fused-B pair kernel
       if (epi != EPI_STD || p.b_batched || p.chunk_kb < 1)
         return fail(EFTS_ERR_ARG, "long-tap launches are plain weight GEMMs");
@@ -895,6 +902,7 @@ int efts_set_option(efts_ctx* c, const char* name, int32_t value) {
   if (strcmp(name, "voc_group") == 0) { c->voc_group = value != 0; return EFTS_OK; }
   if (strcmp(name, "voc_narrow") == 0) { c->voc_narrow = value != 0; return EFTS_OK; }
   if (strcmp(name, "voc_short_box") == 0) { c->voc_short_box = value != 0; return EFTS_OK; }
+  if (strcmp(name, "voc_wide") == 0) { c->voc_wide = value != 0; return EFTS_OK; }
   if (strcmp(name, "imv_version") == 0) {
     if (value != 1 && value != 2) return fail(EFTS_ERR_ARG, "imv_version must be 1 or 2");
     c->imv_version = value;
