@@ -276,3 +276,33 @@ def test_load_hifigan_generator_mirror_reads_a_checkpoint(tmp_path):
     sd = g.state_dict()
     assert "conv_pre.weight" in sd and "conv_pre.weight_g" not in sd           # remove_weight_norm() ran
     assert torch.allclose(sd["conv_pre.weight"], hor.conv_weight(w, "conv_pre"), atol=1e-7)
+
+
+def test_committed_bench_line_follows_the_contract():
+    """The last bench line of the round (profiles/r01/bench_round1_final.json, produced on a B200 by
+    tools/gpu_final.sh) carries every key the measurement contract names."""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = os.path.join(root, "profiles", "r01", "bench_round1_final.json")
+    lines = [ln for ln in open(path).read().splitlines() if ln.strip()]
+    assert len(lines) == 1                                   # exactly one line reached stdout
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert k in d, k
+    assert d["config"]["workload"].startswith("C3") and "model" not in d["config"]
+    assert d["vs_baseline"] is None and d["higher_is_better"] is True and d["scaling"] == "weak"
+    assert d["gpu_launches"] > 0 and d["warmup"] >= 3
+    for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
+        assert k in d["e2e"], k
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert k in d["roofline"], k
+    assert abs(d["roofline"]["frac"] - d["roofline"]["achieved"] / d["roofline"]["peak"]) < 1e-9
+    for k in ("value", "unit", "cores", "kind", "sample"):
+        assert k in d["cpu_baseline"], k
+    assert d["cpu_baseline"]["kind"] in ("port", "reference")
+    for k in ("sm_mhz", "sm_max_mhz", "reasons"):
+        assert k in d["clocks"], k
+    assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    assert abs(d["value"] - d["config"]["valid_frames_per_gpu"] * d["n_gpus"] / (d["ms_per_step"] * 1e-3)) < 1e-3 * d["value"]
