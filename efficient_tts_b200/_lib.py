@@ -72,6 +72,8 @@ SIGNATURES = {
     "efts_vocoder_finalize": (c_i32, [c_void_p]),
     "efts_vocoder_workspace_bytes": (c_size_t, [c_void_p, c_i32, c_i32]),
     "efts_vocoder_forward": (c_i32, [c_void_p, c_void_p, c_i32, c_i32, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "efts_host_map_transposed": (c_i32, [c_void_p, c_i32, c_i32, c_i32, c_i32, c_void_p]),
+    "efts_host_map_grouped": (c_i32, [c_void_p, c_i32, c_i32, c_i32, c_i32, c_void_p, ctypes.POINTER(c_i32)]),
     "efts_set_option": (c_i32, [c_void_p, c_char_p, c_i32]),
     "efts_launch_count": (c_i64, [c_void_p]),
     "efts_error_flags": (c_i32, [c_void_p, c_void_p, ctypes.POINTER(c_i32)]),

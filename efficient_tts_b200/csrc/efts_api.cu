@@ -5,6 +5,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -1498,6 +1499,36 @@ int voc_conv(efts_ctx* c, cudaStream_t st, const PackedW& w, int dil, const __ha
 }
 
 // ConvTranspose1d weight [Cin, Cout, k] (k = 2u, padding u/2) -> 3-tap GEMM planes [3][u*Cout][Cin], bias tiled.
+// fp32 weights [taps][N][K] (tap-major GEMM layout) -> fp16 hi / lo operand planes on the device.
+int upload_planes(efts_ctx* c, const std::vector<float>& t, const std::string& what, __half** hi_dev, __half** lo_dev) {
+  std::vector<__half> hi(t.size()), lo(t.size());
+  for (size_t i = 0; i < t.size(); ++i) {
+    const float x = t[i];
+    if (!(fabsf(x) <= 65504.0f))
+      return fail(EFTS_ERR_UNSUPPORTED, "weight '%s' has a value outside the fp16 operand range", what.c_str());
+    const __half h = __float2half_rn(x);
+    hi[i] = h;
+    lo[i] = __float2half_rn((x - __half2float(h)) * SPLIT_SCALE);
+  }
+  TRY(upload(c, hi.data(), hi.size() * sizeof(__half), reinterpret_cast<void**>(hi_dev)));
+  TRY(upload(c, lo.data(), lo.size() * sizeof(__half), reinterpret_cast<void**>(lo_dev)));
+  return EFTS_OK;
+}
+
+// ConvTranspose1d weight [Cin, Cout, k] (k = 2u, stride u, padding u/2) -> [3][u*Cout][Cin]: output phase r of input
+// row q takes tap j = u (1 - tau) + r + u/2 of input row q + tau - 1.
+void map_transposed(const float* w, int Cin, int Cout, int k, int u, float* out) {
+  const int N = u * Cout;
+  for (int tau = 0; tau < 3; ++tau)
+    for (int r = 0; r < u; ++r) {
+      const int j = u * (1 - tau) + r + u / 2;
+      for (int co = 0; co < Cout; ++co)
+        for (int ci = 0; ci < Cin; ++ci)
+          out[(static_cast<size_t>(tau) * N + r * Cout + co) * Cin + ci] =
+              (j >= 0 && j < k) ? w[(static_cast<size_t>(ci) * Cout + co) * k + j] : 0.0f;
+    }
+}
+
 int pack_ups(efts_ctx* c, const std::string& wname, const std::string& bname, int Cin, int Cout, int k, int u,
              PackedW* out) {
   const std::vector<float>* w;
@@ -1505,28 +1536,13 @@ int pack_ups(efts_ctx* c, const std::string& wname, const std::string& bname, in
   TRY(need(c, wname, {Cin, Cout, k}, &w));
   TRY(need(c, bname, {Cout}, &b));
   const int N = u * Cout;
-  const size_t n = static_cast<size_t>(3) * N * Cin;
-  std::vector<__half> hi(n), lo(n);
+  std::vector<float> t(static_cast<size_t>(3) * N * Cin);
+  map_transposed(w->data(), Cin, Cout, k, u, t.data());
   std::vector<float> bias(N);
-  for (int tau = 0; tau < 3; ++tau)
-    for (int r = 0; r < u; ++r) {
-      const int j = u * (1 - tau) + r + u / 2;
-      for (int co = 0; co < Cout; ++co)
-        for (int ci = 0; ci < Cin; ++ci) {
-          const float x = (j >= 0 && j < k) ? (*w)[(static_cast<size_t>(ci) * Cout + co) * k + j] : 0.0f;
-          if (!(fabsf(x) <= 65504.0f))
-            return fail(EFTS_ERR_UNSUPPORTED, "weight '%s' has a value outside the fp16 operand range", wname.c_str());
-          const __half h = __float2half_rn(x);
-          const size_t d = (static_cast<size_t>(tau) * N + r * Cout + co) * Cin + ci;
-          hi[d] = h;
-          lo[d] = __float2half_rn((x - __half2float(h)) * SPLIT_SCALE);
-        }
-    }
   for (int r = 0; r < u; ++r)
     for (int co = 0; co < Cout; ++co) bias[r * Cout + co] = (*b)[co];
   out->Z = 3; out->N = N; out->K = Cin;
-  TRY(upload(c, hi.data(), n * sizeof(__half), reinterpret_cast<void**>(&out->hi)));
-  TRY(upload(c, lo.data(), n * sizeof(__half), reinterpret_cast<void**>(&out->lo)));
+  TRY(upload_planes(c, t, wname, &out->hi, &out->lo));
   TRY(upload(c, bias.data(), N * sizeof(float), reinterpret_cast<void**>(&out->bias)));
   return EFTS_OK;
 }
@@ -1542,16 +1558,10 @@ int pack_ups(efts_ctx* c, const std::string& wname, const std::string& bname, in
 // instead of 4 x 11 x 64 x 128 (4.4 x fewer); the dilation moves into the weights.
 int grouped_taps(int k, int d, int G) { return 2 * (((k - 1) / 2 * d + G - 1) / G) + 1; }
 
-int pack_grouped(efts_ctx* c, const std::string& wname, const std::string& bname, int C, int k, int d, int G,
-                 PackedW* out) {
-  const std::vector<float>* w;
-  const std::vector<float>* b;
-  TRY(need(c, wname, {C, C, k}, &w));
-  TRY(need(c, bname, {C}, &b));
+// Conv1d weight [C, C, k] with dilation d -> super-tap weights [S][G*C][G*C] (zero where no tap lands).
+void map_grouped(const float* w, int C, int k, int d, int G, float* out) {
   const int S = grouped_taps(k, d, G), tmax = (S - 1) / 2, pad = (k - 1) / 2, N = G * C;
-  const size_t n = static_cast<size_t>(S) * N * N;
-  std::vector<__half> hi(n, __float2half_rn(0.0f)), lo(n, __float2half_rn(0.0f));
-  std::vector<float> bias(N);
+  std::fill(out, out + static_cast<size_t>(S) * N * N, 0.0f);
   for (int tau = -tmax; tau <= tmax; ++tau)
     for (int r = 0; r < G; ++r)
       for (int rp = 0; rp < G; ++rp) {
@@ -1560,21 +1570,26 @@ int pack_grouped(efts_ctx* c, const std::string& wname, const std::string& bname
         const int j = off / d + pad;
         if (j < 0 || j >= k) continue;
         for (int co = 0; co < C; ++co)
-          for (int ci = 0; ci < C; ++ci) {
-            const float x = (*w)[(static_cast<size_t>(co) * C + ci) * k + j];
-            if (!(fabsf(x) <= 65504.0f))
-              return fail(EFTS_ERR_UNSUPPORTED, "weight '%s' has a value outside the fp16 operand range", wname.c_str());
-            const __half h = __float2half_rn(x);
-            const size_t dst = (static_cast<size_t>(tau + tmax) * N + r * C + co) * N + rp * C + ci;
-            hi[dst] = h;
-            lo[dst] = __float2half_rn((x - __half2float(h)) * SPLIT_SCALE);
-          }
+          for (int ci = 0; ci < C; ++ci)
+            out[(static_cast<size_t>(tau + tmax) * N + r * C + co) * N + rp * C + ci] =
+                w[(static_cast<size_t>(co) * C + ci) * k + j];
       }
+}
+
+int pack_grouped(efts_ctx* c, const std::string& wname, const std::string& bname, int C, int k, int d, int G,
+                 PackedW* out) {
+  const std::vector<float>* w;
+  const std::vector<float>* b;
+  TRY(need(c, wname, {C, C, k}, &w));
+  TRY(need(c, bname, {C}, &b));
+  const int S = grouped_taps(k, d, G), N = G * C;
+  std::vector<float> t(static_cast<size_t>(S) * N * N);
+  map_grouped(w->data(), C, k, d, G, t.data());
+  std::vector<float> bias(N);
   for (int r = 0; r < G; ++r)
     for (int co = 0; co < C; ++co) bias[r * C + co] = (*b)[co];
   out->Z = S; out->N = N; out->K = N;
-  TRY(upload(c, hi.data(), n * sizeof(__half), reinterpret_cast<void**>(&out->hi)));
-  TRY(upload(c, lo.data(), n * sizeof(__half), reinterpret_cast<void**>(&out->lo)));
+  TRY(upload_planes(c, t, wname, &out->hi, &out->lo));
   TRY(upload(c, bias.data(), N * sizeof(float), reinterpret_cast<void**>(&out->bias)));
   return EFTS_OK;
 }
@@ -1771,6 +1786,21 @@ int efts_vocoder_forward(efts_ctx* c, const float* mel, int32_t B, int32_t T, fl
                                                                                  static_cast<int>(L), C, 7, audio);
   CUDA_TRY(cudaGetLastError());
   c->launches++;
+  return EFTS_OK;
+}
+
+
+// Host-only views of the two weight re-arrangements above (no device needed): what the packers feed the tap-GEMM,
+// in fp32, so that the index algebra can be checked against torch's conv1d / conv_transpose1d on the CPU.
+int efts_host_map_transposed(const float* w, int32_t Cin, int32_t Cout, int32_t k, int32_t u, float* out) {
+  if (!w || !out || Cin < 1 || Cout < 1 || u < 2 || (u & 1) || k != 2 * u) return fail(EFTS_ERR_ARG, "efts_host_map_transposed: bad argument");
+  map_transposed(w, Cin, Cout, k, u, out);
+  return EFTS_OK;
+}
+int efts_host_map_grouped(const float* w, int32_t C, int32_t k, int32_t d, int32_t G, float* out, int32_t* taps) {
+  if (!w || !taps || C < 1 || k < 1 || !(k & 1) || d < 1 || G < 1) return fail(EFTS_ERR_ARG, "efts_host_map_grouped: bad argument");
+  *taps = grouped_taps(k, d, G);
+  if (out != nullptr) map_grouped(w, C, k, d, G, out);
   return EFTS_OK;
 }
 

@@ -220,6 +220,13 @@ size_t efts_vocoder_workspace_bytes(const efts_ctx* ctx, int32_t B, int32_t T);
 int efts_vocoder_forward(efts_ctx* ctx, const float* mel, int32_t B, int32_t T, float* audio, void* workspace,
                          size_t workspace_bytes, void* stream);
 
+/* Host-only test hooks (no device): the fp32 weights the generator's packers hand to the tap-GEMM.
+ * efts_host_map_transposed: ConvTranspose1d weight [Cin,Cout,k] (k = 2u) -> [3][u*Cout][Cin] (3-tap polyphase GEMM);
+ * efts_host_map_grouped: Conv1d weight [C,C,k], dilation d, G time steps per GEMM row -> [taps][G*C][G*C]
+ * (`out` may be NULL to query `taps`). */
+int efts_host_map_transposed(const float* w, int32_t Cin, int32_t Cout, int32_t k, int32_t u, float* out);
+int efts_host_map_grouped(const float* w, int32_t C, int32_t k, int32_t d, int32_t G, float* out, int32_t* taps);
+
 /* ---- introspection ---- */
 /* Options: "amode" (A-operand staging of the tap-GEMM: 0 one TMA box per tap, 1 one shifted box
  * per k-block), "skip_pad_tiles" (0/1).  Returns EFTS_ERR_ARG for an unknown name. */

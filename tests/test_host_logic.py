@@ -306,3 +306,55 @@ def test_committed_bench_line_follows_the_contract():
         assert k in d["clocks"], k
     assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
     assert abs(d["value"] - d["config"]["valid_frames_per_gpu"] * d["n_gpus"] / (d["ms_per_step"] * 1e-3)) < 1e-3 * d["value"]
+
+
+# ---------------------------------------------------------------- generator weight re-arrangements (host-only hooks)
+def _tap_gemm(x_blk, w_tkn, pad):
+    """What the tap-GEMM computes: y[b, q] = sum_tau x[b, q + tau - pad] @ w[tau].T with zero rows outside [0, L)."""
+    B, L, K = x_blk.shape
+    S, N, _ = w_tkn.shape
+    xp = torch.nn.functional.pad(x_blk.double(), (0, 0, pad, S - 1 - pad))
+    return sum(xp[:, t:t + L] @ w_tkn[t].double().T for t in range(S))
+
+
+@pytest.mark.parametrize("u,cin,cout", [(8, 16, 8), (2, 8, 8), (4, 8, 16)])
+def test_transposed_conv_is_a_three_tap_polyphase_gemm(u, cin, cout):
+    """efts_host_map_transposed (what pack_ups uploads): ConvTranspose1d(k = 2u, stride u, padding u/2) equals a
+    3-tap GEMM whose N = u * Cout output columns are the u output phases of each input row
+    (vocoders/hifigan_model.py:105-108,124)."""
+    import ctypes
+    from efficient_tts_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(u)
+    k = 2 * u
+    w = torch.randn(cin, cout, k, generator=g)
+    out = torch.empty(3, u * cout, cin)
+    assert lib.efts_host_map_transposed(w.data_ptr(), cin, cout, k, u, out.data_ptr()) == 0
+    x = torch.randn(2, 7, cin, generator=g)                                   # [B, L, Cin] channels-last
+    ref = torch.nn.functional.conv_transpose1d(x.transpose(1, 2).double(), w.double(), stride=u, padding=(k - u) // 2)
+    y = _tap_gemm(x, out, 1).reshape(2, 7 * u, cout)                          # [B, L, u*Cout] IS [B, L*u, Cout]
+    assert torch.allclose(y.transpose(1, 2), ref, atol=1e-10)
+    assert lib.efts_host_map_transposed(w.data_ptr(), cin, cout, k + 2, u, out.data_ptr()) != 0   # k != 2u
+
+
+@pytest.mark.parametrize("C,k,d,G", [(8, 3, 1, 4), (8, 11, 1, 4), (8, 7, 3, 4), (8, 11, 5, 4), (16, 7, 1, 2),
+                                     (16, 3, 5, 2), (4, 5, 2, 8)])
+def test_grouped_packing_is_the_dilated_conv(C, k, d, G):
+    """efts_host_map_grouped (what pack_grouped uploads): a dilated Conv1d over [B, L, C] equals an undilated
+    super-tap GEMM over the same buffer read as [B, L / G, G * C]; the tap count is 2 * floor((pad * d + G - 1) / G) + 1."""
+    import ctypes
+    from efficient_tts_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(C * k + d)
+    w = torch.randn(C, C, k, generator=g)
+    taps = ctypes.c_int32(0)
+    assert lib.efts_host_map_grouped(w.data_ptr(), C, k, d, G, None, ctypes.byref(taps)) == 0
+    S = taps.value
+    assert S == 2 * (((k - 1) // 2 * d + G - 1) // G) + 1
+    out = torch.empty(S, G * C, G * C)
+    assert lib.efts_host_map_grouped(w.data_ptr(), C, k, d, G, out.data_ptr(), ctypes.byref(taps)) == 0
+    L = 5 * G
+    x = torch.randn(2, L, C, generator=g)
+    ref = torch.nn.functional.conv1d(x.transpose(1, 2).double(), w.double(), dilation=d, padding=d * (k - 1) // 2)
+    y = _tap_gemm(x.reshape(2, L // G, G * C), out, (S - 1) // 2).reshape(2, L, C)
+    assert torch.allclose(y.transpose(1, 2), ref, atol=1e-10)
