@@ -223,8 +223,7 @@ int launch_gemm2_t(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, con
   const long long n_rt = static_cast<long long>(p.B) * ((p.T + G2_BM - 1) / G2_BM);
   const long long work = ((n_rt + CG - 1) / CG) * ((p.N + BN - 1) / BN) * (FUSE && p.splits > 1 ? p.splits : 1);
   long long ctas = std::min<long long>(c->sm_count / CG, work) * CG;
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(ctas));
   cfg.blockDim = dim3(WIDE ? G2_THREADS_WIDE : G2_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
@@ -306,8 +305,7 @@ int launch_gemm(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, GemmPa
         q.splits = nchunks; q.split_stride = plane;
         TRY((launch_gemm2_t<2, EPI_STD, 0, 1>(c, st, a, b, q)));
         const size_t n = plane / 4;
-        cudaLaunchConfig_t rc;
-        memset(&rc, 0, sizeof(rc));
+        cudaLaunchConfig_t rc = {};
         rc.gridDim = dim3(static_cast<unsigned>((n + 255) / 256));
         rc.blockDim = dim3(256);
         rc.stream = st;
