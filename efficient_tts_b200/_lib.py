@@ -29,7 +29,8 @@ class EftsVocoderConfig(ctypes.Structure):
                 ("device", c_i32)]
 
 
-# name -> (restype, argtypes); also the export list checked by tests/test_abi.py
+# name -> (restype, argtypes); also the export list checked by
+# tests/test_host_logic.py::test_library_builds_loads_and_exports_the_header
 SIGNATURES = {
     "efts_create": (c_i32, [ctypes.POINTER(EftsConfig), ctypes.POINTER(c_void_p)]),
     "efts_destroy": (None, [c_void_p]),

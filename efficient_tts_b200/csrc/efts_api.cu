@@ -16,7 +16,6 @@
 #include <vector>
 
 #include "../../include/efts_b200.h"
-#include "gemm_sm100.cuh"
 #include "gemm2_sm100.cuh"
 #include "path_kernels.cuh"
 #include "vocoder_kernels.cuh"
@@ -89,14 +88,12 @@ struct Arena {
 struct efts_ctx {
   efts_config cfg;
   int sm_count = 0;
-  int amode = 0;
   int skip_pad_tiles = 1;
-  int gemm_version = 2;      // 1: gemm_sm100.cuh, 2: gemm2_sm100.cuh (persistent, flushed accumulator)
-  int pair = 1;              // v2: CTA pairs (cta_group::2) for the weight GEMMs
+  int pair = 1;              // CTA pairs (cta_group::2) for the weight GEMMs
   int cur_tag = 15;          // ProfTag of the launch being issued (diagnostics)
-  int wide = 1;              // v2: short-reduction launches use the 16-epilogue-warp variant
+  int wide = 1;              // short-reduction launches use the 16-epilogue-warp variant
   int debug_mask = 0;        // timing experiments only
-  int chunk_kb = 2;          // v2: k-blocks per main-accumulator flush (1 = most accurate, 0 = never)
+  int chunk_kb = 2;          // k-blocks per main-accumulator flush (1 = most accurate, 0 = never)
   int voc_group = 1;             // vocoder: grouped (super-tap) packing of the 32 / 64-channel layers (read at finalize)
   int voc_wide = 1;              // vocoder: short-reach, short-reduction layers use the wide-epilogue variant
   int voc_short_box = 0;         // vocoder: layers whose taps reach <= 8 rows use the 136-row A box (A/B switch, off:
@@ -105,10 +102,11 @@ struct efts_ctx {
                                  // Off: measured 36.4 vs 34.5 ms at 16 x 800 frames -- the narrow layers are bound by
                                  // their tile count (A-box halo, epilogue), which the grouped packing halves, not by MMA columns
   int split_k = 1;               // fused-B kernel: split the reduction of small launches over more SMs
-  int pdl = 1;                   // programmatic dependent launch for the v2 GEMM and split-reduce kernels
-  int fuse_b = 1;                // v2 conv layers: Ahi*[Bhi|Blo] as one N = 256 MMA (two MMAs per k-step instead of three)
-  int imv_version = 2;           // 2: block-per-utterance scan / aligned positions, 1: warp-per-utterance / token
-  int reconstruct_version = 3;   // 3: frame-per-lane Gaussian reconstruction, 2: warp-per-frame tiled kernel
+  int pdl = 1;                   // programmatic dependent launch for the GEMM and split-reduce kernels
+  int fuse_b = 1;                // conv layers: Ahi*[Bhi|Blo] as one N = 256 MMA (two MMAs per k-step instead of three)
+  int imv_version = 2;           // 2: block-per-utterance scan / aligned positions out of shared memory; 1: the
+                                 // warp-per-row kernels that serve rows too long for shared memory (same arithmetic
+                                 // in the same order, bitwise equal -- the switch exists so that path stays tested)
   int64_t launches = 0;
   bool finalized = false;
   EncodeTiledFn encode = nullptr;
@@ -173,7 +171,7 @@ int make_map(efts_ctx* c, CUtensorMap* m, const __half* ptr, int inner, int rows
   cuuint64_t dims[3] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(rows),
                         static_cast<cuuint64_t>(z)};
   cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(rows) * ld * 2};
-  cuuint32_t box[3] = {static_cast<cuuint32_t>(GEMM_BK), static_cast<cuuint32_t>(box_rows), 1};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(G2_BK), static_cast<cuuint32_t>(box_rows), 1};
   cuuint32_t estr[3] = {1, 1, 1};
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (strides[0] & 15) != 0)
     return fail(EFTS_ERR_ARG, "TMA operand not 16-byte aligned (ptr %p, ld %d)", (const void*)ptr, ld);
@@ -183,22 +181,6 @@ int make_map(efts_ctx* c, CUtensorMap* m, const __half* ptr, int inner, int rows
   if (r != CUDA_SUCCESS)
     return fail(EFTS_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) inner=%d rows=%d z=%d ld=%d box=%d",
                 (int)r, inner, rows, z, ld, box_rows);
-  return EFTS_OK;
-}
-
-template <int BN, int AMODE>
-int launch_gemm_t(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, const GemmParams& p) {
-  using Cfg = GemmCfg<BN, AMODE>;
-  auto kern = gemm_split_kernel<BN, AMODE>;
-  alignas(64) CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
-  TRY(make_map(c, &ma_hi, a.hi, a.K, a.T, a.B, a.ld, Cfg::A_ROWS));
-  TRY(make_map(c, &ma_lo, a.lo, a.K, a.T, a.B, a.ld, Cfg::A_ROWS));
-  TRY(make_map(c, &mb_hi, b.hi, b.K, b.N, b.Z, b.ld, BN));
-  TRY(make_map(c, &mb_lo, b.lo, b.K, b.N, b.Z, b.ld, BN));
-  dim3 grid((p.N + BN - 1) / BN, (p.T + GEMM_BM - 1) / GEMM_BM, p.B);
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
-  CUDA_TRY(cudaGetLastError());
-  c->launches++;
   return EFTS_OK;
 }
 
@@ -246,7 +228,7 @@ int launch_gemm(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, GemmPa
   p.B = a.B; p.T = a.T; p.K = a.K;
   if (a.K != b.K) return fail(EFTS_ERR_ARG, "gemm K mismatch %d vs %d", a.K, b.K);
   if (p.N % 8 != 0) return fail(EFTS_ERR_ARG, "gemm N=%d must be a multiple of 8", p.N);
-  if (c->gemm_version == 2) {
+  {
     if (p.ntaps > 15) return fail(EFTS_ERR_ARG, "at most 15 taps");
     p.chunk_kb = c->chunk_kb;
     p.debug_mask = c->debug_mask;
@@ -325,38 +307,11 @@ int launch_gemm(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, GemmPa
     if (epi == EPI_FULL) return pair ? launch_gemm2_t<2, EPI_FULL, 0>(c, st, a, b, p) : launch_gemm2_t<1, EPI_FULL, 0>(c, st, a, b, p);
     return pair ? launch_gemm2_t<2, EPI_SOFTMAX, 0>(c, st, a, b, p) : launch_gemm2_t<1, EPI_SOFTMAX, 0>(c, st, a, b, p);
   }
-  p.tile_list = nullptr; p.tile_count = nullptr;
-  if (p.B > 65535 || (p.T + GEMM_BM - 1) / GEMM_BM > 65535) return fail(EFTS_ERR_ARG, "grid too large");
-  const long row_tiles = static_cast<long>(p.B) * ((p.T + GEMM_BM - 1) / GEMM_BM);
-  int bn = p.N <= 64 ? 64 : (p.N <= 128 ? 128 : 256);
-  // small problems (B = 1 synthesis): narrower column tiles spread the layer over more SMs
-  while (bn > 64 && row_tiles * ((p.N + bn - 1) / bn) < c->sm_count / 2) bn >>= 1;
-  const int am = p.ntaps > 1 ? c->amode : 0;
-#define EFTS_DISPATCH(BN_)                                                       \
-  switch (am) {                                                                  \
-    case 0: return launch_gemm_t<BN_, 0>(c, st, a, b, p);                        \
-    case 1: return launch_gemm_t<BN_, 1>(c, st, a, b, p);                        \
-    default: return launch_gemm_t<BN_, 2>(c, st, a, b, p);                       \
-  }
-  if (bn == 256) { EFTS_DISPATCH(256) }
-  if (bn == 128) { EFTS_DISPATCH(128) }
-  EFTS_DISPATCH(64)
-#undef EFTS_DISPATCH
 }
-
-
 
 // Opt every kernel that needs more than 48 KB of dynamic shared memory in, once per context (the attribute
 // is per device, so it is not cached in a process-wide static).
-template <int BN, int AMODE>
-cudaError_t opt_in_v1() {
-  return cudaFuncSetAttribute(gemm_split_kernel<BN, AMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              GemmCfg<BN, AMODE>::SMEM_BYTES);
-}
 int set_kernel_attributes() {
-  CUDA_TRY((opt_in_v1<64, 0>()));  CUDA_TRY((opt_in_v1<64, 1>()));  CUDA_TRY((opt_in_v1<64, 2>()));
-  CUDA_TRY((opt_in_v1<128, 0>())); CUDA_TRY((opt_in_v1<128, 1>())); CUDA_TRY((opt_in_v1<128, 2>()));
-  CUDA_TRY((opt_in_v1<256, 0>())); CUDA_TRY((opt_in_v1<256, 1>())); CUDA_TRY((opt_in_v1<256, 2>()));
 #define EFTS_OPT_IN_V2(CG_, EPI_, W_) \
   CUDA_TRY(cudaFuncSetAttribute(gemm2_kernel<CG_, EPI_, W_>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2Cfg<CG_, W_>::SMEM_BYTES))
   EFTS_OPT_IN_V2(1, EPI_STD, 0); EFTS_OPT_IN_V2(1, EPI_FULL, 0); EFTS_OPT_IN_V2(1, EPI_SOFTMAX, 0);
@@ -374,8 +329,6 @@ int set_kernel_attributes() {
                                 G2Cfg<2, 0, 1, G2_A_ROWS_LONG, 64>::SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(gemm2_kernel<2, EPI_STD, 0, 1, G2_A_ROWS_XLONG, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 G2Cfg<2, 0, 1, G2_A_ROWS_XLONG, 64>::SMEM_BYTES));
-  CUDA_TRY(cudaFuncSetAttribute(reconstruct_alignment_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                static_cast<int>(kReconstructSmemMax)));
   CUDA_TRY(cudaFuncSetAttribute(reconstruct_alignment_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(kReconstructSmemMax)));
   CUDA_TRY(cudaFuncSetAttribute(imv_scan_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -409,19 +362,14 @@ int launch_aligned_positions(int version, cudaStream_t st, const float* imv, con
   return EFTS_OK;
 }
 
-// Gaussian reconstruction launch: version 3 = frame-per-lane kernel, 2 = warp-per-frame tiled kernel (A/B
-// baseline); both fall back to the one-thread-per-frame kernel when the token count does not fit shared memory.
-int launch_reconstruct(int version, cudaStream_t st, const float* e, const int* tl, const int* sl, int B, int T1,
-                       int T2, int T1p, float neg_sigma, float* reconst_alpha, __half* R_hi, __half* R_lo) {
-  const size_t smem2 = (static_cast<size_t>(T1p) * (RT_FRAMES + 1) + T1) * sizeof(float);
-  if (version >= 3 && r3_smem_bytes(T1p) <= kReconstructSmemMax) {
+// Gaussian reconstruction launch: the frame-per-lane kernel; token counts that do not fit its shared-memory tile
+// take the one-thread-per-frame kernel (same arithmetic, partial sums grouped differently).
+int launch_reconstruct(cudaStream_t st, const float* e, const int* tl, const int* sl, int B, int T1, int T2, int T1p,
+                       float neg_sigma, float* reconst_alpha, __half* R_hi, __half* R_lo) {
+  if (r3_smem_bytes(T1p) <= kReconstructSmemMax) {
     dim3 grid((T2 + R3_FRAMES - 1) / R3_FRAMES, B);
     reconstruct_alignment_rows_kernel<<<grid, 32 * R3_WARPS, r3_smem_bytes(T1p), st>>>(
         e, tl, sl, T1, T2, T1p, neg_sigma, reconst_alpha, R_hi, R_lo);
-  } else if (T1 <= 32 * RT_KMAX && smem2 <= kReconstructSmemMax) {
-    dim3 grid((T2 + RT_FRAMES - 1) / RT_FRAMES, B);
-    reconstruct_alignment_tiled_kernel<<<grid, 256, smem2, st>>>(e, tl, sl, T1, T2, T1p, neg_sigma, reconst_alpha,
-                                                                 R_hi, R_lo);
   } else {
     dim3 grid((T2 + 127) / 128, B);
     reconstruct_alignment_kernel<<<grid, 128, T1 * sizeof(float), st>>>(e, tl, sl, T1, T2, T1p, neg_sigma,
@@ -664,7 +612,7 @@ int run_reconstruct_expand(efts_ctx* c, cudaStream_t st, const float* e, const i
   {
     ProfScope ps(c, st, TAG_RECONSTRUCT);
     const float neg_sigma = -1.0f * c->cfg.sigma;
-    TRY(launch_reconstruct(c->reconstruct_version, st, e, tl, sl, B, T1, T2, T1p, neg_sigma, reconst_alpha, R_hi, R_lo));
+    TRY(launch_reconstruct(st, e, tl, sl, B, T1, T2, T1p, neg_sigma, reconst_alpha, R_hi, R_lo));
     c->launches++;
   }
   GemmParams p = gemm_defaults();
@@ -691,33 +639,21 @@ int run_imv(efts_ctx* c, cudaStream_t st, const __half* q_hi, const __half* q_lo
   p.N = T1p;
   p.b_batched = 1;
   p.divisor = static_cast<float>(std::sqrt(static_cast<double>(C)));   // np.sqrt(float(D)), :390
-  // v2 kernel: the token softmax runs in the GEMM epilogue and only (max, sum, weighted sum) per column
-  // tile reaches memory (the buffer S is reused for them); v1 writes the scores and a separate kernel reads them.
-  const bool fused = c->gemm_version == 2;
+  // the token softmax runs in the GEMM epilogue: only (max, sum, weighted sum) per column tile reach memory (the
+  // buffer S holds them); neither the scores nor alpha exist.
   // the wide (16-warp) variant emits one partial per 64-column half tile, the narrow one per 128-column tile
   const bool wide_softmax = c->wide && ((C + G2_BK - 1) / G2_BK) * (G2_BK / 16) <= 40;
   const int n_part = ((T1p + G2_BN - 1) / G2_BN) * (wide_softmax ? 2 : 1);
-  if (fused) {
-    p.softmax_part = reinterpret_cast<float4*>(S);
-    p.col_lens = tl;
-  } else {
-    p.out = S; p.ld_out = T1p;
-  }
+  p.softmax_part = reinterpret_cast<float4*>(S);
+  p.col_lens = tl;
   if (c->skip_pad_tiles) { p.skip_lens = mel->lens; p.tile_list = mel->list; p.tile_count = mel->count; p.skip_halo = 0; }
   {
     ProfScope ps(c, st, TAG_ENERGY);
     TRY(launch_gemm(c, st, OpA{q_hi, q_lo, B, T2, C, C}, OpB{key_hi, key_lo, B, T1, C, C}, p));
   }
-  const size_t rows = static_cast<size_t>(B) * T2;
-  if (!fused) {
-    ProfScope ps(c, st, TAG_SOFTMAX);
-    energy_softmax_expect_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, st>>>(S, T1p, tl, sl, T2, rows,
-                                                                                         imv_raw);
-    CUDA_TRY(cudaGetLastError());
-  }
   {
     ProfScope ps(c, st, TAG_SCAN);
-    TRY(launch_imv_scan(c->imv_version, st, imv_raw, fused ? reinterpret_cast<const float4*>(S) : nullptr, n_part, tl, sl,
+    TRY(launch_imv_scan(c->imv_version, st, imv_raw, reinterpret_cast<const float4*>(S), n_part, tl, sl,
                         B, T2, imv));
   }
   {
@@ -881,17 +817,7 @@ size_t efts_workspace_bytes(const efts_ctx* c, int32_t B, int32_t T1, int32_t T2
 
 int efts_set_option(efts_ctx* c, const char* name, int32_t value) {
   if (c == nullptr || name == nullptr) return fail(EFTS_ERR_ARG, "null argument");
-  if (strcmp(name, "amode") == 0) {
-    if (value < 0 || value > 2) return fail(EFTS_ERR_ARG, "amode must be 0, 1 or 2");
-    c->amode = value;
-    return EFTS_OK;
-  }
   if (strcmp(name, "skip_pad_tiles") == 0) { c->skip_pad_tiles = value != 0; return EFTS_OK; }
-  if (strcmp(name, "gemm_version") == 0) {
-    if (value != 1 && value != 2) return fail(EFTS_ERR_ARG, "gemm_version must be 1 or 2");
-    c->gemm_version = value;
-    return EFTS_OK;
-  }
   if (strcmp(name, "pair") == 0) { c->pair = value != 0; return EFTS_OK; }
   if (strcmp(name, "debug_mask") == 0) { c->debug_mask = value; return EFTS_OK; }
   if (strcmp(name, "wide") == 0) { c->wide = value != 0; return EFTS_OK; }
@@ -905,11 +831,6 @@ int efts_set_option(efts_ctx* c, const char* name, int32_t value) {
   if (strcmp(name, "imv_version") == 0) {
     if (value != 1 && value != 2) return fail(EFTS_ERR_ARG, "imv_version must be 1 or 2");
     c->imv_version = value;
-    return EFTS_OK;
-  }
-  if (strcmp(name, "reconstruct_version") == 0) {
-    if (value != 2 && value != 3) return fail(EFTS_ERR_ARG, "reconstruct_version must be 2 or 3");
-    c->reconstruct_version = value;
     return EFTS_OK;
   }
   if (strcmp(name, "chunk_kb") == 0) {
@@ -1393,7 +1314,7 @@ int efts_reconstruct_alignment(const float* e, const int32_t* text_lengths, cons
   const float neg_sigma = -1.0f * delta;
   CUDA_TRY(cudaFuncSetAttribute(reconstruct_alignment_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(kReconstructSmemMax)));
-  return launch_reconstruct(3, st, e, text_lengths, speech_lengths, B, T1, T2, T1p, neg_sigma, reconst_alpha, nullptr,
+  return launch_reconstruct(st, e, text_lengths, speech_lengths, B, T1, T2, T1p, neg_sigma, reconst_alpha, nullptr,
                             nullptr);
 }
 
@@ -1662,6 +1583,7 @@ int efts_vocoder_finalize(efts_ctx* c) {
   if (c->finalized) return EFTS_OK;
   efts_ctx::Vocoder& v = *c->voc;
   const efts_vocoder_config& g = v.cfg;
+  CUDA_TRY(cudaSetDevice(g.device));
   int C = g.upsample_initial_channel;
   int lmult = 1;                       // L is a multiple of this at the current stage
   TRY(pack_weight(c, "conv_pre.weight", "conv_pre.bias", C, g.num_mels, 7, &v.conv_pre));

@@ -1,7 +1,6 @@
-// Second-generation tap-GEMM: persistent, CTA-pair (tcgen05 cta_group::2) capable, with the main
-// accumulator flushed to fp32 registers every few k-blocks.
+// The tap-GEMM kernel: persistent, CTA-pair (tcgen05 cta_group::2) capable, with the main
+// accumulator flushed to fp32 registers every few k-blocks (contraction and split-fp16 scheme: gemm_params.cuh).
 //
-// Same contraction and epilogue as gemm_sm100.cuh (see there for the split-fp16 scheme), but
 //   * one 136-row A box per k-block serves all taps through row-shifted UMMA descriptors;
 //   * CG = 2: two CTAs (one TPC) form a 256-row x 128-column tile; each loads its own 128 A rows and
 //     half of the W tile, so weight traffic from L2 halves;
@@ -16,7 +15,7 @@
 #include <cuda_fp16.h>
 #include <math_constants.h>
 
-#include "gemm_sm100.cuh"
+#include "gemm_params.cuh"
 #include "sm100_ptx.cuh"
 
 namespace efts {
@@ -141,8 +140,7 @@ __device__ __forceinline__ void g2_store_block32(const GemmParams& p, uint32_t s
       if (tr >= lens_b) v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
       if (p.out != nullptr && !(p.debug_mask & 1)) *reinterpret_cast<float4*>(p.out + out_off + mr * p.ld_out + nn) = v;
       if (p.out_hi != nullptr && !(p.debug_mask & 2)) {
-        const float amax = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
-        if (tr < check_b && amax > 65504.0f && p.err_flag != nullptr) atomicOr(p.err_flag, 8 | p.err_code);
+        if (tr < check_b && outside_fp16_range(v) && p.err_flag != nullptr) atomicOr(p.err_flag, 8 | p.err_code);
         if (p.plane_act) {                          // operand of the next layer = LeakyReLU(0.1) of the stored value
           v.x = v.x > 0.0f ? v.x : v.x * 0.1f; v.y = v.y > 0.0f ? v.y : v.y * 0.1f;
           v.z = v.z > 0.0f ? v.z : v.z * 0.1f; v.w = v.w > 0.0f ? v.w : v.w * 0.1f;
@@ -743,8 +741,7 @@ __global__ void splitk_reduce_kernel(const GemmParams p, const float* __restrict
   if (p.lens != nullptr && tr >= p.lens[b]) v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
   if (p.out != nullptr) *reinterpret_cast<float4*>(p.out + mr * p.ld_out + nn) = v;
   if (p.out_hi != nullptr) {
-    const float amax = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
-    if (amax > 65504.0f && p.err_flag != nullptr) atomicOr(p.err_flag, 8 | p.err_code);
+    if (outside_fp16_range(v) && p.err_flag != nullptr) atomicOr(p.err_flag, 8 | p.err_code);
     if (p.plane_act) {
       v.x = v.x > 0.0f ? v.x : __fmul_rn(v.x, 0.1f); v.y = v.y > 0.0f ? v.y : __fmul_rn(v.y, 0.1f);
       v.z = v.z > 0.0f ? v.z : __fmul_rn(v.z, 0.1f); v.w = v.w > 0.0f ? v.w : __fmul_rn(v.w, 0.1f);

@@ -1,0 +1,81 @@
+// Parameters of the split-fp16 tap-GEMM on tcgen05 tensor cores (gemm2_sm100.cuh).
+//
+// The kernel computes, for every position row m = (b, t) and output column n,
+//
+//     acc[m, n] = sum_{tap < ntaps} sum_{k < K}  A[b, t + (tap - pad) * dil, k] * W[z(tap, b), n, k]
+//
+// which covers the reference's Conv1d residual layers (layers/efts_modules.py:32-36,50: ntaps=5,
+// pad=2), the duration-predictor convs (layers/duration_predictor.py:58: ntaps=3, pad=1), every
+// torch.nn.Linear on the path (ntaps=1) and the two batched matmuls of the alignment block
+// (models/efficient_tts.py:390 and :190: z = b).
+//
+// fp32 parity on fp16 tensor cores: every fp32 operand x is stored as two fp16 planes,
+// hi = fp16(x) and lo = fp16((x - hi) * 2^11), and the product is assembled from three products,
+//     acc0 += Ahi*Bhi            acc1 += Ahi*Blo + Alo*Bhi          acc = acc0 + 2^-11 * acc1
+// with both accumulators in fp32 tensor memory (hard part 1).
+// Operands are staged by TMA into 128-byte-swizzled K-major tiles; out-of-range rows
+// (t < 0, t >= T: the conv zero padding; k >= K; n >= N) are zero-filled by the TMA unit.
+#pragma once
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace efts {
+
+constexpr float SPLIT_SCALE = 2048.0f;           // 2^11
+constexpr float SPLIT_INV_SCALE = 1.0f / 2048.0f;
+
+// True when any of the four values cannot become an fp16 operand: |x| > 65504, +-inf, or NaN.  Compared on the
+// bit patterns (|x| as an unsigned integer is monotone in |x|, and every NaN pattern lies above +inf) because a
+// float max drops NaNs.
+__device__ __forceinline__ bool outside_fp16_range(const float4 v) {
+  const uint32_t m = max(max(__float_as_uint(v.x) & 0x7fffffffu, __float_as_uint(v.y) & 0x7fffffffu),
+                         max(__float_as_uint(v.z) & 0x7fffffffu, __float_as_uint(v.w) & 0x7fffffffu));
+  return m > 0x477fe000u;   // bits of 65504.0f
+}
+
+enum GemmAct { ACT_NONE = 0, ACT_LRELU = 1, ACT_RELU = 2 };
+
+struct GemmParams {
+  int B, T;              // A is [B, T, K]; one CTA tile never crosses a batch row
+  int K;                 // reduction length per tap
+  int N;                 // output columns written (multiple of 8)
+  int ntaps, pad;        // row shift of tap j is (j - pad)
+  int b_batched;         // 0: B-operand z = tap (weights [ntaps, N, K]); 1: z = b ([B, N, K])
+  int act;               // GemmAct
+  float divisor;         // acc is divided by this before bias when != 1 (energy / sqrt(D))
+  const float* bias;     // [N] or nullptr
+  const float* resid;    // fp32 [B, T, ld_out] added after the activation, or nullptr
+  const int* lens;       // [B] or nullptr: rows with t >= lens[b] are written as zeros
+  const int* skip_lens;  // [B] or nullptr: tiles with t0 >= skip_lens[b] + skip_halo are not computed
+  int skip_halo;         //   (their rows cannot reach a valid output; SURVEY.md 7, hard part 2)
+  float* out;            // fp32 [B, T, ld_out] or nullptr
+  int ld_out;
+  __half* out_hi;        // fp16 planes [B, T, ld_pl] or nullptr
+  __half* out_lo;
+  int ld_pl;
+  __half* outT_hi;       // transposed fp16 planes [B, N, ld_t] (t contiguous) or nullptr
+  __half* outT_lo;
+  int ld_t;
+  const int2* tile_list; // compacted live row tiles (b, t0), or nullptr = all B * ceil(T/128)
+  const int* tile_count; // device count of tile_list entries
+  int chunk_kb;          // k-blocks per main-accumulator flush (0 = never flush)
+  // softmax-partial epilogue (energy GEMM): instead of storing the scores, every 128-column tile writes
+  // (max, sum exp, sum exp * column, 0) over its columns n < col_lens[b] to softmax_part[(b*T + t) * n_tiles + tile]
+  float4* softmax_part;
+  const int* col_lens;
+  int err_code;          // extra bits OR-ed into err_flag with bit 3 (identifies the launch kind in diagnostics)
+  int* err_flag;         // |= 8 when an activation leaves the fp16 operand range (|x| > 65504)
+  int debug_mask;        // timing experiments only (results become wrong): 1 = no fp32 store, 2 = no plane stores
+  // split reduction (fused-B kernel, small problems): work item w covers accumulation chunk w % splits of tile
+  // w / splits and stores its raw fp32 partial at out + (w % splits) * split_stride; splitk_reduce_kernel finishes
+  int splits;            // 0 / 1 = off
+  size_t split_stride;   // elements between the partial planes
+  float* split_scratch;  // host side only: room for the partial planes (kSplitScratchBytes), or nullptr = never split
+  // dilated taps / vocoder layers
+  int dil;               // row shift of tap j is (j - pad) * dil; 0 is read as 1
+  int plane_act;         // 1: the fp16 operand planes hold LeakyReLU(0.1) of the stored fp32 value (the next layer's
+                         // input activation, vocoders/hifigan_model.py:58,123), the fp32 store stays pre-activation
+  int long_taps;         // host side only: use the 184-row A box variant (128 + (ntaps - 1) * dil <= 184)
+};
+
+}  // namespace efts

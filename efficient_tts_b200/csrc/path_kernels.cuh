@@ -9,9 +9,15 @@
 #include <math_constants.h>
 #include <stdint.h>
 
+#include "gemm_params.cuh"
+
 namespace efts {
 
-constexpr float kSplitScale = 2048.0f;   // 2^11, see gemm_sm100.cuh
+constexpr float kSplitScale = 2048.0f;   // 2^11, see gemm_params.cuh
+
+// Lengths are loop bounds over rows of T entries (and over shared-memory tiles sized for T): a length outside
+// [0, T] is clamped wherever one is loaded (the forward entry points additionally report it, prep_lengths_kernel).
+__device__ __forceinline__ int clamp_len(int len, int T) { return min(max(len, 0), T); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -45,19 +51,25 @@ __device__ __forceinline__ void split4(const float4 v, uint2* hi, uint2* lo) {
 
 // ------------------------------------------------------------------------------------------------
 // lengths int64 -> int32 (+ the checks the reference performs on the host, utils/nets_utils.py:146-156)
-// flags[0] |= 1 if max(text_lengths) != T1, |= 2 if max(speech_lengths) != T2
+// flags[0] |= 1 if max(text_lengths) != T1, |= 2 if max(speech_lengths) != T2, |= 16 if any length lies outside
+// [0, padded dim] (the stored int32 lengths are clamped, so no kernel ever walks past a row; the reference fails
+// with a shape error on such input and the binding raises when it reads the flags)
 __global__ void prep_lengths_kernel(const int64_t* __restrict__ tl, const int64_t* __restrict__ sl, int B,
                                     int T1, int T2, int* __restrict__ tl32, int* __restrict__ sl32,
                                     int* __restrict__ flags) {
-  int mt = 0, ms = 0;
+  int mt = 0, ms = 0, bad = 0;
   for (int b = threadIdx.x; b < B; b += blockDim.x) {
-    const int a = static_cast<int>(tl[b]);
-    tl32[b] = a;
-    mt = max(mt, a);
+    const int64_t a = tl[b];
+    bad |= (a < 0 || a > T1);
+    const int ac = static_cast<int>(min(max(a, static_cast<int64_t>(0)), static_cast<int64_t>(T1)));
+    tl32[b] = ac;
+    mt = max(mt, ac);
     if (sl != nullptr) {
-      const int c = static_cast<int>(sl[b]);
-      sl32[b] = c;
-      ms = max(ms, c);
+      const int64_t c = sl[b];
+      bad |= (c < 0 || c > T2);
+      const int cc = static_cast<int>(min(max(c, static_cast<int64_t>(0)), static_cast<int64_t>(T2)));
+      sl32[b] = cc;
+      ms = max(ms, cc);
     }
   }
   __shared__ int s_mt, s_ms;
@@ -65,6 +77,7 @@ __global__ void prep_lengths_kernel(const int64_t* __restrict__ tl, const int64_
   __syncthreads();
   atomicMax(&s_mt, mt);
   atomicMax(&s_ms, ms);
+  if (bad) atomicOr(flags, 16);
   __syncthreads();
   if (threadIdx.x == 0) {
     int f = 0;
@@ -101,7 +114,7 @@ __global__ void embed_kernel(const int64_t* __restrict__ text, const float* __re
   const int c = threadIdx.x * 4;
   if (c >= C) return;
   const float4 v = __ldg(reinterpret_cast<const float4*>(table + static_cast<size_t>(id) * C + c));
-  if (!(fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))) <= 65504.0f))
+  if (outside_fp16_range(v))
     atomicOr(flags, 8);                           // outside the fp16 operand range
   *reinterpret_cast<float4*>(out + row * C + c) = v;
   uint2 h, l;
@@ -116,7 +129,7 @@ __global__ void split_planes_kernel(const float* __restrict__ x, size_t n4, __ha
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
-    if (fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))) > 65504.0f && err_flag != nullptr)
+    if (outside_fp16_range(v) && err_flag != nullptr)
       atomicOr(err_flag, 8);                      // outside the fp16 operand range
     uint2 h, l;
     split4(v, &h, &l);
@@ -150,38 +163,6 @@ __global__ void split_transpose_kernel(const float* __restrict__ x, int T, int C
 }
 
 // ------------------------------------------------------------------------------------------------
-// B1: scaled-dot-product softmax over tokens fused with the position expectation
-// (models/efficient_tts.py:392-398 softmax with pad keys at -inf, :168 pad frames zeroed, :312
-// bmm(alpha^T, p) with p[i] = i on valid tokens).  One warp per (b, t) row of the energy matrix
-// S[B*T2, ldS] (already divided by sqrt(D)); alpha itself is never written.
-__global__ void energy_softmax_expect_kernel(const float* __restrict__ S, int ldS,
-                                             const int* __restrict__ tl, const int* __restrict__ sl,
-                                             int T2, size_t rows, float* __restrict__ imv_raw) {
-  const int lane = threadIdx.x & 31;
-  const size_t row = blockIdx.x * static_cast<size_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const int b = static_cast<int>(row / T2);
-  const int t = static_cast<int>(row % T2);
-  if (t >= sl[b]) {
-    if (lane == 0) imv_raw[row] = 0.0f;
-    return;
-  }
-  const int L = tl[b];
-  const float* s = S + row * ldS;
-  float m = -CUDART_INF_F;
-  for (int i = lane; i < L; i += 32) m = fmaxf(m, s[i]);
-  m = warp_max(m);
-  float den = 0.0f, num = 0.0f;
-  for (int i = lane; i < L; i += 32) {
-    const float ev = expf(s[i] - m);
-    den += ev;
-    num = fmaf(ev, static_cast<float>(i), num);
-  }
-  den = warp_sum(den);
-  num = warp_sum(num);
-  if (lane == 0) imv_raw[row] = __fdiv_rn(num, den);
-}
-
 // B2: imv_generator tail (models/efficient_tts.py:314-323): Delta = relu(diff), Delta[0] = 0;
 // prefix sum over frames accumulated in double and rounded to fp32 per prefix (what torch's CPU
 // cumsum does for fp32); * mel_mask; / clamp(max, 1e-8); * (T1_b - 1).  One warp per utterance.
@@ -194,7 +175,7 @@ __global__ void imv_scan_kernel(const float* __restrict__ imv_raw, const float4*
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= B) return;
   float* y = imv + static_cast<size_t>(b) * T2;
-  const int L2 = sl[b];
+  const int L2 = clamp_len(sl[b], T2);
   double carry = 0.0;
   float vmax = -CUDART_INF_F;
   float prev_last = 0.0f;
@@ -258,7 +239,7 @@ __global__ void aligned_positions_kernel(const float* __restrict__ imv, const in
     return;
   }
   const float* x = imv + static_cast<size_t>(b) * T2;
-  const int L2 = sl[b];
+  const int L2 = clamp_len(sl[b], T2);
   const float p = pvec != nullptr ? pvec[static_cast<size_t>(b) * T1 + i] : static_cast<float>(i);
   float m = -CUDART_INF_F;
   for (int t = lane; t < L2; t += 32) {
@@ -293,7 +274,7 @@ imv_scan_block_kernel(const float* __restrict__ imv_raw, const float4* __restric
   __shared__ float s_last;
   const int b = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int L2 = sl[b];
+  const int L2 = clamp_len(sl[b], T2);
   float* y = imv + static_cast<size_t>(b) * T2;
   for (int t = threadIdx.x; t < T2; t += IMV_BLOCK_THREADS) {
     float r = 0.0f;
@@ -359,7 +340,7 @@ aligned_positions_block_kernel(const float* __restrict__ imv, const int* __restr
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.y;
   const int i0 = blockIdx.x * AP_TOKENS;
-  const int L1 = tl[b], L2 = sl[b];
+  const int L1 = clamp_len(tl[b], T1), L2 = clamp_len(sl[b], T2);
   if (i0 < L1) {
     const float* x = imv + static_cast<size_t>(b) * T2;
     for (int t = threadIdx.x; t < L2; t += IMV_BLOCK_THREADS) ap_smem[t] = x[t];
@@ -427,8 +408,8 @@ __global__ void reconstruct_alignment_kernel(const float* __restrict__ e, const 
                                              __half* __restrict__ p_hi, __half* __restrict__ p_lo) {
   extern __shared__ float se[];
   const int b = blockIdx.y;
-  const int L1 = tl != nullptr ? tl[b] : T1;
-  const int L2 = sl != nullptr ? sl[b] : T2;
+  const int L1 = tl != nullptr ? clamp_len(tl[b], T1) : T1;
+  const int L2 = sl != nullptr ? clamp_len(sl[b], T2) : T2;
   for (int i = threadIdx.x; i < T1; i += blockDim.x) se[i] = e[static_cast<size_t>(b) * T1 + i];
   __syncthreads();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -470,93 +451,8 @@ __global__ void reconstruct_alignment_kernel(const float* __restrict__ e, const 
   }
 }
 
-// B4, tiled: same arithmetic as reconstruct_alignment_kernel, organised so that both output layouts are
-// written with full coalescing.  One block per (utterance, 64-frame tile): each warp evaluates the
-// token-softmax of 8 frames with the tokens spread over its lanes (one expf per element, the exps stay
-// in registers between the sum and the normalisation), the 64 x T1 tile is staged in shared memory
-// (row stride 65 words: conflict-free both ways) and then stored as rows of the returned fp32 matrix
-// [B,T1,T2] (256 B per row segment) and as K-major fp16 hi/lo operand rows [B,T2,ldp] (half2 per lane).
-// Frames t >= L2 get zeros in the fp32 matrix; their operand rows are not written (the expansion GEMM
-// masks those rows by select).  Requires T1 <= 32 * RT_KMAX.
-constexpr int RT_FRAMES = 64;
-constexpr int RT_KMAX = 16;
-__global__ void __launch_bounds__(256)
-reconstruct_alignment_tiled_kernel(const float* __restrict__ e, const int* __restrict__ tl,
-                                   const int* __restrict__ sl, int T1, int T2, int ldp, float neg_sigma,
-                                   float* __restrict__ R, __half* __restrict__ p_hi, __half* __restrict__ p_lo) {
-  extern __shared__ float rt_smem[];
-  float* tile = rt_smem;                                   // [ldp][65]
-  float* se = rt_smem + static_cast<size_t>(ldp) * (RT_FRAMES + 1);
-  const int b = blockIdx.y;
-  const int t0 = blockIdx.x * RT_FRAMES;
-  const int L1 = tl != nullptr ? tl[b] : T1;
-  const int L2 = sl != nullptr ? sl[b] : T2;
-  const int nt = min(RT_FRAMES, T2 - t0);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* Rb = R + static_cast<size_t>(b) * T1 * T2 + t0;
-  if (t0 >= L2) {                                          // whole tile is padding
-    for (int i = warp; i < T1; i += 8)
-      for (int tt = lane; tt < nt; tt += 32) Rb[static_cast<size_t>(i) * T2 + tt] = 0.0f;
-    return;
-  }
-  for (int i = threadIdx.x; i < T1; i += 256) se[i] = e[static_cast<size_t>(b) * T1 + i];
-  __syncthreads();
-  const int kcount = (L1 + 31) >> 5;                       // lane-strided token chunks that hold valid tokens
-  for (int tt = warp; tt < RT_FRAMES; tt += 8) {
-    const int t = t0 + tt;
-    const bool live = t < L2;
-    const float q = live ? static_cast<float>(t) : 0.0f;
-    float h[RT_KMAX];
-    float m = -CUDART_INF_F;
-#pragma unroll
-    for (int k = 0; k < RT_KMAX; ++k) {
-      h[k] = 0.0f;
-      if (k < kcount) {                                    // warp-uniform
-        const int i = lane + 32 * k;
-        const float d = __fsub_rn(q, se[min(i, T1 - 1)]);
-        h[k] = i < L1 ? __fmul_rn(neg_sigma, __fmul_rn(d, d)) : -CUDART_INF_F;
-        m = fmaxf(m, h[k]);
-      }
-    }
-    m = warp_max(m);
-    float den = 0.0f;
-#pragma unroll
-    for (int k = 0; k < RT_KMAX; ++k) {
-      if (k < kcount) {
-        h[k] = expf(h[k] - m);                             // exp(-inf) = 0 on pad tokens
-        den += h[k];
-      }
-    }
-    den = warp_sum(den);
-    // one correctly rounded reciprocal per frame instead of a division per element (differs from
-    // exp / sum by at most one ulp of a value <= 1)
-    const float inv = live ? __frcp_rn(den) : 0.0f;
-#pragma unroll
-    for (int k = 0; k < RT_KMAX; ++k) {
-      const int i = lane + 32 * k;
-      if (i < ldp) tile[i * (RT_FRAMES + 1) + tt] = (k < kcount) ? __fmul_rn(h[k], inv) : 0.0f;
-    }
-  }
-  __syncthreads();
-  for (int i = warp; i < T1; i += 8)
-    for (int tt = lane; tt < nt; tt += 32) Rb[static_cast<size_t>(i) * T2 + tt] = tile[i * (RT_FRAMES + 1) + tt];
-  const int nlive = p_hi != nullptr ? min(nt, L2 - t0) : 0;
-  for (int tt = warp; tt < nlive; tt += 8) {
-    const size_t o = (static_cast<size_t>(b) * T2 + t0 + tt) * ldp;
-    for (int i2 = lane; 2 * i2 < ldp; i2 += 32) {
-      const float a = tile[(2 * i2) * (RT_FRAMES + 1) + tt];
-      const float c = tile[(2 * i2 + 1) * (RT_FRAMES + 1) + tt];
-      const __half ah = __float2half_rn(a), ch = __float2half_rn(c);
-      const __half al = __float2half_rn((a - __half2float(ah)) * kSplitScale);
-      const __half cl = __float2half_rn((c - __half2float(ch)) * kSplitScale);
-      *reinterpret_cast<__half2*>(p_hi + o + 2 * i2) = __halves2half2(ah, ch);
-      *reinterpret_cast<__half2*>(p_lo + o + 2 * i2) = __halves2half2(al, cl);
-    }
-  }
-}
-
-// B4, frame-per-lane: the tiled kernel above issues ~150 M warp instructions for 404 MB at C3 and is bound by
-// instruction issue (ncu: 80 % issue-active, 25 % of DRAM peak), not by HBM.  Here every lane owns two frames
+// B4, frame-per-lane: a warp-per-frame organisation issues ~150 M warp instructions for 404 MB at C3 and is bound
+// by instruction issue (ncu: 80 % issue-active, 25 % of DRAM peak), not by HBM.  Here every lane owns two frames
 // of a 64-frame tile and walks the tokens eight at a time (the warps of a block interleave over the 8-token
 // chunks), so that
 //   * the softmax over tokens needs no shuffles: per-frame partial minima of |q - e_i| / partial sums go through
@@ -570,7 +466,7 @@ reconstruct_alignment_tiled_kernel(const float* __restrict__ e, const int* __res
 //     of a chunk become 16 B of hi + 16 B of lo) and are copied out with 16-byte vectors, each frame's row
 //     being one contiguous run in global memory.
 // Pad tokens of the last live chunk carry e = 3e38: d^2 = inf, h = -inf, exp = 0 -- no per-element predicate.
-// Same arithmetic per element as the kernels above (expf(h - m) * rcp(sum)); only the order of the partial sums
+// Same arithmetic per element as the kernel above (expf(h - m) * rcp(sum)); only the order of the partial sums
 // of the denominator differs.
 constexpr int R3_FRAMES = 64;
 constexpr int R3_WARPS = 8;
@@ -608,8 +504,8 @@ reconstruct_alignment_rows_kernel(const float* __restrict__ e, const int* __rest
   const int rowb = r3_row_bytes(ldp);
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * R3_FRAMES;
-  const int L1 = tl != nullptr ? tl[b] : T1;
-  const int L2 = sl != nullptr ? sl[b] : T2;
+  const int L1 = tl != nullptr ? clamp_len(tl[b], T1) : T1;
+  const int L2 = sl != nullptr ? clamp_len(sl[b], T2) : T2;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* Rb = R + static_cast<size_t>(b) * T1 * T2;
   const int ta = t0 + lane, tb = ta + 32;                              // this lane's two frames
@@ -787,7 +683,7 @@ __global__ void attention_alpha_kernel(const float* __restrict__ S, int ldS, con
   const size_t row = blockIdx.x * static_cast<size_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int b = static_cast<int>(row / T2), t = static_cast<int>(row % T2);
-  const int L = tl[b];
+  const int L = clamp_len(tl[b], T1);
   const float* s = S + row * ldS;
   float m = -CUDART_INF_F;
   for (int i = lane; i < L; i += 32) m = fmaxf(m, s[i]);

@@ -52,7 +52,7 @@ __global__ void voc_average_kernel(VocAvgArgs a, size_t n4, float slope, __half*
     v.z = v.z > 0.0f ? v.z : __fmul_rn(v.z, slope); v.w = v.w > 0.0f ? v.w : __fmul_rn(v.w, slope);
     if (out_f != nullptr) reinterpret_cast<float4*>(out_f)[i] = v;
     if (hi != nullptr) {
-      if (fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))) > 65504.0f && err_flag != nullptr)
+      if (outside_fp16_range(v) && err_flag != nullptr)
         atomicOr(err_flag, 8);
       uint2 h, l;
       split4(v, &h, &l);

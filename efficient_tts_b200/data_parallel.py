@@ -11,6 +11,9 @@ import torch
 import torch.distributed as dist
 
 
+ERROR_BITS = (2, 3, 4)     # scalars[7] bits that are errors on every path (include/efts_b200.h)
+
+
 def shard_range(n_items, rank, world_size):
     """Contiguous [lo, hi) of ``n_items`` owned by ``rank``; sizes differ by at most one."""
     base, rem = divmod(int(n_items), int(world_size))
@@ -59,9 +62,19 @@ class DataParallelForward:
         lo, hi = shard_range(B, rank, world)
         imv, ra, mel, scal = self.shard_forward(text[lo:hi], text_lengths[lo:hi], speech[lo:hi],
                                                 speech_lengths[lo:hi])
-        part = scal[3:7].clone()                        # sum_sq, n_mel, sum_abs, n_tok
+        # one collective for everything that crosses shards: the four loss partial sums and, as 0/1 counters, the
+        # error bits a single-process forward() raises on (bit 2 token id, bit 3 fp16 operand range, bit 4 length
+        # outside the padded dims) -- a rank that hit one must stop every rank, not just itself
+        flags = scal[7].to(torch.int32)
+        bits = torch.stack([(flags >> k) & 1 for k in ERROR_BITS]).to(scal.dtype)
+        part = torch.cat([scal[3:7], bits])             # sum_sq, n_mel, sum_abs, n_tok, bit counters
         dist.all_reduce(part, op=dist.ReduceOp.SUM, group=self.group)
-        loss, mel_loss, dur_loss = combine_loss_partials(part.tolist())
+        host = part.tolist()
+        raised = sum((1 << k) for k, n in zip(ERROR_BITS, host[4:]) if n > 0)
+        if raised:
+            from .models import raise_on_flags
+            raise_on_flags(raised)
+        loss, mel_loss, dur_loss = combine_loss_partials(host[:4])
         stats = dict(loss=loss, mel_loss=mel_loss, duration_loss=dur_loss)
         if gather_outputs:
             sizes = [shard_range(B, r, world)[1] - shard_range(B, r, world)[0] for r in range(world)]

@@ -11,6 +11,24 @@ import torch
 from .layers import DurationPredictor, ResConvBlock, _EngineOwner
 
 
+def raise_on_flags(flags, check_padded_dims=False):
+    """Turn the device error word of a forward pass (include/efts_b200.h, ``scalars[7]``) into the exception the
+    reference raises for the same input.  ``check_padded_dims`` applies the max(lengths) == padded-dim rule of the
+    reference's mask builder, which a data-parallel shard with global padded dims is exempt from."""
+    if flags & 4:
+        raise IndexError("index out of range in self")          # torch.nn.Embedding, models/efficient_tts.py:144
+    if flags & 8:
+        from .engine import RANGE_MESSAGE
+        raise FloatingPointError(RANGE_MESSAGE + " [flags 0x%x]" % flags)
+    if flags & 16:
+        raise RuntimeError("a length lies outside [0, padded dim] (the reference's mask broadcast fails on such "
+                           "input, utils/nets_utils.py:148-168)")
+    if check_padded_dims and flags & 3:
+        which = "text" if flags & 1 else "speech"
+        raise RuntimeError("The padded %s length must equal max(%s_lengths) (the reference builds its "
+                           "masks with maxlen = max(lengths), utils/nets_utils.py:148)" % (which, which))
+
+
 class EfficientTTSCNN(_EngineOwner):
     """EFTS-CNN, forward path on B200.  Constructor: models/efficient_tts.py:26-49."""
 
@@ -86,16 +104,7 @@ class EfficientTTSCNN(_EngineOwner):
         eng = self._get_engine()
         imv, reconst_alpha, mel_pred, scal = eng.forward(text, text_lengths, speech, speech_lengths)
         host = scal.cpu()                      # the reference's three .item() syncs (:225-227) in one
-        flags = int(host[7])
-        if flags & 4:
-            raise IndexError("index out of range in self")          # torch.nn.Embedding, :144
-        if flags & 8:
-            from .engine import RANGE_MESSAGE
-            raise FloatingPointError(RANGE_MESSAGE + " [flags 0x%x]" % flags)
-        if flags & 3:
-            which = "text" if flags & 1 else "speech"
-            raise RuntimeError("The padded %s length must equal max(%s_lengths) (the reference builds its "
-                               "masks with maxlen = max(lengths), utils/nets_utils.py:148)" % (which, which))
+        raise_on_flags(int(host[7]), check_padded_dims=True)
         stats = dict(loss=float(host[0]), mel_loss=float(host[1]), duration_loss=float(host[2]))
         return scal[0], stats, imv, reconst_alpha, mel_pred, speech
 

@@ -87,7 +87,9 @@ size_t efts_workspace_bytes(const efts_ctx* ctx, int32_t B, int32_t T1, int32_t 
  *   flags (as float-encoded int): bit0 max(text_lengths) != T1, bit1 max(speech_lengths) != T2,
  *   bit2 a text id outside [0, num_symbols), bit3 an activation left the fp16 operand range
  *   (|x| > 65504: the split-fp16 tensor-core scheme cannot represent it; nothing in the reference
- *   corresponds to this, it is reported instead of returning inf/NaN)  -- bits 0-2 are the conditions the reference raises on
+ *   corresponds to this, it is reported instead of returning inf/NaN; NaN / inf inputs raise it too), bit4 a
+ *   length outside [0, padded dim] (the int32 lengths the kernels use are clamped, so nothing is read or written
+ *   out of bounds)  -- bits 0-2 and 4 are the conditions the reference raises on
  *   (utils/nets_utils.py:148-156 size mismatch, embedding IndexError); the binding checks them
  *   when it reads the scalars back (the read-back the reference does with .item(), :225-227). */
 int efts_forward(efts_ctx* ctx, const int64_t* text, const int64_t* text_lengths, const float* speech,
@@ -228,8 +230,14 @@ int efts_host_map_transposed(const float* w, int32_t Cin, int32_t Cout, int32_t 
 int efts_host_map_grouped(const float* w, int32_t C, int32_t k, int32_t d, int32_t G, float* out, int32_t* taps);
 
 /* ---- introspection ---- */
-/* Options: "amode" (A-operand staging of the tap-GEMM: 0 one TMA box per tap, 1 one shifted box
- * per k-block), "skip_pad_tiles" (0/1).  Returns EFTS_ERR_ARG for an unknown name. */
+/* Tuning / test switches, all of which keep results within the parity budget (most are bitwise neutral):
+ * "skip_pad_tiles" (0/1: skip row tiles that cannot reach a valid output), "pair" (CTA pairs for the weight GEMMs),
+ * "wide" (16-epilogue-warp variant for short reductions), "fuse_b" (Ahi x [Bhi|Blo] as one N = 256 MMA),
+ * "chunk_kb" (k-blocks per main-accumulator flush), "split_k" (split reduction for small launches), "pdl"
+ * (programmatic dependent launch), "imv_version" (2: block-per-utterance IMV kernels, 1: the warp-per-row kernels
+ * that serve rows too long for shared memory -- bitwise equal), "voc_group" / "voc_wide" / "voc_narrow" /
+ * "voc_short_box" (vocoder layer packing), "debug_mask" (timing experiments only; results become wrong).
+ * No option selects a kernel outside the precision budget.  Returns EFTS_ERR_ARG for an unknown name. */
 int efts_set_option(efts_ctx* ctx, const char* name, int32_t value);
 /* Measurement hooks: while a tag's bit is set in `tag_mask`, every launch of that kind is bracketed
  * by a CUDA-event pair on the caller's stream (no extra synchronisation).  Tags: 0 text-encoder conv

@@ -5,7 +5,7 @@ This file restates, on the CPU, the arithmetic of the reference
 duration predictor / length regulator.  It is the *checker* for the CUDA path in
 ``efficient_tts_b200``; only ``tests/``, ``__graft_entry__.smoke()`` and the
 ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import it.  The product
-package never does (``tests/test_no_oracle_in_product.py`` enforces that).
+package never does (``tests/test_host_logic.py::test_product_never_imports_the_oracle`` enforces that).
 
 Where the arithmetic lives: the reference is pure Python on top of PyTorch, so its
 numbers are "reference Python + this image's torch CPU kernels" (SURVEY.md 8c).  The
@@ -22,6 +22,7 @@ Reference citations are relative to ``/root/reference/nntts``.
 """
 from __future__ import annotations
 
+import contextlib
 import math
 from typing import Dict, Optional, Tuple
 
@@ -253,6 +254,29 @@ def forward(w: Weights, text, text_lengths, speech, speech_lengths, sigma=0.01, 
                      dur_pred=dur_pred, log_delta_e=log_delta_e, dec=dec)
         return (loss, stats, imv, reconst, mel_pred, speech), inter
     return loss, stats, imv, reconst, mel_pred, speech
+
+
+@contextlib.contextmanager
+def float_is_double():
+    """Inside the block ``Tensor.float()`` returns float64: the restatement's mask / index casts then stay in
+    double when its inputs are double ("simplest fp64 restatement")."""
+    orig = torch.Tensor.float
+    torch.Tensor.float = lambda self, *a, **k: self.double()
+    try:
+        yield
+    finally:
+        torch.Tensor.float = orig
+
+
+def forward_fp64(w: Weights, text, text_lengths, speech, speech_lengths, **kw):
+    """The same teacher-forced pass evaluated in float64 (SURVEY.md 8c recipe: double weights and inputs, and
+    ``Tensor.float`` patched to ``.double()`` for the duration of the call so the mask / index casts of
+    models/efficient_tts.py:296,317,323,343,368 stay in double).  It is the tie-breaker where the reference's own
+    fp32 rounding noise exceeds the parity budget: the distance of an implementation to this result
+    is its own error, the distance of ``forward`` (fp32) to it is the reference's."""
+    w64 = {k: v.double() for k, v in w.items()}
+    with float_is_double(), torch.no_grad():
+        return forward(w64, text, text_lengths, speech.double(), speech_lengths, **kw)
 
 
 def inference(w: Weights, text, sigma=0.01, duration_offset=1.0, return_intermediates=False):

@@ -82,18 +82,12 @@ def check_forward(ref, out, t1max):
     dict(B=2, T=50, K=512, N=512, ntaps=3),         # duration-predictor conv
     dict(B=48, T=1100, K=512, N=512, ntaps=5),      # several tiles per persistent CTA (both epilogue groups)
 ])
-@pytest.mark.parametrize("variant", ["v2_pair", "v2_single", "v1_amode0", "v1_amode1"])
+@pytest.mark.parametrize("variant", ["pair", "single"])
 def test_tap_gemm_against_float64(model, dev, shape, variant):
-    """The tensor-core tap-GEMM (split-fp16, 3 MMAs) reproduces an fp64 evaluation to fp32 level.
-    v2 (accumulator flushed every 2 k-blocks) must stay within 8e-6; v1 (one 160-step truncating chain)
-    within 3e-5."""
-    opts = {"v2_pair": dict(gemm_version=2, pair=1), "v2_single": dict(gemm_version=2, pair=0),
-            "v1_amode0": dict(gemm_version=1, amode=0), "v1_amode1": dict(gemm_version=1, amode=1)}[variant]
-    if variant == "v1_amode1" and shape["ntaps"] == 1:
-        pytest.skip("amode only changes multi-tap staging")
+    """The tensor-core tap-GEMM (split-fp16, three products, main accumulator flushed every 2 k-blocks)
+    reproduces an fp64 evaluation to fp32 level: within 8e-6, as CTA pairs and as single CTAs."""
     eng = model._get_engine()
-    for k, v in opts.items():
-        eng.set_option(k, v)
+    eng.set_option("pair", 1 if variant == "pair" else 0)
     try:
         g = torch.Generator().manual_seed(5)
         B, T, K, N, nt = shape["B"], shape["T"], shape["K"], shape["N"], shape["ntaps"]
@@ -104,10 +98,9 @@ def test_tap_gemm_against_float64(model, dev, shape, variant):
         ref = sum(xp[:, j:j + T] @ w[j].double().T for j in range(nt))
         err = (out.double() - ref).abs().max().item()
         print("tap_gemm", shape, variant, "max-abs err %.3e" % err)
-        assert err <= (8e-6 if variant.startswith("v2") else 3e-5)
+        assert err <= 8e-6
     finally:
-        for k, v in dict(gemm_version=2, pair=1, amode=0).items():
-            eng.set_option(k, v)
+        eng.set_option("pair", 1)
 
 
 def test_batched_gemm_against_float64(model, dev):
@@ -236,8 +229,7 @@ def test_skip_pad_tiles_does_not_change_results(model, dev):
 
 def test_block_imv_kernels_equal_the_per_warp_kernels(model, dev):
     """The block-per-utterance scan / aligned-position kernels do the same arithmetic in the same order as the
-    warp-per-row ones: imv bitwise equal.  The frame-per-lane reconstruction only reorders the partial sums of
-    the softmax denominator: reconst_alpha within 1e-6, mel within 1e-5."""
+    warp-per-row ones that serve rows too long for shared memory: every output bitwise equal."""
     text, tl, speech, sl = make_forward_inputs(23, [77, 200, 9, 130], [460, 1200, 50, 777])
     args = dict(text=text.to(dev), text_lengths=tl.to(dev), speech=speech.to(dev), speech_lengths=sl.to(dev))
     eng = model._get_engine()
@@ -249,15 +241,7 @@ def test_block_imv_kernels_equal_the_per_warp_kernels(model, dev):
         eng.set_option("imv_version", 2)
     for k in (2, 3, 4):
         assert torch.equal(a[k], b[k])
-    eng.set_option("reconstruct_version", 2)
-    try:
-        c = model(**args)
-    finally:
-        eng.set_option("reconstruct_version", 3)
-    assert torch.equal(a[2], c[2])
-    assert (a[3] - c[3]).abs().max().item() <= 1e-6
-    assert (a[4] - c[4]).abs().max().item() <= 1e-5
-    # pad tokens / pad frames of the returned matrix are exact zeros in both
+    # pad tokens / pad frames of the returned matrix are exact zeros
     for bi in range(4):
         assert a[3][bi, int(tl[bi]):, :].abs().max().item() == 0.0 if int(tl[bi]) < a[3].shape[1] else True
         assert a[3][bi, :, int(sl[bi]):].abs().max().item() == 0.0 if int(sl[bi]) < a[3].shape[2] else True
@@ -271,9 +255,85 @@ def test_forward_rejects_what_the_reference_rejects(model, dev):
     bad[0, 0] = 76
     with pytest.raises(IndexError):         # embedding index out of range
         model(text=bad.to(dev), text_lengths=tl.to(dev), speech=speech.to(dev), speech_lengths=sl.to(dev))
+    long_sl = sl.clone()
+    long_sl[1] = 5000                        # a length beyond the padded dim: clamped on the device, reported, no fault
+    with pytest.raises(RuntimeError):
+        model(text=text.to(dev), text_lengths=tl.to(dev), speech=speech.to(dev), speech_lengths=long_sl.to(dev))
+    neg_tl = tl.clone()
+    neg_tl[1] = -3
+    with pytest.raises(RuntimeError):
+        model(text=text.to(dev), text_lengths=neg_tl.to(dev), speech=speech.to(dev), speech_lengths=sl.to(dev))
+    ok = model(text=text.to(dev), text_lengths=tl.to(dev), speech=speech.to(dev), speech_lengths=sl.to(dev))
+    assert torch.isfinite(ok[4]).all()       # the context is still healthy after the rejected calls
     with pytest.raises(RuntimeError):       # forward-only engine
         model.train()(text=text.to(dev), text_lengths=tl.to(dev), speech=speech.to(dev), speech_lengths=sl.to(dev))
     model.eval()
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json sizes against the CPU oracle (SURVEY.md 8d recipes): C2, C3 (seed 0 and two of the C4 shard
+# seeds), C5.  Contract: every returned tensor is within 1e-4 abs of the fp32 reference -- or, where
+# the reference's own fp32 rounding noise exceeds what any independent implementation can track, within 1e-4 of
+# the reference evaluated in float64 AND closer to that float64 result than the fp32 reference itself is.
+_PRECISION = {}
+
+
+def _dump_precision():
+    import json
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "precision_suite.json"), "w") as f:
+            json.dump(_PRECISION, f, indent=1, sort_keys=True)
+    except OSError:
+        pass
+
+
+FULL_SIZE_CASES = [("C2", 0), ("C3", 0), ("C3", 3), ("C3", 6), ("C5", 0)]
+
+
+@pytest.mark.parametrize("name,seed", FULL_SIZE_CASES, ids=["%s_seed%d" % c for c in FULL_SIZE_CASES])
+def test_forward_full_size_matches_oracle(model, dev, name, seed):
+    import time
+    from tests.cases import config_lengths
+    w = orc.make_weights(seed=1234)
+    t1, t2 = config_lengths(name, seed=seed)
+    text, tl, speech, sl = make_forward_inputs(seed, t1, t2)
+    out = model(text=text.to(dev), text_lengths=tl.to(dev), speech=speech.to(dev), speech_lengths=sl.to(dev))
+    t0 = time.time()
+    with torch.no_grad():
+        ref = orc.forward(w, text, tl, speech, sl)
+    cpu_s = time.time() - t0
+    r64 = None
+    rec = {"cpu_oracle_seconds": cpu_s, "cpu_threads": torch.get_num_threads(), "B": len(t1)}
+    failures = []
+    for key, i, tol in (("mel", 4, MEL_TOL), ("reconst_alpha", 3, RA_TOL), ("imv", 2, 1e-4)):
+        ours = out[i].cpu()
+        d32 = (ours - ref[i]).abs().max().item()
+        rec[key] = {"ours_vs_ref32_max": d32, "n_over_1e4": int(((ours - ref[i]).abs() > 1e-4).sum()),
+                    "numel": ours.numel(), "rule": "direct"}
+        if d32 <= tol:
+            continue
+        # the documented exception: the fp32 reference is itself further than the budget from the exact result
+        if r64 is None:
+            r64 = orc.forward_fp64(w, text, tl, speech, sl)
+        ours64 = (ours.double() - r64[i]).abs().max().item()
+        ref64 = (ref[i].double() - r64[i]).abs().max().item()
+        rec[key].update(rule="fp64", ours_vs_fp64_max=ours64, ref32_vs_fp64_max=ref64)
+        if not (ours64 <= tol and ours64 < ref64):
+            failures.append("%s: %.3e from the fp32 reference, %.3e from fp64 (reference itself %.3e)" %
+                            (key, d32, ours64, ref64))
+    for k in ("loss", "mel_loss", "duration_loss"):
+        rec[k] = [out[1][k], ref[1][k]]
+        if abs(out[1][k] - ref[1][k]) > 1e-4 * max(1.0, abs(ref[1][k])):
+            failures.append("%s: %r vs %r" % (k, out[1][k], ref[1][k]))
+    _PRECISION["%s_seed%d" % (name, seed)] = rec
+    _dump_precision()
+    print(name, seed, rec)
+    assert not failures, failures
+    if name in ("C2", "C3"):
+        # the bench configuration and its shards meet the north_star contract directly (no exception needed)
+        assert rec["mel"]["rule"] == "direct" and rec["reconst_alpha"]["rule"] == "direct"
 
 
 @pytest.mark.parametrize("name", ["C3", "C5"])
@@ -365,6 +425,12 @@ def test_fp16_range_violation_is_reported(dev):
         m(text=text.to(dev), text_lengths=tl.to(dev), speech=speech.to(dev), speech_lengths=sl.to(dev))
     with pytest.raises(FloatingPointError):
         m.inference(text[:1, :12].to(dev))
+    # NaN / inf in the inputs trip the same check (a float max would drop the NaN)
+    m2 = build_model(orc.make_weights(seed=1234), dev)
+    bad = speech.clone()
+    bad[0, 3, 7] = float("nan")
+    with pytest.raises(FloatingPointError):
+        m2(text=text.to(dev), text_lengths=tl.to(dev), speech=bad.to(dev), speech_lengths=sl.to(dev))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -481,7 +547,14 @@ def test_helper_methods_match_oracle(model, dev):
     imv = model.imv_generator(alpha_r.to(dev), p, mmd, tl.to(dev))
     assert (imv.cpu() - imv_r).abs().max().item() <= 1e-4
     e = model.get_aligned_positions(imv_r.to(dev), p, mmd, tmd, sigma=0.5)
-    assert (e.cpu() - e_r).abs().max().item() <= 2e-3        # e spans [0, T2): fp32 noise of a 190-term expectation
+    # e spans [0, T2): held to the distance of the fp32 reference from its own float64 evaluation (a 190-term
+    # softmax expectation), both against the reference and against float64
+    with orc.float_is_double(), torch.no_grad():
+        e64 = orc.aligned_positions(imv_r.double(), p_r.double(), mel_mask, text_mask, 0.5)
+    ref_noise = (e_r.double() - e64).abs().max().item()
+    d_e32, d_e64 = (e.cpu() - e_r).abs().max().item(), (e.cpu().double() - e64).abs().max().item()
+    print("aligned positions: ours-ref32 %.3e  ours-fp64 %.3e  ref32-fp64 %.3e" % (d_e32, d_e64, ref_noise))
+    assert d_e64 <= max(1e-4, 2.0 * ref_noise) and d_e32 <= max(1e-4, 3.0 * ref_noise)
     ra = model.reconstruct_align_from_aligned_position(e_r.to(dev), delta=0.01, mel_mask=mmd, text_mask=tmd)
     ra_ref = ra_r.masked_fill(~(text_mask.unsqueeze(-1) & mel_mask.unsqueeze(1)), 0.0)
     assert (ra.cpu() - ra_ref).abs().max().item() <= 1e-5

@@ -167,6 +167,16 @@ assert torch.equal(imv, ref[0]) and torch.equal(ra, ref[1]) and torch.equal(mel,
 lo, hi = shard_range(B, rank, world)
 _, _, imv_s, _, _ = dp(text, tl, speech, sl)             # outputs stay sharded by default
 assert torch.equal(imv_s, ref[0][lo:hi])
+# an error bit raised on ONE shard (token id out of range on rank 1's rows) stops every rank, like forward()
+def flagged_forward(text, tl, speech, sl):
+    out = fake_forward(text, tl, speech, sl)
+    out[3][7] = 4.0 if rank == 1 else 0.0
+    return out
+try:
+    DataParallelForward(flagged_forward)(text, tl, speech, sl)
+    raise SystemExit("flag was not propagated on rank %%d" %% rank)
+except IndexError:
+    pass
 dist.barrier(); dist.destroy_process_group()
 print("rank", rank, "ok")
 '''
