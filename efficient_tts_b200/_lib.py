@@ -77,9 +77,12 @@ SIGNATURES = {
     "efts_host_map_grouped": (c_i32, [c_void_p, c_i32, c_i32, c_i32, c_i32, c_void_p, ctypes.POINTER(c_i32)]),
     "efts_set_option": (c_i32, [c_void_p, c_char_p, c_i32]),
     "efts_launch_count": (c_i64, [c_void_p]),
+    "efts_read_words": (c_i32, [c_void_p, c_void_p, ctypes.POINTER(c_i32), c_i32, c_void_p]),
     "efts_error_flags": (c_i32, [c_void_p, c_void_p, ctypes.POINTER(c_i32)]),
     "efts_profile_enable": (c_i32, [c_void_p, ctypes.c_uint32]),
     "efts_profile_read": (c_i32, [c_void_p, c_i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_i64)]),
+    "efts_profile_stack_trace": (c_i32, [c_void_p, ctypes.POINTER(c_i64), c_i32]),
+    "efts_profile_kernel_name": (c_i32, [c_void_p, c_i32, c_char_p, c_size_t]),
     "efts_last_error": (c_char_p, []),
     "efts_version": (c_char_p, []),
 }

@@ -18,6 +18,18 @@ NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]
 
 
+def source_hash():
+    """sha256 (first 16 hex digits) over the sources the library is built from; compiled into the library
+    (``efts_version()``) and stamped into profiles/ so that a profile can be matched to the binary it describes."""
+    import hashlib
+    h = hashlib.sha256()
+    for p in sorted(SOURCES + HEADERS):
+        h.update(os.path.basename(p).encode())
+        with open(p, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
 def find_nvcc():
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
@@ -36,7 +48,8 @@ def build_library(force=False, verbose=False):
     """Compile ``csrc/*.cu`` for sm_100a into ``libefts_b200.so``; returns its path."""
     if not force and not is_stale():
         return LIB_PATH
-    cmd = [find_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
+    cmd = [find_nvcc()] + NVCC_FLAGS + ['-DEFTS_SOURCE_SHA="%s"' % source_hash()] + \
+        (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout)

@@ -18,6 +18,7 @@
 #include "../../include/efts_b200.h"
 #include "gemm2_sm100.cuh"
 #include "path_kernels.cuh"
+#include "stack_sm100.cuh"
 #include "vocoder_kernels.cuh"
 
 namespace {
@@ -101,6 +102,11 @@ struct efts_ctx {
   int voc_narrow = 0;            // vocoder: 64-column tiles for layers with N <= 64 (read at finalize and at launch).
                                  // Off: measured 36.4 vs 34.5 ms at 16 x 800 frames -- the narrow layers are bound by
                                  // their tile count (A-box halo, epilogue), which the grouped packing halves, not by MMA columns
+  int stack = 1;                 // B = 1 synthesis: resident layer-stack kernel (stack_sm100.cuh) instead of one launch
+                                 // per layer (bitwise the same results; the switch keeps the per-layer path tested)
+  unsigned* sync_ctr = nullptr;  // grid-barrier counter of the stack kernel (device, monotonic)
+  unsigned sync_base = 0;        // its value once every enqueued stack launch has finished
+  long long* stack_trace = nullptr;   // device buffer [64] for the stack kernel's phase stamps (debug_mask bit 4)
   int split_k = 1;               // fused-B kernel: split the reduction of small launches over more SMs
   int pdl = 1;                   // programmatic dependent launch for the GEMM and split-reduce kernels
   int fuse_b = 1;                // conv layers: Ahi*[Bhi|Blo] as one N = 256 MMA (two MMAs per k-step instead of three)
@@ -137,6 +143,10 @@ struct efts_ctx {
   struct ProfRec { cudaEvent_t a, b; int tag; };
   std::vector<ProfRec> prof;
   size_t prof_used = 0;
+  typedef std::tuple<const void*, int, int, int, int, int> MapKey;   // (pointer, inner, rows, z, ld, box rows)
+  std::map<MapKey, CUtensorMap> map_cache;                           // encoded TMA tensor maps (make_map)
+  int32_t* pinned_words = nullptr;                                   // host staging of efts_read_words (pinned, 64 words)
+  char tag_kernel[16][64] = {};    // instantiation of the last GEMM launched under each tag (efts_profile_kernel_name)
   uint32_t profile_mask = 0;
 };
 
@@ -166,8 +176,16 @@ enum ProfTag { TAG_TEXT_CONV = 0, TAG_MEL_CONV = 1, TAG_DEC_CONV = 2, TAG_LINEAR
 
 // ------------------------------------------------------------------------------------------------
 // tensor maps
+// Encoding a map costs ~1 us of host time and every GEMM launch needs four; the operands of a schedule recur
+// (weights always, activations whenever the caller's workspace and sizes repeat), so encoded maps are kept per context.
 int make_map(efts_ctx* c, CUtensorMap* m, const __half* ptr, int inner, int rows, int z, int ld,
              int box_rows) {
+  const efts_ctx::MapKey key{ptr, inner, rows, z, ld, box_rows};
+  auto it = c->map_cache.find(key);
+  if (it != c->map_cache.end()) {
+    *m = it->second;
+    return EFTS_OK;
+  }
   cuuint64_t dims[3] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(rows),
                         static_cast<cuuint64_t>(z)};
   cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(rows) * ld * 2};
@@ -181,6 +199,8 @@ int make_map(efts_ctx* c, CUtensorMap* m, const __half* ptr, int inner, int rows
   if (r != CUDA_SUCCESS)
     return fail(EFTS_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) inner=%d rows=%d z=%d ld=%d box=%d",
                 (int)r, inner, rows, z, ld, box_rows);
+  if (c->map_cache.size() >= 4096) c->map_cache.clear();
+  c->map_cache.emplace(key, *m);
   return EFTS_OK;
 }
 
@@ -221,6 +241,9 @@ int launch_gemm2_t(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, con
   cfg.numAttrs = c->pdl ? 2 : 1;
   CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ma_hi, ma_lo, mb_hi, mb_lo, p));
   c->launches++;
+  if (c->profile_mask)
+    snprintf(c->tag_kernel[c->cur_tag & 15], sizeof(c->tag_kernel[0]), "gemm2_kernel<%d, %d, %d, %d, %d, %d>", CG, EPI,
+             WIDE, FUSE, AR, BN);
   return EFTS_OK;
 }
 
@@ -329,6 +352,7 @@ int set_kernel_attributes() {
                                 G2Cfg<2, 0, 1, G2_A_ROWS_LONG, 64>::SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(gemm2_kernel<2, EPI_STD, 0, 1, G2_A_ROWS_XLONG, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 G2Cfg<2, 0, 1, G2_A_ROWS_XLONG, 64>::SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(reconstruct_alignment_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(kReconstructSmemMax)));
   CUDA_TRY(cudaFuncSetAttribute(imv_scan_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -664,6 +688,79 @@ int run_imv(efts_ctx* c, cudaStream_t st, const __half* q_hi, const __half* q_lo
   return EFTS_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Resident layer stack (stack_sm100.cuh): B = 1 synthesis as two kernels instead of ~32 launches.
+struct StackBuilder {
+  efts_ctx* c;
+  StackParams sp;
+  int max_items = 1;
+  size_t max_plane = 0;
+  int barriers = 0;
+  explicit StackBuilder(efts_ctx* c_) : c(c_) { memset(&sp, 0, sizeof(sp)); }
+
+  // one tensor-core layer: A planes [T, K] x weights w -> epilogue described by the caller through the returned slot
+  int add(const __half* a_hi, const __half* a_lo, int T, int K, const PackedW& w, int chunk_kb, int tag, StackLayer** out) {
+    if (sp.n_layers >= ST_MAX_LAYERS) return fail(EFTS_ERR_UNSUPPORTED, "layer stack holds at most %d layers", ST_MAX_LAYERS);
+    if (w.K != K) return fail(EFTS_ERR_ARG, "stack layer K mismatch %d vs %d", w.K, K);
+    StackMaps& M = sp.maps[sp.n_layers];
+    StackLayer& L = sp.layer[sp.n_layers++];
+    TRY(make_map(c, &M.a_hi, a_hi, K, T, 1, K, G2_A_ROWS));
+    TRY(make_map(c, &M.a_lo, a_lo, K, T, 1, K, G2_A_ROWS));
+    TRY(make_map(c, &M.b_hi, w.hi, w.K, w.N, w.Z, w.K, G2_BN));
+    TRY(make_map(c, &M.b_lo, w.lo, w.K, w.N, w.Z, w.K, G2_BN));
+    L.T = T; L.K = K; L.N = w.N; L.ntaps = w.Z; L.pad = (w.Z - 1) / 2;
+    L.chunk_kb = chunk_kb;
+    L.bias = w.bias;
+    L.err_code = 1 << (8 + tag);
+    const int num_kb = (K + G2_BK - 1) / G2_BK;
+    const int ckb = chunk_kb < 1 ? num_kb : chunk_kb;
+    const int nchunks = (num_kb + ckb - 1) / ckb;
+    max_items = std::max(max_items, ((T + G2_BM - 1) / G2_BM) * ((w.N + G2_BN - 1) / G2_BN) * nchunks);
+    max_plane = std::max(max_plane, static_cast<size_t>(T) * w.N);
+    sp.split_stride = std::max(sp.split_stride, static_cast<size_t>(T) * w.N);
+    if (nchunks > 8) return fail(EFTS_ERR_UNSUPPORTED, "layer stack: at most 8 accumulation chunks per layer");
+    if (static_cast<size_t>(T) * w.N * nchunks * sizeof(float) > kSplitScratchBytes)
+      return fail(EFTS_ERR_WORKSPACE, "layer stack: %d rows do not fit the partial-plane scratch", T);
+    barriers += 2;
+    *out = &L;
+    return EFTS_OK;
+  }
+
+  int launch(cudaStream_t st, float* scratch) {
+    sp.scratch = scratch;
+    sp.sync = c->sync_ctr;
+    sp.sync_base = c->sync_base;
+    sp.err_flag = c->err_flag;
+    sp.trace = (c->debug_mask & 16) ? c->stack_trace : nullptr;
+    if (sp.text != nullptr) barriers += 1;
+    // enough CTAs for the widest layer's work items and one (row, four columns) unit per thread of the largest
+    // reduce, never more than SMs (every CTA must be resident: the layers synchronise through a grid barrier)
+    size_t units = static_cast<size_t>(sp.T_embed) * 32;
+    for (int i = 0; i < sp.n_layers; ++i)
+      units = std::max(units, static_cast<size_t>(sp.layer[i].T) * (sp.layer[i].mode == ST_PLAIN ? sp.layer[i].N / 4 : 32));
+    const int grid = std::max(1, std::min(c->sm_count, std::max(max_items, static_cast<int>((units + ST_THREADS - 1) / ST_THREADS))));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(grid));
+    cfg.blockDim = dim3(ST_THREADS);
+    cfg.dynamicSmemBytes = ST_SMEM_BYTES;
+    cfg.stream = st;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, stack_kernel, sp));
+    c->sync_base += static_cast<unsigned>(grid) * static_cast<unsigned>(barriers);
+    c->launches++;
+    return EFTS_OK;
+  }
+};
+
+// Whether the B = 1 schedules may take the resident stack: default numerics (fused-B pairs, flushed accumulator)
+// and sizes the partial-plane scratch holds; anything else runs one launch per layer.
+bool stack_usable(const efts_ctx* c, int T, int n_layers) {
+  const int nchunks = c->chunk_kb < 1 ? 1 : (c->cfg.n_channels / G2_BK + c->chunk_kb - 1) / c->chunk_kb;
+  return c->stack && c->pair && c->fuse_b && c->wide && c->split_k && c->chunk_kb >= 1 && (c->debug_mask & ~16) == 0 &&
+         n_layers <= ST_MAX_LAYERS && c->cfg.n_channels == 512 && c->profile_mask == 0 &&
+         static_cast<size_t>(T) * c->cfg.n_channels * nchunks * sizeof(float) <= kSplitScratchBytes;
+}
+
 int check_ready(const efts_ctx* c) {
   if (c == nullptr) return fail(EFTS_ERR_ARG, "null context");
   if (!c->finalized) return fail(EFTS_ERR_STATE, "weights not finalised (call efts_finalize_weights)");
@@ -688,7 +785,10 @@ namespace { int create_base(int device, efts_ctx** out); }
 extern "C" {
 
 const char* efts_last_error(void) { return g_err; }
-const char* efts_version(void) { return "efts_b200 0.1 (sm_100a, split-fp16 tcgen05)"; }
+#ifndef EFTS_SOURCE_SHA
+#define EFTS_SOURCE_SHA "unknown"
+#endif
+const char* efts_version(void) { return "efts_b200 0.2 (sm_100a, split-fp16 tcgen05) src " EFTS_SOURCE_SHA; }
 
 int efts_create(const efts_config* cfg, efts_ctx** out) {
   if (cfg == nullptr || out == nullptr) return fail(EFTS_ERR_ARG, "null argument");
@@ -743,6 +843,17 @@ int create_base(int device, efts_ctx** out) {
     return fail(EFTS_ERR_CUDA, "cudaMalloc failed");
   }
   c->device_allocs.push_back(c->err_flag);
+  if (cudaMalloc(reinterpret_cast<void**>(&c->sync_ctr), sizeof(unsigned)) != cudaSuccess ||
+      cudaMemset(c->sync_ctr, 0, sizeof(unsigned)) != cudaSuccess) {
+    delete c;
+    return fail(EFTS_ERR_CUDA, "cudaMalloc failed");
+  }
+  c->device_allocs.push_back(c->sync_ctr);
+  if (cudaMalloc(reinterpret_cast<void**>(&c->stack_trace), 64 * sizeof(long long)) != cudaSuccess) {
+    delete c;
+    return fail(EFTS_ERR_CUDA, "cudaMalloc failed");
+  }
+  c->device_allocs.push_back(c->stack_trace);
   *out = c;
   return EFTS_OK;
 }
@@ -754,6 +865,7 @@ void efts_destroy(efts_ctx* c) {
   if (c == nullptr) return;
   for (void* p : c->device_allocs) cudaFree(p);
   for (auto& r : c->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  if (c->pinned_words != nullptr) cudaFreeHost(c->pinned_words);
   delete c->voc;
   delete c;
 }
@@ -823,6 +935,7 @@ int efts_set_option(efts_ctx* c, const char* name, int32_t value) {
   if (strcmp(name, "wide") == 0) { c->wide = value != 0; return EFTS_OK; }
   if (strcmp(name, "fuse_b") == 0) { c->fuse_b = value != 0; return EFTS_OK; }
   if (strcmp(name, "split_k") == 0) { c->split_k = value != 0; return EFTS_OK; }
+  if (strcmp(name, "stack") == 0) { c->stack = value != 0; return EFTS_OK; }
   if (strcmp(name, "pdl") == 0) { c->pdl = value != 0; return EFTS_OK; }
   if (strcmp(name, "voc_group") == 0) { c->voc_group = value != 0; return EFTS_OK; }
   if (strcmp(name, "voc_narrow") == 0) { c->voc_narrow = value != 0; return EFTS_OK; }
@@ -845,10 +958,7 @@ int64_t efts_launch_count(const efts_ctx* c) { return c ? c->launches : 0; }
 
 int efts_error_flags(efts_ctx* c, void* stream, int32_t* flags_host) {
   if (c == nullptr || flags_host == nullptr) return fail(EFTS_ERR_ARG, "null argument");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  CUDA_TRY(cudaMemcpyAsync(flags_host, c->err_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaStreamSynchronize(st));
-  return EFTS_OK;
+  return efts_read_words(c, c->err_flag, flags_host, 1, stream);
 }
 
 int efts_profile_enable(efts_ctx* c, uint32_t tag_mask) {
@@ -872,6 +982,28 @@ int efts_profile_read(efts_ctx* c, int32_t tag, double* total_ms, int64_t* count
   }
   *total_ms = ms;
   *count = n;
+  return EFTS_OK;
+}
+
+int efts_read_words(efts_ctx* c, const int32_t* dev, int32_t* host, int32_t n, void* stream) {
+  if (c == nullptr || dev == nullptr || host == nullptr || n < 1 || n > 64) return fail(EFTS_ERR_ARG, "bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (c->pinned_words == nullptr) CUDA_TRY(cudaMallocHost(reinterpret_cast<void**>(&c->pinned_words), 64 * sizeof(int32_t)));
+  CUDA_TRY(cudaMemcpyAsync(c->pinned_words, dev, static_cast<size_t>(n) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  memcpy(host, c->pinned_words, static_cast<size_t>(n) * sizeof(int32_t));
+  return EFTS_OK;
+}
+
+int efts_profile_stack_trace(efts_ctx* c, int64_t* out, int32_t n) {
+  if (c == nullptr || out == nullptr || n < 1 || n > 64) return fail(EFTS_ERR_ARG, "bad argument");
+  CUDA_TRY(cudaMemcpy(out, c->stack_trace, static_cast<size_t>(n) * sizeof(long long), cudaMemcpyDeviceToHost));
+  return EFTS_OK;
+}
+
+int efts_profile_kernel_name(const efts_ctx* c, int32_t tag, char* buf, size_t n) {
+  if (c == nullptr || buf == nullptr || n == 0 || tag < 0 || tag > 15) return fail(EFTS_ERR_ARG, "bad argument");
+  snprintf(buf, n, "%s", c->tag_kernel[tag]);
   return EFTS_OK;
 }
 
@@ -998,6 +1130,44 @@ int efts_inference_phase1(efts_ctx* c, const int64_t* text, int32_t T1, int32_t*
   if (!a.ok) return fail(EFTS_ERR_WORKSPACE, "workspace too small: need %zu, have %zu", a.off, workspace_bytes);
   CUDA_TRY(cudaMemsetAsync(t2_dev, 0, 2 * sizeof(int), st));
   CUDA_TRY(cudaMemsetAsync(c->err_flag, 0, sizeof(int), st));
+  const int nl = g.n_duration_layer;
+  if (stack_usable(c, T1, g.n_text_encoder_layer + 1 + nl)) {
+    // one resident kernel: embedding, text encoder, value projection, duration predictor, cumsum / T2
+    StackBuilder sb(c);
+    sb.sp.text = text; sb.sp.emb = c->emb; sb.sp.num_symbols = g.num_symbols; sb.sp.T_embed = T1;
+    sb.sp.x0_f = w.xt_f[0]; sb.sp.x0_hi = w.xt_hi[0]; sb.sp.x0_lo = w.xt_lo[0]; sb.sp.flags = t2_dev + 1;
+    int cur = 0;
+    StackLayer* L;
+    for (int l = 0; l < g.n_text_encoder_layer; ++l, cur ^= 1) {
+      TRY(sb.add(w.xt_hi[cur], w.xt_lo[cur], T1, C, c->text[l], c->chunk_kb, TAG_TEXT_CONV, &L));
+      L->act = ACT_LRELU; L->resid = w.xt_f[cur]; L->out = w.xt_f[cur ^ 1];
+      L->out_hi = w.xt_hi[cur ^ 1]; L->out_lo = w.xt_lo[cur ^ 1];
+    }
+    // value only: the key projection at :251 is computed by the reference but never used
+    TRY(sb.add(w.xt_hi[cur], w.xt_lo[cur], T1, C, c->value, 0, TAG_LINEAR, &L));
+    L->out_hi = w.val_hi; L->out_lo = w.val_lo; L->outT_hi = w.valT_hi; L->outT_lo = w.valT_lo; L->ld_t = w.T1p;
+    if (w.T1p != T1) {
+      CUDA_TRY(cudaMemsetAsync(w.valT_hi, 0, static_cast<size_t>(C) * w.T1p * sizeof(__half), st));
+      CUDA_TRY(cudaMemsetAsync(w.valT_lo, 0, static_cast<size_t>(C) * w.T1p * sizeof(__half), st));
+    }
+    // durations clamp(exp(x) - offset, 0) (:258): [conv k3 -> ReLU -> LayerNorm] x n, Linear head
+    const __half* ahi = w.val_hi;
+    const __half* alo = w.val_lo;
+    for (int l = 0; l < nl; ++l) {
+      TRY(sb.add(ahi, alo, T1, C, c->dp[l], c->chunk_kb, TAG_DURATION, &L));
+      L->act = ACT_RELU; L->ln_g = c->ln_g[l]; L->ln_b = c->ln_b[l];
+      if (l < nl - 1) {
+        L->mode = ST_LN_PLANES; L->out_hi = w.dp_hi; L->out_lo = w.dp_lo;
+      } else {
+        L->mode = ST_LN_HEAD; L->head_w = c->head_w; L->head_b = c->head_b; L->head_mode = 1;
+        L->head_offset = g.duration_offset; L->head_out = w.dur;
+      }
+      ahi = w.dp_hi; alo = w.dp_lo;
+    }
+    // their cumsum (:260); T2 = round(e[-1]) (:361)
+    sb.sp.dur = w.dur; sb.sp.e = w.e; sb.sp.t2_out = t2_dev; sb.sp.T_cumsum = T1;
+    return sb.launch(st, w.splitk);
+  }
   embed_kernel<<<T1, C / 4, 0, st>>>(text, c->emb, g.num_symbols, C, w.xt_f[0], w.xt_hi[0], w.xt_lo[0], t2_dev + 1,
                                      nullptr, T1);
   CUDA_TRY(cudaGetLastError());
@@ -1041,6 +1211,20 @@ int efts_inference_phase2(efts_ctx* c, int32_t T1, int32_t T2, float* mel_pred, 
   if (!a.ok) return fail(EFTS_ERR_WORKSPACE, "workspace too small: need %zu, have %zu", a.off, workspace_bytes);
   TRY(run_reconstruct_expand(c, st, w.e, nullptr, nullptr, 1, T1, T2, w.T1p, w.R_hi, w.R_lo, w.valT_hi, w.valT_lo,
                              reconst_alpha, w.xm_f[0], w.xm_hi[0], w.xm_lo[0]));
+  if (stack_usable(c, T2, g.n_decoder_layer + 1)) {
+    // decoder (:282) and mel head (:283-284) as one resident kernel
+    StackBuilder sb(c);
+    int cur = 0;
+    StackLayer* L;
+    for (int l = 0; l < g.n_decoder_layer; ++l, cur ^= 1) {
+      TRY(sb.add(w.xm_hi[cur], w.xm_lo[cur], T2, C, c->dec[l], c->chunk_kb, TAG_DEC_CONV, &L));
+      L->act = ACT_LRELU; L->resid = w.xm_f[cur]; L->out = w.xm_f[cur ^ 1];
+      L->out_hi = w.xm_hi[cur ^ 1]; L->out_lo = w.xm_lo[cur ^ 1];
+    }
+    TRY(sb.add(w.xm_hi[cur], w.xm_lo[cur], T2, C, c->melout, 0, TAG_LINEAR, &L));
+    L->out = mel_pred;
+    return sb.launch(st, w.splitk);
+  }
   int curm = 0;
   TRY(run_conv_stack(c, st, c->dec, g.n_decoder_layer, 1, T2, w.xm_f, w.xm_hi, w.xm_lo, nullptr, nullptr, nullptr,
                      &curm, TAG_DEC_CONV, false, w.splitk));

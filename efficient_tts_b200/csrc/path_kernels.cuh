@@ -714,25 +714,17 @@ __global__ void alpha_expectation_kernel(const float* __restrict__ alpha, const 
 // HEAD == 1: fuses the Linear(C -> 1) head (layers/duration_predictor.py:76) and the output mode:
 //   0 log domain, 1 clamp(exp(x) - offset, 0), 2 clamp(round(exp(x) - offset), 0) as int64
 //   (layers/duration_predictor.py:79-88); rows t >= lens[b] are written as 0.
+// The row arithmetic, shared with the resident layer-stack kernel (stack_sm100.cuh) so both produce the same bits.
+// v[j] holds columns (j * 32 + lane) * 4 .. + 3 of the row.  HEAD == 0: writes operand planes at hi / lo (row
+// base pointers; zeros when !live).  HEAD == 1: returns the Linear(C -> 1) dot product (valid on every lane).
 template <int HEAD>
-__global__ void layernorm_kernel(const float* __restrict__ x, size_t rows, int T,
-                                 const float* __restrict__ gamma, const float* __restrict__ beta,
-                                 __half* __restrict__ hi, __half* __restrict__ lo,
-                                 const float* __restrict__ head_w, const float* __restrict__ head_b,
-                                 const int* __restrict__ lens, int mode, float offset,
-                                 void* __restrict__ out) {
+__device__ __forceinline__ float layernorm_row(const float4 (&v)[4], int lane, const float* __restrict__ gamma,
+                                               const float* __restrict__ beta, __half* __restrict__ hi,
+                                               __half* __restrict__ lo, const float* __restrict__ head_w, bool live) {
   constexpr int C = 512;
-  const int lane = threadIdx.x & 31;
-  const size_t row = blockIdx.x * static_cast<size_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const float4* xr = reinterpret_cast<const float4*>(x + row * C);
-  float4 v[4];
   float s = 0.0f;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    v[j] = xr[j * 32 + lane];
-    s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
-  }
+  for (int j = 0; j < 4; ++j) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
   const float mean = warp_sum(s) * (1.0f / C);
   float ss = 0.0f;
 #pragma unroll
@@ -754,34 +746,53 @@ __global__ void layernorm_kernel(const float* __restrict__ x, size_t rows, int T
     y.z = (v[j].z - mean) * rstd * g.z + bb.z;
     y.w = (v[j].w - mean) * rstd * g.w + bb.w;
     if (HEAD == 0) {
-      if (lens != nullptr && static_cast<int>(row % T) >= lens[row / T]) y = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      if (!live) y = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
       uint2 h, l;
       split4(y, &h, &l);
-      *reinterpret_cast<uint2*>(hi + row * C + c) = h;
-      *reinterpret_cast<uint2*>(lo + row * C + c) = l;
+      *reinterpret_cast<uint2*>(hi + c) = h;
+      *reinterpret_cast<uint2*>(lo + c) = l;
     } else {
       const float4 w = __ldg(reinterpret_cast<const float4*>(head_w + c));
       dot += (y.x * w.x + y.y * w.y) + (y.z * w.z + y.w * w.w);
     }
   }
-  if (HEAD == 1) {
-    dot = warp_sum(dot);
-    if (lane == 0) {
-      float r = dot + head_b[0];
-      const int b = static_cast<int>(row / T);
-      const int t = static_cast<int>(row % T);
-      const bool live = lens == nullptr || t < lens[b];
-      if (mode == 0) {
-        reinterpret_cast<float*>(out)[row] = live ? r : 0.0f;
-      } else if (mode == 1) {
-        r = fmaxf(__fsub_rn(expf(r), offset), 0.0f);
-        reinterpret_cast<float*>(out)[row] = live ? r : 0.0f;
-      } else {
-        r = fmaxf(rintf(__fsub_rn(expf(r), offset)), 0.0f);
-        reinterpret_cast<long long*>(out)[row] = live ? static_cast<long long>(r) : 0ll;
-      }
-    }
+  return HEAD == 1 ? warp_sum(dot) : 0.0f;
+}
+
+// Output mode of the duration head (layers/duration_predictor.py:79-88) for one row; call from one lane.
+__device__ __forceinline__ void duration_head_store(float dot, const float* __restrict__ head_b, bool live, int mode,
+                                                    float offset, void* __restrict__ out, size_t row) {
+  float r = dot + head_b[0];
+  if (mode == 0) {
+    reinterpret_cast<float*>(out)[row] = live ? r : 0.0f;
+  } else if (mode == 1) {
+    r = fmaxf(__fsub_rn(expf(r), offset), 0.0f);
+    reinterpret_cast<float*>(out)[row] = live ? r : 0.0f;
+  } else {
+    r = fmaxf(rintf(__fsub_rn(expf(r), offset)), 0.0f);
+    reinterpret_cast<long long*>(out)[row] = live ? static_cast<long long>(r) : 0ll;
   }
+}
+
+template <int HEAD>
+__global__ void layernorm_kernel(const float* __restrict__ x, size_t rows, int T,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta,
+                                 __half* __restrict__ hi, __half* __restrict__ lo,
+                                 const float* __restrict__ head_w, const float* __restrict__ head_b,
+                                 const int* __restrict__ lens, int mode, float offset,
+                                 void* __restrict__ out) {
+  constexpr int C = 512;
+  const int lane = threadIdx.x & 31;
+  const size_t row = blockIdx.x * static_cast<size_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * C);
+  float4 v[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) v[j] = xr[j * 32 + lane];
+  const bool live = lens == nullptr || static_cast<int>(row % T) < lens[row / T];
+  const float dot = layernorm_row<HEAD>(v, lane, gamma, beta, HEAD == 0 ? hi + row * C : nullptr,
+                                        HEAD == 0 ? lo + row * C : nullptr, head_w, live);
+  if (HEAD == 1 && lane == 0) duration_head_store(dot, head_b, live, mode, offset, out, row);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -893,9 +904,9 @@ __global__ void duration_cumsum_batch_kernel(const float* __restrict__ d, const 
   if (lane == 0) t2_out[b] = L > 0 ? static_cast<int>(rintf(static_cast<float>(carry))) : 0;
 }
 
-__global__ void duration_cumsum_kernel(const float* __restrict__ d, int T1, float* __restrict__ e,
-                                       int* __restrict__ t2_out) {
-  const int lane = threadIdx.x;
+// One warp: e = cumsum(d[0..T1)), t2_out[0] = round_half_even(e[T1-1]).
+__device__ __forceinline__ void duration_cumsum_warp(const float* __restrict__ d, int T1, float* __restrict__ e,
+                                                     int* __restrict__ t2_out, int lane) {
   double carry = 0.0;
   float last = 0.0f;
   for (int base = 0; base < T1; base += 32) {
@@ -915,6 +926,11 @@ __global__ void duration_cumsum_kernel(const float* __restrict__ d, int T1, floa
   }
   last = __shfl_sync(0xffffffffu, last, (T1 - 1) & 31);
   if (lane == 0) t2_out[0] = static_cast<int>(rintf(last));
+}
+
+__global__ void duration_cumsum_kernel(const float* __restrict__ d, int T1, float* __restrict__ e,
+                                       int* __restrict__ t2_out) {
+  duration_cumsum_warp(d, T1, e, t2_out, threadIdx.x);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -69,6 +69,8 @@ class Engine:
                 _lib.check(self.lib.efts_set_weight(self._h, name.encode(), _ptr(t), shape, t.dim()))
             _lib.check(self.lib.efts_finalize_weights(self._h))
         self._ws = None
+        self._t2_dev = None
+        self._host_words = (ctypes.c_int32 * 8)()
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
@@ -97,6 +99,12 @@ class Engine:
         ms, n = ctypes.c_double(), ctypes.c_int64()
         _lib.check(self.lib.efts_profile_read(self._h, int(tag), ctypes.byref(ms), ctypes.byref(n)))
         return ms.value, n.value
+
+    def profile_kernel_name(self, tag):
+        """Instantiation of the last tensor-core GEMM launched under ``tag`` while profiling was enabled."""
+        buf = ctypes.create_string_buffer(96)
+        _lib.check(self.lib.efts_profile_kernel_name(self._h, int(tag), buf, 96))
+        return buf.value.decode()
 
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -153,12 +161,16 @@ class Engine:
                                "B=1 like the reference, models/efficient_tts.py:361)" % text.shape[0])
         T1 = text.shape[1]
         with torch.cuda.device(self.device):
-            t2_dev = torch.empty(2, dtype=torch.int32, device=self.device)
+            if self._t2_dev is None:
+                self._t2_dev = torch.empty(2, dtype=torch.int32, device=self.device)
+            t2_dev = self._t2_dev
             # phase 1 only touches the text-sized part of the workspace
             ws, n = self.workspace_for(1, T1, 1)
             _lib.check(self.lib.efts_inference_phase1(self._h, _ptr(text), T1, _ptr(t2_dev), _ptr(ws), n,
                                                       self._stream()))
-            t2, flags = (int(v) for v in t2_dev.cpu())        # the reference's .item() sync (:361)
+            # the reference's .item() sync (:361), through the context's pinned staging words
+            _lib.check(self.lib.efts_read_words(self._h, _ptr(t2_dev), self._host_words, 2, self._stream()))
+            t2, flags = self._host_words[0], self._host_words[1]
             if flags & 4:
                 raise IndexError("index out of range in self")   # embedding lookup, :246
             if flags & 8:

@@ -10,8 +10,26 @@ import torch
 from . import engine as _engine
 
 
+# Walking ``module.parameters()`` costs ~100 us for this model -- as much as a B = 1 synthesis takes on the GPU.  The
+# list of Parameter objects is therefore cached per module and dropped whenever ANY module registers a parameter
+# (weight-norm removal / application re-register ``weight``; plain ``.to()`` and ``load_state_dict`` keep the objects
+# and show up as new ``data_ptr`` / ``_version`` values, which the fingerprint reads on every call).
+_PARAM_GENERATION = [0]
+
+
+def _on_parameter_registration(module, name, param):
+    _PARAM_GENERATION[0] += 1
+
+
+torch.nn.modules.module.register_module_parameter_registration_hook(_on_parameter_registration)
+
+
 def _fingerprint(module):
-    return tuple((p.data_ptr(), p._version, p.device) for p in module.parameters())
+    cache = module.__dict__.get("_efts_param_cache")
+    if cache is None or cache[0] != _PARAM_GENERATION[0]:
+        cache = (_PARAM_GENERATION[0], list(module.parameters()))
+        module.__dict__["_efts_param_cache"] = cache
+    return tuple([(p.data_ptr(), p._version) for p in cache[1]])
 
 
 class _EngineOwner(torch.nn.Module):

@@ -247,13 +247,26 @@ int efts_set_option(efts_ctx* ctx, const char* name, int32_t value);
  * `efts_profile_enable` also clears what was recorded. */
 int efts_profile_enable(efts_ctx* ctx, uint32_t tag_mask);
 int efts_profile_read(efts_ctx* ctx, int32_t tag, double* total_ms, int64_t* count);
+/* Template instantiation of the last tensor-core GEMM launched under `tag` while profiling was enabled, e.g.
+ * "gemm2_kernel<2, 0, 0, 1, 136, 128>" (empty if none): bench.py matches it against the kernel name of the
+ * committed ncu capture before quoting that capture's numbers. */
+int efts_profile_kernel_name(const efts_ctx* ctx, int32_t tag, char* buf, size_t n);
+/* SM clock stamps (clock64 of CTA 0) the resident layer-stack kernel of B = 1 synthesis recorded at every phase
+ * boundary of its last launch while option "debug_mask" had bit 4 set: start, [after embedding, after its barrier,]
+ * then per layer {GEMM done, barrier passed, reduce done, barrier passed}.  Synchronising copy of `n` <= 64 values. */
+int efts_profile_stack_trace(efts_ctx* ctx, int64_t* out, int32_t n);
 /* Data-dependent error bits raised by the kernels of the calls issued on `stream` since the last
  * efts_forward / efts_inference_phase1 (bit 3: activation outside the fp16 operand range).
  * Synchronises the stream (4-byte read-back); efts_forward reports the same bits in scalars[7]. */
 int efts_error_flags(efts_ctx* ctx, void* stream, int32_t* flags_host);
+/* Synchronising read-back of `n` <= 64 device words through the context's pinned staging buffer (the T2 / flags
+ * read of efts_inference_phase1 -- the reference's .item() at models/efficient_tts.py:361 -- without a pageable
+ * copy).  One call in flight per context. */
+int efts_read_words(efts_ctx* ctx, const int32_t* dev, int32_t* host, int32_t n, void* stream);
 /* Kernels launched by this context since creation (bench.py's `gpu_launches`). */
 int64_t efts_launch_count(const efts_ctx* ctx);
 const char* efts_last_error(void);
+/* "efts_b200 <ver> (...) src <sha16>": sha16 = hash of the sources this binary was built from (build.py). */
 const char* efts_version(void);
 
 #ifdef __cplusplus

@@ -473,25 +473,39 @@ def test_inference_c1_shape_matches_oracle(dev):
         m.inference(torch.zeros(2, 5, dtype=torch.long, device=dev))
 
 
-def test_split_reduction_is_bitwise_the_unsplit_result(dev):
-    """B = 1 synthesis splits every conv layer's reduction into one work item per accumulation chunk
-    (splitk_reduce_kernel adds the partial planes in chunk order): same bits as the unsplit kernel."""
+def test_resident_stack_and_split_reduction_are_bitwise_the_per_layer_result(dev):
+    """B = 1 synthesis runs as two resident layer-stack kernels (stack_sm100.cuh: grid barriers between layers, every
+    conv's reduction split into one work item per accumulation chunk and summed in chunk order).  Same bits as one
+    launch per layer with the split reduction (splitk_reduce_kernel), and as the unsplit kernels."""
     w1 = orc.make_weights(seed=1234, dur_bias=1.7917594692, dur_weight_scale=0.05)
     m = build_model(w1, dev)
     eng = m._get_engine()
-    for n_tok in (7, 40, 64):
+    modes = {"stack": dict(stack=1, split_k=1), "per_layer_split": dict(stack=0, split_k=1),
+             "per_layer_unsplit": dict(stack=0, split_k=0)}
+    for n_tok in (7, 40, 64, 129, 200):
         t = make_inference_inputs(11 + n_tok, n_tok).to(dev)
         res, launches = {}, {}
         try:
-            for mode in (1, 0):
-                eng.set_option("split_k", mode)
+            for name, opts in modes.items():
+                for k, v in opts.items():
+                    eng.set_option(k, v)
                 n0 = eng.launch_count()
-                res[mode] = m.inference(t)
-                launches[mode] = eng.launch_count() - n0
+                res[name] = m.inference(t)
+                launches[name] = eng.launch_count() - n0
         finally:
+            eng.set_option("stack", 1)
             eng.set_option("split_k", 1)
-        assert launches[1] > launches[0]    # the reduce launches are there: the split path really ran
-        assert torch.equal(res[1][0], res[0][0]) and torch.equal(res[1][1], res[0][1])
+        # the paths really differ: 4 launches (stack, reconstruct, expand, stack) against one or two per layer
+        assert launches["stack"] <= 5 < launches["per_layer_unsplit"] < launches["per_layer_split"], launches
+        for name in ("per_layer_split", "per_layer_unsplit"):
+            assert res[name][0].shape == res["stack"][0].shape
+            assert torch.equal(res[name][0], res["stack"][0]) and torch.equal(res[name][1], res["stack"][1]), name
+    # repeated runs of the resident kernel are deterministic (a missing grid barrier would show up as a race)
+    t = make_inference_inputs(3, 64).to(dev)
+    first = m.inference(t)
+    for _ in range(10):
+        again = m.inference(t)
+        assert torch.equal(first[0], again[0]) and torch.equal(first[1], again[1])
 
 
 def test_programmatic_dependent_launch_does_not_change_results(model, dev):
