@@ -7,8 +7,13 @@
 
 Metric (BASELINE.json): mel frames/s of ``EfficientTTSCNN.forward`` at batch=256 mixed-length
 (config C3: 256 utterances, 50-200 tokens, 6 frames per token, padded to (200, 1200); 196 950 valid
-frames per 256-utterance draw).  One step = one forward over one such batch per GPU; at N > 1 every
-rank runs its own 256-utterance draw (C4 = 8 x C3, weak scaling, no data-path collective).
+frames per 256-utterance draw).  One step = one forward over one such batch per GPU.  At N > 1 rank r
+runs the C3 draw of seed r (C4 = 8 x C3, weak scaling) through ``DataParallelForward``: the step's only
+exchange, the NCCL all-reduce of the loss partial sums and error bits, is inside the timed region.
+
+Every number that comes from a committed profile (ncu traffic, tensor-pipe activity) is printed only when the
+profile was taken from the binary that is running: ``profiles/roofline_traffic.json`` carries the hash of the
+sources it was captured from and the kernel's template instantiation; both are checked against the library.
 """
 import argparse
 import json
@@ -28,7 +33,8 @@ from efficient_tts_b200 import workloads as wl  # noqa: E402
 WORKLOAD = "C3: batch=256 mixed-length 50-200 tokens, 6 frames/token, 80-bin mel, padded (200,1200)"
 UNIT = "mel_frames/s"
 METRIC = "mel_frames_per_sec_forward_b256"
-
+TAGS = ["text_conv", "mel_conv", "dec_conv", "linear", "energy_gemm", "softmax_expect", "imv_scan",
+        "aligned_pos", "reconstruct", "expand_gemm", "duration", "loss", "embed_split"]
 
 # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on the first
 # communicator), so file descriptor 1 is pointed at stderr for the whole run and the line goes to the saved stdout.
@@ -127,13 +133,55 @@ def computed_rows(lengths, T, halo):
     return n
 
 
+def round8(x):
+    return (x + 7) // 8 * 8
+
+
+def cuda_timed(fn, n, dev):
+    """Milliseconds per call of ``fn`` over ``n`` back-to-back calls, CUDA events on the current stream."""
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    a.record()
+    for _ in range(n):
+        fn()
+    b.record()
+    torch.cuda.synchronize(dev)
+    return a.elapsed_time(b) / n
+
+
+def library_source_sha(eng):
+    v = eng.lib.efts_version().decode()
+    return v.split(" src ")[-1] if " src " in v else None
+
+
+def committed_profile(eng, tag):
+    """The committed ncu capture of the kernel this library launches under `tag`, or (None, why)."""
+    path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if not os.path.exists(path):
+        return None, "profiles/roofline_traffic.json is missing"
+    try:
+        with open(path) as f:
+            tj = json.load(f)
+    except Exception as exc:
+        return None, "profiles/roofline_traffic.json unreadable: %s" % exc
+    sha = library_source_sha(eng)
+    if tj.get("source_sha16") != sha:
+        return None, ("profiles/roofline_traffic.json was captured from sources %s, this library is built from %s: "
+                      "its ncu numbers are not quoted" % (tj.get("source_sha16"), sha))
+    name = eng.profile_kernel_name(tag) if isinstance(tag, int) else tag
+    for k in tj.get("kernels", []):
+        if k.get("kernel") == name:
+            return k, None
+    return None, "no capture of %s in profiles/roofline_traffic.json" % name
+
+
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_forward(state_dict, sample_b, seed, steps, warmup, threads):
-    """The reference's CPU forward (oracle port: same torch CPU ops, same order) on a bounded sample
-    of the C3 workload.  Returns (frames/s, seconds per step, sample description)."""
+def cpu_reference_forward(state_dict, config, sample_b, seed, steps, warmup, threads):
+    """The reference's CPU forward (oracle port: same torch CPU ops, same order) on a draw of the named config.
+    Returns (frames/s, seconds per step, sample description)."""
     from oracle import efts_oracle as orc
     torch.set_num_threads(threads)
-    t1, t2 = wl.config_lengths("C3", seed=seed, batch=sample_b)
+    t1, t2 = wl.config_lengths(config, seed=seed, batch=sample_b)
     text, tl, speech, sl = wl.make_forward_inputs(seed, t1, t2)
     w = {k: v.detach().cpu() for k, v in state_dict.items()}
     frames = int(sl.sum())
@@ -144,23 +192,29 @@ def cpu_reference_forward(state_dict, sample_b, seed, steps, warmup, threads):
         for _ in range(steps):
             orc.forward(w, text, tl, speech, sl)
         dt = (time.perf_counter() - t0) / max(steps, 1)
-    desc = "%d-utterance draw of the C3 length distribution (padded (200,1200), %d valid frames), %d step(s)" % (
-        sample_b, frames, steps)
+    full = sample_b is None or sample_b == len(wl.config_lengths(config)[0])
+    desc = "%s %s: %d utterances, padded (%d,%d), %d valid frames, %d step(s)" % (
+        "the full" if full else "a bounded draw of", config, len(t1), text.shape[1], speech.shape[1], frames, steps)
     return frames / dt, dt, desc
 
 
 def run_reference(args, rank, world):
+    """The reference's own CPU implementation of the path (the oracle port -- the reference is Python on torch CPU
+    ops, there is nothing to compile) on the FULL C3 batch, all host threads.  One process: under torchrun rank 0
+    runs it alone, so at N > 1 the value is still one host's throughput."""
     if rank != 0:
         return 0
     import efficient_tts_b200 as E
     torch.manual_seed(1234)
     sd = E.EfficientTTSCNN(**wl.MODEL_KWARGS).state_dict()
     threads = os.cpu_count() or 1
-    fps, dt, desc = cpu_reference_forward(sd, args.cpu_sample, 0, max(1, args.steps), max(1, min(args.warmup, 1)), threads)
+    sample = None if args.cpu_sample in (0, 256) else args.cpu_sample
+    fps, dt, desc = cpu_reference_forward(sd, "C3", sample, 0, max(1, args.steps), max(1, min(args.warmup, 1)), threads)
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample": desc},
+            "config": {"workload": WORKLOAD, "sample": desc, "utterances_per_step": sample or 256,
+                       "note": "one CPU process on rank 0 whatever N is (the host does not scale with the GPU count)"},
             "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -169,9 +223,59 @@ def run_reference(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------------------
+def time_forward_config(eng, dev, name, steps=5, warmup=2):
+    """Device-resident forward time of another BASELINE config (C2 / C5): ms per step and valid frames/s."""
+    t1, t2 = wl.config_lengths(name)
+    text, tl, speech, sl = (t.to(dev) for t in wl.make_forward_inputs(0, t1, t2))
+    for _ in range(warmup):
+        eng.forward(text, tl, speech, sl)
+    ms = cuda_timed(lambda: eng.forward(text, tl, speech, sl), steps, dev)
+    frames = int(sum(t2))
+    flops = forward_flops(len(t1), max(t1), max(t2))
+    return {"config": "%s: B=%d, T1=%d, T2=%d (padded)" % (name, len(t1), max(t1), max(t2)), "ms_per_step": ms,
+            "valid_frames_per_s": frames / (ms * 1e-3), "padded_algorithmic_tflops": flops / (ms * 1e-3) / 1e12,
+            "steps": steps}
+
+
+def forward_flops(B, T1, T2, C=512, odim=80):
+    """Single-pass algorithmic FLOPs of one padded forward."""
+    conv = lambda T, k, n: 2.0 * B * T * C * C * k * n
+    return (conv(T1, 5, 5) + conv(T2, 5, 3) + conv(T2, 5, 6) + conv(T1, 3, 2) + 2 * 2.0 * B * T1 * C * C +
+            2.0 * B * T2 * odim * C * 2 + 2 * 2.0 * B * T1 * T2 * C)
+
+
+def time_length_regulator(dev, peaks):
+    """LengthRegulator.forward at the C3 shape (layers/length_regulator.py:35-79): bytes per SURVEY.md 8d."""
+    from efficient_tts_b200 import engine as E
+    t1, _ = wl.config_lengths("C3", seed=0)
+    B, T1, D = len(t1), max(t1), 512
+    g = torch.Generator().manual_seed(3)
+    xs = torch.randn(B, T1, D, generator=g).to(dev)
+    ds = torch.randint(3, 10, (B, T1), generator=g)
+    il = torch.tensor(t1, dtype=torch.int64)
+    for b in range(B):
+        ds[b, t1[b]:] = 0
+    ds, il = ds.to(dev), il.to(dev)
+    for _ in range(3):
+        out, idx = E.length_regulator(xs, ds, il, return_index=True)
+    ms = cuda_timed(lambda: E.length_regulator(xs, ds, il, return_index=True), 10, dev)
+    tout = int(ds.sum())
+    by = 4 * D * (int(il.sum()) + tout) + 8 * B * T1 + 8 * tout
+    padded = by - 4 * D * tout + 4 * D * B * out.shape[1]
+    return {"config": "LengthRegulator B=%d T1=%d D=%d -> %d frames (Tout_max %d)" % (B, T1, D, tout, out.shape[1]),
+            "ms_per_call": ms, "algorithmic_bytes": by, "bytes_incl_padded_rows": padded,
+            "achieved_gbs": by / ms / 1e6, "achieved_gbs_incl_padded_rows": padded / ms / 1e6, "peak_gbs": peaks["hbm"],
+            "frac": by / ms / 1e6 / peaks["hbm"], "frac_incl_padded_rows": padded / ms / 1e6 / peaks["hbm"],
+            "note": "the call includes the plan kernel, the Tout read-back and the output allocation (the reference's "
+                    "contract: the padded length is data dependent); bytes per SURVEY.md 8d, rows up to max_b Tout_b are "
+                    "written as padding (pad_list)"}
+
+
+# ------------------------------------------------------------------------------------------------
 def run_ours(args, rank, local_rank, world):
     import torch.distributed as dist
     import efficient_tts_b200 as E
+    from efficient_tts_b200.data_parallel import DataParallelForward, combine_loss_partials
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py measures the CUDA path; no CUDA device is visible (no CPU fallback)")
     torch.cuda.set_device(local_rank)
@@ -192,6 +296,14 @@ def run_ours(args, rank, local_rank, world):
     text, tl, speech, sl = (t.to(dev) for t in host)
     frames = int(host[3].sum())
     B, T1p, T2p = text.shape[0], text.shape[1], speech.shape[1]
+    dp = DataParallelForward(model.forward_shard) if world > 1 else None
+
+    def step(a=text, b=tl, c=speech, d=sl):
+        """One step, nothing read back: the forward over this rank's 256 utterances and, at N > 1, the all-reduce
+        of the loss partial sums / error bits that turns the shards into the B = 256 N forward of C4."""
+        if dp is None:
+            return eng.forward(a, b, c, d)
+        return dp.launch_local(a, b, c, d)
 
     def barrier():
         if world > 1:
@@ -200,16 +312,16 @@ def run_ours(args, rank, local_rank, world):
 
     # ---- device-resident throughput (value) ---------------------------------------------------
     for _ in range(max(args.warmup, 3)):
-        eng.forward(text, tl, speech, sl)
+        step()
     barrier()
     # one untimed profiled pass creates every CUDA event the per-kernel breakdown needs; the timed pass reuses them
     eng.profile_enable(0x1FFF)
     for _ in range(args.steps):
-        eng.forward(text, tl, speech, sl)
+        step()
     barrier()
     t_host0 = time.perf_counter()                # host cost of enqueueing one step (launch queue empty: 2 steps fit)
     for _ in range(2):
-        eng.forward(text, tl, speech, sl)
+        step()
     host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / 2
     barrier()
     sampler = ClockSampler(physical_gpu_index(local_rank))
@@ -220,12 +332,13 @@ def run_ours(args, rank, local_rank, world):
     barrier()
     ev0.record()
     for _ in range(args.steps):
-        out = eng.forward(text, tl, speech, sl)
+        out = step()
     ev1.record()
     barrier()
     ms_sampled = ev0.elapsed_time(ev1)
     launches = eng.launch_count() - launches0
     prof = {tag: eng.profile_read(tag) for tag in range(13)}
+    dec_kernel = eng.profile_kernel_name(2)
     eng.profile_enable(0)
     clocks = sampler.stop()
     # The same K steps once more, immediately, without the NVML sampler thread: on some boxes every NVML query
@@ -236,7 +349,7 @@ def run_ours(args, rank, local_rank, world):
     ev4, ev5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev4.record()
     for _ in range(args.steps):
-        out = eng.forward(text, tl, speech, sl)
+        out = step()
     ev5.record()
     barrier()
     ms_unsampled = ev4.elapsed_time(ev5)
@@ -248,13 +361,30 @@ def run_ours(args, rank, local_rank, world):
               "reported": "unsampled pass (NVML queries took %.1f ms each and stalled the sampled pass; clocks are "
                           "from the sampled pass of the same K steps run immediately before)" % clocks["nvml_ms_per_query"]
               if use_unsampled else "clock-sampled pass"}
+    dp_check = None
+    if dp is not None:
+        # the reduced loss of the last timed step, and -- on rank 0 -- the same B = 256 N batch run shard by shard in
+        # ONE process: the two must agree (the all-reduce really produced the loss of the whole C4 batch)
+        loss_dp, stats_dp = dp.finish(out[3])
+        if rank == 0:
+            acc = np.zeros(4, dtype=np.float64)
+            for r in range(world):
+                a1, a2 = wl.config_lengths("C3", seed=r)
+                sh = [t.to(dev) for t in wl.make_forward_inputs(r, a1, a2)]
+                acc += eng.forward(*sh)[3][3:7].double().cpu().numpy()
+            loss_1p = combine_loss_partials(acc)[0]
+            dp_check = {"loss_all_reduced": loss_dp, "loss_single_process_B%d" % (B * world): loss_1p,
+                        "rel_diff": abs(loss_dp - loss_1p) / abs(loss_1p)}
+            assert dp_check["rel_diff"] <= 1e-5, dp_check
 
     # ---- end to end through the public API: pinned host inputs -> H2D -> forward -> stats read-back.
     # Like a prefetching loader (the reference trains with pin_memory + non_blocking copies), the copy of
     # step i + 1 is issued on a second stream while step i computes; every step's inputs cross PCIe inside
-    # the timed region and every step ends with the host reading its loss statistics.
+    # the timed region and every step ends with the host reading its loss statistics.  A second variant also brings
+    # mel_pred back to pinned host memory every step (what the reference's _eval_step plots, trainers/...:218).
     copy_stream = torch.cuda.Stream(dev)
     dbuf = [[torch.empty_like(t, device=dev) for t in host] for _ in range(2)]
+    mel_host = [torch.empty(B, T2p, wl.ODIM, dtype=torch.float32).pin_memory() for _ in range(2)]
 
     def issue_copy(slot):
         with torch.cuda.stream(copy_stream):
@@ -264,34 +394,61 @@ def run_ours(args, rank, local_rank, world):
             ev.record(copy_stream)
         return ev
 
-    def e2e_run(n):
+    def e2e_run(n, mel_back):
         stats = None
         ready = issue_copy(0)
+        pending = None
         for i in range(n):
             torch.cuda.current_stream(dev).wait_event(ready)
             d = dbuf[i % 2]
             if i + 1 < n:
                 ready = issue_copy((i + 1) % 2)      # slot (i+1)%2 was released by step i-1's read-back
-            loss, stats, imv, ra, mel, _ = model(text=d[0], text_lengths=d[1], speech=d[2], speech_lengths=d[3])
+            if dp is None:
+                loss, stats, imv, ra, mel, _ = model(text=d[0], text_lengths=d[1], speech=d[2], speech_lengths=d[3])
+            else:
+                imv, ra, mel, part = dp.launch_local(d[0], d[1], d[2], d[3])
+                loss, stats = dp.finish(part)
+            if mel_back:
+                # D2H of this step's mel_pred on the copy stream, overlapping the next step's compute
+                done = torch.cuda.Event()
+                done.record(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(done)
+                    mel_host[i % 2].copy_(mel, non_blocking=True)
+                    mel.record_stream(copy_stream)
+                    fin = torch.cuda.Event()
+                    fin.record(copy_stream)
+                if pending is not None:
+                    pending.synchronize()            # the previous step's mel is on the host
+                pending = fin
+        if pending is not None:
+            pending.synchronize()
         return stats
-    e2e_run(2)
-    barrier()
-    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev2.record()
-    stats = e2e_run(args.steps)
-    ev3.record()
-    barrier()
-    ms_e2e = ev2.elapsed_time(ev3)
+    e2e_ms = {}
+    for mel_back in (False, True):
+        e2e_run(2, mel_back)
+        barrier()
+        ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev2.record()
+        stats = e2e_run(args.steps, mel_back)
+        ev3.record()
+        barrier()
+        e2e_ms[mel_back] = ev2.elapsed_time(ev3)
     h2d = sum(t.numel() * t.element_size() for t in host)
-    d2h = 8 * 4
+    mel_bytes = B * T2p * wl.ODIM * 4
 
     # ---- max over ranks, totals -----------------------------------------------------------------
-    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, e2e_ms[False], e2e_ms[True]], dtype=torch.float64, device=dev)
     tot = torch.tensor([float(frames)], dtype=torch.float64, device=dev)
+    per_rank = None
     if world > 1:
+        mine = torch.tensor([ms / args.steps, clocks.get("sm_mhz") or 0.0], dtype=torch.float64, device=dev)
+        gathered = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine)
+        per_rank = {"ms_per_step": [float(g[0]) for g in gathered], "sm_mhz": [float(g[1]) for g in gathered]}
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    ms, ms_e2e = (float(v) for v in t.tolist())
+    ms, ms_e2e, ms_e2e_mel = (float(v) for v in t.tolist())
     total_frames = float(tot.item())
     value = total_frames * args.steps / (ms * 1e-3)
     e2e_value = total_frames * args.steps / (ms_e2e * 1e-3)
@@ -306,30 +463,26 @@ def run_ours(args, rank, local_rank, world):
         rows = np.mean([computed_rows(t2, T2p, 2 * (n_dec - 1 - l)) for l in range(n_dec)])
         flops_per_launch = 2.0 * rows * 512 * 512 * 5
         ach = flops_per_launch / (dec_ms / max(dec_n, 1) * 1e-3) / 1e12 if dec_n else None
-        traffic, pipe_ncu, rec_traffic = None, None, None
-        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-        if os.path.exists(tp):
-            try:
-                tj = json.load(open(tp))
-                traffic = tj.get("decoder_conv_dram_bytes_per_launch")
-                pipe_ncu = tj.get("decoder_conv_tensor_pipe_active_pct")
-                rec_traffic = tj.get("reconstruct_dram_bytes_per_launch")
-            except Exception:
-                traffic = None
-        roof = {"bound": "tensor", "kernel": "gemm2_kernel<2,0,0,1> (CTA-pair tcgen05 tap-GEMM, fused-B) on the decoder Conv1d layers (k=5, 512->512)",
+        cap, why = committed_profile(eng, dec_kernel)
+        roof = {"bound": "tensor",
+                "kernel": "%s (CTA-pair tcgen05 tap-GEMM, fused-B) on the decoder Conv1d layers (k=5, 512->512)" % dec_kernel,
                 "achieved": ach, "peak": peaks["tf"], "unit": "TFLOP/s", "frac": (ach / peaks["tf"]) if ach else None,
-                "traffic": traffic, "tensor_pipe_active_pct_ncu": pipe_ncu, "peak_source": peaks["src"], "passes": 3,
+                "traffic": cap.get("dram_bytes") if cap else None,
+                "tensor_pipe_active_pct_ncu": cap.get("tensor_pipe_active_pct") if cap else None,
+                "ncu_duration_ms": cap.get("duration_ms") if cap else None,
+                "ncu_source": cap.get("source") if cap else why,
+                "library_source_sha16": library_source_sha(eng),
+                "peak_source": peaks["src"], "passes": 3,
                 "executed_frac": (3 * ach / peaks["tf"]) if ach else None,
                 "flops_per_launch": flops_per_launch, "launches_timed": dec_n,
                 "avg_launch_ms": dec_ms / max(dec_n, 1),
                 "share_of_step": dec_ms / ms if ms else None,
+                "algorithmic_bytes_per_launch": 8.0 * rows * 512,
                 "note": "achieved = single-pass algorithmic FLOPs; the split-fp16 scheme executes 3 tensor passes "
-                        "(executed_frac = 3 x frac, against the power-capped cuBLAS bf16 rate)"}
-        names = ["text_conv", "mel_conv", "dec_conv", "linear", "energy_gemm", "softmax_expect", "imv_scan",
-                 "aligned_pos", "reconstruct", "expand_gemm", "duration", "loss", "embed_split"]
-        breakdown = {names[k]: round(v[0] / args.steps, 4) for k, v in prof.items()}
-        # IMV (HBM-bound) kernels: algorithmic bytes per forward against measured HBM peak.
-        # The token softmax is fused into the energy GEMM epilogue (16 B per row and column tile reach memory).
+                        "(executed_frac = 3 x frac, against the power-capped cuBLAS bf16 rate); algorithmic bytes = "
+                        "read 4 B + write 4 B per element of the computed rows"}
+        breakdown = {TAGS[k]: round(v[0] / args.steps, 4) for k, v in prof.items()}
+        # IMV (HBM-bound) kernels: algorithmic bytes per forward against the measured HBM peak, two definitions.
         m2, m1r = B * T2p, B * T1p
         live2 = float(sum(t2))
         n_part = -(-round8(T1p) // 128)
@@ -339,130 +492,76 @@ def run_ours(args, rank, local_rank, world):
         imv_bytes = scan_bytes + aligned_bytes + recon_bytes
         imv_ms = sum(prof[k][0] for k in (5, 6, 7, 8)) / args.steps
         rec_ms = prof[8][0] / args.steps
-        hbm = {"kernels": "imv_scan_block + aligned_positions_block + reconstruct_alignment_rows", "bytes_per_step": imv_bytes,
+        rcap, rwhy = committed_profile(eng, "reconstruct_alignment_rows_kernel")
+        # fused minimum of the whole block = 4 [B T2 D (mel_h) + 2 B T1 D (key, value) + B T2 (imv)
+        # + B T1 (e) + B T1 T2 (reconst_alpha) + B T2 D (expanded)], padded sizes, over energy + scan + aligned
+        # positions + reconstruction + expansion
+        block_bytes = 4.0 * (m2 * 512 + 2 * m1r * 512 + m2 + m1r + B * T1p * T2p + m2 * 512)
+        block_ms = sum(prof[k][0] for k in (4, 5, 6, 7, 8, 9)) / args.steps
+        hbm = {"definition": "per-kernel bytes actually required by the three streaming kernels (partials in, imv / e / "
+                             "reconst_alpha + operand planes out)",
+               "kernels": "imv_scan_block + aligned_positions_block + reconstruct_alignment_rows", "bytes_per_step": imv_bytes,
                "ms_per_step": imv_ms, "achieved_gbs": imv_bytes / (imv_ms * 1e-3) / 1e9 if imv_ms else None,
                "peak_gbs": peaks["hbm"], "frac": (imv_bytes / (imv_ms * 1e-3) / 1e9 / peaks["hbm"]) if imv_ms else None,
                "note": "scan and aligned positions move ~11 MB and are latency / exp-throughput bound; the HBM-bound "
                        "kernel of the chain is the Gaussian reconstruction (97 % of the bytes)",
-               "reconstruct": {"bytes": recon_bytes, "ms": rec_ms, "traffic": rec_traffic,
+               "reconstruct": {"bytes": recon_bytes, "ms": rec_ms, "traffic": rcap.get("dram_bytes") if rcap else None,
+                               "ncu_source": rcap.get("source") if rcap else rwhy,
                                "achieved_gbs": recon_bytes / (rec_ms * 1e-3) / 1e9 if rec_ms else None,
-                               "frac": (recon_bytes / (rec_ms * 1e-3) / 1e9 / peaks["hbm"]) if rec_ms else None}}
+                               "frac": (recon_bytes / (rec_ms * 1e-3) / 1e9 / peaks["hbm"]) if rec_ms else None,
+                               "frac_of_8tbs_nominal": (recon_bytes / (rec_ms * 1e-3) / 1e9 / 8000.0) if rec_ms else None},
+               "block_survey_8d": {"definition": "SURVEY.md 8d fused-minimum bytes of the whole alignment block (padded sizes) "
+                                                 "over energy GEMM + scan + aligned positions + reconstruction + expansion GEMM",
+                                   "bytes": block_bytes, "ms": block_ms,
+                                   "achieved_gbs": block_bytes / (block_ms * 1e-3) / 1e9 if block_ms else None,
+                                   "frac": (block_bytes / (block_ms * 1e-3) / 1e9 / peaks["hbm"]) if block_ms else None,
+                                   "frac_of_8tbs_nominal": (block_bytes / (block_ms * 1e-3) / 1e9 / 8000.0) if block_ms else None}}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "dtype_note": "fp32 in/out; split-fp16 (hi/lo) tensor-core operands, fp32 accumulation",
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "utterances_per_gpu": B, "valid_frames_per_gpu": frames,
                            "padded": [T1p, T2p], "l2": "working set per step ~3.3 GB >> 126 MB L2 (no flush needed)",
-                           "parallelism": "dp%d (utterance shards, no data-path collective)" % world},
+                           "parallelism": ("dp%d: utterance shards (C3 draw of seed r on rank r = C4), one NCCL all-reduce of "
+                                           "the loss partial sums + error bits per step inside the timed region" % world)
+                           if world > 1 else "dp1 (single GPU, no collective)"},
                 "padded_frames_per_s": float(B * T2p) * world * args.steps / (ms * 1e-3),
                 "clocks": clocks, "timing": timing, "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms,
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8 * 4,
                         "ms_per_step": ms_e2e / args.steps, "stats": stats,
-                        "pipeline": "H2D of step i+1 on a copy stream overlaps step i; loss read back every step"},
+                        "outputs": "loss statistics read back every step (what the reference's _train_step consumes); "
+                                   "imv / reconst_alpha / mel_pred stay device-resident",
+                        "pipeline": "H2D of step i+1 on a copy stream overlaps step i; loss read back every step",
+                        "with_mel_pred_d2h": {"value": total_frames * args.steps / (ms_e2e_mel * 1e-3), "unit": UNIT,
+                                              "ms_per_step": ms_e2e_mel / args.steps,
+                                              "d2h_bytes_per_step": 8 * 4 + mel_bytes,
+                                              "note": "additionally copies mel_pred to pinned host memory every step on the "
+                                                      "copy stream (what _eval_step plots, trainers/efficient_tts_trainer.py:218)"}},
                 "roofline": roof, "roofline_hbm_imv": hbm, "kernel_ms_per_step": breakdown}
-    # ---- extras on rank 0 at N = 1: RTF at batch 1 (C1) and the CPU baseline ----------------------
+        if per_rank is not None:
+            line["per_rank"] = per_rank
+            line["data_parallel_check"] = dp_check
+    # ---- extras on rank 0 at N = 1: other configs, RTF at batch 1 (C1), vocoder, CPU baselines -------------------
     if rank == 0 and world == 1:
         try:
-            mc1 = E.EfficientTTSCNN(**wl.MODEL_KWARGS)
-            mc1.load_state_dict(wl.c1_weights_patch(state))
-            mc1 = mc1.eval().to(dev)
-            txt = wl.make_inference_inputs(0, 64).to(dev)
-            for _ in range(3):
-                mel, _ = mc1.inference(txt)
-            torch.cuda.synchronize(dev)
-            t0 = time.perf_counter()
-            n = 20
-            for _ in range(n):
-                mel, _ = mc1.inference(txt)
-            torch.cuda.synchronize(dev)
-            dt = (time.perf_counter() - t0) / n
-            line["rtf_batch1"] = {"config": "C1: inference, B=1, 64 phonemes -> %d frames" % mel.shape[1],
-                                  "ms": dt * 1e3, "rtf_mel_only": dt / (mel.shape[1] * 256 / 22050.0),
-                                  "frames_per_s": mel.shape[1] / dt,
-                                  "note": "mel-only RTF; the reference's RTF also includes HiFi-GAN (bin/inference.py:100-111)"}
-            # batched variable-length synthesis: 64 utterances of 32-64 tokens in one call
-            g = torch.Generator().manual_seed(7)
-            lens = torch.randint(32, 65, (64,), generator=g)
-            btxt = torch.randint(0, wl.NUM_SYMBOLS, (64, 64), generator=g).to(dev)
-            for _ in range(2):
-                bmel, blen, _ = mc1.inference_batch(btxt, lens.to(dev))
-            torch.cuda.synchronize(dev)
-            t0 = time.perf_counter()
-            n = 10
-            for _ in range(n):
-                bmel, blen, _ = mc1.inference_batch(btxt, lens.to(dev))
-            torch.cuda.synchronize(dev)
-            dt = (time.perf_counter() - t0) / n
-            line["inference_batch64"] = {"config": "inference_batch, 64 utterances x 32-64 tokens -> %d frames" % int(blen.sum()),
-                                         "ms": dt * 1e3, "frames_per_s": float(blen.sum()) / dt,
-                                         "rtf_mel_only": dt / (float(blen.sum()) * 256 / 22050.0)}
-            # the step right after the path: HiFi-GAN V1 generator, and the text -> waveform RTF
-            # the reference defines (bin/inference.py:100-111 times inference + vocoder)
-            from efficient_tts_b200.vocoder import Generator
-            voc = Generator(wl.AttrDict(wl.HIFIGAN_V1))
-            voc.load_state_dict(wl.vocoder_state_dict())
-            voc = voc.eval().to(dev)
-            vmel = wl.make_mel(1, 16, 800).to(dev)
-            for _ in range(2):
-                wav = voc(vmel)
-            torch.cuda.synchronize(dev)
-            t0 = time.perf_counter()
-            n = 5
-            for _ in range(n):
-                wav = voc(vmel)
-            torch.cuda.synchronize(dev)
-            dt = (time.perf_counter() - t0) / n
-            vline = {"config": "HiFi-GAN V1 generator, 16 x 800 frames -> %d samples" % wav.numel(),
-                     "ms": dt * 1e3, "samples_per_s": wav.numel() / dt, "rtf": dt / (wav.numel() / 22050.0)}
-            vfl = vocoder_flops(wl.HIFIGAN_V1, 16, 800)
-            vpk = load_peaks()
-            vline["roofline"] = {"bound": "tensor", "achieved": vfl / dt / 1e12, "peak": vpk["tf"], "unit": "TFLOP/s",
-                                 "frac": vfl / dt / 1e12 / vpk["tf"], "flops_per_call": vfl, "passes": 3,
-                                 "note": "single-pass algorithmic FLOPs of the 78 convolutions over the whole forward "
-                                         "(2 * Cin * Cout * k per output sample; transposed convs 2 * Cin * Cout * k per "
-                                         "input sample); the split-fp16 scheme executes 3 passes"}
-
-            def tts():
-                m_, _ = mc1.inference(txt)
-                return voc(m_.transpose(1, 2))
-            for _ in range(3):
-                wav = tts()
-            torch.cuda.synchronize(dev)
-            t0 = time.perf_counter()
-            n = 20
-            for _ in range(n):
-                wav = tts()
-            torch.cuda.synchronize(dev)
-            dt = (time.perf_counter() - t0) / n
-            vline["text_to_wave_c1"] = {"config": "inference(64 phonemes) + generator, B=1 -> %d samples" % wav.shape[-1],
-                                        "ms": dt * 1e3, "rtf": dt / (wav.shape[-1] / 22050.0)}
-            if not args.no_cpu_baseline:
-                from oracle import hifigan_oracle as hor
-                torch.set_num_threads(os.cpu_count() or 1)
-                cmel = wl.make_mel(2, 1, 64)
-                cw = wl.vocoder_state_dict()
-                with torch.no_grad():
-                    hor.generator_forward(cw, cmel)
-                    t0 = time.perf_counter()
-                    cy = hor.generator_forward(cw, cmel)
-                    cdt = time.perf_counter() - t0
-                vline["cpu_baseline"] = {"value": cy.numel() / cdt, "unit": "samples/s", "cores": os.cpu_count() or 1,
-                                         "kind": "port", "sample": "B=1 x 64 frames (16 384 samples), 1 pass",
-                                         "rtf": cdt / (cy.numel() / 22050.0)}
-            line["vocoder"] = vline
-            del voc
-            del mc1
+            line["other_configs"] = {"C2": time_forward_config(eng, dev, "C2"), "C5": time_forward_config(eng, dev, "C5")}
+            line["length_regulator"] = time_length_regulator(dev, load_peaks())
+        except Exception as exc:
+            line["other_configs"] = {"error": str(exc)[:200]}
+        try:
+            extras_c1_and_vocoder(line, E, state, dev, args)
         except Exception as exc:  # the headline line must still print
             line["rtf_batch1"] = {"error": str(exc)[:200]}
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            fps, dt, desc = cpu_reference_forward(state, args.cpu_sample, 0, 1, 1, threads)
+            sample = None if args.cpu_sample in (0, 256) else args.cpu_sample
+            fps, dt, desc = cpu_reference_forward(state, "C3", sample, 0, 1, 1, threads)
             line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc,
                                     "seconds_per_sample": dt}
             try:
                 # the reference's recipes pin OMP_NUM_THREADS=1 (egs/lj/path.sh:13, distributed/launch.py:84-85):
-                # the same CPU path on one thread, on a quarter of the sample; and its B = 1 synthesis latency (C1)
-                fps1, dt1, desc1 = cpu_reference_forward(state, max(2, args.cpu_sample // 4), 0, 1, 0, 1)
+                # the same CPU path on one thread, on an 8-utterance draw; and its B = 1 synthesis latency (C1)
+                fps1, dt1, desc1 = cpu_reference_forward(state, "C3", 8, 0, 1, 0, 1)
                 line["cpu_baseline"]["one_thread"] = {"value": fps1, "sample": desc1, "seconds_per_sample": dt1}
                 from oracle import efts_oracle as orc
                 torch.set_num_threads(threads)
@@ -488,6 +587,81 @@ def run_ours(args, rank, local_rank, world):
     return 0
 
 
+def extras_c1_and_vocoder(line, E, state, dev, args):
+    """RTF at batch 1 (C1), batched synthesis, the HiFi-GAN generator and text -> waveform (rank 0, N = 1)."""
+    def wall(fn, n, warm=3):
+        for _ in range(warm):
+            r = fn()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(n):
+            r = fn()
+        torch.cuda.synchronize(dev)
+        return (time.perf_counter() - t0) / n, r
+
+    mc1 = E.EfficientTTSCNN(**wl.MODEL_KWARGS)
+    mc1.load_state_dict(wl.c1_weights_patch(state))
+    mc1 = mc1.eval().to(dev)
+    eng1 = mc1._get_engine()
+    txt = wl.make_inference_inputs(0, 64).to(dev)
+    n0 = eng1.launch_count()
+    mc1.inference(txt)
+    c1_launches = eng1.launch_count() - n0
+    dt, (mel, _) = wall(lambda: mc1.inference(txt), 50)
+    line["rtf_batch1"] = {"config": "C1: inference, B=1, 64 phonemes -> %d frames" % mel.shape[1],
+                          "ms": dt * 1e3, "rtf_mel_only": dt / (mel.shape[1] * 256 / 22050.0),
+                          "frames_per_s": mel.shape[1] / dt, "gpu_launches_per_call": c1_launches,
+                          "path": "resident layer-stack kernels (stack_sm100.cuh): phase 1, reconstruct, expand, phase 2",
+                          "note": "wall time of the public call incl. the T2 read-back and the trailing error-flag read; "
+                                  "mel-only RTF; the reference's RTF also includes HiFi-GAN (bin/inference.py:100-111)"}
+    eng1.set_option("stack", 0)
+    dt_pl, _ = wall(lambda: mc1.inference(txt), 30)
+    eng1.set_option("stack", 1)
+    line["rtf_batch1"]["ms_one_launch_per_layer"] = dt_pl * 1e3
+    # batched variable-length synthesis (SURVEY.md 8f-1): 64 utterances of 32-64 tokens in one call
+    g = torch.Generator().manual_seed(7)
+    lens = torch.randint(32, 65, (64,), generator=g).to(dev)
+    btxt = torch.randint(0, wl.NUM_SYMBOLS, (64, 64), generator=g).to(dev)
+    dt, (bmel, blen, _) = wall(lambda: mc1.inference_batch(btxt, lens), 10, 2)
+    line["inference_batch64"] = {"config": "inference_batch, 64 utterances x 32-64 tokens -> %d frames" % int(blen.sum()),
+                                 "ms": dt * 1e3, "frames_per_s": float(blen.sum()) / dt,
+                                 "rtf_mel_only": dt / (float(blen.sum()) * 256 / 22050.0)}
+    # the step right after the path (SURVEY.md 8f-2): HiFi-GAN V1 generator, and the text -> waveform RTF
+    # the reference defines (bin/inference.py:100-111 times inference + vocoder)
+    from efficient_tts_b200.vocoder import Generator
+    voc = Generator(wl.AttrDict(wl.HIFIGAN_V1))
+    voc.load_state_dict(wl.vocoder_state_dict())
+    voc = voc.eval().to(dev)
+    vmel = wl.make_mel(1, 16, 800).to(dev)
+    dt, wav = wall(lambda: voc(vmel), 5, 2)
+    vline = {"config": "HiFi-GAN V1 generator, 16 x 800 frames -> %d samples" % wav.numel(),
+             "ms": dt * 1e3, "samples_per_s": wav.numel() / dt, "rtf": dt / (wav.numel() / 22050.0)}
+    vfl = vocoder_flops(wl.HIFIGAN_V1, 16, 800)
+    vpk = load_peaks()
+    vline["roofline"] = {"bound": "tensor", "achieved": vfl / dt / 1e12, "peak": vpk["tf"], "unit": "TFLOP/s",
+                         "frac": vfl / dt / 1e12 / vpk["tf"], "flops_per_call": vfl, "passes": 3,
+                         "note": "single-pass algorithmic FLOPs of the 78 convolutions over the whole forward "
+                                 "(2 * Cin * Cout * k per output sample; transposed convs 2 * Cin * Cout * k per "
+                                 "input sample); the split-fp16 scheme executes 3 passes"}
+    dt, wav1 = wall(lambda: voc(mc1.inference(txt)[0].transpose(1, 2)), 20)
+    vline["text_to_wave_c1"] = {"config": "inference(64 phonemes) + generator, B=1 -> %d samples" % wav1.shape[-1],
+                                "ms": dt * 1e3, "rtf": dt / (wav1.shape[-1] / 22050.0)}
+    if not args.no_cpu_baseline:
+        from oracle import hifigan_oracle as hor
+        torch.set_num_threads(os.cpu_count() or 1)
+        cmel = wl.make_mel(1, 16, 800)             # the same 16 x 800 frames the GPU arm runs
+        cw = wl.vocoder_state_dict()
+        with torch.no_grad():
+            hor.generator_forward(cw, cmel[:1, :, :64])
+            t0 = time.perf_counter()
+            cy = hor.generator_forward(cw, cmel)
+            cdt = time.perf_counter() - t0
+        vline["cpu_baseline"] = {"value": cy.numel() / cdt, "unit": "samples/s", "cores": os.cpu_count() or 1,
+                                 "kind": "port", "sample": "the same 16 x 800 frames (%d samples), 1 pass" % cy.numel(),
+                                 "seconds": cdt, "rtf": cdt / (cy.numel() / 22050.0)}
+    line["vocoder"] = vline
+
+
 def vocoder_flops(h, batch, frames):
     """Algorithmic FLOPs of one Generator.forward (vocoders/hifigan_model.py:120-136)."""
     c = h["upsample_initial_channel"]
@@ -503,17 +677,14 @@ def vocoder_flops(h, batch, frames):
     return fl * batch
 
 
-def round8(x):
-    return (x + 7) // 8 * 8
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-sample", type=int, default=32, help="utterances in the bounded CPU sample")
+    ap.add_argument("--cpu-sample", type=int, default=256,
+                    help="utterances of the C3 draw the CPU legs run (256 = the full batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     capture_stdout()

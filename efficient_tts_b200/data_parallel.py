@@ -56,26 +56,37 @@ class DataParallelForward:
         self.shard_forward = shard_forward
         self.group = group
 
-    def __call__(self, text, text_lengths, speech, speech_lengths, gather_outputs=False):
-        rank, world = dist.get_rank(self.group), dist.get_world_size(self.group)
-        B = text.shape[0]
-        lo, hi = shard_range(B, rank, world)
-        imv, ra, mel, scal = self.shard_forward(text[lo:hi], text_lengths[lo:hi], speech[lo:hi],
-                                                speech_lengths[lo:hi])
-        # one collective for everything that crosses shards: the four loss partial sums and, as 0/1 counters, the
-        # error bits a single-process forward() raises on (bit 2 token id, bit 3 fp16 operand range, bit 4 length
-        # outside the padded dims) -- a rank that hit one must stop every rank, not just itself
+    def launch_local(self, text, text_lengths, speech, speech_lengths):
+        """This rank's shard (tensors with the GLOBAL padded dims) -> ``(imv, reconst_alpha, mel_pred, part)``, all on
+        the device and nothing read back: ``part`` is the all-reduced vector (sum_sq, n_mel, sum_abs, n_tok, bit
+        counters).  One collective for everything that crosses shards: the four loss partial sums and, as 0/1
+        counters, the error bits a single-process forward() raises on (bit 2 token id, bit 3 fp16 operand range,
+        bit 4 length outside the padded dims) -- a rank that hit one must stop every rank, not just itself."""
+        imv, ra, mel, scal = self.shard_forward(text, text_lengths, speech, speech_lengths)
         flags = scal[7].to(torch.int32)
         bits = torch.stack([(flags >> k) & 1 for k in ERROR_BITS]).to(scal.dtype)
-        part = torch.cat([scal[3:7], bits])             # sum_sq, n_mel, sum_abs, n_tok, bit counters
+        part = torch.cat([scal[3:7], bits])
         dist.all_reduce(part, op=dist.ReduceOp.SUM, group=self.group)
+        return imv, ra, mel, part
+
+    @staticmethod
+    def finish(part):
+        """Host side of ``launch_local``: reads the reduced vector (the reference's ``.item()`` on the loss), raises
+        what ``forward()`` raises, returns ``(loss, stats)`` of the whole batch."""
         host = part.tolist()
         raised = sum((1 << k) for k, n in zip(ERROR_BITS, host[4:]) if n > 0)
         if raised:
             from .models import raise_on_flags
             raise_on_flags(raised)
         loss, mel_loss, dur_loss = combine_loss_partials(host[:4])
-        stats = dict(loss=loss, mel_loss=mel_loss, duration_loss=dur_loss)
+        return loss, dict(loss=loss, mel_loss=mel_loss, duration_loss=dur_loss)
+
+    def __call__(self, text, text_lengths, speech, speech_lengths, gather_outputs=False):
+        rank, world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        B = text.shape[0]
+        lo, hi = shard_range(B, rank, world)
+        imv, ra, mel, part = self.launch_local(text[lo:hi], text_lengths[lo:hi], speech[lo:hi], speech_lengths[lo:hi])
+        loss, stats = self.finish(part)
         if gather_outputs:
             sizes = [shard_range(B, r, world)[1] - shard_range(B, r, world)[0] for r in range(world)]
             imv = all_gather_rows(imv, sizes, self.group)
