@@ -229,6 +229,18 @@ int efts_vocoder_forward(efts_ctx* ctx, const float* mel, int32_t B, int32_t T, 
 int efts_host_map_transposed(const float* w, int32_t Cin, int32_t Cout, int32_t k, int32_t u, float* out);
 int efts_host_map_grouped(const float* w, int32_t C, int32_t k, int32_t d, int32_t G, float* out, int32_t* taps);
 
+/* ---- data parallelism ----
+ * The survey's sketch of this ABI listed efts_dp_init / efts_dp_allgather / efts_dp_allreduce_loss.  They are
+ * deliberately NOT exported: the reference's only parallelism is torch DDP with a DistributedSampler
+ * (bin/train.py:64-68,136-150,210-216) -- the process group, its NCCL communicator and its streams belong to
+ * torch.distributed in the reference and in every caller of this library, and a second communicator owned by this
+ * library would have to be bootstrapped out of band and ordered against torch's.  What the library provides for a
+ * shard is everything the exchange needs, device-resident and without a read-back: efts_forward returns the four
+ * loss partial sums and the error bits in scalars[3..7], and a shard is called with the GLOBAL padded (T1, T2) so
+ * per-utterance outputs are bitwise independent of the shard count.  The exchange itself -- ONE all-reduce of a
+ * 7-float vector per step, optionally an all-gather of the outputs -- is efficient_tts_b200/data_parallel.py on the
+ * caller's process group (NCCL over NVLink; gloo in the CPU tests).  bench.py times it inside the step at N > 1. */
+
 /* ---- introspection ---- */
 /* Tuning / test switches, all of which keep results within the parity budget (most are bitwise neutral):
  * "skip_pad_tiles" (0/1: skip row tiles that cannot reach a valid output), "pair" (CTA pairs for the weight GEMMs),
