@@ -271,6 +271,38 @@ def time_length_regulator(dev, peaks):
                     "written as padding (pad_list)"}
 
 
+def time_frontend(dev, peaks):
+    """Log-mel front-end (datasets/meldataset.py:49-82) on the audio of a C3 batch: 256 utterances
+    of 300-1200 frames (76 800 - 307 200 samples), one batched call."""
+    from efficient_tts_b200.frontend import LogMelFrontend
+    t1, t2 = wl.config_lengths("C3", seed=0)
+    lengths = [f * 256 for f in t2]
+    g = torch.Generator().manual_seed(9)
+    audio = (torch.rand(len(t2), max(lengths), generator=g) * 2 - 1) * 0.5
+    lens = torch.tensor(lengths)
+    audio = (audio * (torch.arange(max(lengths))[None] < lens[:, None])).to(dev)
+    lens = lens.to(dev)
+    fe = LogMelFrontend(dev)
+    for _ in range(3):
+        fe(audio, lens)
+    n0 = fe.launch_count()
+    ms = cuda_timed(lambda: fe(audio, lens, check=False), 10, dev)
+    launches = (fe.launch_count() - n0) // 10
+    frames = int(sum(t2))
+    rows = len(t2) * (max(t2) + 3)                       # chunk-matrix rows the STFT GEMM computes (padded batch)
+    flops = 2.0 * rows * 1024 * 1024 + 2.0 * len(t2) * max(t2) * 520 * 80
+    by = 4.0 * sum(lengths) + 4.0 * 80 * frames         # audio in, log-mel out
+    return {"config": "mel_spectrogram (n_fft 1024, hop 256, 80 mels) on a C3 batch: %d utterances, %d valid frames, "
+                      "%.1f M samples" % (len(t2), frames, sum(lengths) / 1e6),
+            "ms_per_call": ms, "valid_frames_per_s": frames / (ms * 1e-3), "gpu_launches_per_call": launches,
+            "algorithmic_tflops": flops / (ms * 1e-3) / 1e12, "frac_of_tensor_peak": flops / (ms * 1e-3) / 1e12 / peaks["tf"],
+            "executed_frac": 3 * flops / (ms * 1e-3) / 1e12 / peaks["tf"],
+            "io_bytes": by, "io_gbs": by / ms / 1e6,
+            "note": "STFT as a 4-tap GEMM over 256-sample chunks (N = 1024 real / imaginary columns, K = 4 x 256) and the "
+                    "mel projection (K = 520, N = 80, log in the epilogue) on the tcgen05 tap-GEMM, split-fp16 x 3 passes; "
+                    "FLOPs counted on the padded batch the GEMM computes"}
+
+
 # ------------------------------------------------------------------------------------------------
 def run_ours(args, rank, local_rank, world):
     import torch.distributed as dist
@@ -546,6 +578,7 @@ def run_ours(args, rank, local_rank, world):
         try:
             line["other_configs"] = {"C2": time_forward_config(eng, dev, "C2"), "C5": time_forward_config(eng, dev, "C5")}
             line["length_regulator"] = time_length_regulator(dev, load_peaks())
+            line["frontend"] = time_frontend(dev, load_peaks())
         except Exception as exc:
             line["other_configs"] = {"error": str(exc)[:200]}
         try:

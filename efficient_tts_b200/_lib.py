@@ -29,6 +29,10 @@ class EftsVocoderConfig(ctypes.Structure):
                 ("device", c_i32)]
 
 
+class EftsFrontendConfig(ctypes.Structure):
+    _fields_ = [("n_fft", c_i32), ("hop_size", c_i32), ("win_size", c_i32), ("num_mels", c_i32), ("device", c_i32)]
+
+
 # name -> (restype, argtypes); also the export list checked by
 # tests/test_host_logic.py::test_library_builds_loads_and_exports_the_header
 SIGNATURES = {
@@ -73,6 +77,12 @@ SIGNATURES = {
     "efts_vocoder_finalize": (c_i32, [c_void_p]),
     "efts_vocoder_workspace_bytes": (c_size_t, [c_void_p, c_i32, c_i32]),
     "efts_vocoder_forward": (c_i32, [c_void_p, c_void_p, c_i32, c_i32, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "efts_frontend_create": (c_i32, [ctypes.POINTER(EftsFrontendConfig), ctypes.POINTER(c_void_p)]),
+    "efts_frontend_finalize": (c_i32, [c_void_p]),
+    "efts_frontend_frames": (c_i32, [c_void_p, c_i64]),
+    "efts_frontend_workspace_bytes": (c_size_t, [c_void_p, c_i32, c_i32]),
+    "efts_frontend_forward": (c_i32, [c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_void_p, c_void_p, c_void_p,
+                                      c_size_t, c_void_p]),
     "efts_host_map_transposed": (c_i32, [c_void_p, c_i32, c_i32, c_i32, c_i32, c_void_p]),
     "efts_host_map_grouped": (c_i32, [c_void_p, c_i32, c_i32, c_i32, c_i32, c_void_p, ctypes.POINTER(c_i32)]),
     "efts_set_option": (c_i32, [c_void_p, c_char_p, c_i32]),

@@ -507,6 +507,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
             } else if (p.act == ACT_RELU) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) vv[j] = fmaxf(vv[j], 0.0f);
+            } else if (p.act == ACT_LOGCLAMP) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) vv[j] = logf(fmaxf(vv[j], 1e-5f));
             }
             if (EPI == EPI_FULL && p.outT_hi != nullptr && row_ok && nn < p.N) {   // t-contiguous planes: thread = row
 #pragma unroll
@@ -674,6 +677,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
           } else if (p.act == ACT_RELU) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) vv[j] = fmaxf(vv[j], 0.0f);
+          } else if (p.act == ACT_LOGCLAMP) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) vv[j] = logf(fmaxf(vv[j], 1e-5f));
           }
           if (EPI == EPI_FULL && p.outT_hi != nullptr && row_ok && nn < p.N) {   // t-contiguous planes: thread = row
 #pragma unroll
@@ -732,6 +738,8 @@ __global__ void splitk_reduce_kernel(const GemmParams p, const float* __restrict
     v.z = v.z > 0.0f ? v.z : __fmul_rn(v.z, 0.1f); v.w = v.w > 0.0f ? v.w : __fmul_rn(v.w, 0.1f);
   } else if (p.act == ACT_RELU) {
     v.x = fmaxf(v.x, 0.0f); v.y = fmaxf(v.y, 0.0f); v.z = fmaxf(v.z, 0.0f); v.w = fmaxf(v.w, 0.0f);
+  } else if (p.act == ACT_LOGCLAMP) {
+    v.x = logf(fmaxf(v.x, 1e-5f)); v.y = logf(fmaxf(v.y, 1e-5f)); v.z = logf(fmaxf(v.z, 1e-5f)); v.w = logf(fmaxf(v.w, 1e-5f));
   }
   if (p.resid != nullptr) {
     const float4 r = *reinterpret_cast<const float4*>(p.resid + mr * p.ld_out + nn);

@@ -33,7 +33,8 @@ __device__ __forceinline__ bool outside_fp16_range(const float4 v) {
   return m > 0x477fe000u;   // bits of 65504.0f
 }
 
-enum GemmAct { ACT_NONE = 0, ACT_LRELU = 1, ACT_RELU = 2 };
+// ACT_LOGCLAMP: log(max(x, 1e-5)), the dynamic-range compression of the log-mel front-end (datasets/meldataset.py:29-30)
+enum GemmAct { ACT_NONE = 0, ACT_LRELU = 1, ACT_RELU = 2, ACT_LOGCLAMP = 3 };
 
 struct GemmParams {
   int B, T;              // A is [B, T, K]; one CTA tile never crosses a batch row

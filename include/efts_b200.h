@@ -229,6 +229,34 @@ int efts_vocoder_forward(efts_ctx* ctx, const float* mel, int32_t B, int32_t T, 
 int efts_host_map_transposed(const float* w, int32_t Cin, int32_t Cout, int32_t k, int32_t u, float* out);
 int efts_host_map_grouped(const float* w, int32_t C, int32_t k, int32_t d, int32_t G, float* out, int32_t* taps);
 
+/* ---- log-mel front-end: nntts.datasets.meldataset.mel_spectrogram, datasets/meldataset.py:49-82 ----
+ * reflect padding of (n_fft - hop) / 2 -> STFT (Hann window, center = False, one-sided) -> sqrt(re^2 + im^2 + 1e-9)
+ * -> mel filter bank -> log(clamp(x, 1e-5)).  The STFT runs as a tap-GEMM over hop-sized chunks of the padded
+ * waveform, the mel projection as a GEMM with the log in its epilogue, both on the tcgen05 kernel of the path.
+ * Weights (host fp32, set with efts_set_weight, then efts_frontend_finalize):
+ *   "stft.weight" [n_fft, hop, n_fft / hop] -- output column n < n_fft/2 + 1: w[s] cos(2 pi n s / n_fft) (re_n),
+ *   column n > n_fft / 2: -w[s] sin(2 pi (n - n_fft/2) s / n_fft) (im of bins 1 .. n_fft/2 - 1; im_0 and im_{n_fft/2}
+ *   vanish), with s = tap * hop + k; "stft.bias" [n_fft] zeros; "mel_basis.weight" [num_mels, round8(n_fft/2 + 1)]
+ *   (librosa.filters.mel, zero-padded columns); "mel_basis.bias" [num_mels] zeros. */
+typedef struct efts_frontend_config {
+  int32_t n_fft, hop_size, win_size, num_mels;
+  int32_t device;
+} efts_frontend_config;
+int efts_frontend_create(const efts_frontend_config* cfg, efts_ctx** out);
+int efts_frontend_finalize(efts_ctx* ctx);
+/* Frames of an utterance of `length` samples: 1 + (length + 2 * ((n_fft - hop) / 2) - n_fft) / hop (reflect padding on
+ * both sides, center = False); 0 when the padded utterance is shorter than one window. */
+int32_t efts_frontend_frames(const efts_ctx* ctx, int64_t length);
+size_t efts_frontend_workspace_bytes(const efts_ctx* ctx, int32_t B, int32_t Lmax);
+/* audio fp32 [B, Lmax] in [-1, 1]; lengths int64 [B] or NULL (all Lmax): every utterance is reflect-padded at its OWN
+ * length, exactly as if mel_spectrogram had been called on it alone (TextMelLoader.get_mel, datasets/taco2_data.py:
+ * 72-78).  Outputs: mel fp32 [B, Tmax, num_mels] with Tmax = frames(Lmax), zero beyond each utterance's frames (the
+ * layout and padding TextMelCollate hands to the model, datasets/taco2_data.py:125-139), mel_lengths int64 [B] or
+ * NULL.  Error bits (efts_error_flags): 3 sample outside the fp16 operand range, 4 length outside [0, Lmax], 5 an
+ * utterance not longer than the reflect padding (torch raises on such input). */
+int efts_frontend_forward(efts_ctx* ctx, const float* audio, const int64_t* lengths, int32_t B, int32_t Lmax, float* mel,
+                          int64_t* mel_lengths, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- data parallelism ----
  * The survey's sketch of this ABI listed efts_dp_init / efts_dp_allgather / efts_dp_allreduce_loss.  They are
  * deliberately NOT exported: the reference's only parallelism is torch DDP with a DistributedSampler

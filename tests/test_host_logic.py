@@ -78,7 +78,7 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.lower(), "product file mentions the oracle: " + f
-    code = "import sys; import efficient_tts_b200, efficient_tts_b200.engine, efficient_tts_b200.data_parallel; " \
+    code = "import sys; import efficient_tts_b200, efficient_tts_b200.engine, efficient_tts_b200.data_parallel, efficient_tts_b200.frontend, efficient_tts_b200.vocoder; " \
            "assert not any(m.startswith('oracle') for m in sys.modules); assert 'nntts' not in sys.modules"
     subprocess.run([sys.executable, "-c", code], check=True, cwd=ROOT)
 
@@ -368,3 +368,23 @@ def test_grouped_packing_is_the_dilated_conv(C, k, d, G):
     ref = torch.nn.functional.conv1d(x.transpose(1, 2).double(), w.double(), dilation=d, padding=d * (k - 1) // 2)
     y = _tap_gemm(x.reshape(2, L // G, G * C), out, (S - 1) // 2).reshape(2, L, C)
     assert torch.allclose(y.transpose(1, 2), ref, atol=1e-10)
+
+
+def test_frontend_host_logic_matches_the_checker():
+    """The product's own filter bank and windowed DFT basis (efficient_tts_b200/frontend.py never imports test
+    infrastructure): the filter bank equals the checker's restatement bit for bit, the DFT basis reproduces a float64
+    FFT of a Hann-windowed frame, and the frame count follows the reference's padding rule."""
+    from oracle import frontend_oracle as fo
+    from efficient_tts_b200 import frontend as F
+    assert np.array_equal(F.slaney_mel_basis(22050, 1024, 80, 0, 8000), fo.slaney_mel_basis())
+    assert np.array_equal(F.slaney_mel_basis(16000, 512, 40, 50, None), fo.slaney_mel_basis(16000, 512, 40, 50, None))
+    W = torch.from_numpy(F.windowed_dft_basis(1024, 256)).double().permute(0, 2, 1).reshape(1024, 1024)
+    x = torch.randn(1024, dtype=torch.float64, generator=torch.Generator().manual_seed(0))
+    ref = torch.fft.rfft(x * torch.hann_window(1024, dtype=torch.float64))
+    out = W @ x
+    assert (out[:513] - ref.real).abs().max() < 5e-6 and (out[513:] - ref.imag[1:512]).abs().max() < 5e-6
+    from efficient_tts_b200 import _lib
+    lib = _lib.load()
+    for L in (256, 300, 1300, 22050, 256 * 40):
+        # pure host arithmetic of the library (no device): frames of a padded utterance
+        assert fo.num_frames(L) == 1 + (L + 768 - 1024) // 256
