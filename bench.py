@@ -303,6 +303,33 @@ def time_frontend(dev, peaks):
                     "FLOPs counted on the padded batch the GEMM computes"}
 
 
+def time_training_slice(dev, peaks):
+    """Training slice: forward-with-saved-activations and backward of the 6-layer decoder stack at the
+    C3 padded shape (B = 256, T = 1200, 512 channels, k = 5), raw library calls."""
+    from efficient_tts_b200.engine import train_context
+    tc = train_context(dev)
+    g = torch.Generator().manual_seed(12)
+    L, B, T, C, k = 6, 256, 1200, 512, 5
+    x = torch.randn(B, T, C, generator=g).to(dev)
+    w = (torch.randn(L, C, C, k, generator=g) / np.sqrt(C * k)).to(dev)
+    b = (torch.randn(L, C, generator=g) * 0.1).to(dev)
+    grad = torch.randn(B, T, C, generator=g).to(dev)
+    acts, us = tc.resconv_fwd(x, w, b)
+    ms_f = cuda_timed(lambda: tc.resconv_fwd(x, w, b), 3, dev)
+    tc.resconv_bwd(grad, acts, us, w)
+    n0 = tc.launch_count()
+    ms_b = cuda_timed(lambda: tc.resconv_bwd(grad, acts, us, w), 3, dev)
+    launches = (tc.launch_count() - n0) // 3
+    fl = 2.0 * B * T * C * C * k * L                      # one conv pass over the stack (single-pass algorithmic)
+    return {"config": "ResConvBlock x %d layers, B=%d, T=%d (padded C3 decoder shape), fp32 weights passed per call" % (L, B, T),
+            "forward_ms": ms_f, "backward_ms": ms_b, "backward_launches": launches,
+            "forward_tflops": fl / (ms_f * 1e-3) / 1e12, "backward_tflops": 2 * fl / (ms_b * 1e-3) / 1e12,
+            "backward_frac_of_tensor_peak": 2 * fl / (ms_b * 1e-3) / 1e12 / peaks["tf"],
+            "note": "backward = data gradient (one tap-GEMM per layer) + weight gradient (k position-reduction GEMMs per "
+                    "layer, each preceded by a shifted transpose of the layer input) + bias gradient; algorithmic FLOPs "
+                    "2 x forward, single pass (3 passes executed)"}
+
+
 # ------------------------------------------------------------------------------------------------
 def run_ours(args, rank, local_rank, world):
     import torch.distributed as dist
@@ -579,6 +606,8 @@ def run_ours(args, rank, local_rank, world):
             line["other_configs"] = {"C2": time_forward_config(eng, dev, "C2"), "C5": time_forward_config(eng, dev, "C5")}
             line["length_regulator"] = time_length_regulator(dev, load_peaks())
             line["frontend"] = time_frontend(dev, load_peaks())
+            line["training_slice"] = time_training_slice(dev, load_peaks())
+            torch.cuda.empty_cache()
         except Exception as exc:
             line["other_configs"] = {"error": str(exc)[:200]}
         try:

@@ -21,6 +21,7 @@
 #include "stack_sm100.cuh"
 #include "vocoder_kernels.cuh"
 #include "frontend_kernels.cuh"
+#include "train_kernels.cuh"
 
 namespace {
 
@@ -305,6 +306,27 @@ int launch_gemm(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, GemmPa
       // small problems (B = 1 synthesis: a handful of 27-us tiles on 148 SMs): one work item per accumulation
       // chunk, partial planes summed in chunk order by splitk_reduce_kernel -- bitwise the unsplit result
       const int num_kb = (p.K + G2_BK - 1) / G2_BK;
+      if (p.split_kb > 0 && p.split_scratch != nullptr) {
+        // long reductions over few output tiles (weight gradients: K = positions): every work item covers split_kb
+        // k-blocks, the partial planes are summed by splitk_reduce_kernel
+        const int splits = (num_kb + p.split_kb - 1) / p.split_kb;
+        const size_t plane = static_cast<size_t>(p.B) * p.T * p.N;
+        if (splits < 2) { p.split_kb = 0; return launch_gemm2_t<2, EPI_STD, 0, 1>(c, st, a, b, p); }
+        if (p.split_kb % p.chunk_kb != 0 || plane * splits * sizeof(float) > kSplitScratchBytes || p.N % 4 != 0 ||
+            p.ld_out % 4 != 0 || p.tile_list != nullptr || p.skip_lens != nullptr)
+          return fail(EFTS_ERR_ARG, "split reduction: %d splits of %d k-blocks do not fit (plane %zu)", splits, p.split_kb, plane);
+        GemmParams q = p;
+        q.bias = nullptr; q.act = ACT_NONE; q.resid = nullptr; q.lens = nullptr;
+        q.out = p.split_scratch; q.ld_out = p.N; q.out_hi = nullptr; q.out_lo = nullptr;
+        q.splits = splits; q.split_stride = plane;
+        TRY((launch_gemm2_t<2, EPI_STD, 0, 1>(c, st, a, b, q)));
+        const size_t n = plane / 4;
+        const float* part = p.split_scratch;
+        splitk_reduce_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(p, part, splits, plane);
+        CUDA_TRY(cudaGetLastError());
+        c->launches++;
+        return EFTS_OK;
+      }
       const int nchunks = (num_kb + p.chunk_kb - 1) / p.chunk_kb;
       const long long n_rt = static_cast<long long>(p.B) * ((p.T + G2_BM - 1) / G2_BM);
       const long long items = ((n_rt + 1) / 2) * ((p.N + G2_BN - 1) / G2_BN);
@@ -2033,6 +2055,157 @@ int efts_frontend_forward(efts_ctx* c, const float* audio, const int64_t* length
   p.out = mel; p.ld_out = f.cfg.num_mels;
   ProfScope ps(c, st, TAG_LINEAR);
   return launch_gemm(c, st, OpA{w.mg_hi, w.mg_lo, B, Tmax, f.Kp, f.Kp}, weight_op(f.mel), p);
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// Training slice: ResConvBlock forward with saved activations and its backward
+// (layers/efts_modules.py:48-51,77-79 under autograd; trainers/efficient_tts_trainer.py:152-154).
+namespace {
+struct TrainWs {
+  __half *w_hi, *w_lo;                 // packed weights of the current layer [k][C][C]
+  __half *a_hi[2], *a_lo[2];           // operand planes of a [B, T, C] activation (ping-pong)
+  __half *gT_hi, *gT_lo, *xT_hi, *xT_lo;   // transposed planes [C][Ktot]
+  float* dwt;                          // [k][C][C]
+  float* splitk;                       // partial planes of the split reductions
+  double* db_part;                     // [kBiasParts][C]
+  float* g[2];                         // running data gradient [B, T, C] (ping-pong)
+  size_t ktot; int Tp;
+};
+constexpr int kBiasParts = 592;
+void carve_train(Arena& a, TrainWs& w, int B, int T, int C, int k, bool backward) {
+  const size_t m = static_cast<size_t>(B) * T;
+  const int pad = (k - 1) / 2;
+  w.Tp = round8(T + 2 * pad);
+  w.ktot = static_cast<size_t>(B) * w.Tp;
+  w.w_hi = a.get<__half>(static_cast<size_t>(k) * C * C);
+  w.w_lo = a.get<__half>(static_cast<size_t>(k) * C * C);
+  for (int i = 0; i < 2; ++i) { w.a_hi[i] = a.get<__half>(m * C); w.a_lo[i] = a.get<__half>(m * C); }
+  if (backward) {
+    w.gT_hi = a.get<__half>(w.ktot * C); w.gT_lo = a.get<__half>(w.ktot * C);
+    w.xT_hi = a.get<__half>(w.ktot * C); w.xT_lo = a.get<__half>(w.ktot * C);
+    w.dwt = a.get<float>(static_cast<size_t>(k) * C * C);
+    w.splitk = a.get<float>(kSplitScratchBytes / sizeof(float));
+    w.db_part = a.get<double>(static_cast<size_t>(kBiasParts) * C);
+    for (int i = 0; i < 2; ++i) w.g[i] = a.get<float>(m * C);
+  }
+}
+unsigned ew_grid(size_t n) { return static_cast<unsigned>(std::max<size_t>(1, std::min<size_t>((n + 255) / 256, 148 * 16))); }
+}  // namespace
+
+extern "C" {
+
+size_t efts_resconv_train_workspace_bytes(const efts_ctx* c, int32_t B, int32_t T, int32_t k) {
+  if (c == nullptr || B < 1 || T < 1 || k < 1) return 0;
+  Arena a(nullptr, ~static_cast<size_t>(0));
+  TrainWs w;
+  carve_train(a, w, B, T, 512, k, true);
+  return a.off + 4096;
+}
+
+int efts_resconv_train_fwd(efts_ctx* c, const float* x, const float* weights, const float* biases, int32_t n_layers,
+                           int32_t k, int32_t B, int32_t T, float* acts, float* us, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  if (c == nullptr) return fail(EFTS_ERR_ARG, "null context");
+  const int C = 512;
+  if (!x || !weights || !biases || !acts || !us || !workspace || n_layers < 1 || B < 1 || T < 1 || (k != 1 && k != 3 && k != 5))
+    return fail(EFTS_ERR_ARG, "efts_resconv_train_fwd: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Arena a(workspace, workspace_bytes);
+  TrainWs w;
+  carve_train(a, w, B, T, C, k, false);
+  if (!a.ok) return fail(EFTS_ERR_WORKSPACE, "workspace too small: need %zu, have %zu", a.off, workspace_bytes);
+  const size_t n = static_cast<size_t>(B) * T * C;
+  CUDA_TRY(cudaMemsetAsync(c->err_flag, 0, sizeof(int), st));
+  CUDA_TRY(cudaMemcpyAsync(acts, x, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  TRY(split_planes(c, st, x, n, w.a_hi[0], w.a_lo[0]));
+  int cur = 0;
+  for (int l = 0; l < n_layers; ++l, cur ^= 1) {
+    const size_t wn = static_cast<size_t>(k) * C * C;
+    pack_conv_weight_kernel<false><<<ew_grid(wn), 256, 0, st>>>(weights + l * wn, C, C, k, w.w_hi, w.w_lo, c->err_flag);
+    CUDA_TRY(cudaGetLastError());
+    float* u = us + l * n;
+    GemmParams p = gemm_defaults();
+    p.N = C; p.ntaps = k; p.pad = (k - 1) / 2; p.act = ACT_LRELU; p.bias = biases + static_cast<size_t>(l) * C;
+    p.out = u; p.ld_out = C;
+    { ProfScope ps(c, st, TAG_DEC_CONV); TRY(launch_gemm(c, st, OpA{w.a_hi[cur], w.a_lo[cur], B, T, C, C}, OpB{w.w_hi, w.w_lo, k, C, C, C}, p)); }
+    residual_add_split_kernel<<<ew_grid(n / 4), 256, 0, st>>>(acts + l * n, u, n / 4, acts + (l + 1) * n, w.a_hi[cur ^ 1],
+                                                              w.a_lo[cur ^ 1], c->err_flag);
+    CUDA_TRY(cudaGetLastError());
+    c->launches += 2;
+  }
+  return EFTS_OK;
+}
+
+int efts_resconv_train_bwd(efts_ctx* c, const float* grad_out, const float* acts, const float* us, const float* weights,
+                           int32_t n_layers, int32_t k, int32_t B, int32_t T, float* grad_x, float* grad_w, float* grad_b,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+  if (c == nullptr) return fail(EFTS_ERR_ARG, "null context");
+  const int C = 512;
+  if (!grad_out || !acts || !us || !weights || !grad_x || !grad_w || !grad_b || !workspace || n_layers < 1 || B < 1 || T < 1 ||
+      (k != 1 && k != 3 && k != 5) || B > 65535)
+    return fail(EFTS_ERR_ARG, "efts_resconv_train_bwd: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Arena a(workspace, workspace_bytes);
+  TrainWs w;
+  carve_train(a, w, B, T, C, k, true);
+  if (!a.ok) return fail(EFTS_ERR_WORKSPACE, "workspace too small: need %zu, have %zu", a.off, workspace_bytes);
+  const int pad = (k - 1) / 2;
+  const size_t rows = static_cast<size_t>(B) * T, n = rows * C, wn = static_cast<size_t>(k) * C * C;
+  CUDA_TRY(cudaMemsetAsync(c->err_flag, 0, sizeof(int), st));
+  // the margins of the transposed planes stay zero for the whole call (the kernels only write positions t < T)
+  CUDA_TRY(cudaMemsetAsync(w.gT_hi, 0, w.ktot * C * sizeof(__half), st));
+  CUDA_TRY(cudaMemsetAsync(w.gT_lo, 0, w.ktot * C * sizeof(__half), st));
+  // split of the position reduction: ~one work item per CTA pair
+  const int num_kb = static_cast<int>((w.ktot + G2_BK - 1) / G2_BK);
+  const int items = ((C / G2_BM + 1) / 2) * (C / G2_BN);
+  int want = std::max(1, std::min(16, (c->sm_count / 2) / items));
+  int split_kb = (num_kb + want - 1) / want;
+  split_kb = (split_kb + c->chunk_kb - 1) / std::max(1, c->chunk_kb) * std::max(1, c->chunk_kb);
+  const float* g = grad_out;
+  const dim3 tgrid((T + 31) / 32, C / 32, B), tblock(32, 8);
+  for (int l = n_layers - 1; l >= 0; --l) {
+    const float* u = us + l * n;
+    const float* xl = acts + l * n;
+    float* dx = l == 0 ? grad_x : w.g[l & 1];
+    // G' planes (data gradient), G'^T and x^T planes (weight gradient), bias gradient
+    lrelu_grad_split_kernel<<<ew_grid(n / 4), 256, 0, st>>>(g, u, n / 4, w.a_hi[0], w.a_lo[0], c->err_flag);
+    CUDA_TRY(cudaGetLastError());
+    transpose_split_kernel<<<tgrid, tblock, 0, st>>>(g, u, T, C, w.Tp, pad, 0, w.ktot, w.gT_hi, w.gT_lo);
+    CUDA_TRY(cudaGetLastError());
+    bias_grad_partial_kernel<<<dim3(kBiasParts, C / 128), 128, 0, st>>>(g, u, rows, C, w.db_part);
+    CUDA_TRY(cudaGetLastError());
+    bias_grad_finish_kernel<<<(C + 127) / 128, 128, 0, st>>>(w.db_part, kBiasParts, C, grad_b + static_cast<size_t>(l) * C);
+    CUDA_TRY(cudaGetLastError());
+    c->launches += 4;
+    // dL/dW[o, c, j] = sum_k G'^T[o, k] x^T[c, k + j - pad]: one position-reduction GEMM per tap
+    for (int j = 0; j < k; ++j) {
+      // x^T shifted by the tap: xTs[c, q] = x^T[c, q + j - pad] (TMA coordinates cannot carry a 2-byte shift)
+      CUDA_TRY(cudaMemsetAsync(w.xT_hi, 0, w.ktot * C * sizeof(__half), st));
+      CUDA_TRY(cudaMemsetAsync(w.xT_lo, 0, w.ktot * C * sizeof(__half), st));
+      transpose_split_kernel<<<tgrid, tblock, 0, st>>>(xl, nullptr, T, C, w.Tp, pad, j - pad, w.ktot, w.xT_hi, w.xT_lo);
+      CUDA_TRY(cudaGetLastError());
+      c->launches++;
+      GemmParams p = gemm_defaults();
+      p.N = C; p.out = w.dwt + static_cast<size_t>(j) * C * C; p.ld_out = C;
+      p.split_kb = split_kb; p.split_scratch = w.splitk;
+      ProfScope ps(c, st, TAG_LINEAR);
+      TRY(launch_gemm(c, st, OpA{w.gT_hi, w.gT_lo, 1, C, static_cast<int>(w.ktot), static_cast<int>(w.ktot)},
+                      OpB{w.xT_hi, w.xT_lo, 1, C, static_cast<int>(w.ktot), static_cast<int>(w.ktot)}, p));
+    }
+    weight_grad_permute_kernel<<<ew_grid(wn), 256, 0, st>>>(w.dwt, C, C, k, grad_w + l * wn);
+    CUDA_TRY(cudaGetLastError());
+    // dL/dx = g + conv^T(G'): the tap-GEMM with flipped, transposed weights, residual = g
+    pack_conv_weight_kernel<true><<<ew_grid(wn), 256, 0, st>>>(weights + l * wn, C, C, k, w.w_hi, w.w_lo, c->err_flag);
+    CUDA_TRY(cudaGetLastError());
+    c->launches += 2;
+    GemmParams p = gemm_defaults();
+    p.N = C; p.ntaps = k; p.pad = pad; p.resid = g; p.out = dx; p.ld_out = C;
+    { ProfScope ps(c, st, TAG_DEC_CONV); TRY(launch_gemm(c, st, OpA{w.a_hi[0], w.a_lo[0], B, T, C, C}, OpB{w.w_hi, w.w_lo, k, C, C, C}, p)); }
+    g = dx;
+  }
+  return EFTS_OK;
 }
 
 }  // extern "C"

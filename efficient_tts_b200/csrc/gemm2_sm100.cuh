@@ -244,8 +244,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
   const int splits = (FUSE && p.splits > 1) ? p.splits : 1;
   const long long total = static_cast<long long>(n_prt) * n_nt * splits;
   const int cid = blockIdx.x / CG, ncl = gridDim.x / CG;
-  const int item_kb = splits > 1 ? chunk_kb : num_kb;              // k-blocks per work item
-  auto kb_first = [&](long long w) { return splits > 1 ? static_cast<int>(w % splits) * chunk_kb : 0; };
+  const int item_kb = splits > 1 ? (p.split_kb > 0 ? p.split_kb : chunk_kb) : num_kb;   // k-blocks per work item
+  auto kb_first = [&](long long w) { return splits > 1 ? static_cast<int>(w % splits) * item_kb : 0; };
 
   auto locate = [&](long long w_in, int& b, int& t0, int& n0, bool& valid) {
     const long long w = w_in / splits;
@@ -305,18 +305,18 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
               const uint32_t bar = ptx::map_to_cta(fullB(s), 0);
               if (leader) ptx::mbar_expect_tx(fullB(s), 2 * Cfg::B_STAGE);
               const CUtensorMap* own = leader ? &tmB_hi : &tmB_lo;
-              ptx::tma_load_3d_pair(own, bar, dst, kb * G2_BK, n0, z);
-              ptx::tma_load_3d_pair(own, bar, dst + Cfg::B_PLANE, kb * G2_BK, n0 + Cfg::B_ROWS, z);
-              ptx::tma_load_3d_pair(&tmB_hi, bar, dst + 2 * Cfg::B_PLANE, kb * G2_BK, nrow, z);
+              ptx::tma_load_3d_pair(own, bar, dst, kb * G2_BK + p.b_koff, n0, z);
+              ptx::tma_load_3d_pair(own, bar, dst + Cfg::B_PLANE, kb * G2_BK + p.b_koff, n0 + Cfg::B_ROWS, z);
+              ptx::tma_load_3d_pair(&tmB_hi, bar, dst + 2 * Cfg::B_PLANE, kb * G2_BK + p.b_koff, nrow, z);
             } else if (CG == 2) {
               const uint32_t bar = ptx::map_to_cta(fullB(s), 0);
               if (leader) ptx::mbar_expect_tx(fullB(s), 2 * Cfg::B_STAGE);
-              ptx::tma_load_3d_pair(&tmB_hi, bar, dst, kb * G2_BK, nrow, z);
-              ptx::tma_load_3d_pair(&tmB_lo, bar, dst + Cfg::B_PLANE, kb * G2_BK, nrow, z);
+              ptx::tma_load_3d_pair(&tmB_hi, bar, dst, kb * G2_BK + p.b_koff, nrow, z);
+              ptx::tma_load_3d_pair(&tmB_lo, bar, dst + Cfg::B_PLANE, kb * G2_BK + p.b_koff, nrow, z);
             } else {
               ptx::mbar_expect_tx(fullB(s), Cfg::B_STAGE);
-              ptx::tma_load_3d(&tmB_hi, fullB(s), dst, kb * G2_BK, nrow, z);
-              ptx::tma_load_3d(&tmB_lo, fullB(s), dst + Cfg::B_PLANE, kb * G2_BK, nrow, z);
+              ptx::tma_load_3d(&tmB_hi, fullB(s), dst, kb * G2_BK + p.b_koff, nrow, z);
+              ptx::tma_load_3d(&tmB_lo, fullB(s), dst + Cfg::B_PLANE, kb * G2_BK + p.b_koff, nrow, z);
             }
             ++ib;
           }
@@ -540,7 +540,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
     const uint32_t grp = static_cast<uint32_t>(warp - 4) >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    const uint32_t nchunks = static_cast<uint32_t>((item_kb + chunk_kb - 1) / chunk_kb);
+    // accumulation chunks of work item w (the last split of a reduction may be shorter than the others)
+    auto chunks_of = [&](long long w) {
+      const int kbf = kb_first(w);
+      return static_cast<uint32_t>((min(kbf + item_kb, num_kb) - kbf + chunk_kb - 1) / chunk_kb);
+    };
     auto release = [&](uint32_t bar) {            // one arrival per warp, on the leader's barrier
       ptx::tc_fence_before();
       __syncwarp();
@@ -551,6 +555,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
     uint32_t g = 0, it = 0;
     uint32_t uses0 = 0u, uses1 = 0u;              // completed waits on this group's acc0_full[buf]
     for (long long w = cid; w < total; w += ncl, ++it) {
+      const uint32_t nchunks = chunks_of(w);
       if ((it & 1u) != grp) { g += nchunks; continue; }
       int b, t0, n0; bool valid;
       locate(w, b, t0, n0, valid);

@@ -77,6 +77,10 @@ struct GemmParams {
   int plane_act;         // 1: the fp16 operand planes hold LeakyReLU(0.1) of the stored fp32 value (the next layer's
                          // input activation, vocoders/hifigan_model.py:58,123), the fp32 store stays pre-activation
   int long_taps;         // host side only: use the 184-row A box variant (128 + (ntaps - 1) * dil <= 184)
+  // weight-gradient GEMMs (reduction over positions)
+  int b_koff;            // element offset added to the B operand's K coordinate: B[n, k + b_koff]; must be a multiple
+                         // of 8 (TMA box coordinates are 16-byte aligned); out-of-range columns are zero-filled
+  int split_kb;          // > 0 with splits > 1: every work item covers split_kb k-blocks (several accumulation chunks)
 };
 
 }  // namespace efts

@@ -410,3 +410,108 @@ def length_regulator(xs, ds, ilens, alpha=1.0, pad_value=0.0, return_index=False
                                                  tout, float(pad_value), _ptr(out), _ptr(idx), st))
     out = out.to(xs.dtype)
     return (out, idx) if return_index else out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# training slice (include/efts_b200.h, efts_resconv_train_*): ResConvBlock forward with saved activations + backward
+class TrainContext:
+    """A weight-less library context on one device for the training entry points, which take the caller's CURRENT
+    fp32 weights on every call (they change every optimiser step, so nothing is prepacked on the host)."""
+
+    def __init__(self, device):
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("efts_b200 trains on CUDA (sm_100a) devices only; got %s" % (self.device,))
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", idx)
+        cfg = _lib.EftsConfig(1, 8, N_CHANNELS, 5, 1, 1, 1, 1, 3, 0.01, 0.5, 1.0, 0.1, 1, idx)
+        h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.efts_create(ctypes.byref(cfg), ctypes.byref(h)))
+        self._h = h
+        self._ws = None
+
+    def launch_count(self):
+        return int(self.lib.efts_launch_count(self._h))
+
+    def _workspace(self, B, T, k):
+        n = int(self.lib.efts_resconv_train_workspace_bytes(self._h, B, T, k))
+        if self._ws is None or self._ws.numel() < n:
+            self._ws = None
+            self._ws = torch.empty(n, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def _check(self):
+        flags = ctypes.c_int32(0)
+        st = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        _lib.check(self.lib.efts_error_flags(self._h, st, ctypes.byref(flags)))
+        if flags.value & 8:
+            raise FloatingPointError(RANGE_MESSAGE)
+
+    def resconv_fwd(self, x_btc, w_all, b_all):
+        """x [B, T, 512], w_all [L, 512, 512, k], b_all [L, 512] -> (acts [L + 1, B, T, 512], us [L, B, T, 512])."""
+        x = x_btc.detach().to(torch.float32).contiguous()
+        w = w_all.detach().to(torch.float32).contiguous()
+        b = b_all.detach().to(torch.float32).contiguous()
+        B, T, C = x.shape
+        L, k = w.shape[0], w.shape[3]
+        if C != N_CHANNELS or tuple(w.shape[1:3]) != (C, C) or tuple(b.shape) != (L, C):
+            raise RuntimeError("ResConv training kernels are built for %d channels; got x %s, weights %s" % (
+                N_CHANNELS, tuple(x.shape), tuple(w.shape)))
+        with torch.cuda.device(self.device):
+            acts = torch.empty(L + 1, B, T, C, dtype=torch.float32, device=self.device)
+            us = torch.empty(L, B, T, C, dtype=torch.float32, device=self.device)
+            ws = self._workspace(B, T, k)
+            st = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            _lib.check(self.lib.efts_resconv_train_fwd(self._h, _ptr(x), _ptr(w), _ptr(b), L, k, B, T, _ptr(acts), _ptr(us),
+                                                       _ptr(ws), ws.numel(), st))
+        return acts, us
+
+    def resconv_bwd(self, grad_out, acts, us, w_all):
+        g = grad_out.detach().to(torch.float32).contiguous()
+        w = w_all.detach().to(torch.float32).contiguous()
+        L, B, T, C = us.shape
+        k = w.shape[3]
+        with torch.cuda.device(self.device):
+            gx = torch.empty(B, T, C, dtype=torch.float32, device=self.device)
+            gw = torch.empty_like(w)
+            gb = torch.empty(L, C, dtype=torch.float32, device=self.device)
+            ws = self._workspace(B, T, k)
+            st = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            _lib.check(self.lib.efts_resconv_train_bwd(self._h, _ptr(g), _ptr(acts), _ptr(us), _ptr(w), L, k, B, T, _ptr(gx),
+                                                       _ptr(gw), _ptr(gb), _ptr(ws), ws.numel(), st))
+            self._check()
+        return gx, gw, gb
+
+
+_TRAIN_CONTEXTS = {}
+
+
+def train_context(device):
+    dev = torch.device(device)
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    tc = _TRAIN_CONTEXTS.get(key)
+    if tc is None:
+        tc = _TRAIN_CONTEXTS[key] = TrainContext(dev)
+    return tc
+
+
+class ResConvStackFunction(torch.autograd.Function):
+    """y = stack of ``x + lrelu(conv_k(x) + b)`` layers on channels-last activations, differentiable: forward and
+    backward are library calls (efts_resconv_train_fwd / _bwd); ``w_all`` are the EFFECTIVE conv weights
+    [L, C, C, k] (the weight-norm fold is left to torch so that weight_g / weight_v receive their gradients)."""
+
+    @staticmethod
+    def forward(ctx, x_btc, w_all, b_all):
+        tc = train_context(x_btc.device)
+        acts, us = tc.resconv_fwd(x_btc, w_all, b_all)
+        ctx.save_for_backward(acts, us, w_all)
+        ctx.tc = tc
+        return acts[-1]
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        acts, us, w_all = ctx.saved_tensors
+        gx, gw, gb = ctx.tc.resconv_bwd(grad_out, acts, us, w_all)
+        return gx, gw, gb

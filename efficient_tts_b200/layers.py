@@ -105,7 +105,9 @@ def _remove_weight_norm(module):
 
 
 class ResConvBlock(_EngineOwner):
-    """``ResConvBlock(num_layers, ...).forward(x[B, C, T])`` (layers/efts_modules.py:54-79)."""
+    """``ResConvBlock(num_layers, ...).forward(x[B, C, T])`` (layers/efts_modules.py:54-79).  Forward-only through the
+    prepacked engine under ``torch.no_grad()`` / ``.eval()``; with gradients enabled it runs the training slice
+    (``engine.ResConvStackFunction``): same results, plus gradients for the input and every parameter."""
 
     def __init__(self, num_layers, n_channels=512, k_size=5, nonlinear_activation="LeakyReLU",
                  nonlinear_activation_params={"negative_slope": 0.1}, dropout_rate=0.1, use_weight_norm=True):
@@ -140,8 +142,31 @@ class ResConvBlock(_EngineOwner):
             sd["decoder." + key] = v
         return sd
 
+    def effective_weights(self):
+        """Stacked effective conv weights [L, C, C, k] and biases [L, C], differentiable w.r.t. the module's
+        parameters (``g * v / ||v||`` per output channel while weight norm is applied, layers/efts_modules.py:92-99)."""
+        ws, bs = [], []
+        for layer in self.layers:
+            conv = layer.conv[0]
+            if hasattr(conv, "weight_g"):
+                ws.append(torch._weight_norm(conv.weight_v, conv.weight_g, 0))
+            else:
+                ws.append(conv.weight)
+            bs.append(conv.bias)
+        return torch.stack(ws), torch.stack(bs)
+
     def forward(self, x):
-        self._require_eval()
+        needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
+        if self.training or needs_grad:
+            # training slice (SURVEY.md 8f-3): forward that keeps what the backward needs, gradients from the library
+            if self.training and any(isinstance(m, torch.nn.Dropout) and m.p > 0 for m in self.modules()):
+                raise NotImplementedError("train-mode dropout is outside the B200 path (the production recipe sets "
+                                          "dropout_rate=0.0, egs/lj/conf/*.yaml)")
+            if x.device.type != "cuda":
+                raise RuntimeError("efficient_tts_b200 modules compute on a CUDA sm_100a device only")
+            w_all, b_all = self.effective_weights()
+            y = _engine.ResConvStackFunction.apply(x.transpose(1, 2).contiguous(), w_all, b_all)
+            return y.transpose(1, 2)
         y = self._get_engine().conv_stack(2, x.transpose(1, 2))
         return y.transpose(1, 2)
 

@@ -257,6 +257,26 @@ size_t efts_frontend_workspace_bytes(const efts_ctx* ctx, int32_t B, int32_t Lma
 int efts_frontend_forward(efts_ctx* ctx, const float* audio, const int64_t* lengths, int32_t B, int32_t Lmax, float* mel,
                           int64_t* mel_lengths, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- training slice: ResConvBlock under autograd ----
+ * The first piece of the reference's training step (trainers/efficient_tts_trainer.py:152-154, loss.backward()):
+ * forward of a stack of residual conv layers y = x + lrelu_{0.1}(conv_k(x) + b) (layers/efts_modules.py:48-51,77-79)
+ * that keeps what the backward needs, and the backward itself -- data gradient as the tap-GEMM with flipped,
+ * transposed weights, weight gradient as one GEMM per tap that reduces over positions (split over the SMs), bias
+ * gradient as a column sum.  Weights are the caller's CURRENT fp32 device tensors (they change every step), stacked:
+ * weights [n_layers, 512, 512, k], biases [n_layers, 512]; activations are channels-last [B, T, 512].
+ *   fwd: acts [n_layers + 1, B, T, 512] (acts[0] = x, acts[l + 1] = output of layer l; the last slice is the result)
+ *        and us [n_layers, B, T, 512] (the activated conv outputs; their sign is LeakyReLU') are written.
+ *   bwd: grad_out = dL/d acts[n_layers] -> grad_x [B, T, 512], grad_w [n_layers, 512, 512, k], grad_b [n_layers, 512].
+ * efficient_tts_b200/layers.py wraps the pair in a torch.autograd.Function so that ResConvBlock trains; the
+ * weight-norm reparametrisation (weight_g, weight_v) is differentiated by torch on top of grad_w. */
+size_t efts_resconv_train_workspace_bytes(const efts_ctx* ctx, int32_t B, int32_t T, int32_t k);
+int efts_resconv_train_fwd(efts_ctx* ctx, const float* x, const float* weights, const float* biases, int32_t n_layers,
+                           int32_t k, int32_t B, int32_t T, float* acts, float* us, void* workspace,
+                           size_t workspace_bytes, void* stream);
+int efts_resconv_train_bwd(efts_ctx* ctx, const float* grad_out, const float* acts, const float* us, const float* weights,
+                           int32_t n_layers, int32_t k, int32_t B, int32_t T, float* grad_x, float* grad_w, float* grad_b,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- data parallelism ----
  * The survey's sketch of this ABI listed efts_dp_init / efts_dp_allgather / efts_dp_allreduce_loss.  They are
  * deliberately NOT exported: the reference's only parallelism is torch DDP with a DistributedSampler

@@ -1,0 +1,171 @@
+"""Training slice: ResConvBlock forward + backward on the GPU against torch autograd on the CPU
+oracle (fp32).
+
+Tolerances.  Forward as everywhere (1e-4 abs).  LeakyReLU' is discontinuous at 0: wherever a pre-activation lies
+within the two implementations' fp32 noise of zero (a handful of the ~10^6 elements of a test) the two backward
+passes legitimately take different slopes for that element, which moves single gradient entries by O(|g| |w|).  So
+  * against torch autograd the gradients are compared in relative L2 norm (<= 1e-3; measured ~1e-6 without a flip), and
+  * the exact check -- max error <= 5e-5 of the largest entry -- is made against a float64 evaluation of the same
+    backward formulas that uses the slopes the device forward actually took (test_backward_matches_float64_...)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import efts_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda", 0)
+
+
+def reference_grads(state, n_layers, x_bct, grad_bct):
+    """torch autograd through the oracle's residual stack with the weight-norm parametrisation as leaves."""
+    leaves = {k: v.clone().requires_grad_(True) for k, v in state.items()}
+    x = x_bct.clone().requires_grad_(True)
+    y = orc.res_conv_stack(x, {"blk." + k: v for k, v in leaves.items()}, "blk", n_layers)
+    y.backward(grad_bct)
+    return y.detach(), x.grad, {k: v.grad for k, v in leaves.items()}
+
+
+@pytest.mark.parametrize("n_layers,B,T,seed", [(2, 2, 150, 0), (6, 3, 300, 1), (3, 1, 37, 2)])
+def test_resconvblock_trains_like_the_reference(dev, n_layers, B, T, seed):
+    from efficient_tts_b200.layers import ResConvBlock
+    torch.manual_seed(seed)
+    blk = ResConvBlock(n_layers, dropout_rate=0.0)
+    state = {k: v.detach().clone() for k, v in blk.state_dict().items()}
+    g = torch.Generator().manual_seed(100 + seed)
+    x = torch.randn(B, 512, T, generator=g)
+    grad = torch.randn(B, 512, T, generator=g)
+    y_ref, gx_ref, gp_ref = reference_grads(state, n_layers, x, grad)
+
+    blk = blk.to(dev).train()
+    xd = x.to(dev).requires_grad_(True)
+    y = blk(xd)
+    assert y.shape == y_ref.shape and y.requires_grad
+    y.backward(grad.to(dev))
+    assert (y.detach().cpu() - y_ref).abs().max().item() <= 1e-4
+
+    def rel(a, b):
+        return (a.cpu() - b).norm().item() / max(b.norm().item(), 1e-12)
+    r = rel(xd.grad, gx_ref)
+    print("dL/dx: relative L2 error %.2e" % r)
+    assert r <= 1e-3
+    params = dict(blk.named_parameters())
+    assert set(params) == set(gp_ref)
+    for k in sorted(params):
+        assert params[k].grad is not None, k
+        r = rel(params[k].grad, gp_ref[k])
+        print("%s: relative L2 error %.2e" % (k, r))
+        assert r <= 1e-3, k
+    # the forward of the training path against the forward of the inference path: the only difference is where
+    # the weight-norm fold g * v / ||v|| is evaluated (device vs host, one ulp on some weights)
+    blk.eval()
+    with torch.no_grad():
+        y_inf = blk(x.to(dev))
+    assert (y_inf - y.detach()).abs().max().item() <= 1e-5
+    # without the reparametrisation both paths see the same weights: bit-identical results
+    plain = ResConvBlock(2, dropout_rate=0.0, use_weight_norm=False).to(dev)
+    y_train = plain.train()(x.to(dev).requires_grad_(True)).detach()
+    with torch.no_grad():
+        y_eval = plain.eval()(x.to(dev))
+    assert torch.equal(y_train, y_eval)
+
+
+@pytest.mark.parametrize("n_layers,B,T,k", [(3, 2, 200, 5), (2, 3, 131, 3), (1, 1, 40, 5)])
+def test_backward_matches_float64_formulas_with_the_device_slopes(dev, n_layers, B, T, k):
+    """dL/dx = g + conv^T(G'), dL/dW = sum_pos G' x_shifted, dL/db = sum_pos G' with G' = g * slope, evaluated in
+    float64 on the CPU from the activations and slopes the device forward produced: max error <= 5e-5 of the largest
+    entry of each gradient."""
+    import torch.nn.functional as F
+    from efficient_tts_b200.engine import train_context
+    tc = train_context(dev)
+    g = torch.Generator().manual_seed(40 + T)
+    C = 512
+    x = torch.randn(B, T, C, generator=g)
+    w = torch.randn(n_layers, C, C, k, generator=g) / np.sqrt(C * k)
+    b = torch.randn(n_layers, C, generator=g) * 0.1
+    grad = torch.randn(B, T, C, generator=g)
+    acts, us = tc.resconv_fwd(x.to(dev), w.to(dev), b.to(dev))
+    gx, gw, gb = tc.resconv_bwd(grad.to(dev), acts, us, w.to(dev))
+    acts64, us64 = acts.double().cpu(), us.double().cpu()
+    # forward consistency of what was saved: acts[l + 1] = acts[l] + us[l], us[l] = lrelu(conv(acts[l]) + b)
+    for l in range(n_layers):
+        pre = F.conv1d(acts64[l].transpose(1, 2), w[l].double(), b[l].double(), padding=(k - 1) // 2).transpose(1, 2)
+        assert (F.leaky_relu(pre, 0.1) - us64[l]).abs().max().item() <= 2e-5
+        assert torch.equal(acts[l + 1], acts[l] + us[l])
+    gcur = grad.double()
+    for l in reversed(range(n_layers)):
+        gp = gcur * torch.where(us64[l] > 0, 1.0, 0.1)                       # the slopes the device took
+        gp_ct, x_ct = gp.transpose(1, 2), acts64[l].transpose(1, 2)
+        dw = torch.nn.grad.conv1d_weight(x_ct, (C, C, k), gp_ct, padding=(k - 1) // 2)
+        db = gp.sum((0, 1))
+        gcur = gcur + F.conv_transpose1d(gp_ct, w[l].double(), padding=(k - 1) // 2).transpose(1, 2)
+        for name, got, want in (("dW", gw[l], dw), ("db", gb[l], db)):
+            err = (got.double().cpu() - want).abs().max().item() / want.abs().max().item()
+            print("layer %d %s: max err %.2e of the largest entry" % (l, name, err))
+            assert err <= 5e-5, (l, name)
+    err = (gx.double().cpu() - gcur).abs().max().item() / gcur.abs().max().item()
+    print("dL/dx: max err %.2e of the largest entry" % err)
+    assert err <= 5e-5
+
+
+def test_one_sgd_step_follows_the_reference(dev):
+    """loss.backward() + optimiser step (trainers/efficient_tts_trainer.py:152-160 on the block alone): after one SGD
+    step the parameters agree with the reference's step, and the loss goes down on the next forward."""
+    from efficient_tts_b200.layers import ResConvBlock
+    torch.manual_seed(5)
+    blk = ResConvBlock(3, dropout_rate=0.0)
+    state = {k: v.detach().clone() for k, v in blk.state_dict().items()}
+    g = torch.Generator().manual_seed(6)
+    x, target = torch.randn(2, 512, 96, generator=g), torch.randn(2, 512, 96, generator=g)
+    # reference step on the CPU
+    leaves = {k: v.clone().requires_grad_(True) for k, v in state.items()}
+    loss_ref = ((orc.res_conv_stack(x, {"blk." + k: v for k, v in leaves.items()}, "blk", 3) - target) ** 2).mean()
+    loss_ref.backward()
+    stepped = {k: (v - 0.05 * v.grad).detach() for k, v in leaves.items()}
+    # the same step through the library
+    blk = blk.to(dev).train()
+    opt = torch.optim.SGD(blk.parameters(), lr=0.05)
+    loss = ((blk(x.to(dev)) - target.to(dev)) ** 2).mean()
+    opt.zero_grad()
+    loss.backward()
+    opt.step()
+    assert abs(loss.item() - loss_ref.item()) <= 1e-5 * max(1.0, abs(loss_ref.item()))
+    for k, v in blk.state_dict().items():
+        assert (v.cpu() - stepped[k]).abs().max().item() <= 1e-6 + 1e-4 * (stepped[k] - state[k]).abs().max().item(), k
+    loss2 = ((blk(x.to(dev)) - target.to(dev)) ** 2).mean()
+    assert loss2.item() < loss.item()
+
+
+def test_weight_gradient_at_training_size_is_linear_and_matches_a_sample(dev):
+    """Mid-size check (B = 16, T = 800: 12 800 positions per output element, several split items per tile): the weight
+    gradient is linear in grad_out (exactly additive inputs -> additive outputs up to fp32 rounding) and a random
+    sample of its entries matches a float64 evaluation of the defining sum."""
+    from efficient_tts_b200.engine import train_context
+    tc = train_context(dev)
+    g = torch.Generator().manual_seed(9)
+    B, T, C, k = 16, 800, 512, 5
+    x = torch.randn(B, T, C, generator=g).to(dev)
+    w = (torch.randn(1, C, C, k, generator=g) / np.sqrt(C * k)).to(dev)
+    b = (torch.randn(1, C, generator=g) * 0.1).to(dev)
+    acts, us = tc.resconv_fwd(x, w, b)
+    g1 = torch.randn(B, T, C, generator=g).to(dev)
+    g2 = torch.randn(B, T, C, generator=g).to(dev)
+    _, gw1, gb1 = tc.resconv_bwd(g1, acts, us, w)
+    _, gw2, gb2 = tc.resconv_bwd(g2, acts, us, w)
+    _, gw12, gb12 = tc.resconv_bwd(g1 + g2, acts, us, w)
+    scale = gw12.abs().max().item()
+    assert (gw1 + gw2 - gw12).abs().max().item() <= 2e-5 * scale
+    assert (gb1 + gb2 - gb12).abs().max().item() <= 2e-5 * gb12.abs().max().item()
+    # float64 evaluation of dW[o, c, j] = sum_{b,t} G'[b,t,o] x[b, t + j - 2, c] on sampled (o, c, j)
+    gp = (g1.double() * torch.where(us[0] > 0, 1.0, 0.1).double()).cpu()
+    xp = torch.nn.functional.pad(x.double().cpu(), (0, 0, 2, 2))
+    rng = np.random.default_rng(0)
+    for _ in range(12):
+        o, c, j = int(rng.integers(C)), int(rng.integers(C)), int(rng.integers(k))
+        want = (gp[:, :, o] * xp[:, j:j + T, c]).sum().item()
+        got = gw1[0, o, c, j].item()
+        assert abs(got - want) <= 2e-4 * scale, (o, c, j, got, want)
