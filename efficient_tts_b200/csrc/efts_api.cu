@@ -95,12 +95,10 @@ struct efts_ctx {
   int pair = 1;              // CTA pairs (cta_group::2) for the weight GEMMs
   int cur_tag = 15;          // ProfTag of the launch being issued (diagnostics)
   int wide = 1;              // short-reduction launches use the 16-epilogue-warp variant
-  int debug_mask = 0;        // timing experiments only
+  int stack_trace_on = 0;    // measurement hook: the stack kernel records its phase stamps (efts_profile_stack_trace)
   int chunk_kb = 2;          // k-blocks per main-accumulator flush (1 = most accurate, 0 = never)
   int voc_group = 1;             // vocoder: grouped (super-tap) packing of the 32 / 64-channel layers (read at finalize)
   int voc_wide = 1;              // vocoder: short-reach, short-reduction layers use the wide-epilogue variant
-  int voc_short_box = 0;         // vocoder: layers whose taps reach <= 8 rows use the 136-row A box (A/B switch, off:
-                                 // -1 % at 16 x 800 frames, +12 % latency at B = 1 from alternating two kernel images)
   int voc_narrow = 0;            // vocoder: 64-column tiles for layers with N <= 64 (read at finalize and at launch).
                                  // Off: measured 36.4 vs 34.5 ms at 16 x 800 frames -- the narrow layers are bound by
                                  // their tile count (A-box halo, epilogue), which the grouped packing halves, not by MMA columns
@@ -108,7 +106,7 @@ struct efts_ctx {
                                  // per layer (bitwise the same results; the switch keeps the per-layer path tested)
   unsigned* sync_ctr = nullptr;  // grid-barrier counter of the stack kernel (device, monotonic)
   unsigned sync_base = 0;        // its value once every enqueued stack launch has finished
-  long long* stack_trace = nullptr;   // device buffer [64] for the stack kernel's phase stamps (debug_mask bit 4)
+  long long* stack_trace = nullptr;   // device buffer [64] for the stack kernel's phase stamps (option "stack_trace")
   int split_k = 1;               // fused-B kernel: split the reduction of small launches over more SMs
   int pdl = 1;                   // programmatic dependent launch for the GEMM and split-reduce kernels
   int fuse_b = 1;                // conv layers: Ahi*[Bhi|Blo] as one N = 256 MMA (two MMAs per k-step instead of three)
@@ -263,7 +261,6 @@ int launch_gemm(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, GemmPa
   {
     if (p.ntaps > 15) return fail(EFTS_ERR_ARG, "at most 15 taps");
     p.chunk_kb = c->chunk_kb;
-    p.debug_mask = c->debug_mask;
     p.err_flag = c->err_flag;
     p.err_code = 1 << (8 + c->cur_tag);
     if (!c->skip_pad_tiles) { p.tile_list = nullptr; p.tile_count = nullptr; p.skip_lens = nullptr; }
@@ -284,10 +281,6 @@ int launch_gemm(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, GemmPa
         return fail(EFTS_ERR_ARG, "long-tap launches are plain weight GEMMs");
       p.splits = 0;
       const int box = G2_BM + (p.ntaps - 1) * (p.dil > 1 ? p.dil : 1);
-      // the halo rows of the A box are pure overhead for these tile-count-bound layers: short-reach layers (most
-      // grouped ones, k = 3, the transposed convs) take the 136-row box of the acoustic model's kernel
-      if (box <= G2_A_ROWS && c->voc_short_box && (p.bias == nullptr || p.N <= G2_BIAS_MAX))
-        return launch_gemm2_t<2, EPI_STD, 0, 1>(c, st, a, b, p);
       const bool xlong = box > G2_A_ROWS_LONG;
       if (p.N <= 64 && c->voc_narrow)     // 64-column tiles: half the MMA columns of a 128-column tile
         return xlong ? launch_gemm2_t<2, EPI_STD, 0, 1, G2_A_ROWS_XLONG, 64>(c, st, a, b, p)
@@ -296,6 +289,8 @@ int launch_gemm(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, GemmPa
       return launch_gemm2_t<2, EPI_STD, 0, 1, G2_A_ROWS_LONG>(c, st, a, b, p);
     }
     const bool wide = c->wide && steps <= 40;
+    if (p.act == ACT_LOGCLAMP && !wide)
+      return fail(EFTS_ERR_UNSUPPORTED, "the log epilogue is compiled into the short-reduction (wide) variant only");
     if (wide) {
       p.chunk_kb = 0;
       if (epi == EPI_STD) return pair ? launch_gemm2_t<2, EPI_STD, 1>(c, st, a, b, p) : launch_gemm2_t<1, EPI_STD, 1>(c, st, a, b, p);
@@ -762,7 +757,7 @@ struct StackBuilder {
     sp.sync = c->sync_ctr;
     sp.sync_base = c->sync_base;
     sp.err_flag = c->err_flag;
-    sp.trace = (c->debug_mask & 16) ? c->stack_trace : nullptr;
+    sp.trace = c->stack_trace_on ? c->stack_trace : nullptr;
     if (sp.text != nullptr) barriers += 1;
     // enough CTAs for the widest layer's work items and one (row, four columns) unit per thread of the largest
     // reduce, never more than SMs (every CTA must be resident: the layers synchronise through a grid barrier)
@@ -786,7 +781,7 @@ struct StackBuilder {
 // and sizes the partial-plane scratch holds; anything else runs one launch per layer.
 bool stack_usable(const efts_ctx* c, int T, int n_layers) {
   const int nchunks = c->chunk_kb < 1 ? 1 : (c->cfg.n_channels / G2_BK + c->chunk_kb - 1) / c->chunk_kb;
-  return c->stack && c->pair && c->fuse_b && c->wide && c->split_k && c->chunk_kb >= 1 && (c->debug_mask & ~16) == 0 &&
+  return c->stack && c->pair && c->fuse_b && c->wide && c->split_k && c->chunk_kb >= 1 &&
          n_layers <= ST_MAX_LAYERS && c->cfg.n_channels == 512 && c->profile_mask == 0 &&
          static_cast<size_t>(T) * c->cfg.n_channels * nchunks * sizeof(float) <= kSplitScratchBytes;
 }
@@ -962,7 +957,7 @@ int efts_set_option(efts_ctx* c, const char* name, int32_t value) {
   if (c == nullptr || name == nullptr) return fail(EFTS_ERR_ARG, "null argument");
   if (strcmp(name, "skip_pad_tiles") == 0) { c->skip_pad_tiles = value != 0; return EFTS_OK; }
   if (strcmp(name, "pair") == 0) { c->pair = value != 0; return EFTS_OK; }
-  if (strcmp(name, "debug_mask") == 0) { c->debug_mask = value; return EFTS_OK; }
+  if (strcmp(name, "stack_trace") == 0) { c->stack_trace_on = value != 0; return EFTS_OK; }
   if (strcmp(name, "wide") == 0) { c->wide = value != 0; return EFTS_OK; }
   if (strcmp(name, "fuse_b") == 0) { c->fuse_b = value != 0; return EFTS_OK; }
   if (strcmp(name, "split_k") == 0) { c->split_k = value != 0; return EFTS_OK; }
@@ -970,7 +965,6 @@ int efts_set_option(efts_ctx* c, const char* name, int32_t value) {
   if (strcmp(name, "pdl") == 0) { c->pdl = value != 0; return EFTS_OK; }
   if (strcmp(name, "voc_group") == 0) { c->voc_group = value != 0; return EFTS_OK; }
   if (strcmp(name, "voc_narrow") == 0) { c->voc_narrow = value != 0; return EFTS_OK; }
-  if (strcmp(name, "voc_short_box") == 0) { c->voc_short_box = value != 0; return EFTS_OK; }
   if (strcmp(name, "voc_wide") == 0) { c->voc_wide = value != 0; return EFTS_OK; }
   if (strcmp(name, "imv_version") == 0) {
     if (value != 1 && value != 2) return fail(EFTS_ERR_ARG, "imv_version must be 1 or 2");

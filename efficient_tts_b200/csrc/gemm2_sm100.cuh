@@ -110,6 +110,7 @@ __global__ void build_tile_list_kernel(const int* __restrict__ lens, int B, int 
 // accesses cost the LSU two cycles per row and instruction and an L2 request per half sector.  Adds the fp32
 // residual (all eight row loads are issued before the first store), zeroes rows past the utterance, writes the
 // fp32 result and its fp16 hi/lo operand planes, and range-checks what becomes an operand.
+template <bool VOC = true>
 __device__ __forceinline__ void g2_store_block32(const GemmParams& p, uint32_t stg, int b, int t_base, int n,
                                                  int lens_b, int check_b, int lane, size_t out_off = 0) {
   const int sub_row = lane >> 3, sub_col = (lane & 7) * 4;
@@ -138,10 +139,10 @@ __device__ __forceinline__ void g2_store_block32(const GemmParams& p, uint32_t s
         v.x = res[itr].x + v.x; v.y = res[itr].y + v.y; v.z = res[itr].z + v.z; v.w = res[itr].w + v.w;
       }
       if (tr >= lens_b) v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-      if (p.out != nullptr && !(p.debug_mask & 1)) *reinterpret_cast<float4*>(p.out + out_off + mr * p.ld_out + nn) = v;
-      if (p.out_hi != nullptr && !(p.debug_mask & 2)) {
+      if (p.out != nullptr) *reinterpret_cast<float4*>(p.out + out_off + mr * p.ld_out + nn) = v;
+      if (p.out_hi != nullptr) {
         if (tr < check_b && outside_fp16_range(v) && p.err_flag != nullptr) atomicOr(p.err_flag, 8 | p.err_code);
-        if (p.plane_act) {                          // operand of the next layer = LeakyReLU(0.1) of the stored value
+        if (VOC && p.plane_act) {                   // operand of the next layer = LeakyReLU(0.1) of the stored value
           v.x = v.x > 0.0f ? v.x : v.x * 0.1f; v.y = v.y > 0.0f ? v.y : v.y * 0.1f;
           v.z = v.z > 0.0f ? v.z : v.z * 0.1f; v.w = v.w > 0.0f ? v.w : v.w * 0.1f;
         }
@@ -179,7 +180,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
   constexpr int G2_BN = BN;                          // column tile of this instantiation (shadows the default)
   constexpr int G2_A_PLANE = Cfg::A_PLANE;
   constexpr int G2_A_STAGE = Cfg::A_STAGE;
-  const int dil = p.dil > 1 ? p.dil : 1;
+  // dilated taps and activated operand planes exist for the vocoder's layers only (long A boxes, and its short layers
+  // on the wide variant); the acoustic model's conv instantiation compiles them out
+  constexpr bool VOC = WIDE || AR != G2_A_ROWS;
+  const int dil = (VOC && p.dil > 1) ? p.dil : 1;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = smem_base;
@@ -278,9 +282,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
             const int s = ia % Cfg::A_STAGES; const uint32_t ph = (ia / Cfg::A_STAGES) & 1;
             ptx::mbar_wait(emptyA(s), ph ^ 1u);
             const uint32_t dst = sA + s * G2_A_STAGE;
-            if ((p.debug_mask & 8) && ia >= static_cast<uint32_t>(Cfg::A_STAGES)) {   // timing experiment: no A traffic
-              if (leader || CG == 1) ptx::mbar_arrive(fullA(s));
-            } else if (CG == 2) {
+            if (CG == 2) {
               const uint32_t bar = ptx::map_to_cta(fullA(s), 0);
               if (leader) ptx::mbar_expect_tx(fullA(s), 2 * G2_A_STAGE);
               ptx::tma_load_3d_pair(&tmA_hi, bar, dst, kb * G2_BK, t0 - p.pad * dil, b);
@@ -298,9 +300,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
             const uint32_t dst = sB + s * Cfg::B_STAGE;
             const int z = p.b_batched ? b : tap;
             const int nrow = n0 + static_cast<int>(rank) * Cfg::B_ROWS;
-            if ((p.debug_mask & 4) && ib >= static_cast<uint32_t>(Cfg::B_STAGES)) {   // timing experiment: no W traffic
-              if (leader || CG == 1) ptx::mbar_arrive(fullB(s));
-            } else if (FUSE) {
+            if (FUSE) {
               // leader: Bhi[0:64], Bhi[64:128], Bhi[0:64] again; peer: Blo[0:64], Blo[64:128], Bhi[64:128]
               const uint32_t bar = ptx::map_to_cta(fullB(s), 0);
               if (leader) ptx::mbar_expect_tx(fullB(s), 2 * Cfg::B_STAGE);
@@ -527,7 +527,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
         }
         __syncwarp();
         if (!tile_live) continue;                   // warp-uniform
-        g2_store_block32(p, stg, b, t0 + q * 32, n, lens_b, check_b, lane);
+        g2_store_block32<VOC>(p, stg, b, t0 + q * 32, n, lens_b, check_b, lane);
       }
     }
   } else {
@@ -682,10 +682,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
           } else if (p.act == ACT_RELU) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) vv[j] = fmaxf(vv[j], 0.0f);
-          } else if (p.act == ACT_LOGCLAMP) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) vv[j] = logf(fmaxf(vv[j], 1e-5f));
-          }
+          }                                           // ACT_LOGCLAMP exists in the wide variant only (launch_gemm checks)
           if (EPI == EPI_FULL && p.outT_hi != nullptr && row_ok && nn < p.N) {   // t-contiguous planes: thread = row
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -700,7 +697,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
                        "f"(vv[0]), "f"(vv[1]), "f"(vv[2]), "f"(vv[3]) : "memory");
         }
         __syncwarp();
-        g2_store_block32(p, stg, b, t0 + q * 32, n, lens_b, check_b, lane,
+        g2_store_block32<VOC>(p, stg, b, t0 + q * 32, n, lens_b, check_b, lane,
                          splits > 1 ? static_cast<size_t>(w % splits) * p.split_stride : 0);
       }
     }

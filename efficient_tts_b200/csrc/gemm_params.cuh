@@ -66,7 +66,6 @@ struct GemmParams {
   const int* col_lens;
   int err_code;          // extra bits OR-ed into err_flag with bit 3 (identifies the launch kind in diagnostics)
   int* err_flag;         // |= 8 when an activation leaves the fp16 operand range (|x| > 65504)
-  int debug_mask;        // timing experiments only (results become wrong): 1 = no fp32 store, 2 = no plane stores
   // split reduction (fused-B kernel, small problems): work item w covers accumulation chunk w % splits of tile
   // w / splits and stores its raw fp32 partial at out + (w % splits) * split_stride; splitk_reduce_kernel finishes
   int splits;            // 0 / 1 = off

@@ -295,8 +295,9 @@ int efts_resconv_train_bwd(efts_ctx* ctx, const float* grad_out, const float* ac
  * "wide" (16-epilogue-warp variant for short reductions), "fuse_b" (Ahi x [Bhi|Blo] as one N = 256 MMA),
  * "chunk_kb" (k-blocks per main-accumulator flush), "split_k" (split reduction for small launches), "pdl"
  * (programmatic dependent launch), "imv_version" (2: block-per-utterance IMV kernels, 1: the warp-per-row kernels
- * that serve rows too long for shared memory -- bitwise equal), "voc_group" / "voc_wide" / "voc_narrow" /
- * "voc_short_box" (vocoder layer packing), "debug_mask" (timing experiments only; results become wrong).
+ * that serve rows too long for shared memory -- bitwise equal), "voc_group" / "voc_wide" / "voc_narrow"
+ * (vocoder layer packing), "stack" (resident layer-stack kernels for B = 1 synthesis; 0 = one launch per layer,
+ * bitwise the same results), "stack_trace" (measurement hook of efts_profile_stack_trace).
  * No option selects a kernel outside the precision budget.  Returns EFTS_ERR_ARG for an unknown name. */
 int efts_set_option(efts_ctx* ctx, const char* name, int32_t value);
 /* Measurement hooks: while a tag's bit is set in `tag_mask`, every launch of that kind is bracketed
@@ -312,7 +313,7 @@ int efts_profile_read(efts_ctx* ctx, int32_t tag, double* total_ms, int64_t* cou
  * committed ncu capture before quoting that capture's numbers. */
 int efts_profile_kernel_name(const efts_ctx* ctx, int32_t tag, char* buf, size_t n);
 /* SM clock stamps (clock64 of CTA 0) the resident layer-stack kernel of B = 1 synthesis recorded at every phase
- * boundary of its last launch while option "debug_mask" had bit 4 set: start, [after embedding, after its barrier,]
+ * boundary of its last launch while option "stack_trace" was on: start, [after embedding, after its barrier,]
  * then per layer {GEMM done, barrier passed, reduce done, barrier passed}.  Synchronising copy of `n` <= 64 values. */
 int efts_profile_stack_trace(efts_ctx* ctx, int64_t* out, int32_t n);
 /* Data-dependent error bits raised by the kernels of the calls issued on `stream` since the last

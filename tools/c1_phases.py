@@ -58,7 +58,7 @@ def main():
     eng.set_option("stack", 1)
     print("C1PH " + json.dumps(out))
     # phase stamps of the resident kernel (SM cycles of CTA 0)
-    eng.set_option("debug_mask", 16)
+    eng.set_option("stack_trace", 1)
     buf = (ctypes.c_int64 * 64)()
     for phase in (1, 2):
         t2_dev = torch.empty(2, dtype=torch.int32, device=dev)
@@ -78,7 +78,7 @@ def main():
                   phase, *[buf[48 + k] - buf[base - 1 + 0] for k in range(5)], buf[base] - buf[base - 1],
                   buf[53] - buf[base - 1], buf[54] - buf[base - 1], buf[base + 2] - buf[base - 1],
                   *[buf[k] - buf[base - 1] for k in (55, 56, 57, 58)]))
-    eng.set_option("debug_mask", 0)
+    eng.set_option("stack_trace", 0)
 
 
 if __name__ == "__main__":
