@@ -601,7 +601,9 @@ def run_ours(args, rank, local_rank, world):
             line["per_rank"] = per_rank
             line["data_parallel_check"] = dp_check
     # ---- extras on rank 0 at N = 1: other configs, RTF at batch 1 (C1), vocoder, CPU baselines -------------------
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and args.no_extras:
+        line["cpu_baseline"] = None
+    elif rank == 0 and world == 1:
         try:
             line["other_configs"] = {"C2": time_forward_config(eng, dev, "C2"), "C5": time_forward_config(eng, dev, "C5")}
             line["length_regulator"] = time_length_regulator(dev, load_peaks())
@@ -748,6 +750,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=256,
                     help="utterances of the C3 draw the CPU legs run (256 = the full batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="only the headline C3 measurement (kernel experiments)")
     args = ap.parse_args()
     capture_stdout()
     rank = int(os.environ.get("RANK", "0"))

@@ -231,6 +231,7 @@ int launch_gemm2_t(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, con
   // persistent: one CTA per SM (CTA pairs when CG == 2), never more than there are tiles
   const long long n_rt = static_cast<long long>(p.B) * ((p.T + G2_BM - 1) / G2_BM);
   const long long work = ((n_rt + CG - 1) / CG) * ((p.N + BN - 1) / BN) * (FUSE && p.splits > 1 ? p.splits : 1);
+  if (work >= (1ll << 31)) return fail(EFTS_ERR_ARG, "launch of %lld work items exceeds the kernel's 32-bit item index", work);
   long long ctas = std::min<long long>(c->sm_count / CG, work) * CG;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(ctas));

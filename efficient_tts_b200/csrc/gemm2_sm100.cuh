@@ -246,15 +246,18 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
   const int chunk_kb = p.chunk_kb < 1 ? num_kb : p.chunk_kb;
   // split reduction: item w is chunk (w % splits) of tile (w / splits); every item is one accumulation chunk
   const int splits = (FUSE && p.splits > 1) ? p.splits : 1;
-  const long long total = static_cast<long long>(n_prt) * n_nt * splits;
+  // work items are counted in 32 bits (launch_gemm2_t checks the range): every epilogue thread locates its tile once per
+  // item, and 64-bit divisions cost ~100 instructions each
+  const unsigned total = static_cast<unsigned>(n_prt) * n_nt * splits;
   const int cid = blockIdx.x / CG, ncl = gridDim.x / CG;
   const int item_kb = splits > 1 ? (p.split_kb > 0 ? p.split_kb : chunk_kb) : num_kb;   // k-blocks per work item
-  auto kb_first = [&](long long w) { return splits > 1 ? static_cast<int>(w % splits) * item_kb : 0; };
+  auto kb_first = [&](unsigned w) { return splits > 1 ? static_cast<int>(w % static_cast<unsigned>(splits)) * item_kb : 0; };
 
-  auto locate = [&](long long w_in, int& b, int& t0, int& n0, bool& valid) {
-    const long long w = w_in / splits;
-    const int nt = static_cast<int>(w % n_nt);
-    const int rt = static_cast<int>(w / n_nt) * CG + static_cast<int>(rank);
+  auto locate = [&](unsigned w_in, int& b, int& t0, int& n0, bool& valid) {
+    const unsigned w = splits > 1 ? w_in / static_cast<unsigned>(splits) : w_in;
+    const unsigned wq = w / static_cast<unsigned>(n_nt);
+    const int nt = static_cast<int>(w - wq * n_nt);
+    const int rt = static_cast<int>(wq) * CG + static_cast<int>(rank);
     n0 = nt * G2_BN;
     valid = rt < n_rt;
     if (!valid) { b = p.B; t0 = 0; return; }                 // b == B: every TMA row is out of range -> zeros
@@ -273,7 +276,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       ptx::prefetch_tensormap(&tmA_hi); ptx::prefetch_tensormap(&tmA_lo);
       ptx::prefetch_tensormap(&tmB_hi); ptx::prefetch_tensormap(&tmB_lo);
       uint32_t ia = 0, ib = 0;
-      for (long long w = cid; w < total; w += ncl) {
+      for (unsigned w = cid; w < total; w += ncl) {
         int b, t0, n0; bool valid;
         locate(w, b, t0, n0, valid);
         const int kbf = kb_first(w);
@@ -333,7 +336,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
         if (CG == 2) ptx::tc_commit_pair(bar, 3); else ptx::tc_commit(bar);
       };
       uint32_t ia = 0, ib = 0, g = 0, it = 0;
-      for (long long w = cid; w < total; w += ncl) {
+      for (unsigned w = cid; w < total; w += ncl) {
         const uint32_t tb = it & 1u;
         if (!FUSE) ptx::mbar_wait(acc1_empty(tb), ((it >> 1) & 1u) ^ 1u);
         const uint32_t acc1 = tmem_base + 256u + tb * G2_BN;
@@ -413,7 +416,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       }
     };
     uint32_t g = 0, it = 0, uses0 = 0u, uses1 = 0u;
-    for (long long w = cid; w < total; w += ncl, ++it, ++g) {       // exactly one chunk per tile
+    for (unsigned w = cid; w < total; w += ncl, ++it, ++g) {       // exactly one chunk per tile
       if ((it & 1u) != grp) continue;
       int b, t0, n0; bool valid;
       locate(w, b, t0, n0, valid);
@@ -541,7 +544,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
     const int row = q * 32 + lane;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     // accumulation chunks of work item w (the last split of a reduction may be shorter than the others)
-    auto chunks_of = [&](long long w) {
+    auto chunks_of = [&](unsigned w) {
       const int kbf = kb_first(w);
       return static_cast<uint32_t>((min(kbf + item_kb, num_kb) - kbf + chunk_kb - 1) / chunk_kb);
     };
@@ -554,7 +557,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
     };
     uint32_t g = 0, it = 0;
     uint32_t uses0 = 0u, uses1 = 0u;              // completed waits on this group's acc0_full[buf]
-    for (long long w = cid; w < total; w += ncl, ++it) {
+    for (unsigned w = cid; w < total; w += ncl, ++it) {
       const uint32_t nchunks = chunks_of(w);
       if ((it & 1u) != grp) { g += nchunks; continue; }
       int b, t0, n0; bool valid;
@@ -698,7 +701,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
         }
         __syncwarp();
         g2_store_block32<VOC>(p, stg, b, t0 + q * 32, n, lens_b, check_b, lane,
-                         splits > 1 ? static_cast<size_t>(w % splits) * p.split_stride : 0);
+                         splits > 1 ? static_cast<size_t>(w % static_cast<unsigned>(splits)) * p.split_stride : 0);
       }
     }
   }
