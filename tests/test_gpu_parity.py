@@ -508,6 +508,26 @@ def test_resident_stack_and_split_reduction_are_bitwise_the_per_layer_result(dev
         assert torch.equal(first[0], again[0]) and torch.equal(first[1], again[1])
 
 
+def test_long_synthesis_leaves_the_resident_stack_and_still_matches_the_oracle(dev):
+    """The resident stack holds its partial planes in a 16 MB scratch (T2 <= 2048 frames at 4 chunks); a longer
+    synthesis takes one launch per layer.  Both sides of the limit against the oracle, and the launch counts show
+    which path ran."""
+    w = orc.make_weights(seed=1234, dur_bias=float(np.log(24.0)), dur_weight_scale=0.05)
+    m = build_model(w, dev)
+    eng = m._get_engine()
+    for n_tok, stack_expected in ((80, True), (100, False)):
+        t = make_inference_inputs(70 + n_tok, n_tok)
+        with torch.no_grad():
+            rmel, rra = orc.inference(w, t)
+        n0 = eng.launch_count()
+        mel, ra = m.inference(t.to(dev))
+        launches = eng.launch_count() - n0
+        assert mel.shape == rmel.shape and (mel.shape[1] <= 2048) == stack_expected, mel.shape
+        assert (launches <= 6) == stack_expected, launches       # 4 launches with the stack, 10+ with one launch per layer
+        assert (mel.cpu() - rmel).abs().max().item() <= MEL_TOL
+        assert (ra.cpu() - rra).abs().max().item() <= RA_TOL
+
+
 def test_programmatic_dependent_launch_does_not_change_results(model, dev):
     """GEMM launches carry the programmatic-stream-serialization attribute (their prologue overlaps the previous
     kernel's tail, `griddepcontrol.wait` guards the first touch of activations): bitwise the serialized result,
