@@ -720,9 +720,10 @@ int run_imv(efts_ctx* c, cudaStream_t st, const __half* q_hi, const __half* q_lo
 struct StackBuilder {
   efts_ctx* c;
   StackParams sp;
-  int max_items = 1;
+  int max_items = 1, max_items64 = 1;
   size_t max_plane = 0;
   int barriers = 0;
+  const PackedW* wts[ST_MAX_LAYERS] = {};
   explicit StackBuilder(efts_ctx* c_) : c(c_) { memset(&sp, 0, sizeof(sp)); }
 
   // one tensor-core layer: A planes [T, K] x weights w -> epilogue described by the caller through the returned slot
@@ -733,8 +734,7 @@ struct StackBuilder {
     StackLayer& L = sp.layer[sp.n_layers++];
     TRY(make_map(c, &M.a_hi, a_hi, K, T, 1, K, G2_A_ROWS));
     TRY(make_map(c, &M.a_lo, a_lo, K, T, 1, K, G2_A_ROWS));
-    TRY(make_map(c, &M.b_hi, w.hi, w.K, w.N, w.Z, w.K, G2_BN));
-    TRY(make_map(c, &M.b_lo, w.lo, w.K, w.N, w.Z, w.K, G2_BN));
+    wts[sp.n_layers - 1] = &w;                         // weight maps are encoded at launch (their box depends on the tile)
     L.T = T; L.K = K; L.N = w.N; L.ntaps = w.Z; L.pad = (w.Z - 1) / 2;
     L.chunk_kb = chunk_kb;
     L.bias = w.bias;
@@ -743,6 +743,7 @@ struct StackBuilder {
     const int ckb = chunk_kb < 1 ? num_kb : chunk_kb;
     const int nchunks = (num_kb + ckb - 1) / ckb;
     max_items = std::max(max_items, ((T + G2_BM - 1) / G2_BM) * ((w.N + G2_BN - 1) / G2_BN) * nchunks);
+    max_items64 = std::max(max_items64, ((T + G2_BM - 1) / G2_BM) * ((w.N + 63) / 64) * nchunks);
     max_plane = std::max(max_plane, static_cast<size_t>(T) * w.N);
     sp.split_stride = std::max(sp.split_stride, static_cast<size_t>(T) * w.N);
     if (nchunks > 8) return fail(EFTS_ERR_UNSUPPORTED, "layer stack: at most 8 accumulation chunks per layer");
@@ -760,6 +761,13 @@ struct StackBuilder {
     sp.err_flag = c->err_flag;
     sp.trace = c->stack_trace_on ? c->stack_trace : nullptr;
     if (sp.text != nullptr) barriers += 1;
+    // 64-column tiles when they still fit one wave: twice the CTAs, half the MMA depth per layer
+    sp.bn = max_items64 <= c->sm_count ? 64 : G2_BN;
+    if (sp.bn == 64) max_items = max_items64;
+    for (int i = 0; i < sp.n_layers; ++i) {
+      TRY(make_map(c, &sp.maps[i].b_hi, wts[i]->hi, wts[i]->K, wts[i]->N, wts[i]->Z, wts[i]->K, sp.bn));
+      TRY(make_map(c, &sp.maps[i].b_lo, wts[i]->lo, wts[i]->K, wts[i]->N, wts[i]->Z, wts[i]->K, sp.bn));
+    }
     // enough CTAs for the widest layer's work items and one (row, four columns) unit per thread of the largest
     // reduce, never more than SMs (every CTA must be resident: the layers synchronise through a grid barrier)
     size_t units = static_cast<size_t>(sp.T_embed) * 32;

@@ -77,6 +77,8 @@ struct StackParams {
   StackMaps maps[ST_MAX_LAYERS];
   StackLayer layer[ST_MAX_LAYERS];
   int n_layers;
+  int bn;                      // column tile of this launch: 128, or 64 when that still fits one wave of CTAs (twice the
+                               // work items of half the MMA depth each; same per-element arithmetic)
   float* scratch;              // partial planes [chunk][T][N]
   size_t split_stride;         // elements between partial planes (>= max T * N)
   unsigned* sync;              // grid barrier counter (monotonic across launches)
@@ -213,7 +215,8 @@ stack_kernel(const __grid_constant__ StackParams sp) {
   for (int li = 0; li < sp.n_layers; ++li) {
     const StackLayer& L = layers[li];
     const StackMaps& M = sp.maps[li];
-    const int n_nt = (L.N + G2_BN - 1) / G2_BN;
+    const int BN = sp.bn;
+    const int n_nt = (L.N + BN - 1) / BN;
     const int n_rt = (L.T + G2_BM - 1) / G2_BM;
     const int num_kb = (L.K + G2_BK - 1) / G2_BK;
     const int ckb = L.chunk_kb < 1 ? num_kb : L.chunk_kb;
@@ -229,15 +232,15 @@ stack_kernel(const __grid_constant__ StackParams sp) {
           const int s = ib % ST_B_STAGES;
           ptx::mbar_wait(emptyB(s), ((ib / ST_B_STAGES) & 1u) ^ 1u);
           const uint32_t dst = sB + s * ST_B_STAGE;
-          ptx::mbar_expect_tx(fullB(s), ST_B_STAGE);
+          ptx::mbar_expect_tx(fullB(s), 2 * BN * 128);              // [Bhi (BN rows) ; Blo (BN rows)], one 2 BN-row tile
           ptx::tma_load_3d(&Mx.b_hi, fullB(s), dst, kb * G2_BK, n0, tap);
-          ptx::tma_load_3d(&Mx.b_lo, fullB(s), dst + ST_B_PLANE, kb * G2_BK, n0, tap);
+          ptx::tma_load_3d(&Mx.b_lo, fullB(s), dst + BN * 128, kb * G2_BK, n0, tap);
           ++ib;
         };
         int skip_b = pre_b;                          // weight tiles of the first item that were issued ahead
         for (int w = blockIdx.x; w < total; w += gridDim.x) {
           const int ch = w % nchunks, tile = w / nchunks;
-          const int n0 = (tile % n_nt) * G2_BN, t0 = (tile / n_nt) * G2_BM;
+          const int n0 = (tile % n_nt) * BN, t0 = (tile / n_nt) * G2_BM;
           const int kb1 = min(ch * ckb + ckb, num_kb);
           for (int kb = ch * ckb; kb < kb1; ++kb) {
             {
@@ -263,13 +266,13 @@ stack_kernel(const __grid_constant__ StackParams sp) {
           const StackMaps& Mn = sp.maps[li + 1];
           ptx::prefetch_tensormap(&Mn.b_hi); ptx::prefetch_tensormap(&Mn.b_lo);
           ptx::prefetch_tensormap(&Mn.a_hi); ptx::prefetch_tensormap(&Mn.a_lo);
-          const int nn_nt = (Ln.N + G2_BN - 1) / G2_BN, nn_rt = (Ln.T + G2_BM - 1) / G2_BM;
+          const int nn_nt = (Ln.N + BN - 1) / BN, nn_rt = (Ln.T + G2_BM - 1) / G2_BM;
           const int nnum_kb = (Ln.K + G2_BK - 1) / G2_BK;
           const int nckb = Ln.chunk_kb < 1 ? nnum_kb : Ln.chunk_kb;
           const int nnch = (nnum_kb + nckb - 1) / nckb;
           const int w = blockIdx.x;
           if (w < nn_rt * nn_nt * nnch) {
-            const int ch = w % nnch, n0 = ((w / nnch) % nn_nt) * G2_BN;
+            const int ch = w % nnch, n0 = ((w / nnch) % nn_nt) * BN;
             const int kb0 = ch * nckb, kb1 = min(kb0 + nckb, nnum_kb);
             const int avail = (kb1 - kb0) * Ln.ntaps;
             for (int q = 0; q < min(ST_B_STAGES, avail); ++q) {
@@ -282,8 +285,8 @@ stack_kernel(const __grid_constant__ StackParams sp) {
     } else if (warp == 1) {
       // ---------------------------------------------------------- MMA issuer (one thread)
       if (lane == 0) {
-        constexpr uint32_t idesc_n256 = ptx::make_idesc_f16(G2_BM, 2 * G2_BN);
-        constexpr uint32_t idesc_n128 = ptx::make_idesc_f16(G2_BM, G2_BN);
+        const uint32_t idesc_n256 = ptx::make_idesc_f16(G2_BM, 2 * BN);     // Ahi x [Bhi ; Blo]
+        const uint32_t idesc_n128 = ptx::make_idesc_f16(G2_BM, BN);         // Alo x Bhi
         for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
           const int ch = w % nchunks;
           const int kb1 = min(ch * ckb + ckb, num_kb);
@@ -312,7 +315,7 @@ stack_kernel(const __grid_constant__ StackParams sp) {
                 const uint64_t ko = static_cast<uint64_t>(k * 2);
                 // columns [0,128): Ahi*Bhi, [128,256): Ahi*Blo + Alo*Bhi
                 ptx::mma_f16_ss(acc, dAh + ko, dB + ko, idesc_n256, first ? 0u : 1u);
-                ptx::mma_f16_ss(acc + G2_BN, dAl + ko, dB + ko, idesc_n128, 1u);
+                ptx::mma_f16_ss(acc + BN, dAl + ko, dB + ko, idesc_n128, 1u);
                 first = 0;
               }
               ptx::tc_commit(emptyB(sb));
@@ -333,20 +336,20 @@ stack_kernel(const __grid_constant__ StackParams sp) {
       const int sub_row = lane >> 3, sub_col = (lane & 7) * 4;
       for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
         const int ch = w % nchunks, tile = w / nchunks;
-        const int n0 = (tile % n_nt) * G2_BN, t0 = (tile / n_nt) * G2_BM;
+        const int n0 = (tile % n_nt) * BN, t0 = (tile / n_nt) * G2_BM;
         const uint32_t buf = it & 1u;
         float* part = sp.scratch + static_cast<size_t>(ch) * sp.split_stride;
         ptx::mbar_wait(acc_full(buf), (it >> 1) & 1u);
         ptx::tc_fence_after();
         if (q == 0 && lane == 0) stamp_role(li, 2);
 #pragma unroll 1
-        for (int c32 = 0; c32 < G2_BN / 32; ++c32) {
+        for (int c32 = 0; c32 < BN / 32; ++c32) {
           __syncwarp();                               // the previous block's transposed reads are done
           uint32_t r0[32], r1[32];
           ptx::tmem_ld_32x32(lane_addr + buf * (2 * G2_BN) + c32 * 32, r0);
-          ptx::tmem_ld_32x32(lane_addr + buf * (2 * G2_BN) + G2_BN + c32 * 32, r1);
+          ptx::tmem_ld_32x32(lane_addr + buf * (2 * G2_BN) + BN + c32 * 32, r1);
           ptx::tmem_ld_wait();
-          if (c32 == G2_BN / 32 - 1) {                // everything this warp needs has left tensor memory
+          if (c32 == BN / 32 - 1) {                   // everything this warp needs has left tensor memory
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(acc_empty(buf));
