@@ -214,10 +214,11 @@ int make_map(efts_ctx* c, CUtensorMap* m, const __half* ptr, int inner, int rows
 constexpr size_t kReconstructSmemMax = 200 * 1024;
 constexpr size_t kSplitScratchBytes = 16u << 20;       // partial planes of a split reduction (workspace, text side)
 
-template <int CG, int EPI, int WIDE, int FUSE = 0, int AR = G2_A_ROWS, int BN = G2_BN>
+template <int CG, int EPI, int WIDE, int FUSE = 0, int AR = G2_A_ROWS, int BN = G2_BN, int SPLIT = 0>
 int launch_gemm2_t(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, const GemmParams& p) {
   using Cfg = G2Cfg<CG, WIDE, FUSE, AR, BN>;
-  auto kern = gemm2_kernel<CG, EPI, WIDE, FUSE, AR, BN>;
+  auto kern = gemm2_kernel<CG, EPI, WIDE, FUSE, AR, BN, SPLIT>;
+  if (!SPLIT && p.splits > 1) return fail(EFTS_ERR_ARG, "split reduction requested from an unsplit kernel instantiation");
   const int dil = p.dil > 1 ? p.dil : 1;
   if (G2_BM + (p.ntaps - 1) * dil > AR)
     return fail(EFTS_ERR_ARG, "%d taps with dilation %d need a %d-row A box (this variant holds %d)", p.ntaps, dil,
@@ -230,7 +231,7 @@ int launch_gemm2_t(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, con
   TRY(make_map(c, &mb_lo, b.lo, b.K, b.N, b.Z, b.ld, Cfg::B_ROWS));
   // persistent: one CTA per SM (CTA pairs when CG == 2), never more than there are tiles
   const long long n_rt = static_cast<long long>(p.B) * ((p.T + G2_BM - 1) / G2_BM);
-  const long long work = ((n_rt + CG - 1) / CG) * ((p.N + BN - 1) / BN) * (FUSE && p.splits > 1 ? p.splits : 1);
+  const long long work = ((n_rt + CG - 1) / CG) * ((p.N + BN - 1) / BN) * (SPLIT && p.splits > 1 ? p.splits : 1);
   if (work >= (1ll << 31)) return fail(EFTS_ERR_ARG, "launch of %lld work items exceeds the kernel's 32-bit item index", work);
   long long ctas = std::min<long long>(c->sm_count / CG, work) * CG;
   cudaLaunchConfig_t cfg = {};
@@ -250,8 +251,8 @@ int launch_gemm2_t(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, con
   CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ma_hi, ma_lo, mb_hi, mb_lo, p));
   c->launches++;
   if (c->profile_mask)
-    snprintf(c->tag_kernel[c->cur_tag & 15], sizeof(c->tag_kernel[0]), "gemm2_kernel<%d, %d, %d, %d, %d, %d>", CG, EPI,
-             WIDE, FUSE, AR, BN);
+    snprintf(c->tag_kernel[c->cur_tag & 15], sizeof(c->tag_kernel[0]), "gemm2_kernel<%d, %d, %d, %d, %d, %d, %d>", CG, EPI,
+             WIDE, FUSE, AR, BN, SPLIT);
   return EFTS_OK;
 }
 
@@ -315,7 +316,7 @@ int launch_gemm(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, GemmPa
         q.bias = nullptr; q.act = ACT_NONE; q.resid = nullptr; q.lens = nullptr;
         q.out = p.split_scratch; q.ld_out = p.N; q.out_hi = nullptr; q.out_lo = nullptr;
         q.splits = splits; q.split_stride = plane;
-        TRY((launch_gemm2_t<2, EPI_STD, 0, 1>(c, st, a, b, q)));
+        TRY((launch_gemm2_t<2, EPI_STD, 0, 1, G2_A_ROWS, G2_BN, 1>(c, st, a, b, q)));
         const size_t n = plane / 4;
         const float* part = p.split_scratch;
         splitk_reduce_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(p, part, splits, plane);
@@ -334,7 +335,7 @@ int launch_gemm(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, GemmPa
         q.bias = nullptr; q.act = ACT_NONE; q.resid = nullptr; q.lens = nullptr;
         q.out = p.split_scratch; q.ld_out = p.N; q.out_hi = nullptr; q.out_lo = nullptr;
         q.splits = nchunks; q.split_stride = plane;
-        TRY((launch_gemm2_t<2, EPI_STD, 0, 1>(c, st, a, b, q)));
+        TRY((launch_gemm2_t<2, EPI_STD, 0, 1, G2_A_ROWS, G2_BN, 1>(c, st, a, b, q)));
         const size_t n = plane / 4;
         cudaLaunchConfig_t rc = {};
         rc.gridDim = dim3(static_cast<unsigned>((n + 255) / 256));
@@ -369,6 +370,8 @@ int set_kernel_attributes() {
   EFTS_OPT_IN_V2(2, EPI_STD, 1); EFTS_OPT_IN_V2(2, EPI_FULL, 1); EFTS_OPT_IN_V2(2, EPI_SOFTMAX, 1);
 #undef EFTS_OPT_IN_V2
   CUDA_TRY(cudaFuncSetAttribute(gemm2_kernel<2, EPI_STD, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                G2Cfg<2, 0, 1>::SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(gemm2_kernel<2, EPI_STD, 0, 1, G2_A_ROWS, G2_BN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 G2Cfg<2, 0, 1>::SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(gemm2_kernel<2, EPI_STD, 0, 1, G2_A_ROWS_LONG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 G2Cfg<2, 0, 1, G2_A_ROWS_LONG>::SMEM_BYTES));

@@ -31,7 +31,7 @@ constexpr int G2_THREADS = 128 + 32 * G2_EPI_WARPS;   // warpgroup 0: TMA, MMA, 
 constexpr int G2_BIAS_MAX = 1024;                     // columns whose bias is staged in shared memory
 constexpr int G2_BIAS_MAX_LONG = 2048;                // long-tap variant (the transposed-conv GEMM has N = stride * C)
 constexpr int G2_REGS_CTRL = 72;                     // setmaxnreg budgets: 3 warps per SM sub-partition,
-constexpr int G2_REGS_EPI = 216;                     // 32 * (72 + 2 * 216) = 16128 <= 16384 registers
+constexpr int G2_REGS_EPI = 216;                     // 32 * (72 + 2 * 216) = 16128 <= 16384 registers (an exact fit, 80 + 2 * 216, fails to launch)
 
 constexpr int G2_STAGE_ROW_BYTES = 144;               // wide epilogue staging: 32 fp32 + pad per row (conflict-free v4 stores)
 constexpr int G2_STAGE_WARP_BYTES = 32 * G2_STAGE_ROW_BYTES;
@@ -171,7 +171,11 @@ enum Gemm2Epi { EPI_STD = 0, EPI_FULL = 1, EPI_SOFTMAX = 2 };
 // columns at a time -- no running sums, 96 registers per thread, twice the warps to hide the store latency.
 constexpr int G2_THREADS_WIDE = 128 + 32 * 16;
 
-template <int CG, int EPI, int WIDE, int FUSE = 0, int AR = G2_A_ROWS, int BN = 128>
+// SPLIT = 1 compiles the split-reduction bookkeeping in (work item = k-block range of a tile, partial planes).  It is a
+// template parameter because the run-time form of it cost the unsplit conv launches 7.5 % more issued instructions and
+// 6.7 points of tensor-pipe activity (measured by bisecting the commits on one box: 198 M -> 213 M warp instructions,
+// 86.6 % -> 79.9 %).
+template <int CG, int EPI, int WIDE, int FUSE = 0, int AR = G2_A_ROWS, int BN = 128, int SPLIT = 0>
 __global__ void __launch_bounds__(WIDE ? G2_THREADS_WIDE : G2_THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
              const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
@@ -245,16 +249,17 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
   const int num_kb = (p.K + G2_BK - 1) / G2_BK;
   const int chunk_kb = p.chunk_kb < 1 ? num_kb : p.chunk_kb;
   // split reduction: item w is chunk (w % splits) of tile (w / splits); every item is one accumulation chunk
-  const int splits = (FUSE && p.splits > 1) ? p.splits : 1;
+  static_assert(!SPLIT || FUSE, "split reductions run on the fused-B kernel");
+  const int splits = (SPLIT && p.splits > 1) ? p.splits : 1;
   // work items are counted in 32 bits (launch_gemm2_t checks the range): every epilogue thread locates its tile once per
   // item, and 64-bit divisions cost ~100 instructions each
   const unsigned total = static_cast<unsigned>(n_prt) * n_nt * splits;
   const int cid = blockIdx.x / CG, ncl = gridDim.x / CG;
-  const int item_kb = splits > 1 ? (p.split_kb > 0 ? p.split_kb : chunk_kb) : num_kb;   // k-blocks per work item
-  auto kb_first = [&](unsigned w) { return splits > 1 ? static_cast<int>(w % static_cast<unsigned>(splits)) * item_kb : 0; };
+  const int item_kb = (SPLIT && splits > 1) ? (p.split_kb > 0 ? p.split_kb : chunk_kb) : num_kb;   // k-blocks per work item
+  auto kb_first = [&](unsigned w) { return (SPLIT && splits > 1) ? static_cast<int>(w % static_cast<unsigned>(splits)) * item_kb : 0; };
 
   auto locate = [&](unsigned w_in, int& b, int& t0, int& n0, bool& valid) {
-    const unsigned w = splits > 1 ? w_in / static_cast<unsigned>(splits) : w_in;
+    const unsigned w = (SPLIT && splits > 1) ? w_in / static_cast<unsigned>(splits) : w_in;
     const unsigned wq = w / static_cast<unsigned>(n_nt);
     const int nt = static_cast<int>(w - wq * n_nt);
     const int rt = static_cast<int>(wq) * CG + static_cast<int>(rank);
@@ -327,13 +332,21 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer (leader CTA, one thread)
+    // ------------------------------------------------------------ MMA issuer (leader CTA)
+    // The WHOLE warp walks the schedule and lane 0 issues.  With a lane-dependent branch around the loop the compiler
+    // keeps the stage / descriptor arithmetic in per-thread registers and moves every operand of every tcgen05.mma into
+    // uniform registers through an elect + R2UR.BROADCAST sequence right before the instruction -- five dependent
+    // moves on the issue path of each MMA, 6.7 points of tensor-pipe activity on the conv layers (found by bisecting
+    // the round-1 commits on one box).  Warp-uniform control flow keeps that arithmetic on the uniform datapath.
     if (!WIDE) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(G2_REGS_CTRL));
-    if (lane == 0 && leader) {
+    if (leader) {
+      const bool issuer = lane == 0;
       constexpr uint32_t idesc = ptx::make_idesc_f16(G2_BM * CG, G2_BN);
       constexpr uint32_t idesc_wide = ptx::make_idesc_f16(G2_BM * CG, 2 * G2_BN);
       auto commit = [&](uint32_t bar) {
-        if (CG == 2) ptx::tc_commit_pair(bar, 3); else ptx::tc_commit(bar);
+        if (issuer) {
+          if (CG == 2) ptx::tc_commit_pair(bar, 3); else ptx::tc_commit(bar);
+        }
       };
       uint32_t ia = 0, ib = 0, g = 0, it = 0;
       for (unsigned w = cid; w < total; w += ncl) {
@@ -364,25 +377,28 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
               const uint64_t dAl = ptx::make_desc_sw128(a_addr + G2_A_PLANE, 0);
               const uint64_t dBh = ptx::make_desc_sw128(b_addr, 0);
               const uint64_t dBl = ptx::make_desc_sw128(b_addr + Cfg::B_PLANE, 0);
+              const uint64_t dB3 = ptx::make_desc_sw128(b_addr + 2 * Cfg::B_PLANE, 0);
+              if (issuer) {
 #pragma unroll
-              for (int k = 0; k < G2_BK / 16; ++k) {
-                const uint64_t ko = static_cast<uint64_t>(k * 2);
-                if (FUSE) {
-                  // columns [0,128): Ahi*Bhi, [128,256): Ahi*Blo + Alo*Bhi (dBl + one plane = the third block)
-                  const uint64_t dB3 = ptx::make_desc_sw128(b_addr + 2 * Cfg::B_PLANE, 0);
-                  ptx::mma_f16_ss_pair(acc0, dAh + ko, dBh + ko, idesc_wide, first0 ? 0u : 1u);
-                  ptx::mma_f16_ss_pair(acc0 + G2_BN, dAl + ko, dB3 + ko, idesc, 1u);
-                } else if (CG == 2) {
-                  ptx::mma_f16_ss_pair(acc0, dAh + ko, dBh + ko, idesc, first0 ? 0u : 1u);
-                  ptx::mma_f16_ss_pair(acc1, dAh + ko, dBl + ko, idesc, first1 ? 0u : 1u);
-                  ptx::mma_f16_ss_pair(acc1, dAl + ko, dBh + ko, idesc, 1u);
-                } else {
-                  ptx::mma_f16_ss(acc0, dAh + ko, dBh + ko, idesc, first0 ? 0u : 1u);
-                  ptx::mma_f16_ss(acc1, dAh + ko, dBl + ko, idesc, first1 ? 0u : 1u);
-                  ptx::mma_f16_ss(acc1, dAl + ko, dBh + ko, idesc, 1u);
+                for (int k = 0; k < G2_BK / 16; ++k) {
+                  const uint64_t ko = static_cast<uint64_t>(k * 2);
+                  if (FUSE) {
+                    // columns [0,128): Ahi*Bhi, [128,256): Ahi*Blo + Alo*Bhi (dBl + one plane = the third block)
+                    ptx::mma_f16_ss_pair(acc0, dAh + ko, dBh + ko, idesc_wide, (first0 && k == 0) ? 0u : 1u);
+                    ptx::mma_f16_ss_pair(acc0 + G2_BN, dAl + ko, dB3 + ko, idesc, 1u);
+                  } else if (CG == 2) {
+                    ptx::mma_f16_ss_pair(acc0, dAh + ko, dBh + ko, idesc, (first0 && k == 0) ? 0u : 1u);
+                    ptx::mma_f16_ss_pair(acc1, dAh + ko, dBl + ko, idesc, (first1 && k == 0) ? 0u : 1u);
+                    ptx::mma_f16_ss_pair(acc1, dAl + ko, dBh + ko, idesc, 1u);
+                  } else {
+                    ptx::mma_f16_ss(acc0, dAh + ko, dBh + ko, idesc, (first0 && k == 0) ? 0u : 1u);
+                    ptx::mma_f16_ss(acc1, dAh + ko, dBl + ko, idesc, (first1 && k == 0) ? 0u : 1u);
+                    ptx::mma_f16_ss(acc1, dAl + ko, dBh + ko, idesc, 1u);
+                  }
                 }
-                first0 = 0; first1 = 0;
               }
+              first0 = 0; first1 = 0;
+              __syncwarp();
               commit(emptyB(sb));
             }
             commit(emptyA(sa));
@@ -544,7 +560,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
     const int row = q * 32 + lane;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     // accumulation chunks of work item w (the last split of a reduction may be shorter than the others)
+    const uint32_t nchunks_all = static_cast<uint32_t>((num_kb + chunk_kb - 1) / chunk_kb);
     auto chunks_of = [&](unsigned w) {
+      if (!SPLIT) return nchunks_all;
       const int kbf = kb_first(w);
       return static_cast<uint32_t>((min(kbf + item_kb, num_kb) - kbf + chunk_kb - 1) / chunk_kb);
     };
@@ -701,7 +719,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
         }
         __syncwarp();
         g2_store_block32<VOC>(p, stg, b, t0 + q * 32, n, lens_b, check_b, lane,
-                         splits > 1 ? static_cast<size_t>(w % static_cast<unsigned>(splits)) * p.split_stride : 0);
+                         (SPLIT && splits > 1) ? static_cast<size_t>(w % static_cast<unsigned>(splits)) * p.split_stride : 0);
       }
     }
   }

@@ -283,8 +283,10 @@ stack_kernel(const __grid_constant__ StackParams sp) {
         }
       }
     } else if (warp == 1) {
-      // ---------------------------------------------------------- MMA issuer (one thread)
-      if (lane == 0) {
+      // ---------------------------------------------------------- MMA issuer: the whole warp walks the schedule so that
+      // the descriptor arithmetic stays on the uniform datapath (see gemm2_kernel), lane 0 issues
+      {
+        const bool issuer = lane == 0;
         const uint32_t idesc_n256 = ptx::make_idesc_f16(G2_BM, 2 * BN);     // Ahi x [Bhi ; Blo]
         const uint32_t idesc_n128 = ptx::make_idesc_f16(G2_BM, BN);         // Alo x Bhi
         for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
@@ -304,26 +306,31 @@ stack_kernel(const __grid_constant__ StackParams sp) {
               ptx::mbar_wait(fullB(sb), (ib / ST_B_STAGES) & 1u);
               ++ib;
               ptx::tc_fence_after();
-              if (first) stamp_role(li, 0);
+              if (first && issuer) stamp_role(li, 0);
               const uint32_t a_addr = sA + sa * ST_A_STAGE + tap * 128;       // row shift = tap
               const uint32_t b_addr = sB + sb * ST_B_STAGE;
               const uint64_t dAh = ptx::make_desc_sw128(a_addr, 0);
               const uint64_t dAl = ptx::make_desc_sw128(a_addr + ST_A_PLANE, 0);
               const uint64_t dB = ptx::make_desc_sw128(b_addr, 0);
+              if (issuer) {
 #pragma unroll
-              for (int k = 0; k < G2_BK / 16; ++k) {
-                const uint64_t ko = static_cast<uint64_t>(k * 2);
-                // columns [0,128): Ahi*Bhi, [128,256): Ahi*Blo + Alo*Bhi
-                ptx::mma_f16_ss(acc, dAh + ko, dB + ko, idesc_n256, first ? 0u : 1u);
-                ptx::mma_f16_ss(acc + BN, dAl + ko, dB + ko, idesc_n128, 1u);
-                first = 0;
+                for (int k = 0; k < G2_BK / 16; ++k) {
+                  const uint64_t ko = static_cast<uint64_t>(k * 2);
+                  // columns [0,128): Ahi*Bhi, [128,256): Ahi*Blo + Alo*Bhi
+                  ptx::mma_f16_ss(acc, dAh + ko, dB + ko, idesc_n256, (first && k == 0) ? 0u : 1u);
+                  ptx::mma_f16_ss(acc + BN, dAl + ko, dB + ko, idesc_n128, 1u);
+                }
+                ptx::tc_commit(emptyB(sb));
               }
-              ptx::tc_commit(emptyB(sb));
+              first = 0;
+              __syncwarp();
             }
-            ptx::tc_commit(emptyA(sa));
+            if (issuer) ptx::tc_commit(emptyA(sa));
           }
-          ptx::tc_commit(acc_full(buf));
-          stamp_role(li, 1);
+          if (issuer) {
+            ptx::tc_commit(acc_full(buf));
+            stamp_role(li, 1);
+          }
         }
       }
     } else if (warp >= 4) {
