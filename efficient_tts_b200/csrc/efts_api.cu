@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -258,6 +259,11 @@ int launch_gemm2_t(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, con
 
 int launch_gemm(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, GemmParams p) {
   p.B = a.B; p.T = a.T; p.K = a.K;
+  static const bool trace = getenv("EFTS_TRACE_GEMM") != nullptr;      // diagnostics: one line per tensor-core launch
+  if (trace)
+    fprintf(stderr, "[efts gemm] B=%d T=%d K=%d N=%d taps=%d dil=%d act=%d resid=%d out=%d planes=%d plane_act=%d long=%d batched=%d\n",
+            a.B, a.T, a.K, p.N, p.ntaps, p.dil, p.act, p.resid != nullptr, p.out != nullptr, p.out_hi != nullptr,
+            p.plane_act, p.long_taps, p.b_batched);
   if (a.K != b.K) return fail(EFTS_ERR_ARG, "gemm K mismatch %d vs %d", a.K, b.K);
   if (p.N % 8 != 0) return fail(EFTS_ERR_ARG, "gemm N=%d must be a multiple of 8", p.N);
   {
@@ -274,7 +280,7 @@ int launch_gemm(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, GemmPa
     const int steps = p.ntaps * ((p.K + G2_BK - 1) / G2_BK) * (G2_BK / 16);
     // vocoder layers with a short reach and a short reduction (k = 3, most grouped layers: <= 40 MMA steps) are bound by
     // their store epilogue like the Linear layers: they take the wide variant (16 epilogue warps) through the normal path
-    if (p.long_taps && c->voc_wide && c->wide && epi == EPI_STD && !p.b_batched &&
+    if (p.long_taps && c->voc_wide && c->wide && epi == EPI_STD && !p.b_batched && (p.N > 64 || c->voc_wide > 1) &&
         G2_BM + (p.ntaps - 1) * (p.dil > 1 ? p.dil : 1) <= G2_A_ROWS && (p.bias == nullptr || p.N <= G2_BIAS_MAX) &&
         p.ntaps * ((p.K + G2_BK - 1) / G2_BK) * (G2_BK / 16) <= 40)
       p.long_taps = 0;
@@ -975,9 +981,9 @@ int efts_set_option(efts_ctx* c, const char* name, int32_t value) {
   if (strcmp(name, "split_k") == 0) { c->split_k = value != 0; return EFTS_OK; }
   if (strcmp(name, "stack") == 0) { c->stack = value != 0; return EFTS_OK; }
   if (strcmp(name, "pdl") == 0) { c->pdl = value != 0; return EFTS_OK; }
-  if (strcmp(name, "voc_group") == 0) { c->voc_group = value != 0; return EFTS_OK; }
+  if (strcmp(name, "voc_group") == 0) { c->voc_group = value; return EFTS_OK; }
   if (strcmp(name, "voc_narrow") == 0) { c->voc_narrow = value != 0; return EFTS_OK; }
-  if (strcmp(name, "voc_wide") == 0) { c->voc_wide = value != 0; return EFTS_OK; }
+  if (strcmp(name, "voc_wide") == 0) { c->voc_wide = value; return EFTS_OK; }
   if (strcmp(name, "imv_version") == 0) {
     if (value != 1 && value != 2) return fail(EFTS_ERR_ARG, "imv_version must be 1 or 2");
     c->imv_version = value;
@@ -1750,7 +1756,7 @@ int pack_voc_conv(efts_ctx* c, const std::string& prefix, int C, int k, int d, i
   int G = 1;
   if (c->voc_group)
     for (int g2 = 2; g2 * C <= 128; g2 *= 2)
-      if (Lmult % g2 == 0 && cost(g2) < cost(G)) G = g2;
+      if (Lmult % g2 == 0 && (cost(g2) < cost(G) || (c->voc_group > 1 && cost(g2) < c->voc_group * cost(G)))) G = g2;
   *group = G;
   *dil = G == 1 ? d : 1;
   if (G == 1) return pack_weight(c, prefix + ".weight", prefix + ".bias", C, C, k, out);
@@ -1923,8 +1929,12 @@ int efts_vocoder_forward(efts_ctx* c, const float* mel, int32_t B, int32_t T, fl
     c->launches++;
   }
   // conv_post + tanh (:133-134)
-  voc_post_kernel<<<dim3(static_cast<unsigned>((L + 255) / 256), B), 256, 0, st>>>(w.x_f, v.post_w, v.post_b,
-                                                                                 static_cast<int>(L), C, 7, audio);
+  if (C <= VOC_POST_CMAX && C % 4 == 0)
+    voc_post_tiled_kernel<<<dim3(static_cast<unsigned>((L + VOC_POST_BLOCK - 1) / VOC_POST_BLOCK), B), VOC_POST_BLOCK, 0, st>>>(
+        w.x_f, v.post_w, v.post_b, static_cast<int>(L), C, 7, audio);
+  else
+    voc_post_kernel<<<dim3(static_cast<unsigned>((L + 255) / 256), B), 256, 0, st>>>(w.x_f, v.post_w, v.post_b,
+                                                                                   static_cast<int>(L), C, 7, audio);
   CUDA_TRY(cudaGetLastError());
   c->launches++;
   return EFTS_OK;
