@@ -758,7 +758,6 @@ struct StackBuilder {
     if (nchunks > 8) return fail(EFTS_ERR_UNSUPPORTED, "layer stack: at most 8 accumulation chunks per layer");
     if (static_cast<size_t>(T) * w.N * nchunks * sizeof(float) > kSplitScratchBytes)
       return fail(EFTS_ERR_WORKSPACE, "layer stack: %d rows do not fit the partial-plane scratch", T);
-    barriers += 2;
     *out = &L;
     return EFTS_OK;
   }
@@ -784,10 +783,11 @@ struct StackBuilder {
       units = std::max(units, static_cast<size_t>(sp.layer[i].T) * (sp.layer[i].mode == ST_PLAIN ? sp.layer[i].N / 4 : 32));
     const int grid = std::max(1, std::min(c->sm_count, std::max(max_items, static_cast<int>((units + ST_THREADS - 1) / ST_THREADS))));
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(static_cast<unsigned>(grid));
     cfg.blockDim = dim3(ST_THREADS);
     cfg.dynamicSmemBytes = ST_SMEM_BYTES;
     cfg.stream = st;
+    barriers += 2 * sp.n_layers;
+    cfg.gridDim = dim3(static_cast<unsigned>(grid));
     CUDA_TRY(cudaLaunchKernelEx(&cfg, stack_kernel, sp));
     c->sync_base += static_cast<unsigned>(grid) * static_cast<unsigned>(barriers);
     c->launches++;

@@ -207,7 +207,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
   const uint32_t sBias = sBar + 512u;              // [G2_BIAS_MAX] fp32 copy of the bias (epilogue reads it per row)
   const uint32_t sStage = sBias + 4u * Cfg::BIAS_MAX; // per-warp transposition buffers [warps][32 rows][144 B]
 
-  const int warp = threadIdx.x >> 5;
+  // through a shuffle: the compiler then knows the role branches below are warp-uniform (and keeps the MMA warp's
+  // stage / descriptor arithmetic on the uniform datapath in every instantiation)
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const uint32_t rank = CG == 2 ? ptx::cluster_ctarank() : 0u;
   const bool leader = rank == 0;

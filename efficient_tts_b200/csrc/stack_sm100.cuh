@@ -31,7 +31,8 @@ constexpr int ST_A_STAGE = 2 * ST_A_PLANE;      // hi + lo
 constexpr int ST_B_PLANE = G2_BN * 128;
 constexpr int ST_B_STAGE = 2 * ST_B_PLANE;      // [Bhi ; Blo]: one 256-row K-major tile
 constexpr int ST_A_STAGES = 2;
-constexpr int ST_B_STAGES = 4;
+constexpr int ST_B_STAGES = 4;                  // of 256 weight rows; with 64-column tiles the same bytes hold 8 stages
+constexpr int ST_B_STAGES_MAX = 8;
 constexpr int ST_SMEM_TILES = ST_A_STAGES * ST_A_STAGE + ST_B_STAGES * ST_B_STAGE;
 constexpr int ST_LAYER_SMEM = 2048;              // shared-memory copy of the layer table
 constexpr int ST_SMEM_BYTES = ST_SMEM_TILES + 1024 + 512 + 4 * G2_STAGE_WARP_BYTES + ST_LAYER_SMEM;
@@ -90,7 +91,7 @@ struct StackParams {
   const float* emb;
   int num_symbols, T_embed;
   float* x0_f; __half* x0_hi; __half* x0_lo;
-  int* flags;                  // |= 4 token id out of range, |= 8 operand range
+  int* flags;                  // |= 4 token id out of range, |= 8 operand range, |= 64 grid barrier timed out
   // epilogue: e = cumsum(durations), T2 = round(e[-1]) (:260, :361) when dur != nullptr
   const float* dur; float* e; int* t2_out; int T_cumsum;
 };
@@ -109,18 +110,24 @@ __device__ __forceinline__ long long clock_after(float a, float b, float c, floa
 // the matching fence before its first load of the next layer).
 // One releasing reduction and relaxed polling per CTA; the acquire fence is paid once, after the last arrival.
 template <bool PROXY>
-__device__ __forceinline__ void stack_grid_barrier(unsigned* ctr, unsigned& target) {
+__device__ __forceinline__ void stack_grid_barrier(unsigned* ctr, unsigned& target, bool& dead, int* err_flag) {
   if (PROXY) asm volatile("fence.proxy.async.global;" ::: "memory");
   __syncthreads();
   target += gridDim.x;
   if (threadIdx.x == 0) {
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
     const long long t0 = clock64();
-    for (;;) {
+    while (!dead) {
       unsigned v;
       asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
       if (static_cast<int>(v - target) >= 0) break;
-      if (clock64() - t0 > 4000000000LL) __trap();   // a protocol bug traps instead of hanging the GPU
+      // A protocol bug must not hang the GPU: give up after ~2 s, flag it (bit 6), and let this CTA run through the
+      // remaining barriers without waiting.  (Not __trap(): an abort edge inside the layer loop makes the compiler
+      // treat the loop's state as divergent, and the MMA warp's descriptor arithmetic leaves the uniform datapath.)
+      if (clock64() - t0 > 4000000000LL) {
+        dead = true;
+        if (err_flag != nullptr) atomicOr(err_flag, 64);
+      }
     }
     asm volatile("fence.acq_rel.gpu;" ::: "memory");
   }
@@ -146,12 +153,16 @@ stack_kernel(const __grid_constant__ StackParams sp) {
                                                                               ptx::smem_u32(smem_raw)));
   static_assert(sizeof(StackLayer) * ST_MAX_LAYERS <= ST_LAYER_SMEM, "layer table does not fit its shared-memory slot");
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);   // provably warp-uniform role index
   const int lane = threadIdx.x & 31;
+  // weight ring: the deeper it is, the more of a layer's weights are in flight while the grid still synchronises
+  const uint32_t nb_stages = sp.bn == 64 ? ST_B_STAGES_MAX : ST_B_STAGES;
+  const uint32_t nb_shift = sp.bn == 64 ? 3u : 2u;
+  const uint32_t b_stage = static_cast<uint32_t>(2 * sp.bn * 128);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < ST_A_STAGES; ++s) { ptx::mbar_init(fullA(s), 1); ptx::mbar_init(emptyA(s), 1); }
-    for (int s = 0; s < ST_B_STAGES; ++s) { ptx::mbar_init(fullB(s), 1); ptx::mbar_init(emptyB(s), 1); }
+    for (int s = 0; s < ST_B_STAGES_MAX; ++s) { ptx::mbar_init(fullB(s), 1); ptx::mbar_init(emptyB(s), 1); }
     for (int s = 0; s < 2; ++s) { ptx::mbar_init(acc_full(s), 1); ptx::mbar_init(acc_empty(s), 4); }
     ptx::fence_barrier_init();
   }
@@ -169,6 +180,7 @@ stack_kernel(const __grid_constant__ StackParams sp) {
   ptx::pdl_wait();
 
   unsigned bar_target = sp.sync_base;
+  bool bar_dead = false;
   int trace_n = 0;
   auto stamp = [&]() {
     if (sp.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) sp.trace[trace_n++] = clock64();
@@ -204,24 +216,33 @@ stack_kernel(const __grid_constant__ StackParams sp) {
       }
     }
     stamp();
-    stack_grid_barrier<true>(sp.sync, bar_target);
+    stack_grid_barrier<true>(sp.sync, bar_target, bar_dead, sp.err_flag);
     stamp();
   }
 
-  // ring positions persist across layers (the pipelines are never torn down)
-  uint32_t ia = 0, ib = 0, it = 0;
+  // ring positions persist across layers (the pipelines are never torn down).  One set per role: the producer's
+  // advance under a lane-dependent branch, and a counter shared with it would no longer be warp-uniform for the compiler
+  // -- the MMA warp's stage and descriptor arithmetic would leave the uniform datapath (see gemm2_kernel).
+  uint32_t p_ia = 0, p_ib = 0;               // TMA producer (lane 0 of warp 0)
+  uint32_t m_ia = 0, m_ib = 0, m_it = 0;     // MMA warp
+  uint32_t d_it = 0;                         // drain warps
   int pre_b = 0;                 // producer: weight tiles of the coming layer's first item already in flight
 
   for (int li = 0; li < sp.n_layers; ++li) {
-    const StackLayer& L = layers[li];
+    const StackLayer& L = layers[li];           // shared-memory copy: what the reduce phase reads per row
+    const StackLayer& Lc = sp.layer[li];        // parameter space: everything that steers control flow (loads through
+                                                // the constant bank are warp-uniform for the compiler; shared-memory
+                                                // loads are not, and would push the MMA warp off the uniform datapath)
     const StackMaps& M = sp.maps[li];
     const int BN = sp.bn;
-    const int n_nt = (L.N + BN - 1) / BN;
-    const int n_rt = (L.T + G2_BM - 1) / G2_BM;
-    const int num_kb = (L.K + G2_BK - 1) / G2_BK;
-    const int ckb = L.chunk_kb < 1 ? num_kb : L.chunk_kb;
+    const int ntaps = Lc.ntaps, pad = Lc.pad;
+    const int n_nt = (Lc.N + BN - 1) / BN;
+    const int n_rt = (Lc.T + G2_BM - 1) / G2_BM;
+    const int num_kb = (Lc.K + G2_BK - 1) / G2_BK;
+    const int ckb = Lc.chunk_kb < 1 ? num_kb : Lc.chunk_kb;
     const int nchunks = (num_kb + ckb - 1) / ckb;
     const int total = n_rt * n_nt * nchunks;
+    const int w_first = blockIdx.x, w_step = gridDim.x;
 
     if (warp == 0) {
       // ---------------------------------------------------------- TMA producer
@@ -229,30 +250,30 @@ stack_kernel(const __grid_constant__ StackParams sp) {
         if (li == 0) { ptx::prefetch_tensormap(&M.a_hi); ptx::prefetch_tensormap(&M.a_lo); }
         asm volatile("fence.proxy.async.global;" ::: "memory");   // reader side of the barrier's proxy fence
         auto load_b = [&](const StackMaps& Mx, int kb, int n0, int tap) {
-          const int s = ib % ST_B_STAGES;
-          ptx::mbar_wait(emptyB(s), ((ib / ST_B_STAGES) & 1u) ^ 1u);
-          const uint32_t dst = sB + s * ST_B_STAGE;
+          const int s = p_ib & (nb_stages - 1u);
+          ptx::mbar_wait(emptyB(s), ((p_ib >> nb_shift) & 1u) ^ 1u);
+          const uint32_t dst = sB + s * b_stage;
           ptx::mbar_expect_tx(fullB(s), 2 * BN * 128);              // [Bhi (BN rows) ; Blo (BN rows)], one 2 BN-row tile
           ptx::tma_load_3d(&Mx.b_hi, fullB(s), dst, kb * G2_BK, n0, tap);
           ptx::tma_load_3d(&Mx.b_lo, fullB(s), dst + BN * 128, kb * G2_BK, n0, tap);
-          ++ib;
+          ++p_ib;
         };
         int skip_b = pre_b;                          // weight tiles of the first item that were issued ahead
-        for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        for (int w = w_first; w < total; w += w_step) {
           const int ch = w % nchunks, tile = w / nchunks;
           const int n0 = (tile % n_nt) * BN, t0 = (tile / n_nt) * G2_BM;
           const int kb1 = min(ch * ckb + ckb, num_kb);
           for (int kb = ch * ckb; kb < kb1; ++kb) {
             {
-              const int s = ia % ST_A_STAGES;
-              ptx::mbar_wait(emptyA(s), ((ia / ST_A_STAGES) & 1u) ^ 1u);
+              const int s = p_ia % ST_A_STAGES;
+              ptx::mbar_wait(emptyA(s), ((p_ia / ST_A_STAGES) & 1u) ^ 1u);
               const uint32_t dst = sA + s * ST_A_STAGE;
               ptx::mbar_expect_tx(fullA(s), ST_A_STAGE);
-              ptx::tma_load_3d(&M.a_hi, fullA(s), dst, kb * G2_BK, t0 - L.pad, 0);
-              ptx::tma_load_3d(&M.a_lo, fullA(s), dst + ST_A_PLANE, kb * G2_BK, t0 - L.pad, 0);
-              ++ia;
+              ptx::tma_load_3d(&M.a_hi, fullA(s), dst, kb * G2_BK, t0 - pad, 0);
+              ptx::tma_load_3d(&M.a_lo, fullA(s), dst + ST_A_PLANE, kb * G2_BK, t0 - pad, 0);
+              ++p_ia;
             }
-            for (int tap = 0; tap < L.ntaps; ++tap) {
+            for (int tap = 0; tap < ntaps; ++tap) {
               if (skip_b > 0) { --skip_b; continue; }
               load_b(M, kb, n0, tap);
             }
@@ -262,7 +283,7 @@ stack_kernel(const __grid_constant__ StackParams sp) {
         // land while the grid reduces and synchronises; only the activation loads wait for the barrier.
         pre_b = 0;
         if (li + 1 < sp.n_layers) {
-          const StackLayer& Ln = layers[li + 1];
+          const StackLayer& Ln = sp.layer[li + 1];
           const StackMaps& Mn = sp.maps[li + 1];
           ptx::prefetch_tensormap(&Mn.b_hi); ptx::prefetch_tensormap(&Mn.b_lo);
           ptx::prefetch_tensormap(&Mn.a_hi); ptx::prefetch_tensormap(&Mn.a_lo);
@@ -275,7 +296,7 @@ stack_kernel(const __grid_constant__ StackParams sp) {
             const int ch = w % nnch, n0 = ((w / nnch) % nn_nt) * BN;
             const int kb0 = ch * nckb, kb1 = min(kb0 + nckb, nnum_kb);
             const int avail = (kb1 - kb0) * Ln.ntaps;
-            for (int q = 0; q < min(ST_B_STAGES, avail); ++q) {
+            for (int q = 0; q < min(static_cast<int>(nb_stages), avail); ++q) {
               load_b(Mn, kb0 + q / Ln.ntaps, n0, q % Ln.ntaps);
               ++pre_b;
             }
@@ -287,28 +308,36 @@ stack_kernel(const __grid_constant__ StackParams sp) {
       // the descriptor arithmetic stays on the uniform datapath (see gemm2_kernel), lane 0 issues
       {
         const bool issuer = lane == 0;
+        // working copies the compiler can see are warp-uniform (the persistent ones merge across the role branches)
+        uint32_t ia = __shfl_sync(0xffffffffu, m_ia, 0), ib = __shfl_sync(0xffffffffu, m_ib, 0);
+        uint32_t it = __shfl_sync(0xffffffffu, m_it, 0);
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+        // ring geometry re-derived from the constant bank (the kernel-scope copies live in per-thread registers)
+        const uint32_t nbm = sp.bn == 64 ? 7u : 3u, nbs = sp.bn == 64 ? 3u : 2u, bsh = sp.bn == 64 ? 14u : 15u;
         const uint32_t idesc_n256 = ptx::make_idesc_f16(G2_BM, 2 * BN);     // Ahi x [Bhi ; Blo]
         const uint32_t idesc_n128 = ptx::make_idesc_f16(G2_BM, BN);         // Alo x Bhi
-        for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+        for (int w = w_first; w < total; w += w_step, ++it) {
           const int ch = w % nchunks;
           const int kb1 = min(ch * ckb + ckb, num_kb);
           const uint32_t buf = it & 1u;
           ptx::mbar_wait(acc_empty(buf), ((it >> 1) & 1u) ^ 1u);
           ptx::tc_fence_after();
-          const uint32_t acc = tmem_base + buf * (2 * G2_BN);
+          const uint32_t acc = tmem_u + buf * (2 * G2_BN);
           uint32_t first = 1;
           for (int kb = ch * ckb; kb < kb1; ++kb) {
             const int sa = ia % ST_A_STAGES;
             ptx::mbar_wait(fullA(sa), (ia / ST_A_STAGES) & 1u);
             ++ia;
-            for (int tap = 0; tap < L.ntaps; ++tap) {
-              const int sb = ib % ST_B_STAGES;
-              ptx::mbar_wait(fullB(sb), (ib / ST_B_STAGES) & 1u);
+            for (int tap = 0; tap < ntaps; ++tap) {
+              const uint32_t sb = ib & nbm;
+              ptx::mbar_wait(fullB(sb), (ib >> nbs) & 1u);
               ++ib;
               ptx::tc_fence_after();
               if (first && issuer) stamp_role(li, 0);
+              if (issuer && sp.trace != nullptr && blockIdx.x == 0 && li == 1 && (kb - ch * ckb) * ntaps + tap < 12)
+                sp.trace[36 + (kb - ch * ckb) * ntaps + tap] = clock64();     // operands of step i landed
               const uint32_t a_addr = sA + sa * ST_A_STAGE + tap * 128;       // row shift = tap
-              const uint32_t b_addr = sB + sb * ST_B_STAGE;
+              const uint32_t b_addr = sB + (sb << bsh);
               const uint64_t dAh = ptx::make_desc_sw128(a_addr, 0);
               const uint64_t dAl = ptx::make_desc_sw128(a_addr + ST_A_PLANE, 0);
               const uint64_t dB = ptx::make_desc_sw128(b_addr, 0);
@@ -332,6 +361,7 @@ stack_kernel(const __grid_constant__ StackParams sp) {
             stamp_role(li, 1);
           }
         }
+        m_ia = ia; m_ib = ib; m_it = it;
       }
     } else if (warp >= 4) {
       // ---------------------------------------------------------- accumulator drain -> raw partial planes
@@ -341,12 +371,12 @@ stack_kernel(const __grid_constant__ StackParams sp) {
       const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
       const uint32_t stg = sStage + static_cast<uint32_t>(q) * G2_STAGE_WARP_BYTES;
       const int sub_row = lane >> 3, sub_col = (lane & 7) * 4;
-      for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+      for (int w = w_first; w < total; w += w_step, ++d_it) {
         const int ch = w % nchunks, tile = w / nchunks;
         const int n0 = (tile % n_nt) * BN, t0 = (tile / n_nt) * G2_BM;
-        const uint32_t buf = it & 1u;
+        const uint32_t buf = d_it & 1u;
         float* part = sp.scratch + static_cast<size_t>(ch) * sp.split_stride;
-        ptx::mbar_wait(acc_full(buf), (it >> 1) & 1u);
+        ptx::mbar_wait(acc_full(buf), (d_it >> 1) & 1u);
         ptx::tc_fence_after();
         if (q == 0 && lane == 0) stamp_role(li, 2);
 #pragma unroll 1
@@ -370,8 +400,7 @@ stack_kernel(const __grid_constant__ StackParams sp) {
               vv[j] = __fadd_rn(0.0f, __fmaf_rn(__uint_as_float(r1[k4 * 4 + j]), SPLIT_INV_SCALE,
                                                 __uint_as_float(r0[k4 * 4 + j])));
             asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};"
-                         ::"r"(stg + lane * G2_STAGE_ROW_BYTES + k4 * 16),
-                         "f"(vv[0]), "f"(vv[1]), "f"(vv[2]), "f"(vv[3]) : "memory");
+                         ::"r"(stg + lane * G2_STAGE_ROW_BYTES + k4 * 16), "f"(vv[0]), "f"(vv[1]), "f"(vv[2]), "f"(vv[3]) : "memory");
           }
           __syncwarp();
           // transposed store (see g2_store_block32): eight lanes write one row's 128 contiguous bytes
@@ -394,11 +423,24 @@ stack_kernel(const __grid_constant__ StackParams sp) {
     __syncwarp();
     __syncthreads();
     stamp();
-    stack_grid_barrier<false>(sp.sync, bar_target);
+    stack_grid_barrier<false>(sp.sync, bar_target, bar_dead, sp.err_flag);
     stamp();
 
     // ------------------------------------------------------------ reduce + epilogue
     // sum of the partial planes in chunk order, four loads in flight at a time, + bias, activation
+    auto bias_act = [&](float4 x, int c) -> float4 {
+      if (L.bias != nullptr) {
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(L.bias + c));
+        x.x = __fadd_rn(x.x, bb.x); x.y = __fadd_rn(x.y, bb.y); x.z = __fadd_rn(x.z, bb.z); x.w = __fadd_rn(x.w, bb.w);
+      }
+      if (L.act == ACT_LRELU) {
+        x.x = x.x > 0.0f ? x.x : __fmul_rn(x.x, 0.1f); x.y = x.y > 0.0f ? x.y : __fmul_rn(x.y, 0.1f);
+        x.z = x.z > 0.0f ? x.z : __fmul_rn(x.z, 0.1f); x.w = x.w > 0.0f ? x.w : __fmul_rn(x.w, 0.1f);
+      } else if (L.act == ACT_RELU) {
+        x.x = fmaxf(x.x, 0.0f); x.y = fmaxf(x.y, 0.0f); x.z = fmaxf(x.z, 0.0f); x.w = fmaxf(x.w, 0.0f);
+      }
+      return x;
+    };
     auto reduced = [&](int row, int c) -> float4 {
       const float* p0 = sp.scratch + static_cast<size_t>(row) * L.N + c;
       float4 x = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -415,51 +457,44 @@ stack_kernel(const __grid_constant__ StackParams sp) {
             x.z = __fadd_rn(x.z, u[s].z); x.w = __fadd_rn(x.w, u[s].w);
           }
       }
-      if (L.bias != nullptr) {
-        const float4 bb = __ldg(reinterpret_cast<const float4*>(L.bias + c));
-        x.x = __fadd_rn(x.x, bb.x); x.y = __fadd_rn(x.y, bb.y); x.z = __fadd_rn(x.z, bb.z); x.w = __fadd_rn(x.w, bb.w);
+      return bias_act(x, c);
+    };
+    // residual, fp32 store, operand planes (+ transposed planes) of one (row, four columns) unit
+    auto store_plain = [&](int row, int c, float4 r, float4 x) {
+      const size_t o = static_cast<size_t>(row) * L.N + c;
+      if (L.resid != nullptr) {
+        x.x = __fadd_rn(r.x, x.x); x.y = __fadd_rn(r.y, x.y); x.z = __fadd_rn(r.z, x.z); x.w = __fadd_rn(r.w, x.w);
       }
-      if (L.act == ACT_LRELU) {
-        x.x = x.x > 0.0f ? x.x : __fmul_rn(x.x, 0.1f); x.y = x.y > 0.0f ? x.y : __fmul_rn(x.y, 0.1f);
-        x.z = x.z > 0.0f ? x.z : __fmul_rn(x.z, 0.1f); x.w = x.w > 0.0f ? x.w : __fmul_rn(x.w, 0.1f);
-      } else if (L.act == ACT_RELU) {
-        x.x = fmaxf(x.x, 0.0f); x.y = fmaxf(x.y, 0.0f); x.z = fmaxf(x.z, 0.0f); x.w = fmaxf(x.w, 0.0f);
+      if (L.out != nullptr) *reinterpret_cast<float4*>(L.out + o) = x;
+      if (L.out_hi != nullptr) {
+        if (outside_fp16_range(x) && sp.err_flag != nullptr) atomicOr(sp.err_flag, 8 | L.err_code);
+        uint2 h, l;
+        split4(x, &h, &l);
+        *reinterpret_cast<uint2*>(L.out_hi + o) = h;
+        *reinterpret_cast<uint2*>(L.out_lo + o) = l;
+        if (L.outT_hi != nullptr) {                 // K-major operand of the expansion matmul: [N, ld_t], t contiguous
+          const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const __half hh = __float2half_rn(xs[k]);
+            const size_t ot = static_cast<size_t>(c + k) * L.ld_t + row;
+            L.outT_hi[ot] = hh;
+            L.outT_lo[ot] = __float2half_rn((xs[k] - __half2float(hh)) * SPLIT_SCALE);
+          }
+        }
       }
-      return x;
     };
     if (sp.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && li == 1) sp.trace[53] = clock64();
     if (L.mode == ST_PLAIN) {
-      // one thread per (row, four columns): residual, fp32 store, operand planes (+ transposed planes)
+      // one thread per (row, four columns)
       const int n4 = L.N >> 2;
       const int units = L.T * n4;
 #pragma unroll 1
       for (int i = blockIdx.x * ST_THREADS + threadIdx.x; i < units; i += gridDim.x * ST_THREADS) {
         const int row = i / n4, c = (i - row * n4) * 4;
-        const size_t o = static_cast<size_t>(row) * L.N + c;
         float4 r = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        if (L.resid != nullptr) r = __ldcg(reinterpret_cast<const float4*>(L.resid + o));
-        float4 x = reduced(row, c);
-        if (L.resid != nullptr) {
-          x.x = __fadd_rn(r.x, x.x); x.y = __fadd_rn(r.y, x.y); x.z = __fadd_rn(r.z, x.z); x.w = __fadd_rn(r.w, x.w);
-        }
-        if (L.out != nullptr) *reinterpret_cast<float4*>(L.out + o) = x;
-        if (L.out_hi != nullptr) {
-          if (outside_fp16_range(x) && sp.err_flag != nullptr) atomicOr(sp.err_flag, 8 | L.err_code);
-          uint2 h, l;
-          split4(x, &h, &l);
-          *reinterpret_cast<uint2*>(L.out_hi + o) = h;
-          *reinterpret_cast<uint2*>(L.out_lo + o) = l;
-          if (L.outT_hi != nullptr) {                 // K-major operand of the expansion matmul: [N, ld_t], t contiguous
-            const float xs[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const __half hh = __float2half_rn(xs[k]);
-              const size_t ot = static_cast<size_t>(c + k) * L.ld_t + row;
-              L.outT_hi[ot] = hh;
-              L.outT_lo[ot] = __float2half_rn((xs[k] - __half2float(hh)) * SPLIT_SCALE);
-            }
-          }
-        }
+        if (L.resid != nullptr) r = __ldcg(reinterpret_cast<const float4*>(L.resid + static_cast<size_t>(row) * L.N + c));
+        store_plain(row, c, r, reduced(row, c));
       }
     } else {
       // LayerNorm over the 512 channels: one warp per row
@@ -479,10 +514,11 @@ stack_kernel(const __grid_constant__ StackParams sp) {
     }
     __syncthreads();
     stamp();
-    stack_grid_barrier<true>(sp.sync, bar_target);
+    stack_grid_barrier<true>(sp.sync, bar_target, bar_dead, sp.err_flag);
     stamp();
   }
 
+  if (bar_dead && sp.flags != nullptr) atomicOr(sp.flags, 64);     // thread 0 only: a grid barrier gave up
   // ---- epilogue: duration cumsum and T2 (one warp)
   if (sp.dur != nullptr && blockIdx.x == 0 && warp == 0) duration_cumsum_warp(sp.dur, sp.T_cumsum, sp.e, sp.t2_out, lane);
 

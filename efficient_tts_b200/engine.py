@@ -10,6 +10,8 @@ import torch
 from . import _lib
 
 N_CHANNELS = 512
+STACK_TIMEOUT_MESSAGE = ("the resident layer-stack kernel gave up waiting at a grid barrier (its CTAs were not all "
+                         "resident); the results of this call are invalid (include/efts_b200.h, flags bit 6)")
 RANGE_MESSAGE = ("an activation left the fp16 operand range (|x| > 65504): the split-fp16 tensor-core "
                  "scheme cannot represent it (include/efts_b200.h, flags bit 3)")
 
@@ -175,6 +177,8 @@ class Engine:
                 raise IndexError("index out of range in self")   # embedding lookup, :246
             if flags & 8:
                 raise FloatingPointError(RANGE_MESSAGE)
+            if flags & 64:
+                raise RuntimeError(STACK_TIMEOUT_MESSAGE)
             if t2 < 1:
                 raise RuntimeError("predicted length T2=%d; the reference's decoder conv rejects an "
                                    "empty sequence" % t2)
@@ -241,6 +245,8 @@ class Engine:
         _lib.check(self.lib.efts_error_flags(self._h, self._stream(), ctypes.byref(flags)))
         if flags.value & 8:
             raise FloatingPointError(RANGE_MESSAGE)
+        if flags.value & 64:
+            raise RuntimeError(STACK_TIMEOUT_MESSAGE)
         return flags.value
 
     # ------------------------------------------------------------------ layer-level calls

@@ -317,7 +317,8 @@ int efts_profile_kernel_name(const efts_ctx* ctx, int32_t tag, char* buf, size_t
  * then per layer {GEMM done, barrier passed, reduce done, barrier passed}.  Synchronising copy of `n` <= 64 values. */
 int efts_profile_stack_trace(efts_ctx* ctx, int64_t* out, int32_t n);
 /* Data-dependent error bits raised by the kernels of the calls issued on `stream` since the last
- * efts_forward / efts_inference_phase1 (bit 3: activation outside the fp16 operand range).
+ * efts_forward / efts_inference_phase1 (bit 3: activation outside the fp16 operand range; bit 6: a grid barrier
+ * of the resident layer-stack kernel timed out -- the call's results are invalid).
  * Synchronises the stream (4-byte read-back); efts_forward reports the same bits in scalars[7]. */
 int efts_error_flags(efts_ctx* ctx, void* stream, int32_t* flags_host);
 /* Synchronising read-back of `n` <= 64 device words through the context's pinned staging buffer (the T2 / flags

@@ -1,5 +1,6 @@
 #!/usr/bin/env python3
-"""GPU time of the two phases of B = 1 synthesis (CUDA events around the library calls) and the host gaps."""
+"""GPU time of the two phases of B = 1 synthesis (CUDA events around the library calls) and the host gaps.
+Usage: python tools/c1_phases.py [opt=val,...]"""
 import ctypes
 import json
 import os
@@ -24,6 +25,9 @@ def main():
     m.load_state_dict(wl.c1_weights_patch(state))
     m = m.eval().to(dev)
     eng = m._get_engine()
+    for kv in (sys.argv[1].split(",") if len(sys.argv) > 1 else []):      # opt=val,... applied to the context
+        k, v = kv.split("=")
+        eng.set_option(k, int(v))
     n_iter = int(os.environ.get("ITERS", "30"))
     txt = wl.make_inference_inputs(0, 64).to(dev)
     T1 = 64
@@ -74,10 +78,12 @@ def main():
         _lib.check(eng.lib.efts_profile_stack_trace(eng._h, buf, 64))
         base = 3 + 4 if phase == 1 else 1 + 4     # index of "layer 1 starts" (= layer 0's second barrier passed)
         print("TRACE phase %d layer 1 roles (cycles since layer start): first operands %d, last commit %d, acc ready %d, "
-              "tmem released %d, stores issued %d | gemm phase done %d | reduce loop entered %d, sums ready %d, loop left %d | first partial %d, partials %d, bias %d, resid %d" % (
+              "tmem released %d, stores issued %d | gemm phase done %d | reduce loop entered %d, first sums ready %d, "
+              "loop left %d, reduce phase done %d" % (
                   phase, *[buf[48 + k] - buf[base - 1 + 0] for k in range(5)], buf[base] - buf[base - 1],
-                  buf[53] - buf[base - 1], buf[54] - buf[base - 1], buf[base + 2] - buf[base - 1],
-                  *[buf[k] - buf[base - 1] for k in (55, 56, 57, 58)]))
+                  buf[53] - buf[base - 1], buf[54] - buf[base - 1], buf[55] - buf[base - 1], buf[base + 2] - buf[base - 1]))
+        print("TRACE phase %d layer 1 MMA steps (operands landed, cycles since layer start): %s" % (
+            phase, [buf[36 + k] - buf[base - 1] for k in range(10)]))
     eng.set_option("stack_trace", 0)
 
 
