@@ -314,7 +314,9 @@ int efts_profile_read(efts_ctx* ctx, int32_t tag, double* total_ms, int64_t* cou
 int efts_profile_kernel_name(const efts_ctx* ctx, int32_t tag, char* buf, size_t n);
 /* SM clock stamps (clock64 of CTA 0) the resident layer-stack kernel of B = 1 synthesis recorded at every phase
  * boundary of its last launch while option "stack_trace" was on: start, [after embedding, after its barrier,]
- * then per layer {GEMM done, barrier passed, reduce done, barrier passed}.  Synchronising copy of `n` <= 64 values. */
+ * then per layer {GEMM done, barrier passed, reduce done, barrier passed}; entries 36..47 and 48..55 hold stamps of
+ * CTA 0's MMA warp (operands of step i landed) and of its roles during layer 1 (tools/c1_phases.py decodes them).
+ * Synchronising copy of `n` <= 64 values. */
 int efts_profile_stack_trace(efts_ctx* ctx, int64_t* out, int32_t n);
 /* Data-dependent error bits raised by the kernels of the calls issued on `stream` since the last
  * efts_forward / efts_inference_phase1 (bit 3: activation outside the fp16 operand range; bit 6: a grid barrier
