@@ -2082,7 +2082,8 @@ namespace {
 struct TrainWs {
   __half *w_hi, *w_lo;                 // packed weights of the current layer [k][C][C]
   __half *a_hi[2], *a_lo[2];           // operand planes of a [B, T, C] activation (ping-pong)
-  __half *gT_hi, *gT_lo, *xT_hi, *xT_lo;   // transposed planes [C][Ktot]
+  __half *gT_hi, *gT_lo;               // transposed planes [C][Ktot] of the masked gradient
+  __half *xT_hi, *xT_lo;               // k copies [C][Ktot] of the transposed layer input, one per tap shift
   float* dwt;                          // [k][C][C]
   float* splitk;                       // partial planes of the split reductions
   double* db_part;                     // [kBiasParts][C]
@@ -2100,7 +2101,7 @@ void carve_train(Arena& a, TrainWs& w, int B, int T, int C, int k, bool backward
   for (int i = 0; i < 2; ++i) { w.a_hi[i] = a.get<__half>(m * C); w.a_lo[i] = a.get<__half>(m * C); }
   if (backward) {
     w.gT_hi = a.get<__half>(w.ktot * C); w.gT_lo = a.get<__half>(w.ktot * C);
-    w.xT_hi = a.get<__half>(w.ktot * C); w.xT_lo = a.get<__half>(w.ktot * C);
+    w.xT_hi = a.get<__half>(static_cast<size_t>(k) * w.ktot * C); w.xT_lo = a.get<__half>(static_cast<size_t>(k) * w.ktot * C);
     w.dwt = a.get<float>(static_cast<size_t>(k) * C * C);
     w.splitk = a.get<float>(kSplitScratchBytes / sizeof(float));
     w.db_part = a.get<double>(static_cast<size_t>(kBiasParts) * C);
@@ -2170,9 +2171,6 @@ int efts_resconv_train_bwd(efts_ctx* c, const float* grad_out, const float* acts
   const int pad = (k - 1) / 2;
   const size_t rows = static_cast<size_t>(B) * T, n = rows * C, wn = static_cast<size_t>(k) * C * C;
   CUDA_TRY(cudaMemsetAsync(c->err_flag, 0, sizeof(int), st));
-  // the margins of the transposed planes stay zero for the whole call (the kernels only write positions t < T)
-  CUDA_TRY(cudaMemsetAsync(w.gT_hi, 0, w.ktot * C * sizeof(__half), st));
-  CUDA_TRY(cudaMemsetAsync(w.gT_lo, 0, w.ktot * C * sizeof(__half), st));
   // split of the position reduction: ~one work item per CTA pair
   const int num_kb = static_cast<int>((w.ktot + G2_BK - 1) / G2_BK);
   const int items = ((C / G2_BM + 1) / 2) * (C / G2_BN);
@@ -2180,7 +2178,8 @@ int efts_resconv_train_bwd(efts_ctx* c, const float* grad_out, const float* acts
   int split_kb = (num_kb + want - 1) / want;
   split_kb = (split_kb + c->chunk_kb - 1) / std::max(1, c->chunk_kb) * std::max(1, c->chunk_kb);
   const float* g = grad_out;
-  const dim3 tgrid((T + 31) / 32, C / 32, B), tblock(32, 8);
+  const dim3 tgrid((w.Tp + TS_COLS - 1) / TS_COLS, C / 32, B);
+  const size_t copy = w.ktot * C;                  // elements between the shifted copies of x^T
   for (int l = n_layers - 1; l >= 0; --l) {
     const float* u = us + l * n;
     const float* xl = acts + l * n;
@@ -2188,27 +2187,24 @@ int efts_resconv_train_bwd(efts_ctx* c, const float* grad_out, const float* acts
     // G' planes (data gradient), G'^T and x^T planes (weight gradient), bias gradient
     lrelu_grad_split_kernel<<<ew_grid(n / 4), 256, 0, st>>>(g, u, n / 4, w.a_hi[0], w.a_lo[0], c->err_flag);
     CUDA_TRY(cudaGetLastError());
-    transpose_split_kernel<<<tgrid, tblock, 0, st>>>(g, u, T, C, w.Tp, pad, 0, w.ktot, w.gT_hi, w.gT_lo);
+    transpose_shift_split_kernel<<<tgrid, 256, 0, st>>>(g, u, T, C, w.Tp, pad, 0, 1, w.ktot, 0, w.gT_hi, w.gT_lo);
+    CUDA_TRY(cudaGetLastError());
+    // x^T once per tap shift: xTs_j[c, q] = x^T[c, q + j - pad] (TMA coordinates cannot carry a 2-byte shift)
+    transpose_shift_split_kernel<<<tgrid, 256, 0, st>>>(xl, nullptr, T, C, w.Tp, pad, -pad, k, w.ktot, copy, w.xT_hi, w.xT_lo);
     CUDA_TRY(cudaGetLastError());
     bias_grad_partial_kernel<<<dim3(kBiasParts, C / 128), 128, 0, st>>>(g, u, rows, C, w.db_part);
     CUDA_TRY(cudaGetLastError());
     bias_grad_finish_kernel<<<(C + 127) / 128, 128, 0, st>>>(w.db_part, kBiasParts, C, grad_b + static_cast<size_t>(l) * C);
     CUDA_TRY(cudaGetLastError());
-    c->launches += 4;
+    c->launches += 5;
     // dL/dW[o, c, j] = sum_k G'^T[o, k] x^T[c, k + j - pad]: one position-reduction GEMM per tap
     for (int j = 0; j < k; ++j) {
-      // x^T shifted by the tap: xTs[c, q] = x^T[c, q + j - pad] (TMA coordinates cannot carry a 2-byte shift)
-      CUDA_TRY(cudaMemsetAsync(w.xT_hi, 0, w.ktot * C * sizeof(__half), st));
-      CUDA_TRY(cudaMemsetAsync(w.xT_lo, 0, w.ktot * C * sizeof(__half), st));
-      transpose_split_kernel<<<tgrid, tblock, 0, st>>>(xl, nullptr, T, C, w.Tp, pad, j - pad, w.ktot, w.xT_hi, w.xT_lo);
-      CUDA_TRY(cudaGetLastError());
-      c->launches++;
       GemmParams p = gemm_defaults();
       p.N = C; p.out = w.dwt + static_cast<size_t>(j) * C * C; p.ld_out = C;
       p.split_kb = split_kb; p.split_scratch = w.splitk;
       ProfScope ps(c, st, TAG_LINEAR);
       TRY(launch_gemm(c, st, OpA{w.gT_hi, w.gT_lo, 1, C, static_cast<int>(w.ktot), static_cast<int>(w.ktot)},
-                      OpB{w.xT_hi, w.xT_lo, 1, C, static_cast<int>(w.ktot), static_cast<int>(w.ktot)}, p));
+                      OpB{w.xT_hi + j * copy, w.xT_lo + j * copy, 1, C, static_cast<int>(w.ktot), static_cast<int>(w.ktot)}, p));
     }
     weight_grad_permute_kernel<<<ew_grid(wn), 256, 0, st>>>(w.dwt, C, C, k, grad_w + l * wn);
     CUDA_TRY(cudaGetLastError());

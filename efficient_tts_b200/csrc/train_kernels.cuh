@@ -78,35 +78,63 @@ __global__ void lrelu_grad_split_kernel(const float* __restrict__ g, const float
   }
 }
 
-// fp32 [B, T, C] (optionally times the LeakyReLU' mask of u) -> transposed operand planes [C][B * Tp], element
-// (b, t, c) at column b * Tp + pad + t - shift of row c (|shift| <= pad).  The margins (pad columns in front of every utterance, the rest of
-// Tp behind it) must be zero: the buffer is cleared by the caller once.  32 x 32 tiles through shared memory; grid
-// (ceil(T / 32), C / 32, B), block (32, 8).
-__global__ void transpose_split_kernel(const float* __restrict__ x, const float* __restrict__ u_mask, int T, int C, int Tp,
-                                       int pad, int shift, size_t ktot, __half* __restrict__ hiT, __half* __restrict__ loT) {
-  __shared__ float tile[32][33];
+// fp32 [B, T, C] (optionally times the LeakyReLU' mask of u) -> transposed operand planes [C][B * Tp], one copy per
+// shift s in [first_shift, first_shift + nshift): column b * Tp + q of row c of copy s holds x[b, q - pad + s, c], zero
+// where that time step does not exist -- so the pad columns in front of every utterance and the rest of Tp behind it are
+// written here too (no memset).  Why copies: the weight gradient's position-reduction GEMM for tap j needs x^T shifted
+// by j - pad along its contiguous dimension, and neither a TMA coordinate nor a UMMA start address can carry a 2-byte
+// offset.  One pass reads x once and writes every copy with aligned 16-byte stores:
+//   block (256 threads) = 64 output columns x 32 channels of one utterance; it stages time steps
+//   [64 j - 4, 64 j + 64) as fp16 hi / lo rows [channel][step] in shared memory (conflict-free strides), then thread
+//   (channel, 8-column group) loads the 12-step window its five possible shifts share and funnel-shifts the words.
+// grid (ceil(Tp / 64), C / 32, B).
+constexpr int TS_COLS = 64, TS_HALO = 4, TS_STRIDE = 70;     // 68 staged steps per channel, row stride 35 words
+__device__ __forceinline__ void ts_store_shifted(const uint32_t (&w)[6], int off, __half* dst) {
+  uint32_t o[4];
+  const int k0 = off >> 1;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    o[k] = (off & 1) ? __funnelshift_r(w[k0 + k], w[k0 + k + 1], 16) : w[k0 + k];
+  *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+__global__ void __launch_bounds__(256)
+transpose_shift_split_kernel(const float* __restrict__ x, const float* __restrict__ u_mask, int T, int C, int Tp, int pad,
+                             int first_shift, int nshift, size_t ktot, size_t copy_stride, __half* __restrict__ hiT,
+                             __half* __restrict__ loT) {
+  __shared__ __align__(16) __half s_hi[32 * TS_STRIDE];
+  __shared__ __align__(16) __half s_lo[32 * TS_STRIDE];
   const int b = blockIdx.z;
-  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-  for (int r = threadIdx.y; r < 32; r += 8) {
-    const int t = t0 + r;
+  const int q0 = blockIdx.x * TS_COLS, c0 = blockIdx.y * 32;
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  // stage: step index i <-> time step q0 - TS_HALO + i
+  for (int i = wrp; i < TS_COLS + TS_HALO; i += 8) {
+    const int t = q0 - TS_HALO + i;
     float v = 0.0f;
-    if (t < T) {
-      const size_t i = (static_cast<size_t>(b) * T + t) * C + c0 + threadIdx.x;
-      v = x[i];
-      if (u_mask != nullptr && !(u_mask[i] > 0.0f)) v = __fmul_rn(v, 0.1f);
+    if (t >= 0 && t < T) {
+      const size_t g = (static_cast<size_t>(b) * T + t) * C + c0 + lane;
+      v = x[g];
+      if (u_mask != nullptr && !(u_mask[g] > 0.0f)) v = __fmul_rn(v, 0.1f);
     }
-    tile[r][threadIdx.x] = v;
+    const __half h = __float2half_rn(v);
+    s_hi[lane * TS_STRIDE + i] = h;
+    s_lo[lane * TS_STRIDE + i] = __float2half_rn((v - __half2float(h)) * kSplitScale);
   }
   __syncthreads();
-  for (int r = threadIdx.y; r < 32; r += 8) {
-    const int t = t0 + threadIdx.x;
-    if (t < T) {
-      const float v = tile[threadIdx.x][r];
-      const __half h = __float2half_rn(v);
-      const size_t o = static_cast<size_t>(c0 + r) * ktot + static_cast<size_t>(b) * Tp + pad + t - shift;
-      hiT[o] = h;
-      loT[o] = __float2half_rn((v - __half2float(h)) * kSplitScale);
-    }
+  const int ch = threadIdx.x >> 3, grp = threadIdx.x & 7;
+  const int q = q0 + 8 * grp;                    // first output column of this thread's group
+  if (q >= Tp) return;
+  uint32_t wh[6], wl[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    wh[k] = *reinterpret_cast<const uint32_t*>(s_hi + ch * TS_STRIDE + 8 * grp + 2 * k);
+    wl[k] = *reinterpret_cast<const uint32_t*>(s_lo + ch * TS_STRIDE + 8 * grp + 2 * k);
+  }
+  const size_t o = static_cast<size_t>(c0 + ch) * ktot + static_cast<size_t>(b) * Tp + q;
+  for (int m = 0; m < nshift; ++m) {
+    // column q + e <- time step q + e - pad + s = staged step 8 grp + e + (TS_HALO - pad + s)
+    const int off = TS_HALO - pad + first_shift + m;           // in [0, 4] for |s| <= pad <= 2
+    ts_store_shifted(wh, off, hiT + m * copy_stride + o);
+    ts_store_shifted(wl, off, loT + m * copy_stride + o);
   }
 }
 

@@ -77,11 +77,12 @@ def main():
         print("TRACE phase %d deltas: %s" % (phase, [st[i + 1] - st[i] for i in range(npts - 1)]))
         _lib.check(eng.lib.efts_profile_stack_trace(eng._h, buf, 64))
         base = 3 + 4 if phase == 1 else 1 + 4     # index of "layer 1 starts" (= layer 0's second barrier passed)
+        # (thread 0's phase stamps are clock reads the compiler may hoist above the CTA barrier in front of them: "gemm
+        # phase done" is when the producer warp finished, the drain warps' own stamps say when the partials were stored)
         print("TRACE phase %d layer 1 roles (cycles since layer start): first operands %d, last commit %d, acc ready %d, "
-              "tmem released %d, stores issued %d | gemm phase done %d | reduce loop entered %d, first sums ready %d, "
-              "loop left %d, reduce phase done %d" % (
+              "tmem released %d, stores issued %d | gemm phase done %d | reduce loop entered %d, reduce phase done %d" % (
                   phase, *[buf[48 + k] - buf[base - 1 + 0] for k in range(5)], buf[base] - buf[base - 1],
-                  buf[53] - buf[base - 1], buf[54] - buf[base - 1], buf[55] - buf[base - 1], buf[base + 2] - buf[base - 1]))
+                  buf[53] - buf[base - 1], buf[base + 2] - buf[base - 1]))
         print("TRACE phase %d layer 1 MMA steps (operands landed, cycles since layer start): %s" % (
             phase, [buf[36 + k] - buf[base - 1] for k in range(10)]))
     eng.set_option("stack_trace", 0)
