@@ -441,6 +441,9 @@ class TrainContext:
     def launch_count(self):
         return int(self.lib.efts_launch_count(self._h))
 
+    def set_option(self, name, value):
+        _lib.check(self.lib.efts_set_option(self._h, name.encode(), int(value)))
+
     def _workspace(self, B, T, k):
         n = int(self.lib.efts_resconv_train_workspace_bytes(self._h, B, T, k))
         if self._ws is None or self._ws.numel() < n:
