@@ -169,3 +169,74 @@ def test_weight_gradient_at_training_size_is_linear_and_matches_a_sample(dev):
         want = (gp[:, :, o] * xp[:, j:j + T, c]).sum().item()
         got = gw1[0, o, c, j].item()
         assert abs(got - want) <= 2e-4 * scale, (o, c, j, got, want)
+
+
+# ---------------------------------------------------------------- data-parallel training (bin/train.py:210-216)
+DDP_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %(root)r)
+from efficient_tts_b200.layers import ResConvBlock
+from torch.nn.parallel import DistributedDataParallel as DDP
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dev = torch.device("cuda", rank)
+dist.init_process_group("nccl", device_id=dev)
+torch.manual_seed(7)                                   # same initial weights on every rank, like the reference's DDP
+blk = ResConvBlock(3, dropout_rate=0.0).to(dev).train()
+g = torch.Generator().manual_seed(11)
+B, T = 4 * world, 173
+x = torch.randn(B, 512, T, generator=g)
+target = torch.randn(B, 512, T, generator=g)
+lo, hi = rank * B // world, (rank + 1) * B // world
+ddp = DDP(blk, device_ids=[rank])
+opt = torch.optim.SGD(ddp.parameters(), lr=0.05)
+y = ddp(x[lo:hi].to(dev))
+loss = torch.nn.functional.mse_loss(y, target[lo:hi].to(dev))          # mean over the shard; DDP averages the gradients
+loss.backward()
+grads = {k: p.grad.detach().clone() for k, p in blk.named_parameters()}
+# every rank holds the same (all-reduced) gradients
+for k, v in grads.items():
+    ref = v.clone(); dist.broadcast(ref, 0)
+    assert torch.equal(v, ref), "rank %%d: gradient of %%s differs from rank 0 after the all-reduce" %% (rank, k)
+# ... and they are the single-process gradients of the mean loss over the whole batch
+torch.manual_seed(7)
+solo = ResConvBlock(3, dropout_rate=0.0).to(dev).train()
+l2 = torch.nn.functional.mse_loss(solo(x.to(dev)), target.to(dev))
+l2.backward()
+for k, p in solo.named_parameters():
+    err = (grads[k] - p.grad).norm().item() / max(p.grad.norm().item(), 1e-20)
+    assert err <= 1e-4, (k, err)
+opt.step()
+w0 = {k: p.detach().clone() for k, p in blk.named_parameters()}
+for k, v in w0.items():
+    ref = v.clone(); dist.broadcast(ref, 0)
+    assert torch.equal(v, ref), "rank %%d: parameter %%s diverged after the step" %% (rank, k)
+dist.barrier(); dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_resconvblock_trains_under_distributed_data_parallel():
+    """The reference trains under torch DDP (bin/train.py:210-216): the gradient all-reduce is torch's bucketed NCCL
+    all-reduce on the parameters' autograd hooks.  The drop-in block produces its gradients through a custom
+    autograd.Function, so the same wrapper applies unchanged: two ranks, half a batch each, equal all-reduced
+    gradients that match the single-process gradients of the whole batch, equal parameters after one SGD step."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    world = 2
+    port = 29900 + os.getpid() % 90
+    code = DDP_WORKER % dict(root=root)
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        out, _ = p.communicate(timeout=600)
+        assert p.returncode == 0, out[-3000:]
+        assert "ok" in out
