@@ -321,7 +321,20 @@ def time_training_slice(dev, peaks):
     ms_b = cuda_timed(lambda: tc.resconv_bwd(grad, acts, us, w), 3, dev)
     launches = (tc.launch_count() - n0) // 3
     fl = 2.0 * B * T * C * C * k * L                      # one conv pass over the stack (single-pass algorithmic)
-    return {"config": "ResConvBlock x %d layers, B=%d, T=%d (padded C3 decoder shape), fp32 weights passed per call" % (L, B, T),
+    # second slice: the duration predictor at the C3 text shape (B = 256, T1 = 200, 2 layers, k = 3), raw library calls
+    dL, dT, dk = 2, 200, 3
+    dx = torch.randn(B, dT, C, generator=g).to(dev)
+    dw = (torch.randn(dL, C, C, dk, generator=g) / np.sqrt(C * dk)).to(dev)
+    dvec = lambda *s: (torch.randn(*s, generator=g) * 0.1).to(dev)
+    dcb, dlg, dlb, dhw, dhb = dvec(dL, C), dvec(dL, C) + 1.0, dvec(dL, C), dvec(C), dvec(1)
+    dgrad = torch.randn(B, dT, generator=g).to(dev)
+    _, dacts, dus = tc.duration_fwd(dx, dw, dcb, dlg, dlb, dhw, dhb)
+    dp_f = cuda_timed(lambda: tc.duration_fwd(dx, dw, dcb, dlg, dlb, dhw, dhb), 3, dev)
+    tc.duration_bwd(dgrad, dacts, dus, dw, dlg, dhw)
+    dp_b = cuda_timed(lambda: tc.duration_bwd(dgrad, dacts, dus, dw, dlg, dhw), 3, dev)
+    duration = {"config": "DurationPredictor (2 x [Conv1d k=3, ReLU, LayerNorm], Linear 512 -> 1), B=%d, T1=%d" % (B, dT),
+                "forward_ms": dp_f, "backward_ms": dp_b}
+    return {"duration_predictor": duration, "config": "ResConvBlock x %d layers, B=%d, T=%d (padded C3 decoder shape), fp32 weights passed per call" % (L, B, T),
             "forward_ms": ms_f, "backward_ms": ms_b, "backward_launches": launches,
             "forward_tflops": fl / (ms_f * 1e-3) / 1e12, "backward_tflops": 2 * fl / (ms_b * 1e-3) / 1e12,
             "backward_frac_of_tensor_peak": 2 * fl / (ms_b * 1e-3) / 1e12 / peaks["tf"],

@@ -2109,6 +2109,56 @@ void carve_train(Arena& a, TrainWs& w, int B, int T, int C, int k, bool backward
   }
 }
 unsigned ew_grid(size_t n) { return static_cast<unsigned>(std::max<size_t>(1, std::min<size_t>((n + 255) / 256, 148 * 16))); }
+
+// Backward of one conv layer  u = act(conv_k(x) + b)  given g = dL/du-side gradient BEFORE the activation mask:
+// G' = g * (u > 0 ? 1 : slope);  grad_w [C][C][k], grad_b [C];  dx = conv_k^T(G') (+ resid when given).
+int conv_layer_bwd(efts_ctx* c, cudaStream_t st, TrainWs& w, const float* g, const float* u, float slope, const float* xl,
+                   const float* weights_l, int k, int B, int T, const float* resid, float* dx, float* grad_w_l,
+                   float* grad_b_l) {
+  const int C = 512;
+  const int pad = (k - 1) / 2;
+  const size_t rows = static_cast<size_t>(B) * T, n = rows * C, wn = static_cast<size_t>(k) * C * C;
+  // split of the position reduction: ~one work item per CTA pair
+  const int num_kb = static_cast<int>((w.ktot + G2_BK - 1) / G2_BK);
+  const int items = ((C / G2_BM + 1) / 2) * (C / G2_BN);
+  int want = std::max(1, std::min(16, (c->sm_count / 2) / items));
+  int split_kb = (num_kb + want - 1) / want;
+  split_kb = (split_kb + c->chunk_kb - 1) / std::max(1, c->chunk_kb) * std::max(1, c->chunk_kb);
+  const dim3 tgrid((w.Tp + TS_COLS - 1) / TS_COLS, C / 32, B);
+  const size_t copy = w.ktot * C;                  // elements between the shifted copies of x^T
+  // G' planes (data gradient), G'^T and x^T planes (weight gradient), bias gradient
+  lrelu_grad_split_kernel<<<ew_grid(n / 4), 256, 0, st>>>(g, u, n / 4, slope, w.a_hi[0], w.a_lo[0], c->err_flag);
+  CUDA_TRY(cudaGetLastError());
+  transpose_shift_split_kernel<<<tgrid, 256, 0, st>>>(g, u, slope, T, C, w.Tp, pad, 0, 1, w.ktot, 0, w.gT_hi, w.gT_lo);
+  CUDA_TRY(cudaGetLastError());
+  // x^T once per tap shift: xTs_j[c, q] = x^T[c, q + j - pad] (TMA coordinates cannot carry a 2-byte shift)
+  transpose_shift_split_kernel<<<tgrid, 256, 0, st>>>(xl, nullptr, 0.0f, T, C, w.Tp, pad, -pad, k, w.ktot, copy, w.xT_hi, w.xT_lo);
+  CUDA_TRY(cudaGetLastError());
+  bias_grad_partial_kernel<<<dim3(kBiasParts, C / 128), 128, 0, st>>>(g, u, slope, rows, C, w.db_part);
+  CUDA_TRY(cudaGetLastError());
+  bias_grad_finish_kernel<<<(C + 127) / 128, 128, 0, st>>>(w.db_part, kBiasParts, C, grad_b_l);
+  CUDA_TRY(cudaGetLastError());
+  c->launches += 5;
+  // dL/dW[o, c, j] = sum_k G'^T[o, k] x^T[c, k + j - pad]: one position-reduction GEMM per tap
+  for (int j = 0; j < k; ++j) {
+    GemmParams p = gemm_defaults();
+    p.N = C; p.out = w.dwt + static_cast<size_t>(j) * C * C; p.ld_out = C;
+    p.split_kb = split_kb; p.split_scratch = w.splitk;
+    ProfScope ps(c, st, TAG_LINEAR);
+    TRY(launch_gemm(c, st, OpA{w.gT_hi, w.gT_lo, 1, C, static_cast<int>(w.ktot), static_cast<int>(w.ktot)},
+                    OpB{w.xT_hi + j * copy, w.xT_lo + j * copy, 1, C, static_cast<int>(w.ktot), static_cast<int>(w.ktot)}, p));
+  }
+  weight_grad_permute_kernel<<<ew_grid(wn), 256, 0, st>>>(w.dwt, C, C, k, grad_w_l);
+  CUDA_TRY(cudaGetLastError());
+  // dL/dx = [resid +] conv^T(G'): the tap-GEMM with flipped, transposed weights
+  pack_conv_weight_kernel<true><<<ew_grid(wn), 256, 0, st>>>(weights_l, C, C, k, w.w_hi, w.w_lo, c->err_flag);
+  CUDA_TRY(cudaGetLastError());
+  c->launches += 2;
+  GemmParams p = gemm_defaults();
+  p.N = C; p.ntaps = k; p.pad = pad; p.resid = resid; p.out = dx; p.ld_out = C;
+  { ProfScope ps(c, st, TAG_DEC_CONV); TRY(launch_gemm(c, st, OpA{w.a_hi[0], w.a_lo[0], B, T, C, C}, OpB{w.w_hi, w.w_lo, k, C, C, C}, p)); }
+  return EFTS_OK;
+}
 }  // namespace
 
 extern "C" {
@@ -2168,54 +2218,106 @@ int efts_resconv_train_bwd(efts_ctx* c, const float* grad_out, const float* acts
   TrainWs w;
   carve_train(a, w, B, T, C, k, true);
   if (!a.ok) return fail(EFTS_ERR_WORKSPACE, "workspace too small: need %zu, have %zu", a.off, workspace_bytes);
-  const int pad = (k - 1) / 2;
+  const size_t n = static_cast<size_t>(B) * T * C, wn = static_cast<size_t>(k) * C * C;
+  CUDA_TRY(cudaMemsetAsync(c->err_flag, 0, sizeof(int), st));
+  const float* g = grad_out;
+  for (int l = n_layers - 1; l >= 0; --l) {
+    float* dx = l == 0 ? grad_x : w.g[l & 1];
+    // y = x + lrelu(conv(x) + b): dL/dx = g + conv^T(G'), the residual slot of the data-gradient GEMM carries g
+    TRY(conv_layer_bwd(c, st, w, g, us + l * n, 0.1f, acts + l * n, weights + l * wn, k, B, T, g, dx, grad_w + l * wn,
+                       grad_b + static_cast<size_t>(l) * C));
+    g = dx;
+  }
+  return EFTS_OK;
+}
+
+// ---- duration predictor, training (layers/duration_predictor.py:57-88) ----
+namespace {
+constexpr int kLnWarps = 148 * 8;     // warps of ln_train_bwd_kernel = partial rows of its column sums
+}
+size_t efts_duration_train_workspace_bytes(const efts_ctx* c, int32_t B, int32_t T, int32_t k) {
+  if (c == nullptr || B < 1 || T < 1 || k < 1) return 0;
+  Arena a(nullptr, ~static_cast<size_t>(0));
+  TrainWs w;
+  carve_train(a, w, B, T, 512, k, true);
+  a.get<double>(static_cast<size_t>(4) * kLnWarps * 512);
+  return a.off + 4096;
+}
+
+int efts_duration_train_fwd(efts_ctx* c, const float* x, const float* conv_w, const float* conv_b, const float* ln_g,
+                            const float* ln_b, const float* head_w, const float* head_b, const uint8_t* mask,
+                            const float* keep, int32_t n_layers, int32_t k, int32_t B, int32_t T, float* acts, float* us,
+                            float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (c == nullptr) return fail(EFTS_ERR_ARG, "null context");
+  const int C = 512;
+  if (!x || !conv_w || !conv_b || !ln_g || !ln_b || !head_w || !head_b || !acts || !us || !out || !workspace ||
+      n_layers < 1 || B < 1 || T < 1 || (k != 1 && k != 3 && k != 5))
+    return fail(EFTS_ERR_ARG, "efts_duration_train_fwd: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Arena a(workspace, workspace_bytes);
+  TrainWs w;
+  carve_train(a, w, B, T, C, k, false);
+  if (!a.ok) return fail(EFTS_ERR_WORKSPACE, "workspace too small: need %zu, have %zu", a.off, workspace_bytes);
   const size_t rows = static_cast<size_t>(B) * T, n = rows * C, wn = static_cast<size_t>(k) * C * C;
   CUDA_TRY(cudaMemsetAsync(c->err_flag, 0, sizeof(int), st));
-  // split of the position reduction: ~one work item per CTA pair
-  const int num_kb = static_cast<int>((w.ktot + G2_BK - 1) / G2_BK);
-  const int items = ((C / G2_BM + 1) / 2) * (C / G2_BN);
-  int want = std::max(1, std::min(16, (c->sm_count / 2) / items));
-  int split_kb = (num_kb + want - 1) / want;
-  split_kb = (split_kb + c->chunk_kb - 1) / std::max(1, c->chunk_kb) * std::max(1, c->chunk_kb);
-  const float* g = grad_out;
-  const dim3 tgrid((w.Tp + TS_COLS - 1) / TS_COLS, C / 32, B);
-  const size_t copy = w.ktot * C;                  // elements between the shifted copies of x^T
-  for (int l = n_layers - 1; l >= 0; --l) {
-    const float* u = us + l * n;
-    const float* xl = acts + l * n;
-    float* dx = l == 0 ? grad_x : w.g[l & 1];
-    // G' planes (data gradient), G'^T and x^T planes (weight gradient), bias gradient
-    lrelu_grad_split_kernel<<<ew_grid(n / 4), 256, 0, st>>>(g, u, n / 4, w.a_hi[0], w.a_lo[0], c->err_flag);
+  CUDA_TRY(cudaMemcpyAsync(acts, x, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  TRY(split_planes(c, st, x, n, w.a_hi[0], w.a_lo[0]));
+  int cur = 0;
+  for (int l = 0; l < n_layers; ++l, cur ^= 1) {
+    pack_conv_weight_kernel<false><<<ew_grid(wn), 256, 0, st>>>(conv_w + l * wn, C, C, k, w.w_hi, w.w_lo, c->err_flag);
     CUDA_TRY(cudaGetLastError());
-    transpose_shift_split_kernel<<<tgrid, 256, 0, st>>>(g, u, T, C, w.Tp, pad, 0, 1, w.ktot, 0, w.gT_hi, w.gT_lo);
-    CUDA_TRY(cudaGetLastError());
-    // x^T once per tap shift: xTs_j[c, q] = x^T[c, q + j - pad] (TMA coordinates cannot carry a 2-byte shift)
-    transpose_shift_split_kernel<<<tgrid, 256, 0, st>>>(xl, nullptr, T, C, w.Tp, pad, -pad, k, w.ktot, copy, w.xT_hi, w.xT_lo);
-    CUDA_TRY(cudaGetLastError());
-    bias_grad_partial_kernel<<<dim3(kBiasParts, C / 128), 128, 0, st>>>(g, u, rows, C, w.db_part);
-    CUDA_TRY(cudaGetLastError());
-    bias_grad_finish_kernel<<<(C + 127) / 128, 128, 0, st>>>(w.db_part, kBiasParts, C, grad_b + static_cast<size_t>(l) * C);
-    CUDA_TRY(cudaGetLastError());
-    c->launches += 5;
-    // dL/dW[o, c, j] = sum_k G'^T[o, k] x^T[c, k + j - pad]: one position-reduction GEMM per tap
-    for (int j = 0; j < k; ++j) {
-      GemmParams p = gemm_defaults();
-      p.N = C; p.out = w.dwt + static_cast<size_t>(j) * C * C; p.ld_out = C;
-      p.split_kb = split_kb; p.split_scratch = w.splitk;
-      ProfScope ps(c, st, TAG_LINEAR);
-      TRY(launch_gemm(c, st, OpA{w.gT_hi, w.gT_lo, 1, C, static_cast<int>(w.ktot), static_cast<int>(w.ktot)},
-                      OpB{w.xT_hi + j * copy, w.xT_lo + j * copy, 1, C, static_cast<int>(w.ktot), static_cast<int>(w.ktot)}, p));
-    }
-    weight_grad_permute_kernel<<<ew_grid(wn), 256, 0, st>>>(w.dwt, C, C, k, grad_w + l * wn);
-    CUDA_TRY(cudaGetLastError());
-    // dL/dx = g + conv^T(G'): the tap-GEMM with flipped, transposed weights, residual = g
-    pack_conv_weight_kernel<true><<<ew_grid(wn), 256, 0, st>>>(weights + l * wn, C, C, k, w.w_hi, w.w_lo, c->err_flag);
+    float* u = us + l * n;
+    GemmParams p = gemm_defaults();
+    p.N = C; p.ntaps = k; p.pad = (k - 1) / 2; p.act = ACT_RELU; p.bias = conv_b + static_cast<size_t>(l) * C;
+    p.out = u; p.ld_out = C;
+    { ProfScope ps(c, st, TAG_DURATION); TRY(launch_gemm(c, st, OpA{w.a_hi[cur], w.a_lo[cur], B, T, C, C}, OpB{w.w_hi, w.w_lo, k, C, C, C}, p)); }
+    const bool last = l == n_layers - 1;
+    ln_train_fwd_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, st>>>(
+        u, rows, ln_g + static_cast<size_t>(l) * C, ln_b + static_cast<size_t>(l) * C, keep ? keep + l * n : nullptr,
+        acts + (l + 1) * n, last ? nullptr : w.a_hi[cur ^ 1], last ? nullptr : w.a_lo[cur ^ 1], last ? head_w : nullptr,
+        head_b, mask, out, c->err_flag);
     CUDA_TRY(cudaGetLastError());
     c->launches += 2;
-    GemmParams p = gemm_defaults();
-    p.N = C; p.ntaps = k; p.pad = pad; p.resid = g; p.out = dx; p.ld_out = C;
-    { ProfScope ps(c, st, TAG_DEC_CONV); TRY(launch_gemm(c, st, OpA{w.a_hi[0], w.a_lo[0], B, T, C, C}, OpB{w.w_hi, w.w_lo, k, C, C, C}, p)); }
-    g = dx;
+  }
+  return EFTS_OK;
+}
+
+int efts_duration_train_bwd(efts_ctx* c, const float* grad_out, const float* acts, const float* us, const float* conv_w,
+                            const float* ln_g, const float* head_w, const uint8_t* mask, const float* keep,
+                            int32_t n_layers, int32_t k, int32_t B, int32_t T, float* grad_x, float* grad_conv_w,
+                            float* grad_conv_b, float* grad_ln_g, float* grad_ln_b, float* grad_head_w,
+                            float* grad_head_b, void* workspace, size_t workspace_bytes, void* stream) {
+  if (c == nullptr) return fail(EFTS_ERR_ARG, "null context");
+  const int C = 512;
+  if (!grad_out || !acts || !us || !conv_w || !ln_g || !head_w || !grad_x || !grad_conv_w || !grad_conv_b || !grad_ln_g ||
+      !grad_ln_b || !grad_head_w || !grad_head_b || !workspace || n_layers < 1 || B < 1 || T < 1 ||
+      (k != 1 && k != 3 && k != 5) || B > 65535)
+    return fail(EFTS_ERR_ARG, "efts_duration_train_bwd: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Arena a(workspace, workspace_bytes);
+  TrainWs w;
+  carve_train(a, w, B, T, C, k, true);
+  double* ln_part = a.get<double>(static_cast<size_t>(4) * kLnWarps * C);
+  if (!a.ok) return fail(EFTS_ERR_WORKSPACE, "workspace too small: need %zu, have %zu", a.off, workspace_bytes);
+  const size_t rows = static_cast<size_t>(B) * T, n = rows * C, wn = static_cast<size_t>(k) * C * C;
+  CUDA_TRY(cudaMemsetAsync(c->err_flag, 0, sizeof(int), st));
+  const float* gh = nullptr;                         // dL/dh of the layer below the one being processed
+  for (int l = n_layers - 1; l >= 0; --l) {
+    const bool last = l == n_layers - 1;
+    float* gu = w.g[0];                              // dL/du before ReLU'
+    float* dx = l == 0 ? grad_x : w.g[1];
+    ln_train_bwd_kernel<<<kLnWarps / 8, 256, 0, st>>>(gh, last ? grad_out : nullptr, mask, head_w, us + l * n,
+                                                      acts + (l + 1) * n, keep ? keep + l * n : nullptr,
+                                                      ln_g + static_cast<size_t>(l) * C, rows, gu, ln_part);
+    CUDA_TRY(cudaGetLastError());
+    ln_train_finish_kernel<<<dim3((C + 127) / 128, 4), 128, 0, st>>>(ln_part, kLnWarps, grad_ln_g + static_cast<size_t>(l) * C,
+                                                                    grad_ln_b + static_cast<size_t>(l) * C,
+                                                                    last ? grad_head_w : nullptr, last ? grad_head_b : nullptr);
+    CUDA_TRY(cudaGetLastError());
+    c->launches += 2;
+    TRY(conv_layer_bwd(c, st, w, gu, us + l * n, 0.0f, acts + l * n, conv_w + l * wn, k, B, T, nullptr, dx,
+                       grad_conv_w + l * wn, grad_conv_b + static_cast<size_t>(l) * C));
+    gh = dx;
   }
   return EFTS_OK;
 }

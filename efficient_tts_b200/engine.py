@@ -494,6 +494,57 @@ class TrainContext:
         return gx, gw, gb
 
 
+    # ---- duration predictor (layers/duration_predictor.py:57-88)
+    def _dp_workspace(self, B, T, k):
+        n = int(self.lib.efts_duration_train_workspace_bytes(self._h, B, T, k))
+        if self._ws is None or self._ws.numel() < n:
+            self._ws = None
+            self._ws = torch.empty(n, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def duration_fwd(self, x_btc, conv_w, conv_b, ln_g, ln_b, head_w, head_b, mask=None, keep=None):
+        """x [B,T,512]; conv_w [L,512,512,k]; conv_b / ln_g / ln_b [L,512]; head_w [512]; head_b [1]; mask bool [B,T]
+        (True = padded); keep [L,B,T,512] scaled dropout masks or None -> (out [B,T], acts, us)."""
+        f = lambda t: t.detach().to(torch.float32).contiguous()
+        x, conv_w, conv_b, ln_g, ln_b, head_w, head_b = (f(t) for t in (x_btc, conv_w, conv_b, ln_g, ln_b, head_w, head_b))
+        B, T, C = x.shape
+        L, k = conv_w.shape[0], conv_w.shape[3]
+        if C != N_CHANNELS or tuple(conv_w.shape[1:3]) != (C, C) or head_w.numel() != C:
+            raise RuntimeError("duration-predictor training kernels are built for %d channels" % N_CHANNELS)
+        m = None if mask is None else mask.to(torch.uint8).contiguous()
+        kp = None if keep is None else f(keep)
+        with torch.cuda.device(self.device):
+            acts = torch.empty(L + 1, B, T, C, dtype=torch.float32, device=self.device)
+            us = torch.empty(L, B, T, C, dtype=torch.float32, device=self.device)
+            out = torch.empty(B, T, dtype=torch.float32, device=self.device)
+            ws = self._dp_workspace(B, T, k)
+            st = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            _lib.check(self.lib.efts_duration_train_fwd(
+                self._h, _ptr(x), _ptr(conv_w), _ptr(conv_b), _ptr(ln_g), _ptr(ln_b), _ptr(head_w), _ptr(head_b),
+                _ptr(m) if m is not None else None, _ptr(kp) if kp is not None else None, L, k, B, T, _ptr(acts), _ptr(us),
+                _ptr(out), _ptr(ws), ws.numel(), st))
+        return out, acts, us
+
+    def duration_bwd(self, grad_out, acts, us, conv_w, ln_g, head_w, mask=None, keep=None):
+        f = lambda t: t.detach().to(torch.float32).contiguous()
+        g, conv_w, ln_g, head_w = f(grad_out), f(conv_w), f(ln_g), f(head_w)
+        L, B, T, C = us.shape
+        k = conv_w.shape[3]
+        m = None if mask is None else mask.to(torch.uint8).contiguous()
+        kp = None if keep is None else f(keep)
+        with torch.cuda.device(self.device):
+            new = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=self.device)
+            gx, gw, gb, gg, gbeta, ghw, ghb = new(B, T, C), torch.empty_like(conv_w), new(L, C), new(L, C), new(L, C), new(C), new(1)
+            ws = self._dp_workspace(B, T, k)
+            st = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            _lib.check(self.lib.efts_duration_train_bwd(
+                self._h, _ptr(g), _ptr(acts), _ptr(us), _ptr(conv_w), _ptr(ln_g), _ptr(head_w),
+                _ptr(m) if m is not None else None, _ptr(kp) if kp is not None else None, L, k, B, T, _ptr(gx), _ptr(gw),
+                _ptr(gb), _ptr(gg), _ptr(gbeta), _ptr(ghw), _ptr(ghb), _ptr(ws), ws.numel(), st))
+            self._check()
+        return gx, gw, gb, gg, gbeta, ghw, ghb
+
+
 _TRAIN_CONTEXTS = {}
 
 
@@ -524,3 +575,23 @@ class ResConvStackFunction(torch.autograd.Function):
         acts, us, w_all = ctx.saved_tensors
         gx, gw, gb = ctx.tc.resconv_bwd(grad_out, acts, us, w_all)
         return gx, gw, gb
+
+
+class DurationPredictorFunction(torch.autograd.Function):
+    """out [B, T] = Linear(LayerNorm(relu(conv(...)))) of layers/duration_predictor.py:69-86 (log domain, masked
+    positions 0), differentiable: forward and backward are library calls (efts_duration_train_fwd / _bwd).  ``keep``
+    holds the train-mode dropout masks (scaled by 1 / (1 - p)) drawn by the caller, or None."""
+
+    @staticmethod
+    def forward(ctx, x_btc, conv_w, conv_b, ln_g, ln_b, head_w, head_b, mask, keep):
+        tc = train_context(x_btc.device)
+        out, acts, us = tc.duration_fwd(x_btc, conv_w, conv_b, ln_g, ln_b, head_w, head_b, mask, keep)
+        ctx.save_for_backward(acts, us, conv_w, ln_g, head_w)
+        ctx.mask, ctx.keep, ctx.tc = mask, keep, tc
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        acts, us, conv_w, ln_g, head_w = ctx.saved_tensors
+        gx, gw, gb, gg, gbeta, ghw, ghb = ctx.tc.duration_bwd(grad_out, acts, us, conv_w, ln_g, head_w, ctx.mask, ctx.keep)
+        return gx, gw, gb, gg, gbeta, ghw.view_as(head_w), ghb, None, None

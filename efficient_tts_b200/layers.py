@@ -213,7 +213,32 @@ class DurationPredictor(_EngineOwner):
             out = out.masked_fill(x_masks, 0.0)      # layers/duration_predictor.py:85-86
         return out
 
+    def _train_forward(self, xs, x_masks):
+        """Training slice: forward that keeps what the backward needs; gradients for every parameter and
+        for ``xs`` come from the library (efts_duration_train_fwd / _bwd).  Train-mode dropout (the reference's default
+        p = 0.1 here, layers/duration_predictor.py:62) uses masks drawn from torch's generator."""
+        if xs.device.type != "cuda":
+            raise RuntimeError("efficient_tts_b200 modules compute on a CUDA sm_100a device only")
+        ws, bs, gs, betas = [], [], [], []
+        for seq in self.conv:
+            conv, ln = seq[0], seq[2]
+            ws.append(torch._weight_norm(conv.weight_v, conv.weight_g, 0) if hasattr(conv, "weight_g") else conv.weight)
+            bs.append(conv.bias)
+            gs.append(ln.weight)
+            betas.append(ln.bias)
+        keep = None
+        p = self.conv[0][3].p
+        if self.training and p > 0:
+            B, T, C = xs.shape
+            keep = torch.nn.functional.dropout(torch.ones(self.n_layers, B, T, C, device=xs.device), p, True)
+        return _engine.DurationPredictorFunction.apply(
+            xs.contiguous(), torch.stack(ws), torch.stack(bs), torch.stack(gs), torch.stack(betas),
+            self.linear.weight.reshape(-1), self.linear.bias, x_masks, keep)
+
     def forward(self, xs, x_masks=None, spembs=None):
+        needs_grad = torch.is_grad_enabled() and (xs.requires_grad or any(p.requires_grad for p in self.parameters()))
+        if self.training or needs_grad:
+            return self._train_forward(xs, x_masks)
         return self._run(xs, x_masks, 0)
 
     def inference(self, xs, x_masks=None, spembs=None, to_round=True):

@@ -277,6 +277,27 @@ int efts_resconv_train_bwd(efts_ctx* ctx, const float* grad_out, const float* ac
                            int32_t n_layers, int32_t k, int32_t B, int32_t T, float* grad_x, float* grad_w, float* grad_b,
                            void* workspace, size_t workspace_bytes, void* stream);
 
+/* Second slice: DurationPredictor (layers/duration_predictor.py:57-88) under autograd -- n_layers x [Conv1d(k) -> ReLU ->
+ * LayerNorm over channels -> Dropout], Linear(512 -> 1), masked positions 0; `forward` semantics (log domain).
+ *   fwd: x fp32 [B,T,512]; conv_w [L,512,512,k], conv_b [L,512], ln_g / ln_b [L,512], head_w [512], head_b [1];
+ *        mask uint8 [B,T] (non-zero = padded position, may be NULL); keep fp32 [L,B,T,512] = the train-mode dropout masks
+ *        already scaled by 1/(1-p), drawn by the caller's generator (NULL = no dropout).
+ *        Saves acts [L+1,B,T,512] (acts[0] = x, acts[l+1] = layer l's output) and us [L,B,T,512] (post-ReLU conv outputs,
+ *        whose sign is ReLU'); out fp32 [B,T].
+ *   bwd: grad_out = dL/dout [B,T] -> grad_x [B,T,512], grad_conv_w [L,512,512,k], grad_conv_b, grad_ln_g, grad_ln_b
+ *        [L,512], grad_head_w [512], grad_head_b [1].  Convolutions: the data- and weight-gradient GEMMs of the first
+ *        slice (ReLU slope 0, no residual); LayerNorm / head: one warp per row, column sums in double, deterministic. */
+size_t efts_duration_train_workspace_bytes(const efts_ctx* ctx, int32_t B, int32_t T, int32_t k);
+int efts_duration_train_fwd(efts_ctx* ctx, const float* x, const float* conv_w, const float* conv_b, const float* ln_g,
+                            const float* ln_b, const float* head_w, const float* head_b, const uint8_t* mask,
+                            const float* keep, int32_t n_layers, int32_t k, int32_t B, int32_t T, float* acts, float* us,
+                            float* out, void* workspace, size_t workspace_bytes, void* stream);
+int efts_duration_train_bwd(efts_ctx* ctx, const float* grad_out, const float* acts, const float* us, const float* conv_w,
+                            const float* ln_g, const float* head_w, const uint8_t* mask, const float* keep,
+                            int32_t n_layers, int32_t k, int32_t B, int32_t T, float* grad_x, float* grad_conv_w,
+                            float* grad_conv_b, float* grad_ln_g, float* grad_ln_b, float* grad_head_w,
+                            float* grad_head_b, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- data parallelism ----
  * The survey's sketch of this ABI listed efts_dp_init / efts_dp_allgather / efts_dp_allreduce_loss.  They are
  * deliberately NOT exported: the reference's only parallelism is torch DDP with a DistributedSampler

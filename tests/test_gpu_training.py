@@ -240,3 +240,95 @@ def test_resconvblock_trains_under_distributed_data_parallel():
         out, _ = p.communicate(timeout=600)
         assert p.returncode == 0, out[-3000:]
         assert "ok" in out
+
+
+# ---------------------------------------------------------------- duration predictor (layers/duration_predictor.py)
+def _dp_inputs(B, T, seed, dev):
+    g = torch.Generator().manual_seed(seed)
+    xs = torch.randn(B, T, 512, generator=g)
+    lengths = torch.randint(max(1, T // 2), T + 1, (B,), generator=g)
+    lengths[0] = T
+    masks = torch.arange(T)[None, :] >= lengths[:, None]            # True = padded (x_masks of the reference)
+    grad = torch.randn(B, T, generator=g)
+    return xs, masks, grad
+
+
+@pytest.mark.parametrize("B,T,seed", [(3, 77, 0), (2, 200, 1)])
+def test_duration_predictor_trains_like_the_reference(dev, B, T, seed):
+    """DurationPredictor.forward under autograd (log-domain output, masked positions 0) against torch autograd through the
+    CPU oracle: output <= 1e-4 abs; gradients of every parameter and of the input in relative L2 (ReLU' is discontinuous
+    at 0, see the module docstring)."""
+    from efficient_tts_b200.layers import DurationPredictor
+    torch.manual_seed(seed)
+    dp = DurationPredictor(512, n_layers=2, n_chans=512, kernel_size=3, dropout_rate=0.0)
+    with torch.no_grad():                                  # non-trivial affine parameters
+        for seq in dp.conv:
+            seq[2].weight.uniform_(0.5, 1.5)
+            seq[2].bias.uniform_(-0.3, 0.3)
+    xs, masks, grad = _dp_inputs(B, T, 40 + seed, dev)
+    leaves = {"duration_predictor." + k: v.detach().clone().requires_grad_(True) for k, v in dp.state_dict().items()}
+    x_ref = xs.clone().requires_grad_(True)
+    out_ref = orc.duration_predictor_forward(x_ref, masks, leaves)
+    out_ref.backward(grad)
+
+    dp = dp.to(dev).train()
+    xd = xs.to(dev).requires_grad_(True)
+    out = dp(xd, masks.to(dev))
+    assert out.shape == out_ref.shape and out.requires_grad
+    out.backward(grad.to(dev))
+    assert (out.detach().cpu() - out_ref.detach()).abs().max().item() <= 1e-4
+    assert torch.all(out.detach().cpu()[masks] == 0)
+
+    def rel(a, b):
+        return (a.cpu() - b).norm().item() / max(b.norm().item(), 1e-12)
+    r = rel(xd.grad, x_ref.grad)
+    print("dL/dxs: relative L2 error %.2e" % r)
+    assert r <= 1e-3
+    for k, p in dp.named_parameters():
+        assert p.grad is not None, k
+        r = rel(p.grad, leaves["duration_predictor." + k].grad)
+        print("%s: relative L2 error %.2e" % (k, r))
+        assert r <= 1e-3, k
+    # eval-mode forward of the same module (the inference kernels) agrees with the training forward
+    dp.eval()
+    with torch.no_grad():
+        out_eval = dp(xs.to(dev), masks.to(dev))
+    assert (out_eval - out.detach()).abs().max().item() <= 2e-5
+
+
+def test_duration_predictor_backward_matches_float64_with_dropout_masks(dev):
+    """The raw library pair with train-mode dropout masks, against a float64 evaluation that applies the same masks and the
+    ReLU slopes the device forward took: max error <= 5e-5 of the largest entry of every gradient."""
+    from efficient_tts_b200.engine import train_context
+    L, B, T, C, k = 2, 2, 131, 512, 3
+    g = torch.Generator().manual_seed(5)
+    xs, masks, grad = _dp_inputs(B, T, 77, dev)
+    conv_w = torch.randn(L, C, C, k, generator=g) / np.sqrt(C * k)
+    conv_b = torch.randn(L, C, generator=g) * 0.1
+    ln_g = torch.rand(L, C, generator=g) + 0.5
+    ln_b = torch.randn(L, C, generator=g) * 0.2
+    head_w = torch.randn(C, generator=g) / np.sqrt(C)
+    head_b = torch.randn(1, generator=g)
+    keep = (torch.rand(L, B, T, C, generator=g) >= 0.1).float() / 0.9
+    tc = train_context(dev)
+    d = lambda t: t.to(dev)
+    out, acts, us = tc.duration_fwd(d(xs), d(conv_w), d(conv_b), d(ln_g), d(ln_b), d(head_w), d(head_b), d(masks), d(keep))
+    got = tc.duration_bwd(d(grad), acts, us, d(conv_w), d(ln_g), d(head_w), d(masks), d(keep))
+
+    leaves = [t.double().clone().requires_grad_(True) for t in (xs, conv_w, conv_b, ln_g, ln_b, head_w, head_b)]
+    x64, w64, b64, g64, be64, hw64, hb64 = leaves
+    h = x64
+    for l in range(L):
+        pre = torch.nn.functional.conv1d(h.transpose(1, 2), w64[l], b64[l], padding=(k - 1) // 2).transpose(1, 2)
+        u = pre * (us[l].cpu() > 0).double()                        # the slopes the device took
+        assert (torch.relu(pre).float() - us[l].cpu()).abs().max().item() <= 2e-5
+        h = torch.nn.functional.layer_norm(u, (C,), g64[l], be64[l], eps=1e-12) * keep[l].double()
+    o64 = (h @ hw64 + hb64).masked_fill(masks, 0.0)
+    assert (out.cpu().double() - o64.detach()).abs().max().item() <= 1e-4
+    o64.backward(grad.double())
+    names = ["x", "conv_w", "conv_b", "ln_g", "ln_b", "head_w", "head_b"]
+    for name, a, leaf in zip(names, got, leaves):
+        want = leaf.grad
+        err = (a.cpu().double().reshape(want.shape) - want).abs().max().item() / max(want.abs().max().item(), 1e-30)
+        print("%s: max error / max |grad| = %.2e" % (name, err))
+        assert err <= 5e-5, name
