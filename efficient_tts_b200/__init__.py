@@ -9,6 +9,8 @@ generator the reference runs on ``inference()``'s output).
 from . import models  # noqa: F401
 from . import vocoder  # noqa: F401
 from .layers import DurationPredictor, LengthRegulator, ResConvBlock  # noqa: F401
+from .losses import FastSpeechLoss  # noqa: F401
 from .models import EfficientTTSCNN  # noqa: F401
 
-__all__ = ["EfficientTTSCNN", "ResConvBlock", "DurationPredictor", "LengthRegulator", "models", "vocoder"]
+__all__ = ["EfficientTTSCNN", "ResConvBlock", "DurationPredictor", "LengthRegulator", "FastSpeechLoss", "models",
+           "vocoder"]

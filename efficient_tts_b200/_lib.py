@@ -91,6 +91,9 @@ SIGNATURES = {
     "efts_duration_train_workspace_bytes": (c_size_t, [c_void_p, c_i32, c_i32, c_i32]),
     "efts_duration_train_fwd": (c_i32, [c_void_p] + [c_void_p] * 9 + [c_i32] * 4 + [c_void_p] * 4 + [c_size_t, c_void_p]),
     "efts_duration_train_bwd": (c_i32, [c_void_p] + [c_void_p] * 8 + [c_i32] * 4 + [c_void_p] * 8 + [c_size_t, c_void_p]),
+    "efts_fastspeech_loss_workspace_bytes": (c_size_t, [c_void_p]),
+    "efts_fastspeech_loss": (c_i32, [c_void_p] + [c_void_p] * 6 + [c_i32] * 6 + [c_void_p] * 4 + [c_size_t, c_void_p]),
+    "efts_scale_by_scalar": (c_i32, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "efts_host_map_transposed": (c_i32, [c_void_p, c_i32, c_i32, c_i32, c_i32, c_void_p]),
     "efts_host_map_grouped": (c_i32, [c_void_p, c_i32, c_i32, c_i32, c_i32, c_void_p, ctypes.POINTER(c_i32)]),
     "efts_set_option": (c_i32, [c_void_p, c_char_p, c_i32]),

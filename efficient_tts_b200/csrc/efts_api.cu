@@ -2322,4 +2322,42 @@ int efts_duration_train_bwd(efts_ctx* c, const float* grad_out, const float* act
   return EFTS_OK;
 }
 
+// ---- criterion with gradients (losses/fastspeech_loss.py:54-67) ----
+size_t efts_fastspeech_loss_workspace_bytes(const efts_ctx* c) {
+  return c == nullptr ? 0 : (2 * static_cast<size_t>(kLossBlocks) + 2) * sizeof(double) + 256;
+}
+
+int efts_fastspeech_loss(efts_ctx* c, const float* before_outs, const float* d_outs, const float* ys, const float* ds,
+                         const int64_t* ilens, const int64_t* olens, int32_t B, int32_t T1, int32_t T2, int32_t odim,
+                         int32_t use_masking, int32_t use_mse, float* losses, float* grad_before, float* grad_d,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+  if (c == nullptr) return fail(EFTS_ERR_ARG, "null context");
+  if (!before_outs || !d_outs || !ys || !ds || !ilens || !olens || !losses || !workspace || B < 1 || T1 < 1 || T2 < 1 || odim < 1)
+    return fail(EFTS_ERR_ARG, "efts_fastspeech_loss: bad argument");
+  if (workspace_bytes < efts_fastspeech_loss_workspace_bytes(c))
+    return fail(EFTS_ERR_WORKSPACE, "workspace too small: need %zu, have %zu", efts_fastspeech_loss_workspace_bytes(c), workspace_bytes);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  double* part = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~static_cast<uintptr_t>(255));
+  CUDA_TRY(cudaMemsetAsync(c->err_flag, 0, sizeof(int), st));
+  const size_t n = static_cast<size_t>(B) * T2 * odim;
+  const int blocks = static_cast<int>(std::max<size_t>(1, std::min<size_t>((n + 255) / 256, kLossBlocks)));
+  fastspeech_loss_kernel<<<blocks, 256, 0, st>>>(before_outs, ys, d_outs, ds, reinterpret_cast<const long long*>(ilens),
+                                                 reinterpret_cast<const long long*>(olens), B, T1, T2, odim, use_masking,
+                                                 use_mse, grad_before, grad_d, part, c->err_flag);
+  CUDA_TRY(cudaGetLastError());
+  fastspeech_loss_finish_kernel<<<1, 32, 0, st>>>(part, blocks, losses);
+  CUDA_TRY(cudaGetLastError());
+  c->launches += 2;
+  return EFTS_OK;
+}
+
+int efts_scale_by_scalar(efts_ctx* c, const float* in, const float* scalar, size_t n, float* out, void* stream) {
+  if (c == nullptr || !in || !scalar || !out) return fail(EFTS_ERR_ARG, "efts_scale_by_scalar: bad argument");
+  if (n == 0) return EFTS_OK;
+  scale_by_scalar_kernel<<<ew_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, scalar, n, out);
+  CUDA_TRY(cudaGetLastError());
+  c->launches++;
+  return EFTS_OK;
+}
+
 }  // extern "C"

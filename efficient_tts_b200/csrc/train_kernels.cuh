@@ -339,4 +339,90 @@ __global__ void ln_train_finish_kernel(const double* __restrict__ part, int W, f
   dst[c] = static_cast<float>(acc);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Criterion with gradients (losses/fastspeech_loss.py:54-67, after_outs = None, use_weighted_masking = False):
+//   mel term  = mean over the selected elements of (before_outs - ys)^2  (use_mse) or |before_outs - ys|
+//   dur term  = mean over the selected tokens of |d_outs - ds|
+// "selected" = positions inside the lengths when use_masking, everything otherwise.  Block partial sums in double,
+// added in block order by fastspeech_loss_finish_kernel (deterministic); the element gradients d(term)/d(input) are
+// written alongside (0 outside the selection; sign(0) = 0 like torch's L1 gradient).
+constexpr int kLossBlocks = 592;
+__global__ void fastspeech_loss_kernel(const float* __restrict__ mel, const float* __restrict__ ys,
+                                       const float* __restrict__ dur, const float* __restrict__ ds,
+                                       const long long* __restrict__ ilens, const long long* __restrict__ olens, int B,
+                                       int T1, int T2, int odim, int use_masking, int use_mse,
+                                       float* __restrict__ grad_mel, float* __restrict__ grad_dur,
+                                       double* __restrict__ part, int* __restrict__ flags) {
+  // selected counts (every block computes them: B is small)
+  __shared__ double s_cnt[2];
+  __shared__ double s_red[2][8];
+  if (threadIdx.x == 0) {
+    double nm = 0.0, nd = 0.0;
+    for (int b = 0; b < B; ++b) {
+      long long ol = olens[b], il = ilens[b];
+      if (ol < 0 || ol > T2 || il < 0 || il > T1) { atomicOr(flags, 16); ol = max(0ll, min(ol, (long long)T2)); il = max(0ll, min(il, (long long)T1)); }
+      nm += use_masking ? static_cast<double>(ol) * odim : static_cast<double>(T2) * odim;
+      nd += use_masking ? static_cast<double>(il) : static_cast<double>(T1);
+    }
+    s_cnt[0] = nm; s_cnt[1] = nd;
+  }
+  __syncthreads();
+  const float inv_m = s_cnt[0] > 0.0 ? static_cast<float>(1.0 / s_cnt[0]) : 0.0f;
+  const float inv_d = s_cnt[1] > 0.0 ? static_cast<float>(1.0 / s_cnt[1]) : 0.0f;
+  double am = 0.0, ad = 0.0;
+  const size_t nmel = static_cast<size_t>(B) * T2 * odim;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < nmel;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t r = i / odim;
+    const int b = static_cast<int>(r / T2), t = static_cast<int>(r % T2);
+    float gr = 0.0f;
+    if (!use_masking || t < min(max(olens[b], 0ll), (long long)T2)) {
+      const float d = __fsub_rn(mel[i], ys[i]);
+      if (use_mse) { am += static_cast<double>(__fmul_rn(d, d)); gr = __fmul_rn(__fmul_rn(2.0f, d), inv_m); }
+      else { am += static_cast<double>(fabsf(d)); gr = d > 0.0f ? inv_m : (d < 0.0f ? -inv_m : 0.0f); }
+    }
+    if (grad_mel != nullptr) grad_mel[i] = gr;
+  }
+  const size_t ntok = static_cast<size_t>(B) * T1;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < ntok;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int b = static_cast<int>(i / T1), t = static_cast<int>(i % T1);
+    float gr = 0.0f;
+    if (!use_masking || t < min(max(ilens[b], 0ll), (long long)T1)) {
+      const float d = __fsub_rn(dur[i], ds[i]);
+      ad += static_cast<double>(fabsf(d));
+      gr = d > 0.0f ? inv_d : (d < 0.0f ? -inv_d : 0.0f);
+    }
+    if (grad_dur != nullptr) grad_dur[i] = gr;
+  }
+  am = warp_sum(am);
+  ad = warp_sum(ad);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) { s_red[0][w] = am; s_red[1][w] = ad; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, d = 0.0;
+    for (int j = 0; j < static_cast<int>(blockDim.x >> 5); ++j) { a += s_red[0][j]; d += s_red[1][j]; }
+    part[2 * blockIdx.x] = a;
+    part[2 * blockIdx.x + 1] = d;
+    if (blockIdx.x == 0) { part[2 * gridDim.x] = s_cnt[0]; part[2 * gridDim.x + 1] = s_cnt[1]; }
+  }
+}
+__global__ void fastspeech_loss_finish_kernel(const double* __restrict__ part, int nblocks, float* __restrict__ losses) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double a = 0.0, d = 0.0;
+  for (int j = 0; j < nblocks; ++j) { a += part[2 * j]; d += part[2 * j + 1]; }
+  const double nm = part[2 * nblocks], nd = part[2 * nblocks + 1];
+  losses[0] = static_cast<float>(nm > 0.0 ? a / nm : 0.0 / 0.0);      // mean over nothing is NaN, like torch
+  losses[1] = static_cast<float>(nd > 0.0 ? d / nd : 0.0 / 0.0);
+}
+// out = in * scalar[0] (the chain rule of a loss term: its upstream gradient is a device scalar)
+__global__ void scale_by_scalar_kernel(const float* __restrict__ in, const float* __restrict__ scalar, size_t n,
+                                       float* __restrict__ out) {
+  const float s = scalar[0];
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    out[i] = __fmul_rn(in[i], s);
+}
+
 }  // namespace efts

@@ -544,6 +544,42 @@ class TrainContext:
             self._check()
         return gx, gw, gb, gg, gbeta, ghw, ghb
 
+    # ---- criterion (losses/fastspeech_loss.py:54-67)
+    def fastspeech_loss(self, before_outs, d_outs, ys, ds, ilens, olens, use_masking, use_mse, want_grads=True):
+        """-> (losses fp32 [2] on the device: mel term, duration term; d mel term / d before_outs; d duration term /
+        d d_outs) -- the gradients are None unless ``want_grads``."""
+        f = lambda t: t.detach().to(device=self.device, dtype=torch.float32).contiguous()
+        mel, dur, ys, ds = f(before_outs), f(d_outs), f(ys), f(ds)
+        il = ilens.detach().to(device=self.device, dtype=torch.int64).contiguous()
+        ol = olens.detach().to(device=self.device, dtype=torch.int64).contiguous()
+        B, T2, odim = mel.shape
+        T1 = dur.shape[1]
+        if ys.shape != mel.shape or ds.shape != dur.shape or il.numel() != B or ol.numel() != B:
+            raise RuntimeError("FastSpeechLoss: shape mismatch (before_outs %s, ys %s, d_outs %s, ds %s)" % (
+                tuple(mel.shape), tuple(ys.shape), tuple(dur.shape), tuple(ds.shape)))
+        with torch.cuda.device(self.device):
+            losses = torch.empty(2, dtype=torch.float32, device=self.device)
+            gm = torch.empty_like(mel) if want_grads else None
+            gd = torch.empty_like(dur) if want_grads else None
+            n = int(self.lib.efts_fastspeech_loss_workspace_bytes(self._h))
+            ws = torch.empty(n, dtype=torch.uint8, device=self.device)
+            st = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            _lib.check(self.lib.efts_fastspeech_loss(
+                self._h, _ptr(mel), _ptr(dur), _ptr(ys), _ptr(ds), _ptr(il), _ptr(ol), B, T1, T2, odim, int(use_masking),
+                int(use_mse), _ptr(losses), _ptr(gm) if gm is not None else None, _ptr(gd) if gd is not None else None,
+                _ptr(ws), ws.numel(), st))
+        return losses, gm, gd
+
+    def scale_by_scalar(self, x, scalar):
+        """x * scalar with the 0-dim ``scalar`` read on the device."""
+        x = x.contiguous()
+        s = scalar.detach().to(device=self.device, dtype=torch.float32).reshape(1).contiguous()
+        with torch.cuda.device(self.device):
+            out = torch.empty_like(x)
+            st = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            _lib.check(self.lib.efts_scale_by_scalar(self._h, _ptr(x), _ptr(s), x.numel(), _ptr(out), st))
+        return out
+
 
 _TRAIN_CONTEXTS = {}
 
@@ -595,3 +631,25 @@ class DurationPredictorFunction(torch.autograd.Function):
         acts, us, conv_w, ln_g, head_w = ctx.saved_tensors
         gx, gw, gb, gg, gbeta, ghw, ghb = ctx.tc.duration_bwd(grad_out, acts, us, conv_w, ln_g, head_w, ctx.mask, ctx.keep)
         return gx, gw, gb, gg, gbeta, ghw.view_as(head_w), ghb, None, None
+
+
+class FastSpeechLossFunction(torch.autograd.Function):
+    """(mel term, duration term) of losses/fastspeech_loss.py:54-67 as 0-dim tensors, differentiable with respect to
+    ``before_outs`` and ``d_outs``: one library call computes both terms and their element gradients; backward scales
+    the saved gradients by the upstream scalars on the device."""
+
+    @staticmethod
+    def forward(ctx, before_outs, d_outs, ys, ds, ilens, olens, use_masking, use_mse):
+        tc = train_context(before_outs.device)
+        need = before_outs.requires_grad or d_outs.requires_grad
+        losses, gm, gd = tc.fastspeech_loss(before_outs, d_outs, ys, ds, ilens, olens, use_masking, use_mse, need)
+        if need:
+            ctx.save_for_backward(gm, gd)
+        ctx.tc = tc
+        return losses[0], losses[1]
+
+    @staticmethod
+    def backward(ctx, g_mel, g_dur):
+        gm, gd = ctx.saved_tensors
+        return (ctx.tc.scale_by_scalar(gm, g_mel) if ctx.needs_input_grad[0] else None,
+                ctx.tc.scale_by_scalar(gd, g_dur) if ctx.needs_input_grad[1] else None, None, None, None, None, None, None)

@@ -298,6 +298,20 @@ int efts_duration_train_bwd(efts_ctx* ctx, const float* grad_out, const float* a
                             float* grad_conv_b, float* grad_ln_g, float* grad_ln_b, float* grad_head_w,
                             float* grad_head_b, void* workspace, size_t workspace_bytes, void* stream);
 
+/* The criterion with gradients: FastSpeechLoss.forward (losses/fastspeech_loss.py:54-67) with after_outs = None and
+ * use_weighted_masking = False -- what models/efficient_tts.py:220 calls.  losses[0] = mean over the selected elements of
+ * (before_outs - ys)^2 (use_mse; |.| otherwise), losses[1] = mean over the selected tokens of |d_outs - ds|; "selected" =
+ * inside olens / ilens when use_masking, everything otherwise.  grad_before [B,T2,odim] / grad_d [B,T1] (either may be
+ * NULL) receive d losses[0] / d before_outs and d losses[1] / d d_outs.  Block partial sums in double, added in block
+ * order (deterministic).  A length outside [0, padded dim] raises flag bit 4 (the reference's mask broadcast fails).
+ * efts_scale_by_scalar: out = in * scalar[0] with the scalar on the device (chain rule of a loss term, no read-back). */
+size_t efts_fastspeech_loss_workspace_bytes(const efts_ctx* ctx);
+int efts_fastspeech_loss(efts_ctx* ctx, const float* before_outs, const float* d_outs, const float* ys, const float* ds,
+                         const int64_t* ilens, const int64_t* olens, int32_t B, int32_t T1, int32_t T2, int32_t odim,
+                         int32_t use_masking, int32_t use_mse, float* losses, float* grad_before, float* grad_d,
+                         void* workspace, size_t workspace_bytes, void* stream);
+int efts_scale_by_scalar(efts_ctx* ctx, const float* in, const float* scalar, size_t n, float* out, void* stream);
+
 /* ---- data parallelism ----
  * The survey's sketch of this ABI listed efts_dp_init / efts_dp_allgather / efts_dp_allreduce_loss.  They are
  * deliberately NOT exported: the reference's only parallelism is torch DDP with a DistributedSampler

@@ -327,3 +327,30 @@ def length_regulator(xs: torch.Tensor, ds: torch.Tensor, ilens: torch.Tensor, al
         idx[b, :len(r)] = r
         out[b, :len(r)] = xs[b][torch.from_numpy(r)]
     return out, torch.from_numpy(idx)
+
+
+# --------------------------------------------------------------------------- criterion (losses/fastspeech_loss.py)
+def make_loss_inputs(seed, B, T1, T2, odim):
+    """Seeded inputs of the criterion: (mel_pred [B,T2,odim], dur_pred [B,T1], ys, ds, ilens, olens); the longest
+    utterance fills the padded dims (make_non_pad_mask builds its masks with maxlen = max(lengths))."""
+    g = torch.Generator().manual_seed(int(seed))
+    mel = torch.randn(B, T2, odim, generator=g)
+    ys = torch.randn(B, T2, odim, generator=g)
+    dur = torch.randn(B, T1, generator=g)
+    ds = torch.randn(B, T1, generator=g)
+    il = torch.randint(1, T1 + 1, (B,), generator=g)
+    ol = torch.randint(1, T2 + 1, (B,), generator=g)
+    il[0], ol[0] = T1, T2
+    return mel, dur, ys, ds, il, ol
+
+
+def fastspeech_loss(before_outs, d_outs, ys, ds, ilens, olens, use_masking=True, use_mse=True):
+    """``FastSpeechLoss.forward`` with after_outs=None and use_weighted_masking=False (losses/fastspeech_loss.py:54-67):
+    masked_select of the valid positions, then the mean criterion (MSE or L1 for the mel term, L1 for the durations)."""
+    if use_masking:
+        dm = non_pad_mask(ilens)
+        d_outs, ds = d_outs.masked_select(dm), ds.masked_select(dm)
+        om = non_pad_mask(olens).unsqueeze(-1)
+        before_outs, ys = before_outs.masked_select(om), ys.masked_select(om)
+    mel_loss = F.mse_loss(before_outs, ys) if use_mse else F.l1_loss(before_outs, ys)
+    return mel_loss, F.l1_loss(d_outs, ds)

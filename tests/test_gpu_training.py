@@ -332,3 +332,74 @@ def test_duration_predictor_backward_matches_float64_with_dropout_masks(dev):
         err = (a.cpu().double().reshape(want.shape) - want).abs().max().item() / max(want.abs().max().item(), 1e-30)
         print("%s: max error / max |grad| = %.2e" % (name, err))
         assert err <= 5e-5, name
+
+
+# ---------------------------------------------------------------- criterion (losses/fastspeech_loss.py)
+def test_fastspeech_loss_module_matches_the_reference_fixture_and_the_oracle(dev):
+    """efficient_tts_b200.losses.FastSpeechLoss: values and gradients against the fixture of the unmodified reference
+    module (tests/golden/loss_cases.npz) and, at a training-sized shape, against autograd through the oracle."""
+    import os
+    from efficient_tts_b200.losses import FastSpeechLoss
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "loss_cases.npz"))
+    for name in ("mask_mse", "nomask_mse", "mask_l1"):
+        seed, B, T1, T2, odim, use_masking, use_mse = (int(v) for v in z[name + ".cfg"])
+        mel, dur, ys, ds, il, ol = (t.to(dev) for t in orc.make_loss_inputs(seed, B, T1, T2, odim))
+        mel.requires_grad_(True)
+        dur.requires_grad_(True)
+        crit = FastSpeechLoss(use_masking=bool(use_masking), use_mse=bool(use_mse))
+        ml, dl = crit(None, mel, dur, ys, ds, il, ol)
+        (ml * 0.7 + dl * 1.3).backward()
+        want = z[name + ".losses"]
+        assert abs(ml.item() - want[0]) <= 2e-6 * max(1.0, abs(want[0])), (name, ml.item(), want[0])
+        assert abs(dl.item() - want[1]) <= 2e-6 * max(1.0, abs(want[1])), (name, dl.item(), want[1])
+        gm, gd = z[name + ".grad_mel"], z[name + ".grad_dur"]
+        assert np.abs(mel.grad.cpu().numpy() - gm).max() <= 1e-6 * np.abs(gm).max(), name
+        assert np.abs(dur.grad.cpu().numpy() - gd).max() <= 1e-6 * np.abs(gd).max(), name
+    # training-sized: B = 32, 200 tokens -> 1200 frames
+    mel, dur, ys, ds, il, ol = orc.make_loss_inputs(9, 32, 200, 1200, 80)
+    mr, dr = mel.clone().requires_grad_(True), dur.clone().requires_grad_(True)
+    a, b = orc.fastspeech_loss(mr, dr, ys, ds, il, ol, True, True)
+    (a + b).backward()
+    md, dd = mel.to(dev).requires_grad_(True), dur.to(dev).requires_grad_(True)
+    ml, dl = FastSpeechLoss()(None, md, dd, ys.to(dev), ds.to(dev), il.to(dev), ol.to(dev))
+    (ml + dl).backward()
+    assert abs(ml.item() - a.item()) <= 2e-6 * abs(a.item()) and abs(dl.item() - b.item()) <= 2e-6 * abs(b.item())
+    assert (md.grad.cpu() - mr.grad).abs().max().item() <= 1e-6 * mr.grad.abs().max().item()
+    assert (dd.grad.cpu() - dr.grad).abs().max().item() <= 1e-6 * dr.grad.abs().max().item()
+    # the reference's mask rule: padded dims must equal the longest length
+    with pytest.raises(RuntimeError):
+        FastSpeechLoss()(None, md, dd, ys.to(dev), ds.to(dev), il.to(dev), (ol - 1).clamp(min=1).to(dev))
+
+
+def test_duration_predictor_training_step_with_the_criterion(dev):
+    """One optimiser step of the duration branch as the reference runs it (models/efficient_tts.py:219-221:
+    dur_pred = duration_predictor(text_value, ~text_mask); criterion(..., dur_pred, ..., log_delta_e, ...)), every
+    gradient from the library: parameters after the step match the CPU reference within 1e-6 + 1e-4 of the update."""
+    from efficient_tts_b200.layers import DurationPredictor
+    from efficient_tts_b200.losses import FastSpeechLoss
+    torch.manual_seed(3)
+    dp = DurationPredictor(512, n_layers=2, n_chans=512, kernel_size=3, dropout_rate=0.0)
+    state = {k: v.detach().clone() for k, v in dp.state_dict().items()}
+    B, T1, T2, odim = 4, 60, 90, 80
+    mel, _, ys, ds, il, ol = orc.make_loss_inputs(21, B, T1, T2, odim)
+    xs = torch.randn(B, T1, 512, generator=torch.Generator().manual_seed(22))
+    masks = torch.arange(T1)[None, :] >= il[:, None]
+    lr = 0.05
+    # CPU reference: oracle forward + torch autograd + SGD
+    leaves = {"duration_predictor." + k: v.clone().requires_grad_(True) for k, v in state.items()}
+    d_ref = orc.duration_predictor_forward(xs, masks, leaves)
+    a, b = orc.fastspeech_loss(mel, d_ref, ys, ds, il, ol, True, True)
+    (a + b).backward()
+    stepped = {k: leaves["duration_predictor." + k].detach() - lr * leaves["duration_predictor." + k].grad for k in state}
+    # device
+    dp = dp.to(dev).train()
+    opt = torch.optim.SGD(dp.parameters(), lr=lr)
+    d_out = dp(xs.to(dev), masks.to(dev))
+    ml, dl = FastSpeechLoss()(None, mel.to(dev), d_out, ys.to(dev), ds.to(dev), il.to(dev), ol.to(dev))
+    loss = ml + dl
+    loss.backward()
+    opt.step()
+    assert abs(loss.item() - (a + b).item()) <= 1e-5 * max(1.0, abs((a + b).item()))
+    for k, v in dp.state_dict().items():
+        upd = (stepped[k] - state[k]).abs().max().item()
+        assert (v.cpu() - stepped[k]).abs().max().item() <= 1e-6 + 1e-4 * upd, k
