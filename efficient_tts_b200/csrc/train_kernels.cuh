@@ -6,11 +6,12 @@
 //                             dL/db[o] = sum_{b,t} G'[b,t,o]
 // The position-reduction GEMM wants both operands K-major with K = positions: G'^T and x^T are laid out
 // [C][B * Tp] with Tp = round8(T + 2 * pad) and `pad` zero columns in front of every utterance, so a tap is a
-// column shift of x^T that never reads across an utterance boundary.  TMA box coordinates must be 16-byte aligned,
-// so the shift cannot be a read offset of one or two fp16 elements: x^T is written once per tap with the shift
-// applied on the store side.  (Known cost: k transposes of x per layer.  The better operand is the activation plane
-// itself read as an MN-major UMMA operand, where a tap is a row shift of the shared-memory tile exactly like in the
-// forward kernel; see DESIGN.md, "what comes next".)
+// column shift of x^T that never reads across an utterance boundary.  TMA box coordinates and UMMA start addresses
+// are 16-byte aligned, so the shift cannot be a read offset of one or two fp16 elements: the GEMM of tap j reads its own
+// copy of x^T, shifted by j - pad; transpose_shift_split_kernel writes all k copies in one pass.  (The better operand is
+// the activation plane itself read as an MN-major UMMA operand, where a tap is a row shift of the shared-memory tile
+// exactly like in the forward kernel; see DESIGN.md, "what comes next".)
+// Further down: the duration predictor's LayerNorm / head kernels and the criterion with gradients.
 #pragma once
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
