@@ -151,7 +151,10 @@ def test_duration_predictor_matches_golden_and_oracle(dev):
     dp = dp.eval().to(dev)
     xs = torch.from_numpy(z["xs"]).to(dev)
     masks = (~orc.non_pad_mask(torch.from_numpy(z["lens"]))).to(dev)
-    log_d = dp(xs, masks).cpu().numpy()
+    with torch.no_grad():                      # with gradients enabled forward() is the differentiable training path
+        log_d = dp(xs, masks).cpu().numpy()
+    log_d_grad = dp(xs, masks)                 # ... which returns the same values, attached to the autograd graph
+    assert log_d_grad.requires_grad and np.abs(log_d_grad.detach().cpu().numpy() - log_d).max() <= 2e-5
     d_float = dp.inference(xs, None, to_round=False).cpu().numpy()
     d_round = dp.inference(xs, masks).cpu()
     np.testing.assert_allclose(log_d, z["log_d"], atol=1e-4, rtol=0)
