@@ -65,7 +65,9 @@ struct PackedW {
   int Z = 0, N = 0, K = 0;
 };
 
-struct OpA { const __half* hi; const __half* lo; int B, T, K, ld; };   // [B, T, ld], K valid columns
+// [B, T, ld], K valid columns.  map_rows > T: every utterance owns map_rows rows in memory of which the kernel computes the
+// first T (its taps may read on into the others): the front-end's chunk matrix, T frames from T + taps - 1 chunk rows.
+struct OpA { const __half* hi; const __half* lo; int B, T, K, ld; int map_rows = 0; };
 struct OpB { const __half* hi; const __half* lo; int Z, N, K, ld; };   // [Z, N, ld], K valid columns
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -144,7 +146,7 @@ struct efts_ctx {
   struct Frontend {
     efts_frontend_config cfg;
     PackedW dft, mel;
-    int taps = 0, half = 0, Kp = 0;
+    int taps = 0, half = 0, Kp = 0;   // Kp: bins kept (a multiple of 8): up to the last one any mel filter weighs
   };
   Frontend* fe = nullptr;
   // measurement hooks (efts_profile_*): CUDA-event pairs around tagged launches
@@ -226,8 +228,9 @@ int launch_gemm2_t(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, con
                 G2_BM + (p.ntaps - 1) * dil, AR);
   if (p.bias != nullptr && p.N > Cfg::BIAS_MAX) return fail(EFTS_ERR_ARG, "bias supports at most %d columns", Cfg::BIAS_MAX);
   alignas(64) CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
-  TRY(make_map(c, &ma_hi, a.hi, a.K, a.T, a.B, a.ld, AR));
-  TRY(make_map(c, &ma_lo, a.lo, a.K, a.T, a.B, a.ld, AR));
+  const int a_rows = a.map_rows > a.T ? a.map_rows : a.T;
+  TRY(make_map(c, &ma_hi, a.hi, a.K, a_rows, a.B, a.ld, AR));
+  TRY(make_map(c, &ma_lo, a.lo, a.K, a_rows, a.B, a.ld, AR));
   TRY(make_map(c, &mb_hi, b.hi, b.K, b.N, b.Z, b.ld, Cfg::B_ROWS));
   TRY(make_map(c, &mb_lo, b.lo, b.K, b.N, b.Z, b.ld, Cfg::B_ROWS));
   // persistent: one CTA per SM (CTA pairs when CG == 2), never more than there are tiles
@@ -295,6 +298,12 @@ int launch_gemm(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, GemmPa
                      : launch_gemm2_t<2, EPI_STD, 0, 1, G2_A_ROWS_LONG, 64>(c, st, a, b, p);
       if (xlong) return launch_gemm2_t<2, EPI_STD, 0, 1, G2_A_ROWS_XLONG>(c, st, a, b, p);
       return launch_gemm2_t<2, EPI_STD, 0, 1, G2_A_ROWS_LONG>(c, st, a, b, p);
+    }
+    if (p.mag_pairs) {                       // STFT of the log-mel front-end: magnitude planes from (re, im) column pairs
+      if (epi != EPI_STD || !pair || !c->fuse_b || p.chunk_kb < 1 || p.N % 16 != 0 || p.out_hi == nullptr || p.out != nullptr ||
+          p.bias != nullptr || p.resid != nullptr)
+        return fail(EFTS_ERR_ARG, "magnitude epilogue: plain paired GEMM with plane output only");
+      return launch_gemm2_t<2, EPI_MAG, 0, 1>(c, st, a, b, p);
     }
     const bool wide = c->wide && steps <= 40;
     if (p.act == ACT_LOGCLAMP && !wide)
@@ -378,6 +387,8 @@ int set_kernel_attributes() {
   CUDA_TRY(cudaFuncSetAttribute(gemm2_kernel<2, EPI_STD, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 G2Cfg<2, 0, 1>::SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(gemm2_kernel<2, EPI_STD, 0, 1, G2_A_ROWS, G2_BN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                G2Cfg<2, 0, 1>::SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(gemm2_kernel<2, EPI_MAG, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 G2Cfg<2, 0, 1>::SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(gemm2_kernel<2, EPI_STD, 0, 1, G2_A_ROWS_LONG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 G2Cfg<2, 0, 1, G2_A_ROWS_LONG>::SMEM_BYTES));
@@ -1963,7 +1974,6 @@ namespace {
 struct FeWs {
   int* lens32;
   __half *ch_hi, *ch_lo;       // chunk matrix planes [B, R, hop]
-  float* stft;                 // [B, R, 2 * half]
   __half *mg_hi, *mg_lo;       // magnitude planes [B, Tmax, Kp]
 };
 void carve_frontend(Arena& a, FeWs& w, const efts_ctx::Frontend& f, int B, int Tmax) {
@@ -1971,7 +1981,6 @@ void carve_frontend(Arena& a, FeWs& w, const efts_ctx::Frontend& f, int B, int T
   w.lens32 = a.get<int>(B);
   w.ch_hi = a.get<__half>(B * R * f.cfg.hop_size);
   w.ch_lo = a.get<__half>(B * R * f.cfg.hop_size);
-  w.stft = a.get<float>(B * R * 2 * f.half);
   w.mg_hi = a.get<__half>(static_cast<size_t>(B) * Tmax * f.Kp);
   w.mg_lo = a.get<__half>(static_cast<size_t>(B) * Tmax * f.Kp);
 }
@@ -1997,7 +2006,7 @@ int efts_frontend_create(const efts_frontend_config* g, efts_ctx** out) {
   c->chunk_kb = 1;
   c->fe->taps = g->n_fft / g->hop_size;
   c->fe->half = g->n_fft / 2;
-  c->fe->Kp = round8(g->n_fft / 2 + 1);
+  c->fe->Kp = round8(g->n_fft / 2 + 1);     // until finalize has seen the mel filter bank
   *out = c;
   return EFTS_OK;
 }
@@ -2007,8 +2016,38 @@ int efts_frontend_finalize(efts_ctx* c) {
   if (c->finalized) return EFTS_OK;
   efts_ctx::Frontend& f = *c->fe;
   CUDA_TRY(cudaSetDevice(f.cfg.device));
-  TRY(pack_weight(c, "stft.weight", "stft.bias", 2 * f.half, f.cfg.hop_size, f.taps, &f.dft));
-  TRY(pack_weight(c, "mel_basis.weight", "mel_basis.bias", f.cfg.num_mels, f.Kp, 1, &f.mel));
+  // Uploaded: "stft.weight" [2 half, hop, taps] (rows 0 .. half: re_0 .. re_half, rows half + 1 ..: im_1 .. im_{half-1}; im_0
+  // and im_half vanish for a real signal) and "mel_basis.weight" [mels, round8(half + 1)].  Packed: only the bins some mel
+  // filter weighs (fmax = 8 kHz at 22.05 kHz keeps 372 of 513 -- the others are multiplied by zero in :74), and the two
+  // columns of a bin side by side, (re_f, im_f), so that the STFT GEMM's epilogue can write the magnitude itself.
+  const int full = round8(f.half + 1);
+  const std::vector<float>* dft;
+  const std::vector<float>* mel;
+  TRY(need(c, "stft.weight", {2 * f.half, f.cfg.hop_size, f.taps}, &dft));
+  TRY(need(c, "mel_basis.weight", {f.cfg.num_mels, full}, &mel));
+  int nb = 1;
+  for (int m = 0; m < f.cfg.num_mels; ++m)
+    for (int k = 0; k <= f.half; ++k)
+      if ((*mel)[static_cast<size_t>(m) * full + k] != 0.0f) nb = std::max(nb, k + 1);
+  f.Kp = round8(nb);
+  const size_t per_col = static_cast<size_t>(f.cfg.hop_size) * f.taps;
+  std::vector<float> pairs(static_cast<size_t>(2) * f.Kp * per_col, 0.0f), trim(static_cast<size_t>(f.cfg.num_mels) * f.Kp, 0.0f);
+  for (int k = 0; k < f.Kp && k <= f.half; ++k) {
+    std::copy(dft->begin() + k * per_col, dft->begin() + (k + 1) * per_col, pairs.begin() + (2 * k) * per_col);
+    if (k > 0 && k < f.half)
+      std::copy(dft->begin() + (f.half + k) * per_col, dft->begin() + (f.half + k + 1) * per_col,
+                pairs.begin() + (2 * k + 1) * per_col);
+  }
+  for (int m = 0; m < f.cfg.num_mels; ++m)
+    for (int k = 0; k < f.Kp && k < full; ++k) trim[static_cast<size_t>(m) * f.Kp + k] = (*mel)[static_cast<size_t>(m) * full + k];
+  c->raw["stft.pairs.weight"] = pairs;
+  c->raw_shape["stft.pairs.weight"] = {2 * f.Kp, f.cfg.hop_size, f.taps};
+  c->raw["stft.pairs.bias"] = std::vector<float>(static_cast<size_t>(2) * f.Kp, 0.0f);
+  c->raw_shape["stft.pairs.bias"] = {2 * f.Kp};
+  c->raw["mel_trim.weight"] = trim;
+  c->raw_shape["mel_trim.weight"] = {f.cfg.num_mels, f.Kp};
+  TRY(pack_weight(c, "stft.pairs.weight", "stft.pairs.bias", 2 * f.Kp, f.cfg.hop_size, f.taps, &f.dft));
+  TRY(pack_weight(c, "mel_trim.weight", "mel_basis.bias", f.cfg.num_mels, f.Kp, 1, &f.mel));
   c->raw.clear();
   c->raw_shape.clear();
   c->finalized = true;
@@ -2052,19 +2091,17 @@ int efts_frontend_forward(efts_ctx* c, const float* audio, const int64_t* length
                                                             reinterpret_cast<long long*>(mel_lengths), w.lens32, c->err_flag);
   CUDA_TRY(cudaGetLastError());
   c->launches++;
-  // 2. STFT (:69-70): frame t = rows t .. t + taps - 1 of the chunk matrix against the windowed DFT basis
+  // 2. STFT (:69-70): frame t = rows t .. t + taps - 1 of the chunk matrix against the windowed DFT basis, and
+  // 3. magnitude sqrt(re^2 + im^2 + 1e-9) (:72) in its epilogue (columns are (re, im) pairs), as operand planes
   {
     GemmParams p = gemm_defaults();
-    p.N = 2 * f.half; p.ntaps = f.taps; p.pad = 0;
-    p.out = w.stft; p.ld_out = 2 * f.half;
+    p.N = 2 * f.Kp; p.ntaps = f.taps; p.pad = 0; p.mag_pairs = 1; p.lens = w.lens32;
+    p.out_hi = w.mg_hi; p.out_lo = w.mg_lo; p.ld_pl = f.Kp;
     ProfScope ps(c, st, TAG_LINEAR);
-    TRY(launch_gemm(c, st, OpA{w.ch_hi, w.ch_lo, B, R, f.cfg.hop_size, f.cfg.hop_size}, weight_op(f.dft), p));
+    OpA chunks{w.ch_hi, w.ch_lo, B, Tmax, f.cfg.hop_size, f.cfg.hop_size};
+    chunks.map_rows = R;
+    TRY(launch_gemm(c, st, chunks, weight_op(f.dft), p));
   }
-  // 3. magnitude sqrt(re^2 + im^2 + 1e-9) (:72) as operand planes
-  frontend_magnitude_kernel<<<dim3((f.Kp / 4 + 127) / 128, Tmax, B), 128, 0, st>>>(w.stft, w.lens32, R, Tmax, f.half, f.Kp,
-                                                                                   w.mg_hi, w.mg_lo, c->err_flag);
-  CUDA_TRY(cudaGetLastError());
-  c->launches++;
   // 4. mel projection (:74) with log(clamp(x, 1e-5)) (:75) in the epilogue; frames beyond an utterance's length are zero
   GemmParams p = gemm_defaults();
   p.N = f.cfg.num_mels; p.act = ACT_LOGCLAMP; p.lens = w.lens32;

@@ -72,37 +72,4 @@ __global__ void frontend_chunk_planes_kernel(const float* __restrict__ audio, co
   }
 }
 
-// STFT fp32 [B, R, 2 * half] (columns [0, half]: re_0 .. re_half, [half + 1, 2 half): im_1 .. im_{half-1}; im_0 and
-// im_half vanish identically for a real signal) -> magnitude operand planes [B, Tmax, Kp] (Kp >= half + 1, a multiple
-// of 8; columns beyond half are zero): sqrt(re^2 + im^2 + 1e-9) evaluated like the reference's
-// spec.pow(2).sum(-1) + 1e-9 (:72).  Rows t >= frames_b are written as zeros.  One thread per four bins.
-__global__ void frontend_magnitude_kernel(const float* __restrict__ stft, const int* __restrict__ lens32, int R, int Tmax,
-                                          int half, int Kp, __half* __restrict__ hi, __half* __restrict__ lo,
-                                          int* __restrict__ flags) {
-  const int b = blockIdx.z, t = blockIdx.y;
-  const int k0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  if (k0 >= Kp) return;
-  const float* row = stft + (static_cast<size_t>(b) * R + t) * (2 * half);
-  const bool live = t < lens32[b];
-  float v[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int k = k0 + j;
-    float m = 0.0f;
-    if (live && k <= half) {
-      const float re = row[k];
-      const float im = (k == 0 || k == half) ? 0.0f : row[half + k];
-      m = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im)), 1e-9f));
-    }
-    v[j] = m;
-  }
-  const float4 f = make_float4(v[0], v[1], v[2], v[3]);
-  if (outside_fp16_range(f)) atomicOr(flags, 8);
-  uint2 h, l;
-  split4(f, &h, &l);
-  const size_t o = (static_cast<size_t>(b) * Tmax + t) * Kp + k0;
-  *reinterpret_cast<uint2*>(hi + o) = h;
-  *reinterpret_cast<uint2*>(lo + o) = l;
-}
-
 }  // namespace efts

@@ -162,8 +162,9 @@ __device__ __forceinline__ void g2_store_block32(const GemmParams& p, uint32_t s
 
 // EPI selects how much epilogue is compiled in (the fully unrolled column loop makes every option cost
 // instruction-cache footprint in all launches): 0 = bias / activation / residual / fp32 + plane stores (conv and
-// Linear layers), 1 = also the divisor and the transposed plane store, 2 = token-softmax partials only.
-enum Gemm2Epi { EPI_STD = 0, EPI_FULL = 1, EPI_SOFTMAX = 2 };
+// Linear layers), 1 = also the divisor and the transposed plane store, 2 = token-softmax partials only, 3 = magnitude
+// of (re, im) column pairs as operand planes (the STFT GEMM of the log-mel front-end; unfused epilogue variant only).
+enum Gemm2Epi { EPI_STD = 0, EPI_FULL = 1, EPI_SOFTMAX = 2, EPI_MAG = 3 };
 
 // WIDE = 1 is the variant for short reductions (a single accumulation chunk: Linear layers, mel prenet, the
 // expansion matmul), whose cost is the epilogue, not the MMAs: sixteen epilogue warps instead of eight (two per
@@ -675,6 +676,58 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
         continue;
       }
       if (EPI == EPI_SOFTMAX) continue;
+      if (EPI == EPI_MAG) {
+        // STFT columns (2f, 2f + 1) = (re_f, im_f): sqrt(re^2 + im^2 + 1e-9) evaluated like the reference's
+        // spec.pow(2).sum(-1) + 1e-9 (datasets/meldataset.py:72), written as operand planes [B, T, N / 2]; frames past an
+        // utterance's length are zero.  32 magnitudes at a time through the transposition buffer, like the fp32 stores.
+        const uint32_t stgm = sStage + static_cast<uint32_t>(warp - 4) * G2_STAGE_WARP_BYTES;
+        const int lens_m = p.lens != nullptr ? p.lens[b] : p.T;
+        const int NM = p.N >> 1;
+        const int sub_row = lane >> 3, sub_col = (lane & 7) * 4;
+#pragma unroll
+        for (int c32 = 0; c32 < G2_BN / 64; ++c32) {
+          const int nm = (n0 >> 1) + c32 * 32;
+          if (nm >= NM) break;                      // warp-uniform
+          __syncwarp();
+#pragma unroll
+          for (int k4 = 0; k4 < 8; ++k4) {
+            float vv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float re = sum[2 * (c32 * 32 + k4 * 4 + j)], im = sum[2 * (c32 * 32 + k4 * 4 + j) + 1];
+              vv[j] = row_live ? sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im)), 1e-9f)) : 0.0f;
+            }
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stgm + lane * G2_STAGE_ROW_BYTES + k4 * 16),
+                         "f"(vv[0]), "f"(vv[1]), "f"(vv[2]), "f"(vv[3]) : "memory");
+          }
+          __syncwarp();
+          const int nn = nm + sub_col;
+          if (nn < NM) {
+#pragma unroll
+            for (int itr = 0; itr < 8; ++itr) {
+              const int rr = itr * 4 + sub_row;
+              const int tr = t0 + q * 32 + rr;
+              float4 v;
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                           : "r"(stgm + rr * G2_STAGE_ROW_BYTES + sub_col * 4) : "memory");
+              if (tr < p.T) {
+                if (tr < lens_m && outside_fp16_range(v) && p.err_flag != nullptr) atomicOr(p.err_flag, 8 | p.err_code);
+                const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
+                const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                const __half2 l01 = __floats2half2_rn((v.x - f01.x) * SPLIT_SCALE, (v.y - f01.y) * SPLIT_SCALE);
+                const __half2 l23 = __floats2half2_rn((v.z - f23.x) * SPLIT_SCALE, (v.w - f23.y) * SPLIT_SCALE);
+                uint2 ph, pl;
+                ph.x = *reinterpret_cast<const uint32_t*>(&h01); ph.y = *reinterpret_cast<const uint32_t*>(&h23);
+                pl.x = *reinterpret_cast<const uint32_t*>(&l01); pl.y = *reinterpret_cast<const uint32_t*>(&l23);
+                const size_t o = (static_cast<size_t>(b) * p.T + tr) * p.ld_pl + nn;
+                *reinterpret_cast<uint2*>(p.out_hi + o) = ph;
+                *reinterpret_cast<uint2*>(p.out_lo + o) = pl;
+              }
+            }
+          }
+        }
+        continue;
+      }
       // stores: 32 columns at a time through this warp's transposition buffer (see g2_store_block32)
       const uint32_t stg = sStage + static_cast<uint32_t>(warp - 4) * G2_STAGE_WARP_BYTES;
       const int lens_b = p.lens != nullptr ? p.lens[b] : p.T;

@@ -237,7 +237,10 @@ int efts_host_map_grouped(const float* w, int32_t C, int32_t k, int32_t d, int32
  *   "stft.weight" [n_fft, hop, n_fft / hop] -- output column n < n_fft/2 + 1: w[s] cos(2 pi n s / n_fft) (re_n),
  *   column n > n_fft / 2: -w[s] sin(2 pi (n - n_fft/2) s / n_fft) (im of bins 1 .. n_fft/2 - 1; im_0 and im_{n_fft/2}
  *   vanish), with s = tap * hop + k; "stft.bias" [n_fft] zeros; "mel_basis.weight" [num_mels, round8(n_fft/2 + 1)]
- *   (librosa.filters.mel, zero-padded columns); "mel_basis.bias" [num_mels] zeros. */
+ *   (librosa.filters.mel, zero-padded columns); "mel_basis.bias" [num_mels] zeros.
+ * efts_frontend_finalize keeps the bins up to the last one some mel filter weighs (the others are multiplied by zero at
+ * :74) and repacks the basis as (re_f, im_f) column pairs, so that the STFT GEMM's epilogue writes the magnitude planes
+ * itself; the fp32 spectrum is never stored. */
 typedef struct efts_frontend_config {
   int32_t n_fft, hop_size, win_size, num_mels;
   int32_t device;
