@@ -607,7 +607,9 @@ int run_conv_stack(efts_ctx* c, cudaStream_t st, const PackedW* layers, int n, i
     p.act = ACT_LRELU;
     p.bias = layers[l].bias;
     p.resid = (l == 0 && first_resid != nullptr) ? first_resid : f[cur];
-    p.out = (l == n - 1 && final_f != nullptr) ? final_f : f[nxt];
+    // the fp32 master of a layer is the next layer's residual; after the last layer only the caller can want it
+    // (final_f) -- the consumers inside the path (Linear layers, energy GEMM, mel head) read the operand planes
+    p.out = l == n - 1 ? final_f : f[nxt];
     p.ld_out = C;
     p.out_hi = hi[nxt]; p.out_lo = lo[nxt]; p.ld_pl = C;
     if (skip != nullptr && c->skip_pad_tiles) {
@@ -1194,7 +1196,7 @@ int efts_inference_phase1(efts_ctx* c, const int64_t* text, int32_t T1, int32_t*
     StackLayer* L;
     for (int l = 0; l < g.n_text_encoder_layer; ++l, cur ^= 1) {
       TRY(sb.add(w.xt_hi[cur], w.xt_lo[cur], T1, C, c->text[l], c->chunk_kb, TAG_TEXT_CONV, &L));
-      L->act = ACT_LRELU; L->resid = w.xt_f[cur]; L->out = w.xt_f[cur ^ 1];
+      L->act = ACT_LRELU; L->resid = w.xt_f[cur]; L->out = l == g.n_text_encoder_layer - 1 ? nullptr : w.xt_f[cur ^ 1];
       L->out_hi = w.xt_hi[cur ^ 1]; L->out_lo = w.xt_lo[cur ^ 1];
     }
     // value only: the key projection at :251 is computed by the reference but never used
@@ -1272,7 +1274,7 @@ int efts_inference_phase2(efts_ctx* c, int32_t T1, int32_t T2, float* mel_pred, 
     StackLayer* L;
     for (int l = 0; l < g.n_decoder_layer; ++l, cur ^= 1) {
       TRY(sb.add(w.xm_hi[cur], w.xm_lo[cur], T2, C, c->dec[l], c->chunk_kb, TAG_DEC_CONV, &L));
-      L->act = ACT_LRELU; L->resid = w.xm_f[cur]; L->out = w.xm_f[cur ^ 1];
+      L->act = ACT_LRELU; L->resid = w.xm_f[cur]; L->out = l == g.n_decoder_layer - 1 ? nullptr : w.xm_f[cur ^ 1];
       L->out_hi = w.xm_hi[cur ^ 1]; L->out_lo = w.xm_lo[cur ^ 1];
     }
     TRY(sb.add(w.xm_hi[cur], w.xm_lo[cur], T2, C, c->melout, 0, TAG_LINEAR, &L));
