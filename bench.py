@@ -342,7 +342,7 @@ def time_training_slice(dev, peaks):
             "forward_tflops": fl / (ms_f * 1e-3) / 1e12, "backward_tflops": 2 * fl / (ms_b * 1e-3) / 1e12,
             "backward_frac_of_tensor_peak": 2 * fl / (ms_b * 1e-3) / 1e12 / peaks["tf"],
             "note": "backward = data gradient (one tap-GEMM per layer) + weight gradient (k position-reduction GEMMs per "
-                    "layer on k shifted copies of the transposed layer input, written by one transpose pass) + bias "
+                    "layer, the layer input read in place as an MN-major operand, the tap as a row offset) + bias "
                     "gradient; algorithmic FLOPs 2 x forward, single pass (3 passes executed)"}
 
 

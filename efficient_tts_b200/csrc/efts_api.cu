@@ -217,10 +217,10 @@ int make_map(efts_ctx* c, CUtensorMap* m, const __half* ptr, int inner, int rows
 constexpr size_t kReconstructSmemMax = 200 * 1024;
 constexpr size_t kSplitScratchBytes = 16u << 20;       // partial planes of a split reduction (workspace, text side)
 
-template <int CG, int EPI, int WIDE, int FUSE = 0, int AR = G2_A_ROWS, int BN = G2_BN, int SPLIT = 0>
+template <int CG, int EPI, int WIDE, int FUSE = 0, int AR = G2_A_ROWS, int BN = G2_BN, int SPLIT = 0, int BMN = 0>
 int launch_gemm2_t(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, const GemmParams& p) {
   using Cfg = G2Cfg<CG, WIDE, FUSE, AR, BN>;
-  auto kern = gemm2_kernel<CG, EPI, WIDE, FUSE, AR, BN, SPLIT>;
+  auto kern = gemm2_kernel<CG, EPI, WIDE, FUSE, AR, BN, SPLIT, BMN>;
   if (!SPLIT && p.splits > 1) return fail(EFTS_ERR_ARG, "split reduction requested from an unsplit kernel instantiation");
   const int dil = p.dil > 1 ? p.dil : 1;
   if (G2_BM + (p.ntaps - 1) * dil > AR)
@@ -255,8 +255,8 @@ int launch_gemm2_t(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, con
   CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ma_hi, ma_lo, mb_hi, mb_lo, p));
   c->launches++;
   if (c->profile_mask)
-    snprintf(c->tag_kernel[c->cur_tag & 15], sizeof(c->tag_kernel[0]), "gemm2_kernel<%d, %d, %d, %d, %d, %d, %d>", CG, EPI,
-             WIDE, FUSE, AR, BN, SPLIT);
+    snprintf(c->tag_kernel[c->cur_tag & 15], sizeof(c->tag_kernel[0]), "gemm2_kernel<%d, %d, %d, %d, %d, %d, %d, %d>", CG, EPI,
+             WIDE, FUSE, AR, BN, SPLIT, BMN);
   return EFTS_OK;
 }
 
@@ -267,7 +267,7 @@ int launch_gemm(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, GemmPa
     fprintf(stderr, "[efts gemm] B=%d T=%d K=%d N=%d taps=%d dil=%d act=%d resid=%d out=%d planes=%d plane_act=%d long=%d batched=%d\n",
             a.B, a.T, a.K, p.N, p.ntaps, p.dil, p.act, p.resid != nullptr, p.out != nullptr, p.out_hi != nullptr,
             p.plane_act, p.long_taps, p.b_batched);
-  if (a.K != b.K) return fail(EFTS_ERR_ARG, "gemm K mismatch %d vs %d", a.K, b.K);
+  if (a.K != b.K && p.bmn_per == 0) return fail(EFTS_ERR_ARG, "gemm K mismatch %d vs %d", a.K, b.K);
   if (p.N % 8 != 0) return fail(EFTS_ERR_ARG, "gemm N=%d must be a multiple of 8", p.N);
   {
     if (p.ntaps > 15) return fail(EFTS_ERR_ARG, "at most 15 taps");
@@ -304,6 +304,27 @@ int launch_gemm(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, GemmPa
           p.bias != nullptr || p.resid != nullptr)
         return fail(EFTS_ERR_ARG, "magnitude epilogue: plain paired GEMM with plane output only");
       return launch_gemm2_t<2, EPI_MAG, 0, 1>(c, st, a, b, p);
+    }
+    if (p.bmn_per > 0) {
+      // Weight gradients: B = activation planes [Z = utterances, N = rows, K = channels] read MN-major by the split
+      // fused-B kernel, whatever the size (the reduction index is the activation's row, so no other variant applies)
+      const int num_kb = (p.K + G2_BK - 1) / G2_BK;
+      if (p.split_kb <= 0) p.split_kb = (num_kb + p.chunk_kb - 1) / std::max(1, p.chunk_kb) * std::max(1, p.chunk_kb);
+      const int splits = (num_kb + p.split_kb - 1) / p.split_kb;
+      const size_t plane = static_cast<size_t>(p.B) * p.T * p.N;
+      if (epi != EPI_STD || !pair || !c->fuse_b || p.chunk_kb < 1 || p.N != b.K || p.N % (2 * G2Cfg<2, 0, 1>::B_ROWS) != 0 ||
+          p.split_scratch == nullptr || p.split_kb % p.chunk_kb != 0 || plane * splits * sizeof(float) > kSplitScratchBytes ||
+          p.ld_out % 4 != 0 || p.tile_list != nullptr || p.skip_lens != nullptr || p.ntaps != 1)
+        return fail(EFTS_ERR_ARG, "MN-major B operand: %d output columns over planes of %d channels, %d splits", p.N, b.K, splits);
+      GemmParams q = p;
+      q.bias = nullptr; q.act = ACT_NONE; q.resid = nullptr; q.lens = nullptr;
+      q.out = p.split_scratch; q.ld_out = p.N; q.out_hi = nullptr; q.out_lo = nullptr;
+      q.splits = splits; q.split_stride = plane;
+      TRY((launch_gemm2_t<2, EPI_STD, 0, 1, G2_A_ROWS, G2_BN, 1, 1>(c, st, a, b, q)));
+      splitk_reduce_kernel<<<static_cast<unsigned>((plane / 4 + 255) / 256), 256, 0, st>>>(p, p.split_scratch, splits, plane);
+      CUDA_TRY(cudaGetLastError());
+      c->launches++;
+      return EFTS_OK;
     }
     const bool wide = c->wide && steps <= 40;
     if (p.act == ACT_LOGCLAMP && !wide)
@@ -389,6 +410,8 @@ int set_kernel_attributes() {
   CUDA_TRY(cudaFuncSetAttribute(gemm2_kernel<2, EPI_STD, 0, 1, G2_A_ROWS, G2_BN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 G2Cfg<2, 0, 1>::SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(gemm2_kernel<2, EPI_MAG, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                G2Cfg<2, 0, 1>::SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(gemm2_kernel<2, EPI_STD, 0, 1, G2_A_ROWS, G2_BN, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 G2Cfg<2, 0, 1>::SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(gemm2_kernel<2, EPI_STD, 0, 1, G2_A_ROWS_LONG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 G2Cfg<2, 0, 1, G2_A_ROWS_LONG>::SMEM_BYTES));
@@ -2121,8 +2144,7 @@ namespace {
 struct TrainWs {
   __half *w_hi, *w_lo;                 // packed weights of the current layer [k][C][C]
   __half *a_hi[2], *a_lo[2];           // operand planes of a [B, T, C] activation (ping-pong)
-  __half *gT_hi, *gT_lo;               // transposed planes [C][Ktot] of the masked gradient
-  __half *xT_hi, *xT_lo;               // k copies [C][Ktot] of the transposed layer input, one per tap shift
+  __half *gT_hi, *gT_lo;               // transposed planes [C][Ktot] of the masked gradient (Ktot = B * round64(T))
   float* dwt;                          // [k][C][C]
   float* splitk;                       // partial planes of the split reductions
   double* db_part;                     // [kBiasParts][C]
@@ -2132,15 +2154,14 @@ struct TrainWs {
 constexpr int kBiasParts = 592;
 void carve_train(Arena& a, TrainWs& w, int B, int T, int C, int k, bool backward) {
   const size_t m = static_cast<size_t>(B) * T;
-  const int pad = (k - 1) / 2;
-  w.Tp = round8(T + 2 * pad);
+  (void)k;
+  w.Tp = (T + G2_BK - 1) / G2_BK * G2_BK;            // positions of an utterance = whole k-blocks of the weight gradient
   w.ktot = static_cast<size_t>(B) * w.Tp;
   w.w_hi = a.get<__half>(static_cast<size_t>(k) * C * C);
   w.w_lo = a.get<__half>(static_cast<size_t>(k) * C * C);
   for (int i = 0; i < 2; ++i) { w.a_hi[i] = a.get<__half>(m * C); w.a_lo[i] = a.get<__half>(m * C); }
   if (backward) {
     w.gT_hi = a.get<__half>(w.ktot * C); w.gT_lo = a.get<__half>(w.ktot * C);
-    w.xT_hi = a.get<__half>(static_cast<size_t>(k) * w.ktot * C); w.xT_lo = a.get<__half>(static_cast<size_t>(k) * w.ktot * C);
     w.dwt = a.get<float>(static_cast<size_t>(k) * C * C);
     w.splitk = a.get<float>(kSplitScratchBytes / sizeof(float));
     w.db_part = a.get<double>(static_cast<size_t>(kBiasParts) * C);
@@ -2164,28 +2185,28 @@ int conv_layer_bwd(efts_ctx* c, cudaStream_t st, TrainWs& w, const float* g, con
   int split_kb = (num_kb + want - 1) / want;
   split_kb = (split_kb + c->chunk_kb - 1) / std::max(1, c->chunk_kb) * std::max(1, c->chunk_kb);
   const dim3 tgrid((w.Tp + TS_COLS - 1) / TS_COLS, C / 32, B);
-  const size_t copy = w.ktot * C;                  // elements between the shifted copies of x^T
-  // G' planes (data gradient), G'^T and x^T planes (weight gradient), bias gradient
+  // G' planes (data gradient), G'^T planes and the planes of the layer input (weight gradient), bias gradient
   lrelu_grad_split_kernel<<<ew_grid(n / 4), 256, 0, st>>>(g, u, n / 4, slope, w.a_hi[0], w.a_lo[0], c->err_flag);
   CUDA_TRY(cudaGetLastError());
-  transpose_shift_split_kernel<<<tgrid, 256, 0, st>>>(g, u, slope, T, C, w.Tp, pad, 0, 1, w.ktot, 0, w.gT_hi, w.gT_lo);
+  transpose_shift_split_kernel<<<tgrid, 256, 0, st>>>(g, u, slope, T, C, w.Tp, 0, 0, 1, w.ktot, 0, w.gT_hi, w.gT_lo);
   CUDA_TRY(cudaGetLastError());
-  // x^T once per tap shift: xTs_j[c, q] = x^T[c, q + j - pad] (TMA coordinates cannot carry a 2-byte shift)
-  transpose_shift_split_kernel<<<tgrid, 256, 0, st>>>(xl, nullptr, 0.0f, T, C, w.Tp, pad, -pad, k, w.ktot, copy, w.xT_hi, w.xT_lo);
-  CUDA_TRY(cudaGetLastError());
+  TRY(split_planes(c, st, xl, n, w.a_hi[1], w.a_lo[1]));
   bias_grad_partial_kernel<<<dim3(kBiasParts, C / 128), 128, 0, st>>>(g, u, slope, rows, C, w.db_part);
   CUDA_TRY(cudaGetLastError());
   bias_grad_finish_kernel<<<(C + 127) / 128, 128, 0, st>>>(w.db_part, kBiasParts, C, grad_b_l);
   CUDA_TRY(cudaGetLastError());
-  c->launches += 5;
-  // dL/dW[o, c, j] = sum_k G'^T[o, k] x^T[c, k + j - pad]: one position-reduction GEMM per tap
+  c->launches += 4;
+  // dL/dW[o, c, j] = sum over positions of G'[pos, o] x[pos + j - pad, c]: one position-reduction GEMM per tap.  A = G'^T
+  // (K-major); B = the layer input's own planes read MN-major, utterance by utterance, the tap as a row offset of the
+  // TMA box (rows outside the utterance are zero-filled: the conv's zero padding) -- no transposed copies of x.
   for (int j = 0; j < k; ++j) {
     GemmParams p = gemm_defaults();
     p.N = C; p.out = w.dwt + static_cast<size_t>(j) * C * C; p.ld_out = C;
     p.split_kb = split_kb; p.split_scratch = w.splitk;
+    p.bmn_per = w.Tp / G2_BK; p.b_koff = j - pad;
     ProfScope ps(c, st, TAG_LINEAR);
     TRY(launch_gemm(c, st, OpA{w.gT_hi, w.gT_lo, 1, C, static_cast<int>(w.ktot), static_cast<int>(w.ktot)},
-                    OpB{w.xT_hi + j * copy, w.xT_lo + j * copy, 1, C, static_cast<int>(w.ktot), static_cast<int>(w.ktot)}, p));
+                    OpB{w.a_hi[1], w.a_lo[1], B, T, C, C}, p));
   }
   weight_grad_permute_kernel<<<ew_grid(wn), 256, 0, st>>>(w.dwt, C, C, k, grad_w_l);
   CUDA_TRY(cudaGetLastError());

@@ -176,7 +176,10 @@ constexpr int G2_THREADS_WIDE = 128 + 32 * 16;
 // template parameter because the run-time form of it cost the unsplit conv launches 7.5 % more issued instructions and
 // 6.7 points of tensor-pipe activity (measured by bisecting the commits on one box: 198 M -> 213 M warp instructions,
 // 86.6 % -> 79.9 %).
-template <int CG, int EPI, int WIDE, int FUSE = 0, int AR = G2_A_ROWS, int BN = 128, int SPLIT = 0>
+// BMN = 1: the B operand is read MN-major from activation planes [B, T, C] (TMA boxes of 64 columns x 64 rows): the
+// position-reduction GEMMs of the weight gradient, where the reduction index is the row of the activation and a conv tap
+// is a row offset of the box -- no transposed copies of the activation (fused-B pair variant only).
+template <int CG, int EPI, int WIDE, int FUSE = 0, int AR = G2_A_ROWS, int BN = 128, int SPLIT = 0, int BMN = 0>
 __global__ void __launch_bounds__(WIDE ? G2_THREADS_WIDE : G2_THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
              const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
@@ -311,7 +314,17 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
             const uint32_t dst = sB + s * Cfg::B_STAGE;
             const int z = p.b_batched ? b : tap;
             const int nrow = n0 + static_cast<int>(rank) * Cfg::B_ROWS;
-            if (FUSE) {
+            if (FUSE && BMN) {
+              // the same three blocks per CTA, each a 64-column x 64-row box of the activation planes (an MN-major atom
+              // column): columns n0 .. n0 + 127 of rows tk .. tk + 63 of utterance bb
+              const uint32_t bar = ptx::map_to_cta(fullB(s), 0);
+              if (leader) ptx::mbar_expect_tx(fullB(s), 2 * Cfg::B_STAGE);
+              const CUtensorMap* own = leader ? &tmB_hi : &tmB_lo;
+              const int bb = kb / p.bmn_per, tk = (kb - bb * p.bmn_per) * G2_BK + p.b_koff;
+              ptx::tma_load_3d_pair(own, bar, dst, n0, tk, bb);
+              ptx::tma_load_3d_pair(own, bar, dst + Cfg::B_PLANE, n0 + Cfg::B_ROWS, tk, bb);
+              ptx::tma_load_3d_pair(&tmB_hi, bar, dst + 2 * Cfg::B_PLANE, nrow, tk, bb);
+            } else if (FUSE) {
               // leader: Bhi[0:64], Bhi[64:128], Bhi[0:64] again; peer: Blo[0:64], Blo[64:128], Bhi[64:128]
               const uint32_t bar = ptx::map_to_cta(fullB(s), 0);
               if (leader) ptx::mbar_expect_tx(fullB(s), 2 * Cfg::B_STAGE);
@@ -344,8 +357,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
     if (!WIDE) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(G2_REGS_CTRL));
     if (leader) {
       const bool issuer = lane == 0;
-      constexpr uint32_t idesc = ptx::make_idesc_f16(G2_BM * CG, G2_BN);
-      constexpr uint32_t idesc_wide = ptx::make_idesc_f16(G2_BM * CG, 2 * G2_BN);
+      constexpr uint32_t idesc = ptx::make_idesc_f16(G2_BM * CG, G2_BN, BMN);
+      constexpr uint32_t idesc_wide = ptx::make_idesc_f16(G2_BM * CG, 2 * G2_BN, BMN);
       auto commit = [&](uint32_t bar) {
         if (issuer) {
           if (CG == 2) ptx::tc_commit_pair(bar, 3); else ptx::tc_commit(bar);
@@ -378,17 +391,19 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
               const uint32_t b_addr = sB + sb * Cfg::B_STAGE;
               const uint64_t dAh = ptx::make_desc_sw128(a_addr, 0);
               const uint64_t dAl = ptx::make_desc_sw128(a_addr + G2_A_PLANE, 0);
-              const uint64_t dBh = ptx::make_desc_sw128(b_addr, 0);
+              const uint64_t dBh = BMN ? ptx::make_desc_sw128_mn(b_addr, Cfg::B_PLANE) : ptx::make_desc_sw128(b_addr, 0);
               const uint64_t dBl = ptx::make_desc_sw128(b_addr + Cfg::B_PLANE, 0);
-              const uint64_t dB3 = ptx::make_desc_sw128(b_addr + 2 * Cfg::B_PLANE, 0);
+              const uint64_t dB3 = BMN ? ptx::make_desc_sw128_mn(b_addr + 2 * Cfg::B_PLANE, Cfg::B_PLANE)
+                                       : ptx::make_desc_sw128(b_addr + 2 * Cfg::B_PLANE, 0);
               if (issuer) {
 #pragma unroll
                 for (int k = 0; k < G2_BK / 16; ++k) {
                   const uint64_t ko = static_cast<uint64_t>(k * 2);
+                  const uint64_t kob = BMN ? static_cast<uint64_t>(k * (16 * 128 / 16)) : ko;   // MN-major: 16 rows on
                   if (FUSE) {
                     // columns [0,128): Ahi*Bhi, [128,256): Ahi*Blo + Alo*Bhi (dBl + one plane = the third block)
-                    ptx::mma_f16_ss_pair(acc0, dAh + ko, dBh + ko, idesc_wide, (first0 && k == 0) ? 0u : 1u);
-                    ptx::mma_f16_ss_pair(acc0 + G2_BN, dAl + ko, dB3 + ko, idesc, 1u);
+                    ptx::mma_f16_ss_pair(acc0, dAh + ko, dBh + kob, idesc_wide, (first0 && k == 0) ? 0u : 1u);
+                    ptx::mma_f16_ss_pair(acc0 + G2_BN, dAl + ko, dB3 + kob, idesc, 1u);
                   } else if (CG == 2) {
                     ptx::mma_f16_ss_pair(acc0, dAh + ko, dBh + ko, idesc, (first0 && k == 0) ? 0u : 1u);
                     ptx::mma_f16_ss_pair(acc1, dAh + ko, dBl + ko, idesc, (first1 && k == 0) ? 0u : 1u);

@@ -75,12 +75,15 @@ struct GemmParams {
   int dil;               // row shift of tap j is (j - pad) * dil; 0 is read as 1
   int plane_act;         // 1: the fp16 operand planes hold LeakyReLU(0.1) of the stored fp32 value (the next layer's
                          // input activation, vocoders/hifigan_model.py:58,123), the fp32 store stays pre-activation
+  int bmn_per;           // MN-major B operand (weight gradients): k-blocks per utterance of the activation planes; k-block kb
+                         // is rows (kb % bmn_per) * 64 + b_koff .. of utterance kb / bmn_per (0 = B is K-major)
   int mag_pairs;         // 1: columns (2f, 2f + 1) are (re_f, im_f) of an STFT; the epilogue writes sqrt(re^2 + im^2 + 1e-9)
                          // as operand planes [B, T, N / 2] (out_hi / out_lo, ld_pl) and nothing else (front-end only)
   int long_taps;         // host side only: use the 184-row A box variant (128 + (ntaps - 1) * dil <= 184)
   // weight-gradient GEMMs (reduction over positions)
-  int b_koff;            // element offset added to the B operand's K coordinate: B[n, k + b_koff]; must be a multiple
-                         // of 8 (TMA box coordinates are 16-byte aligned); out-of-range columns are zero-filled
+  int b_koff;            // offset of the B operand along the reduction: with an MN-major B (bmn_per > 0) a ROW offset of the
+                         // TMA box, any integer (the conv tap; rows outside the utterance are zero-filled); with a K-major B
+                         // an element offset of the K coordinate, which must be a multiple of 8 (16-byte aligned boxes)
   int split_kb;          // > 0 with splits > 1: every work item covers split_kb k-blocks (several accumulation chunks)
 };
 

@@ -144,11 +144,24 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr, uint32_t
   return d;
 }
 
-// kind::f16 instruction descriptor: fp16 x fp16 -> fp32, both operands K-major.
-__host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n) {
+// The same for an MN-major operand (rows of shared memory = K, 128-byte rows of 64 MN elements, as a TMA box of
+// [K rows][64 columns] lands them): atoms of 64 MN elements x 8 K rows, `lbo_bytes` between the atoms along MN (the box
+// height x 128), 1024 bytes between groups of 8 K rows.  A K step of 16 is 2048 bytes further on.
+__device__ __forceinline__ uint64_t make_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);   // start address  [0,14)
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;   // LBO: stride between MN atoms [16,30)
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;                // SBO: stride between 8-row K groups [32,46)
+  d |= static_cast<uint64_t>(1) << 46;                        // version = 1    [46,48)
+  d |= static_cast<uint64_t>(2) << 61;                        // SWIZZLE_128B   [61,64)
+  return d;
+}
+
+// kind::f16 instruction descriptor: fp16 x fp16 -> fp32, both operands K-major (b_mn = 1: B operand MN-major).
+__host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n, int b_mn = 0) {
   return (1u << 4)                                   // D format  = F32
          | (0u << 7) | (0u << 10)                    // A, B format = F16
-         | (0u << 15) | (0u << 16)                   // A, B K-major
+         | (0u << 15) | (static_cast<uint32_t>(b_mn) << 16)   // A K-major; B K-major or MN-major
          | (static_cast<uint32_t>(n >> 3) << 17)     // N / 8
          | (static_cast<uint32_t>(m >> 4) << 24);    // M / 16
 }

@@ -4,13 +4,12 @@
 //                             dL/dx = g + conv_k^T(G')               -> tap-GEMM with flipped, transposed weights
 //                             dL/dW[o, c, j] = sum_{b,t} G'[b,t,o] x[b, t + j - pad, c]   -> GEMM over positions
 //                             dL/db[o] = sum_{b,t} G'[b,t,o]
-// The position-reduction GEMM wants both operands K-major with K = positions: G'^T and x^T are laid out
-// [C][B * Tp] with Tp = round8(T + 2 * pad) and `pad` zero columns in front of every utterance, so a tap is a
-// column shift of x^T that never reads across an utterance boundary.  TMA box coordinates and UMMA start addresses
-// are 16-byte aligned, so the shift cannot be a read offset of one or two fp16 elements: the GEMM of tap j reads its own
-// copy of x^T, shifted by j - pad; transpose_shift_split_kernel writes all k copies in one pass.  (The better operand is
-// the activation plane itself read as an MN-major UMMA operand, where a tap is a row shift of the shared-memory tile
-// exactly like in the forward kernel; see DESIGN.md, "what comes next".)
+// The position-reduction GEMM: A = G'^T [C][B * Tp] (K-major; Tp = round64(T), zero columns behind every utterance, written
+// by transpose_shift_split_kernel), B = the layer input's own operand planes [B, T, C] read as an MN-major UMMA operand
+// (gemm2_kernel's BMN instantiation): the reduction index is the row of the TMA box, a conv tap is a row offset of that
+// box, rows outside the utterance are zero-filled by the TMA unit -- exactly the forward kernel's treatment of taps, and
+// no transposed copy of x exists.  (Rounds 2a / 2b of this slice wrote k shifted transposes of x per layer: a K-major
+// operand cannot be shifted by one element, TMA coordinates and UMMA start addresses being 16-byte aligned.)
 // Further down: the duration predictor's LayerNorm / head kernels and the criterion with gradients.
 #pragma once
 #include <cuda_fp16.h>
@@ -80,15 +79,14 @@ __global__ void lrelu_grad_split_kernel(const float* __restrict__ g, const float
   }
 }
 
-// fp32 [B, T, C] (optionally times the LeakyReLU' mask of u) -> transposed operand planes [C][B * Tp], one copy per
-// shift s in [first_shift, first_shift + nshift): column b * Tp + q of row c of copy s holds x[b, q - pad + s, c], zero
-// where that time step does not exist -- so the pad columns in front of every utterance and the rest of Tp behind it are
-// written here too (no memset).  Why copies: the weight gradient's position-reduction GEMM for tap j needs x^T shifted
-// by j - pad along its contiguous dimension, and neither a TMA coordinate nor a UMMA start address can carry a 2-byte
-// offset.  One pass reads x once and writes every copy with aligned 16-byte stores:
+// fp32 [B, T, C] (optionally times the activation-derivative mask of u) -> transposed operand planes [C][B * Tp], one
+// copy per shift s in [first_shift, first_shift + nshift): column b * Tp + q of row c of copy s holds x[b, q - pad + s, c],
+// zero where that time step does not exist -- so the margins of every utterance are written here too (no memset).  The
+// weight gradient uses it for G'^T (one copy, pad = 0); the shifted copies serve K-major operands that need a tap shift.
 //   block (256 threads) = 64 output columns x 32 channels of one utterance; it stages time steps
 //   [64 j - 4, 64 j + 64) as fp16 hi / lo rows [channel][step] in shared memory (conflict-free strides), then thread
-//   (channel, 8-column group) loads the 12-step window its five possible shifts share and funnel-shifts the words.
+//   (channel, 8-column group) loads the 12-step window its possible shifts share and funnel-shifts the words, so every
+//   copy is written with aligned 16-byte stores.
 // grid (ceil(Tp / 64), C / 32, B).
 constexpr int TS_COLS = 64, TS_HALO = 4, TS_STRIDE = 70;     // 68 staged steps per channel, row stride 35 words
 __device__ __forceinline__ void ts_store_shifted(const uint32_t (&w)[6], int off, __half* dst) {
