@@ -229,8 +229,9 @@ int launch_gemm2_t(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, con
   if (p.bias != nullptr && p.N > Cfg::BIAS_MAX) return fail(EFTS_ERR_ARG, "bias supports at most %d columns", Cfg::BIAS_MAX);
   alignas(64) CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   const int a_rows = a.map_rows > a.T ? a.map_rows : a.T;
-  TRY(make_map(c, &ma_hi, a.hi, a.K, a_rows, a.B, a.ld, AR));
-  TRY(make_map(c, &ma_lo, a.lo, a.K, a_rows, a.B, a.ld, AR));
+  // MN-major A (BMN == 2): 64-row boxes of the planes [B, T, C] themselves, like the B operand's
+  TRY(make_map(c, &ma_hi, a.hi, a.K, a_rows, a.B, a.ld, BMN == 2 ? Cfg::B_ROWS : AR));
+  TRY(make_map(c, &ma_lo, a.lo, a.K, a_rows, a.B, a.ld, BMN == 2 ? Cfg::B_ROWS : AR));
   TRY(make_map(c, &mb_hi, b.hi, b.K, b.N, b.Z, b.ld, Cfg::B_ROWS));
   TRY(make_map(c, &mb_lo, b.lo, b.K, b.N, b.Z, b.ld, Cfg::B_ROWS));
   // persistent: one CTA per SM (CTA pairs when CG == 2), never more than there are tiles
@@ -307,7 +308,14 @@ int launch_gemm(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, GemmPa
     }
     if (p.bmn_per > 0) {
       // Weight gradients: B = activation planes [Z = utterances, N = rows, K = channels] read MN-major by the split
-      // fused-B kernel, whatever the size (the reduction index is the activation's row, so no other variant applies)
+      // fused-B kernel, whatever the size (the reduction index is the activation's row, so no other variant applies).
+      // amn: A is given the same way -- planes [B, T, C] of the masked gradient, M = its channels -- instead of as
+      // K-major transposed planes: the kernel then sees one "utterance" of C rows and K = B * bmn_per k-blocks.
+      if (p.amn) {
+        if (a.B != b.Z || a.T != b.N) return fail(EFTS_ERR_ARG, "MN-major operands: planes of different shapes");
+        p.bmn_batches = a.B;
+        p.K = a.B * p.bmn_per * G2_BK; p.T = a.K; p.B = 1;
+      }
       const int num_kb = (p.K + G2_BK - 1) / G2_BK;
       if (p.split_kb <= 0) p.split_kb = (num_kb + p.chunk_kb - 1) / std::max(1, p.chunk_kb) * std::max(1, p.chunk_kb);
       const int splits = (num_kb + p.split_kb - 1) / p.split_kb;
@@ -320,7 +328,11 @@ int launch_gemm(efts_ctx* c, cudaStream_t st, const OpA& a, const OpB& b, GemmPa
       q.bias = nullptr; q.act = ACT_NONE; q.resid = nullptr; q.lens = nullptr;
       q.out = p.split_scratch; q.ld_out = p.N; q.out_hi = nullptr; q.out_lo = nullptr;
       q.splits = splits; q.split_stride = plane;
-      TRY((launch_gemm2_t<2, EPI_STD, 0, 1, G2_A_ROWS, G2_BN, 1, 1>(c, st, a, b, q)));
+      if (p.amn) {
+        TRY((launch_gemm2_t<2, EPI_STD, 0, 1, G2_A_ROWS, G2_BN, 1, 2>(c, st, a, b, q)));
+      } else {
+        TRY((launch_gemm2_t<2, EPI_STD, 0, 1, G2_A_ROWS, G2_BN, 1, 1>(c, st, a, b, q)));
+      }
       splitk_reduce_kernel<<<static_cast<unsigned>((plane / 4 + 255) / 256), 256, 0, st>>>(p, p.split_scratch, splits, plane);
       CUDA_TRY(cudaGetLastError());
       c->launches++;
@@ -412,6 +424,8 @@ int set_kernel_attributes() {
   CUDA_TRY(cudaFuncSetAttribute(gemm2_kernel<2, EPI_MAG, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 G2Cfg<2, 0, 1>::SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(gemm2_kernel<2, EPI_STD, 0, 1, G2_A_ROWS, G2_BN, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                G2Cfg<2, 0, 1>::SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(gemm2_kernel<2, EPI_STD, 0, 1, G2_A_ROWS, G2_BN, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 G2Cfg<2, 0, 1>::SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(gemm2_kernel<2, EPI_STD, 0, 1, G2_A_ROWS_LONG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 G2Cfg<2, 0, 1, G2_A_ROWS_LONG>::SMEM_BYTES));
@@ -2144,7 +2158,6 @@ namespace {
 struct TrainWs {
   __half *w_hi, *w_lo;                 // packed weights of the current layer [k][C][C]
   __half *a_hi[2], *a_lo[2];           // operand planes of a [B, T, C] activation (ping-pong)
-  __half *gT_hi, *gT_lo;               // transposed planes [C][Ktot] of the masked gradient (Ktot = B * round64(T))
   float* dwt;                          // [k][C][C]
   float* splitk;                       // partial planes of the split reductions
   double* db_part;                     // [kBiasParts][C]
@@ -2161,7 +2174,6 @@ void carve_train(Arena& a, TrainWs& w, int B, int T, int C, int k, bool backward
   w.w_lo = a.get<__half>(static_cast<size_t>(k) * C * C);
   for (int i = 0; i < 2; ++i) { w.a_hi[i] = a.get<__half>(m * C); w.a_lo[i] = a.get<__half>(m * C); }
   if (backward) {
-    w.gT_hi = a.get<__half>(w.ktot * C); w.gT_lo = a.get<__half>(w.ktot * C);
     w.dwt = a.get<float>(static_cast<size_t>(k) * C * C);
     w.splitk = a.get<float>(kSplitScratchBytes / sizeof(float));
     w.db_part = a.get<double>(static_cast<size_t>(kBiasParts) * C);
@@ -2184,29 +2196,26 @@ int conv_layer_bwd(efts_ctx* c, cudaStream_t st, TrainWs& w, const float* g, con
   int want = std::max(1, std::min(16, (c->sm_count / 2) / items));
   int split_kb = (num_kb + want - 1) / want;
   split_kb = (split_kb + c->chunk_kb - 1) / std::max(1, c->chunk_kb) * std::max(1, c->chunk_kb);
-  const dim3 tgrid((w.Tp + TS_COLS - 1) / TS_COLS, C / 32, B);
-  // G' planes (data gradient), G'^T planes and the planes of the layer input (weight gradient), bias gradient
+  // G' planes (both gradients' A operand), the planes of the layer input (weight gradient's B operand), bias gradient
   lrelu_grad_split_kernel<<<ew_grid(n / 4), 256, 0, st>>>(g, u, n / 4, slope, w.a_hi[0], w.a_lo[0], c->err_flag);
-  CUDA_TRY(cudaGetLastError());
-  transpose_shift_split_kernel<<<tgrid, 256, 0, st>>>(g, u, slope, T, C, w.Tp, 0, 0, 1, w.ktot, 0, w.gT_hi, w.gT_lo);
   CUDA_TRY(cudaGetLastError());
   TRY(split_planes(c, st, xl, n, w.a_hi[1], w.a_lo[1]));
   bias_grad_partial_kernel<<<dim3(kBiasParts, C / 128), 128, 0, st>>>(g, u, slope, rows, C, w.db_part);
   CUDA_TRY(cudaGetLastError());
   bias_grad_finish_kernel<<<(C + 127) / 128, 128, 0, st>>>(w.db_part, kBiasParts, C, grad_b_l);
   CUDA_TRY(cudaGetLastError());
-  c->launches += 4;
-  // dL/dW[o, c, j] = sum over positions of G'[pos, o] x[pos + j - pad, c]: one position-reduction GEMM per tap.  A = G'^T
-  // (K-major); B = the layer input's own planes read MN-major, utterance by utterance, the tap as a row offset of the
-  // TMA box (rows outside the utterance are zero-filled: the conv's zero padding) -- no transposed copies of x.
+  c->launches += 3;
+  // dL/dW[o, c, j] = sum over positions of G'[pos, o] x[pos + j - pad, c]: one position-reduction GEMM per tap.  Both
+  // operands are the activations' own planes [B, T, C] read MN-major, utterance by utterance in 64-row boxes (rows
+  // outside the utterance are zero-filled by the TMA unit: the conv's zero padding, and the tail of the last box); the
+  // tap is a row offset of B's box -- no transposed copy of either tensor.
   for (int j = 0; j < k; ++j) {
     GemmParams p = gemm_defaults();
     p.N = C; p.out = w.dwt + static_cast<size_t>(j) * C * C; p.ld_out = C;
     p.split_kb = split_kb; p.split_scratch = w.splitk;
-    p.bmn_per = w.Tp / G2_BK; p.b_koff = j - pad;
+    p.bmn_per = w.Tp / G2_BK; p.b_koff = j - pad; p.amn = 1;
     ProfScope ps(c, st, TAG_LINEAR);
-    TRY(launch_gemm(c, st, OpA{w.gT_hi, w.gT_lo, 1, C, static_cast<int>(w.ktot), static_cast<int>(w.ktot)},
-                    OpB{w.a_hi[1], w.a_lo[1], B, T, C, C}, p));
+    TRY(launch_gemm(c, st, OpA{w.a_hi[0], w.a_lo[0], B, T, C, C}, OpB{w.a_hi[1], w.a_lo[1], B, T, C, C}, p));
   }
   weight_grad_permute_kernel<<<ew_grid(wn), 256, 0, st>>>(w.dwt, C, C, k, grad_w_l);
   CUDA_TRY(cudaGetLastError());

@@ -178,7 +178,8 @@ constexpr int G2_THREADS_WIDE = 128 + 32 * 16;
 // 86.6 % -> 79.9 %).
 // BMN = 1: the B operand is read MN-major from activation planes [B, T, C] (TMA boxes of 64 columns x 64 rows): the
 // position-reduction GEMMs of the weight gradient, where the reduction index is the row of the activation and a conv tap
-// is a row offset of the box -- no transposed copies of the activation (fused-B pair variant only).
+// is a row offset of the box -- no transposed copies of the activation (fused-B pair variant only).  BMN = 2: the A
+// operand as well (the masked gradient's planes [B, T, C]: M = its channels, 64-channel x 64-row boxes, two per plane).
 template <int CG, int EPI, int WIDE, int FUSE = 0, int AR = G2_A_ROWS, int BN = 128, int SPLIT = 0, int BMN = 0>
 __global__ void __launch_bounds__(WIDE ? G2_THREADS_WIDE : G2_THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
@@ -296,7 +297,17 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
             const int s = ia % Cfg::A_STAGES; const uint32_t ph = (ia / Cfg::A_STAGES) & 1;
             ptx::mbar_wait(emptyA(s), ph ^ 1u);
             const uint32_t dst = sA + s * G2_A_STAGE;
-            if (CG == 2) {
+            if (CG == 2 && BMN == 2) {
+              // MN-major A: channels t0 .. t0 + 127 (this CTA's M rows) of rows tk .. tk + 63 of utterance bb, two
+              // 64-column atoms per plane; an invalid tile (b == p.B) reads utterance p.bmn_batches: zeros
+              const uint32_t bar = ptx::map_to_cta(fullA(s), 0);
+              if (leader) ptx::mbar_expect_tx(fullA(s), 2 * 4 * 64 * 128);
+              const int bb = valid ? kb / p.bmn_per : p.bmn_batches, tk = (kb % p.bmn_per) * G2_BK;
+              ptx::tma_load_3d_pair(&tmA_hi, bar, dst, t0, tk, bb);
+              ptx::tma_load_3d_pair(&tmA_hi, bar, dst + 64 * 128, t0 + 64, tk, bb);
+              ptx::tma_load_3d_pair(&tmA_lo, bar, dst + G2_A_PLANE, t0, tk, bb);
+              ptx::tma_load_3d_pair(&tmA_lo, bar, dst + G2_A_PLANE + 64 * 128, t0 + 64, tk, bb);
+            } else if (CG == 2) {
               const uint32_t bar = ptx::map_to_cta(fullA(s), 0);
               if (leader) ptx::mbar_expect_tx(fullA(s), 2 * G2_A_STAGE);
               ptx::tma_load_3d_pair(&tmA_hi, bar, dst, kb * G2_BK, t0 - p.pad * dil, b);
@@ -357,8 +368,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
     if (!WIDE) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(G2_REGS_CTRL));
     if (leader) {
       const bool issuer = lane == 0;
-      constexpr uint32_t idesc = ptx::make_idesc_f16(G2_BM * CG, G2_BN, BMN);
-      constexpr uint32_t idesc_wide = ptx::make_idesc_f16(G2_BM * CG, 2 * G2_BN, BMN);
+      constexpr uint32_t idesc = ptx::make_idesc_f16(G2_BM * CG, G2_BN, BMN != 0, BMN == 2);
+      constexpr uint32_t idesc_wide = ptx::make_idesc_f16(G2_BM * CG, 2 * G2_BN, BMN != 0, BMN == 2);
       auto commit = [&](uint32_t bar) {
         if (issuer) {
           if (CG == 2) ptx::tc_commit_pair(bar, 3); else ptx::tc_commit(bar);
@@ -389,8 +400,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
               ptx::tc_fence_after();
               const uint32_t a_addr = sA + sa * G2_A_STAGE + tap * dil * 128;     // row shift = tap * dilation
               const uint32_t b_addr = sB + sb * Cfg::B_STAGE;
-              const uint64_t dAh = ptx::make_desc_sw128(a_addr, 0);
-              const uint64_t dAl = ptx::make_desc_sw128(a_addr + G2_A_PLANE, 0);
+              const uint64_t dAh = BMN == 2 ? ptx::make_desc_sw128_mn(a_addr, 64 * 128) : ptx::make_desc_sw128(a_addr, 0);
+              const uint64_t dAl = BMN == 2 ? ptx::make_desc_sw128_mn(a_addr + G2_A_PLANE, 64 * 128)
+                                            : ptx::make_desc_sw128(a_addr + G2_A_PLANE, 0);
               const uint64_t dBh = BMN ? ptx::make_desc_sw128_mn(b_addr, Cfg::B_PLANE) : ptx::make_desc_sw128(b_addr, 0);
               const uint64_t dBl = ptx::make_desc_sw128(b_addr + Cfg::B_PLANE, 0);
               const uint64_t dB3 = BMN ? ptx::make_desc_sw128_mn(b_addr + 2 * Cfg::B_PLANE, Cfg::B_PLANE)
@@ -400,10 +412,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
                 for (int k = 0; k < G2_BK / 16; ++k) {
                   const uint64_t ko = static_cast<uint64_t>(k * 2);
                   const uint64_t kob = BMN ? static_cast<uint64_t>(k * (16 * 128 / 16)) : ko;   // MN-major: 16 rows on
+                  const uint64_t koa = BMN == 2 ? kob : ko;
                   if (FUSE) {
                     // columns [0,128): Ahi*Bhi, [128,256): Ahi*Blo + Alo*Bhi (dBl + one plane = the third block)
-                    ptx::mma_f16_ss_pair(acc0, dAh + ko, dBh + kob, idesc_wide, (first0 && k == 0) ? 0u : 1u);
-                    ptx::mma_f16_ss_pair(acc0 + G2_BN, dAl + ko, dB3 + kob, idesc, 1u);
+                    ptx::mma_f16_ss_pair(acc0, dAh + koa, dBh + kob, idesc_wide, (first0 && k == 0) ? 0u : 1u);
+                    ptx::mma_f16_ss_pair(acc0 + G2_BN, dAl + koa, dB3 + kob, idesc, 1u);
                   } else if (CG == 2) {
                     ptx::mma_f16_ss_pair(acc0, dAh + ko, dBh + ko, idesc, (first0 && k == 0) ? 0u : 1u);
                     ptx::mma_f16_ss_pair(acc1, dAh + ko, dBl + ko, idesc, (first1 && k == 0) ? 0u : 1u);

@@ -77,6 +77,8 @@ struct GemmParams {
                          // input activation, vocoders/hifigan_model.py:58,123), the fp32 store stays pre-activation
   int bmn_per;           // MN-major B operand (weight gradients): k-blocks per utterance of the activation planes; k-block kb
                          // is rows (kb % bmn_per) * 64 + b_koff .. of utterance kb / bmn_per (0 = B is K-major)
+  int amn;               // host side: the A operand is MN-major too: OpA describes activation planes [B, T, C] (M = its channels)
+  int bmn_batches;       // utterances of those planes (an invalid M tile of an MN-major A reads utterance bmn_batches: zeros)
   int mag_pairs;         // 1: columns (2f, 2f + 1) are (re_f, im_f) of an STFT; the epilogue writes sqrt(re^2 + im^2 + 1e-9)
                          // as operand planes [B, T, N / 2] (out_hi / out_lo, ld_pl) and nothing else (front-end only)
   int long_taps;         // host side only: use the 184-row A box variant (128 + (ntaps - 1) * dil <= 184)

@@ -158,10 +158,10 @@ __device__ __forceinline__ uint64_t make_desc_sw128_mn(uint32_t smem_addr, uint3
 }
 
 // kind::f16 instruction descriptor: fp16 x fp16 -> fp32, both operands K-major (b_mn = 1: B operand MN-major).
-__host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n, int b_mn = 0) {
+__host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n, int b_mn = 0, int a_mn = 0) {
   return (1u << 4)                                   // D format  = F32
          | (0u << 7) | (0u << 10)                    // A, B format = F16
-         | (0u << 15) | (static_cast<uint32_t>(b_mn) << 16)   // A K-major; B K-major or MN-major
+         | (static_cast<uint32_t>(a_mn) << 15) | (static_cast<uint32_t>(b_mn) << 16)   // K-major (0) or MN-major (1)
          | (static_cast<uint32_t>(n >> 3) << 17)     // N / 8
          | (static_cast<uint32_t>(m >> 4) << 24);    // M / 16
 }

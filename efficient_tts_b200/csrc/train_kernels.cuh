@@ -4,12 +4,13 @@
 //                             dL/dx = g + conv_k^T(G')               -> tap-GEMM with flipped, transposed weights
 //                             dL/dW[o, c, j] = sum_{b,t} G'[b,t,o] x[b, t + j - pad, c]   -> GEMM over positions
 //                             dL/db[o] = sum_{b,t} G'[b,t,o]
-// The position-reduction GEMM: A = G'^T [C][B * Tp] (K-major; Tp = round64(T), zero columns behind every utterance, written
-// by transpose_shift_split_kernel), B = the layer input's own operand planes [B, T, C] read as an MN-major UMMA operand
-// (gemm2_kernel's BMN instantiation): the reduction index is the row of the TMA box, a conv tap is a row offset of that
-// box, rows outside the utterance are zero-filled by the TMA unit -- exactly the forward kernel's treatment of taps, and
-// no transposed copy of x exists.  (Rounds 2a / 2b of this slice wrote k shifted transposes of x per layer: a K-major
-// operand cannot be shifted by one element, TMA coordinates and UMMA start addresses being 16-byte aligned.)
+// The position-reduction GEMM reads BOTH operands from the activations' own operand planes [B, T, C] as MN-major UMMA
+// operands (gemm2_kernel's BMN = 2 instantiation): A = G' (M = its channels), B = the layer input (N = its channels), the
+// reduction index is the row of the 64-row TMA boxes, utterance by utterance; a conv tap is a row offset of B's box and
+// rows outside the utterance are zero-filled by the TMA unit -- exactly the forward kernel's treatment of taps.  No
+// transposed copy of either tensor exists.  (Earlier forms of this slice transposed G' and wrote k shifted transposes of
+// x per layer: a K-major operand cannot be shifted by one element, TMA coordinates and UMMA start addresses being
+// 16-byte aligned.)
 // Further down: the duration predictor's LayerNorm / head kernels and the criterion with gradients.
 #pragma once
 #include <cuda_fp16.h>
@@ -76,65 +77,6 @@ __global__ void lrelu_grad_split_kernel(const float* __restrict__ g, const float
     split4(v, &h, &l);
     reinterpret_cast<uint2*>(hi)[i] = h;
     reinterpret_cast<uint2*>(lo)[i] = l;
-  }
-}
-
-// fp32 [B, T, C] (optionally times the activation-derivative mask of u) -> transposed operand planes [C][B * Tp], one
-// copy per shift s in [first_shift, first_shift + nshift): column b * Tp + q of row c of copy s holds x[b, q - pad + s, c],
-// zero where that time step does not exist -- so the margins of every utterance are written here too (no memset).  The
-// weight gradient uses it for G'^T (one copy, pad = 0); the shifted copies serve K-major operands that need a tap shift.
-//   block (256 threads) = 64 output columns x 32 channels of one utterance; it stages time steps
-//   [64 j - 4, 64 j + 64) as fp16 hi / lo rows [channel][step] in shared memory (conflict-free strides), then thread
-//   (channel, 8-column group) loads the 12-step window its possible shifts share and funnel-shifts the words, so every
-//   copy is written with aligned 16-byte stores.
-// grid (ceil(Tp / 64), C / 32, B).
-constexpr int TS_COLS = 64, TS_HALO = 4, TS_STRIDE = 70;     // 68 staged steps per channel, row stride 35 words
-__device__ __forceinline__ void ts_store_shifted(const uint32_t (&w)[6], int off, __half* dst) {
-  uint32_t o[4];
-  const int k0 = off >> 1;
-#pragma unroll
-  for (int k = 0; k < 4; ++k)
-    o[k] = (off & 1) ? __funnelshift_r(w[k0 + k], w[k0 + k + 1], 16) : w[k0 + k];
-  *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
-}
-__global__ void __launch_bounds__(256)
-transpose_shift_split_kernel(const float* __restrict__ x, const float* __restrict__ u_mask, float slope, int T, int C,
-                             int Tp, int pad, int first_shift, int nshift, size_t ktot, size_t copy_stride, __half* __restrict__ hiT,
-                             __half* __restrict__ loT) {
-  __shared__ __align__(16) __half s_hi[32 * TS_STRIDE];
-  __shared__ __align__(16) __half s_lo[32 * TS_STRIDE];
-  const int b = blockIdx.z;
-  const int q0 = blockIdx.x * TS_COLS, c0 = blockIdx.y * 32;
-  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-  // stage: step index i <-> time step q0 - TS_HALO + i
-  for (int i = wrp; i < TS_COLS + TS_HALO; i += 8) {
-    const int t = q0 - TS_HALO + i;
-    float v = 0.0f;
-    if (t >= 0 && t < T) {
-      const size_t g = (static_cast<size_t>(b) * T + t) * C + c0 + lane;
-      v = x[g];
-      if (u_mask != nullptr && !(u_mask[g] > 0.0f)) v = __fmul_rn(v, slope);
-    }
-    const __half h = __float2half_rn(v);
-    s_hi[lane * TS_STRIDE + i] = h;
-    s_lo[lane * TS_STRIDE + i] = __float2half_rn((v - __half2float(h)) * kSplitScale);
-  }
-  __syncthreads();
-  const int ch = threadIdx.x >> 3, grp = threadIdx.x & 7;
-  const int q = q0 + 8 * grp;                    // first output column of this thread's group
-  if (q >= Tp) return;
-  uint32_t wh[6], wl[6];
-#pragma unroll
-  for (int k = 0; k < 6; ++k) {
-    wh[k] = *reinterpret_cast<const uint32_t*>(s_hi + ch * TS_STRIDE + 8 * grp + 2 * k);
-    wl[k] = *reinterpret_cast<const uint32_t*>(s_lo + ch * TS_STRIDE + 8 * grp + 2 * k);
-  }
-  const size_t o = static_cast<size_t>(c0 + ch) * ktot + static_cast<size_t>(b) * Tp + q;
-  for (int m = 0; m < nshift; ++m) {
-    // column q + e <- time step q + e - pad + s = staged step 8 grp + e + (TS_HALO - pad + s)
-    const int off = TS_HALO - pad + first_shift + m;           // in [0, 4] for |s| <= pad <= 2
-    ts_store_shifted(wh, off, hiT + m * copy_stride + o);
-    ts_store_shifted(wl, off, loT + m * copy_stride + o);
   }
 }
 
