@@ -19,7 +19,12 @@ $NCU --set full --import-source on -k regex:gemm2_kernel -s 36 -c 1 -o $O/dec_co
 $NCU $FULL -k regex:"reconstruct_alignment_rows_kernel|imv_scan_block_kernel|aligned_positions_block_kernel" -s 3 -c 3 -o $O/imv_chain -f python tools/profile_workloads.py c3 3 > /dev/null 2>&1
 $NCU $FULL -k regex:"length_regulator_fwd_kernel" -s 1 -c 1 -o $O/length_regulator -f python tools/profile_workloads.py lr 3 > /dev/null 2>&1
 $NCU $FULL -k regex:"stack_kernel" -s 2 -c 2 -o $O/stack -f python tools/profile_workloads.py c1 3 > /dev/null 2>&1
-for r in dec_conv imv_chain length_regulator stack; do
+# weight-gradient GEMM (both operands MN-major): gemm2 launches of one forward + backward of the 2-layer stack are
+# fwd x2, then per layer 5 weight-gradient launches + the data-gradient launch; the STFT GEMM with the magnitude epilogue
+# is the first gemm2 launch of a front-end call
+$NCU --set full --import-source on -k regex:gemm2_kernel -s 4 -c 1 -o $O/wgrad -f python tools/profile_workloads.py train 1 > /dev/null 2>&1
+$NCU --set full --import-source on -k regex:gemm2_kernel -s 2 -c 1 -o $O/stft_mag -f python tools/profile_workloads.py frontend 2 > /dev/null 2>&1
+for r in dec_conv imv_chain length_regulator stack wgrad stft_mag; do
   ncu -i $O/$r.ncu-rep --page raw --csv > $O/${r}_raw.csv 2> /dev/null
 done
 ls -la $O
